@@ -1,0 +1,87 @@
+"""ctypes binding of the C ABI (include/hpfw_b200.h). Fails loudly if the CUDA library is missing: no fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhpfw_b200.so")
+
+
+class HpfwError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"hpfw_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Match(C.Structure):
+    """= hpfw_match = db::MemoryStorage::SearchResult (storage.h:11-15) with the filename as a DB index."""
+    _fields_ = [("track", C.c_int64), ("cnt", C.c_uint64), ("offset", C.c_int64)]
+
+
+OK, ERR_CUDA, ERR_ARG, ERR_LIMIT, ERR_STATE, ERR_SHORT = 0, -1, -2, -3, -4, -5
+
+_SIGS = {
+    # name: (restype, argtypes)
+    "hpfw_last_error": (C.c_char_p, []),
+    "hpfw_version": (C.c_char_p, []),
+    "hpfw_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "hpfw_ctx_destroy": (None, [C.c_void_p]),
+    "hpfw_ctx_device": (C.c_int, [C.c_void_p]),
+    "hpfw_ctx_launch_count": (C.c_uint64, [C.c_void_p]),
+    "hpfw_ctx_synchronize": (C.c_int, [C.c_void_p]),
+    "hpfw_db_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
+    "hpfw_db_build_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
+                                       C.POINTER(C.c_void_p)]),
+    "hpfw_db_destroy": (None, [C.c_void_p]),
+    "hpfw_db_tracks": (C.c_int, [C.c_void_p]),
+    "hpfw_db_words": (C.c_int64, [C.c_void_p]),
+    "hpfw_db_find": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Match)]),
+    "hpfw_db_find_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Match)]),
+    "hpfw_db_match_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "hpfw_topk_merge_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "hpfw_keys_decode": (None, [C.c_void_p, C.c_int, C.POINTER(Match)]),
+    "hpfw_db_word_ops": (C.c_double, [C.c_void_p, C.c_void_p, C.c_int]),
+    "hpfw_set_filters": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hpfw_get_filters": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hpfw_hashprint_words_for_cols": (C.c_int, [C.c_int]),
+    "hpfw_hashprint_from_spectrogram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    "hpfw_hashprint_from_spectrogram_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                                         C.c_void_p]),
+    "hpfw_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "hpfw_cqt_cols": (C.c_int, [C.c_int64]),
+    "hpfw_cqt_spectrogram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int)]),
+    "hpfw_cqt_spectrogram_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "hpfw_cqt_magnitude": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int)]),
+    "hpfw_hashprint_words_for_samples": (C.c_int, [C.c_int64]),
+    "hpfw_calc_hashprint_audio": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int)]),
+    "hpfw_calc_hashprint_audio_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "hpfw_microbench_pipes": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+}
+
+# every symbol include/hpfw_b200.h declares (tests/test_abi_cpu.py checks the header against this and the .so)
+ABI_SYMBOLS = tuple(_SIGS)
+
+_lib = None
+
+
+def load():
+    """dlopen the C-ABI library. Raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: build it with `python -m hpfw_b200.build` (nvcc, sm_100a). "
+                "hpfw_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)  # AttributeError = ABI symbol missing: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(status: int) -> None:
+    if status != OK:
+        raise HpfwError(status, load().hpfw_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,204 @@
+"""Host-side mirror of the reference's interfaces for the hot path, over the C ABI.
+
+  MemoryStorage   <- hpfw::db::MemoryStorage<Collector>  (include/hpfw/audioproblems/live-song-id/storage.h:8-93)
+  Context         <- one GPU (no equivalent in the CPU-only reference)
+Names, argument meaning and error behaviour follow the reference; the filename of a SearchResult is looked up from the
+names given to build().
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Iterable, List, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import Match, check
+
+SIZE_MAX = (1 << 64) - 1
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One CUDA device. There is no CPU fallback: construction fails without a B200-class GPU."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        check(self._lib.hpfw_ctx_create(device, C.byref(h)))
+        self._h = h
+        self.device = device
+
+    @property
+    def handle(self):
+        return self._h
+
+    def launch_count(self) -> int:
+        return int(self._lib.hpfw_ctx_launch_count(self._h))
+
+    def synchronize(self) -> None:
+        check(self._lib.hpfw_ctx_synchronize(self._h))
+
+    def microbench_pipes(self):
+        out = (C.c_double * 3)()
+        clk = C.c_double()
+        check(self._lib.hpfw_microbench_pipes(self._h, out, C.byref(clk)))
+        return {"popc_per_clk_sm": out[0], "lop3_per_clk_sm": out[1], "wordops_per_clk_sm": out[2],
+                "sm_clock_mhz": clk.value}
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.hpfw_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+@dataclass
+class SearchResult:
+    """= MemoryStorage::SearchResult {filename, cnt, offset} (storage.h:11-15); `track` is the DB index (-1: none)."""
+    filename: str
+    cnt: int
+    offset: int
+    track: int = -1
+
+
+def pack(hashprints: Sequence[np.ndarray]) -> Tuple[np.ndarray, np.ndarray]:
+    offs = np.zeros(len(hashprints) + 1, dtype=np.int64)
+    for i, h in enumerate(hashprints):
+        offs[i + 1] = offs[i] + len(h)
+    if len(hashprints) and offs[-1] > 0:
+        words = np.ascontiguousarray(np.concatenate([np.asarray(h, dtype=np.uint64) for h in hashprints]))
+    else:
+        words = np.zeros(0, dtype=np.uint64)
+    return words, offs
+
+
+class MemoryStorage:
+    """GPU-resident hashprint database with the reference's build()/find() semantics (storage.h:21-64).
+
+    build() takes the collector's output, a list of (filename, hashprint) pairs in DB order (the reference moves a
+    tbb::concurrent_vector<FilenameFingerprintPair> into a std::vector; DB order = arrival order).
+    """
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self._lib = ctx._lib
+        self._db = None
+        self.filenames: List[str] = []
+        self.track_base = 0
+
+    def build(self, pairs: Iterable[Tuple[str, np.ndarray]], track_base: int = 0) -> "MemoryStorage":
+        pairs = list(pairs)
+        self.filenames = [p[0] for p in pairs]
+        words, offs = pack([p[1] for p in pairs])
+        return self.build_packed(words, offs, self.filenames, track_base)
+
+    def build_packed(self, words: np.ndarray, offsets: np.ndarray, filenames=None, track_base: int = 0):
+        self._free()
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        self.filenames = list(filenames) if filenames is not None else [str(track_base + i) for i in range(n)]
+        self.track_base = track_base
+        h = C.c_void_p()
+        check(self._lib.hpfw_db_build(self.ctx.handle, _ptr(words) if words.size else None, _ptr(offsets), n,
+                                      track_base, C.byref(h)))
+        self._db = h
+        self._offsets = offsets
+        return self
+
+    def build_device(self, d_words_ptr: int, offsets: np.ndarray, stream: int = 0, filenames=None, track_base: int = 0):
+        """words already in HBM (e.g. a torch tensor's data_ptr())."""
+        self._free()
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        self.filenames = list(filenames) if filenames is not None else [str(track_base + i) for i in range(n)]
+        self.track_base = track_base
+        h = C.c_void_p()
+        check(self._lib.hpfw_db_build_device(self.ctx.handle, C.c_void_p(d_words_ptr), _ptr(offsets), n, track_base,
+                                             C.c_void_p(stream), C.byref(h)))
+        self._db = h
+        self._offsets = offsets
+        return self
+
+    # ---- reference API ----
+    def find(self, hp: np.ndarray) -> SearchResult:
+        """MemoryStorage::find (storage.h:27-64): best track, its Hamming distance and alignment offset."""
+        hp = np.ascontiguousarray(hp, dtype=np.uint64)
+        m = Match()
+        check(self._lib.hpfw_db_find(self._require(), _ptr(hp) if hp.size else None, len(hp), C.byref(m)))
+        return self._result(m)
+
+    # ---- batched / top-k (notebook semantics, liveid.ipynb:909-927) ----
+    def find_topk(self, queries: Sequence[np.ndarray], topk: int = 10) -> List[List[SearchResult]]:
+        qwords, qoffs = pack(list(queries))
+        nq = len(qoffs) - 1
+        out = (Match * (nq * topk))()
+        check(self._lib.hpfw_db_find_topk(self._require(), _ptr(qwords) if qwords.size else None, _ptr(qoffs), nq, topk,
+                                          out))
+        return [[self._result(out[q * topk + r]) for r in range(topk)] for q in range(nq)]
+
+    def find_topk_packed(self, qwords: np.ndarray, qoffs: np.ndarray, topk: int = 10) -> np.ndarray:
+        """Same, returning a structured array [nq, topk] with fields track/cnt/offset (no Python object per result)."""
+        qwords = np.ascontiguousarray(qwords, dtype=np.uint64)
+        qoffs = np.ascontiguousarray(qoffs, dtype=np.int64)
+        nq = len(qoffs) - 1
+        out = np.zeros((nq, topk), dtype=np.dtype([("track", "<i8"), ("cnt", "<u8"), ("offset", "<i8")]))
+        check(self._lib.hpfw_db_find_topk(self._require(), _ptr(qwords) if qwords.size else None, _ptr(qoffs), nq, topk,
+                                          out.ctypes.data_as(C.POINTER(Match))))
+        return out
+
+    def match_device(self, d_qwords_ptr: int, qoffs: np.ndarray, topk: int, d_keys_out_ptr: int, stream: int = 0):
+        """Device path: query words and the key output live in HBM; enqueues on `stream` without synchronising."""
+        qoffs = np.ascontiguousarray(qoffs, dtype=np.int64)
+        check(self._lib.hpfw_db_match_device(self._require(), C.c_void_p(d_qwords_ptr), _ptr(qoffs), len(qoffs) - 1,
+                                             topk, C.c_void_p(d_keys_out_ptr), C.c_void_p(stream)))
+
+    def word_ops(self, qoffs: np.ndarray) -> float:
+        qoffs = np.ascontiguousarray(qoffs, dtype=np.int64)
+        return float(self._lib.hpfw_db_word_ops(self._require(), _ptr(qoffs), len(qoffs) - 1))
+
+    @property
+    def n_tracks(self) -> int:
+        return int(self._lib.hpfw_db_tracks(self._require()))
+
+    def _result(self, m: Match) -> SearchResult:
+        if m.track < 0:
+            return SearchResult("", SIZE_MAX, 0, -1)   # storage.h:28 initial value
+        local = m.track - self.track_base
+        name = self.filenames[local] if 0 <= local < len(self.filenames) else str(m.track)
+        return SearchResult(name, int(m.cnt), int(m.offset), int(m.track))
+
+    def _require(self):
+        if self._db is None:
+            raise RuntimeError("MemoryStorage: build() has not been called")
+        return self._db
+
+    def _free(self):
+        if self._db is not None:
+            self._lib.hpfw_db_destroy(self._db)
+            self._db = None
+
+    def __del__(self):
+        try:
+            self._free()
+        except Exception:
+            pass
+
+
+def decode_keys(keys: np.ndarray) -> np.ndarray:
+    """Packed keys (dist<<40 | track<<20 | offset) -> structured array with track/cnt/offset."""
+    L = _lib.load()
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    out = np.zeros(keys.shape, dtype=np.dtype([("track", "<i8"), ("cnt", "<u8"), ("offset", "<i8")]))
+    L.hpfw_keys_decode(_ptr(keys), keys.size, out.ctypes.data_as(C.POINTER(Match)))
+    return out

@@ -1,0 +1,130 @@
+// hpfw_b200/csrc/common.cuh — shared host-side plumbing for the C ABI (include/hpfw_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/hpfw_b200.h"
+
+namespace hpfw_b200 {
+
+void set_error(const char *fmt, ...);
+
+#define HPFW_CUDA_TRY(expr)                                                                          \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            hpfw_b200::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,                  \
+                                 cudaGetErrorString(_e));                                            \
+            return HPFW_ERR_CUDA;                                                                    \
+        }                                                                                            \
+    } while (0)
+
+#define HPFW_TRY(expr)                   \
+    do {                                 \
+        int _s = (expr);                 \
+        if (_s != HPFW_OK) return _s;    \
+    } while (0)
+
+#define HPFW_FAIL(code, ...)               \
+    do {                                   \
+        hpfw_b200::set_error(__VA_ARGS__); \
+        return (code);                     \
+    } while (0)
+
+// Grow-only device scratch buffer.
+struct DeviceBuffer {
+    void *ptr = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return HPFW_OK;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        HPFW_CUDA_TRY(cudaMalloc(&ptr, want));
+        cap = want;
+        return HPFW_OK;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return static_cast<T *>(ptr); }
+};
+
+// Grow-only pinned host staging buffer.
+struct PinnedBuffer {
+    void *ptr = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return HPFW_OK;
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        HPFW_CUDA_TRY(cudaMallocHost(&ptr, want));
+        cap = want;
+        return HPFW_OK;
+    }
+    void release() {
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return static_cast<T *>(ptr); }
+};
+
+struct CqtPlanCache;  // cqt.cu
+
+}  // namespace hpfw_b200
+
+struct hpfw_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    cudaStream_t stream = nullptr;  // the context's own stream
+    cudaEvent_t pin_in_free = nullptr;  // recorded after the last H2D copy out of pin_in
+    uint64_t launches = 0;
+
+    // matcher scratch
+    hpfw_b200::DeviceBuffer best;      // [queries_in_chunk][tracks] u64
+    hpfw_b200::DeviceBuffer qmeta;     // query block tables
+    hpfw_b200::DeviceBuffer qwords;    // staged query words (host entry points)
+    hpfw_b200::DeviceBuffer keys;      // staged result keys (host entry points)
+    hpfw_b200::PinnedBuffer pin_in, pin_out;
+
+    // projection state
+    hpfw_b200::DeviceBuffer filters_perm;  // filters permuted to [context][band(padded 128)][filter] etc. (project.cu)
+    std::vector<float> filters_host;       // column-major 64 x 2420 as given
+    bool have_filters = false;
+    hpfw_b200::DeviceBuffer spectro, hp, yproj, colmeta;
+
+    // cqt state
+    hpfw_b200::CqtPlanCache *cqt = nullptr;
+    hpfw_b200::DeviceBuffer audio;
+
+    cudaStream_t pick(void *s) const { return s ? static_cast<cudaStream_t>(s) : stream; }
+};
+
+namespace hpfw_b200 {
+// RAII device guard: every ABI call runs on its context's device.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+void cqt_cache_destroy(CqtPlanCache *);
+}  // namespace hpfw_b200

@@ -1,0 +1,83 @@
+// hpfw_b200/csrc/context.cu — context lifetime, error reporting.
+#include "common.cuh"
+
+namespace hpfw_b200 {
+static thread_local char g_err[1024] = "";
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+#ifndef HPFW_HAVE_CQT
+void cqt_cache_destroy(CqtPlanCache *) {}
+#endif
+}  // namespace hpfw_b200
+
+extern "C" {
+
+const char *hpfw_last_error(void) { return hpfw_b200::g_err; }
+const char *hpfw_version(void) { return "hpfw_b200 0.1 (sm_100a)"; }
+
+int hpfw_ctx_create(int device, hpfw_ctx **out) {
+    if (!out) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_ctx_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        HPFW_FAIL(HPFW_ERR_CUDA, "hpfw_ctx_create: no CUDA device (%s); this library has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_ctx_create: device %d out of range [0,%d)", device, n);
+    hpfw_b200::DeviceGuard g(device);
+    cudaDeviceProp p;
+    HPFW_CUDA_TRY(cudaGetDeviceProperties(&p, device));
+    if (p.major < 10)
+        HPFW_FAIL(HPFW_ERR_CUDA, "hpfw_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                  p.major, p.minor);
+    hpfw_ctx *c = new hpfw_ctx();
+    c->device = device;
+    c->sm_count = p.multiProcessorCount;
+    c->max_smem_optin = int(p.sharedMemPerBlockOptin);
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->pin_in_free, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        delete c;
+        HPFW_FAIL(HPFW_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return HPFW_OK;
+}
+
+void hpfw_ctx_destroy(hpfw_ctx *c) {
+    if (!c) return;
+    hpfw_b200::DeviceGuard g(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->best.release();
+    c->qmeta.release();
+    c->qwords.release();
+    c->keys.release();
+    c->pin_in.release();
+    c->pin_out.release();
+    c->filters_perm.release();
+    c->spectro.release();
+    c->hp.release();
+    c->yproj.release();
+    c->colmeta.release();
+    c->audio.release();
+    hpfw_b200::cqt_cache_destroy(c->cqt);
+    if (c->pin_in_free) cudaEventDestroy(c->pin_in_free);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int hpfw_ctx_device(const hpfw_ctx *c) { return c ? c->device : -1; }
+uint64_t hpfw_ctx_launch_count(const hpfw_ctx *c) { return c ? c->launches : 0; }
+
+int hpfw_ctx_synchronize(hpfw_ctx *c) {
+    if (!c) HPFW_FAIL(HPFW_ERR_ARG, "ctx is NULL");
+    hpfw_b200::DeviceGuard g(c->device);
+    HPFW_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return HPFW_OK;
+}
+
+}  // extern "C"

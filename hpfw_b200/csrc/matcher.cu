@@ -1,0 +1,539 @@
+// hpfw_b200/csrc/matcher.cu — stage 4: exhaustive Hamming cross-correlation matcher.
+//
+// Replaces db::MemoryStorage::build/find (/root/reference/include/hpfw/audioproblems/live-song-id/storage.h:21-64) and the
+// notebook's per-track ranking (examples/python/liveid.ipynb:98-116, 909-927).
+//
+// For a query q[0..k) and a reference track r[0..n):  D[i] = sum_j popc(q[j] ^ r[i+j]),  i = 0 .. n-k  (k = min(k, n)).
+// Per track keep the strict minimum (lowest i on ties); per query rank tracks by (D, track index).
+//
+// Kernel design (XOR + POPC, integer pipes; bound = POPC issue rate):
+//   * a CTA owns a tile of MT_TILE = 2048 consecutive start offsets of ONE track and a group of queries;
+//     the tile's reference words (2048 + k) are staged once in shared memory and reused by every query of the group;
+//   * a thread owns T = 8 consecutive offsets and slides an 16-word register window over the reference: per 8 query
+//     words it issues 4 conflict-free LDS.128 (padded layout, 10-word pitch per 8-word block) + 8 broadcast LDS.128 of
+//     the query, and 128 x (2 LOP3 + 2 POPC + 1 IADD3) for QB = 2 queries — the loads are <2 % of the instruction stream;
+//   * per (tile, query) the minimum is a 32-bit key (dist << 11 | local offset): REDUX.MIN across the warp, a shared
+//     atomicMin across warps, then one global 64-bit atomicMin into best[query][track] (dist << 20 | offset);
+//   * a second kernel selects each query's top-k packed keys (dist << 40 | track << 20 | offset).
+#include "common.cuh"
+
+#include <algorithm>
+#include <numeric>
+
+namespace hpfw_b200 {
+
+constexpr int MT_THREADS = 256;
+constexpr int MT_T = 8;                       // offsets per thread (= words per shared-memory block)
+constexpr int MT_TILE = MT_THREADS * MT_T;    // start offsets per CTA tile
+constexpr int MT_PITCH = 10;                  // shared-memory pitch (words) of an 8-word block: conflict-free LDS.128
+constexpr int MT_QB = 2;                      // queries per register block
+constexpr int MT_LOCAL_BITS = 11;             // log2(MT_TILE)
+constexpr int MT_BLOCKS_PER_CTA = 16;         // query register blocks a CTA runs against its staged tile
+static_assert((1 << MT_LOCAL_BITS) == MT_TILE, "tile / key mismatch");
+
+struct MatchTile {
+    int32_t track;
+    int32_t start;
+};
+
+__device__ __forceinline__ void lds_block8(const uint64_t *p, uint2 (&w)[8]) {
+    const uint4 *v = reinterpret_cast<const uint4 *>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint4 x = v[i];
+        w[2 * i] = make_uint2(x.x, x.y);
+        w[2 * i + 1] = make_uint2(x.z, x.w);
+    }
+}
+
+template <int QB>
+__device__ __forceinline__ void load_q(const uint64_t *p, uint2 (&q)[QB]) {
+    static_assert(QB % 2 == 0, "QB must be even");
+    const uint4 *v = reinterpret_cast<const uint4 *>(p);
+#pragma unroll
+    for (int i = 0; i < QB / 2; ++i) {
+        uint4 x = v[i];
+        q[2 * i] = make_uint2(x.x, x.y);
+        q[2 * i + 1] = make_uint2(x.z, x.w);
+    }
+}
+
+template <int QB>
+__device__ __forceinline__ void step8(const uint64_t *qs, const uint2 (&cur)[8], const uint2 (&nxt)[8],
+                                      uint32_t (&acc)[QB][8], int nsteps) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        if (u < nsteps) {
+            uint2 q[QB];
+            load_q<QB>(qs + u * QB, q);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const uint2 x = (t + u < 8) ? cur[(t + u) & 7] : nxt[(t + u) & 7];
+#pragma unroll
+                for (int qq = 0; qq < QB; ++qq) acc[qq][t] += __popc(q[qq].x ^ x.x) + __popc(q[qq].y ^ x.y);
+            }
+        }
+    }
+}
+
+// best[q_local * n_tracks + track] = min over offsets of (dist << 20 | offset)
+template <int QB>
+__global__ void __launch_bounds__(MT_THREADS, 2)
+match_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ track_start,
+             const MatchTile *__restrict__ tiles, const uint64_t *__restrict__ qwords,
+             const int64_t *__restrict__ qstart, const int32_t *__restrict__ qb_idx, const int32_t *__restrict__ qb_k,
+             int n_qblocks, int qblocks_per_group, int n_tracks, int kpad,
+             unsigned long long *__restrict__ best) {
+    extern __shared__ __align__(16) uint64_t smem[];
+    const int nload = MT_TILE + kpad + 8;
+    uint64_t *ref_s = smem;                              // padded: block b (8 words) at b * MT_PITCH
+    uint64_t *q_s = smem + (nload / 8) * MT_PITCH;       // [j][QB]
+    __shared__ uint32_t red_s[QB];
+
+    const int tid = threadIdx.x;
+    const MatchTile tile = tiles[blockIdx.x];
+    const int64_t tbeg = track_start[tile.track];
+    const int n_r = int(track_start[tile.track + 1] - tbeg);
+    const int tile_start = tile.start;
+
+    // stage the reference tile (zero beyond the end of the track; those offsets are masked below)
+    for (int w = tid; w < nload; w += MT_THREADS) {
+        const int g = tile_start + w;
+        ref_s[(w >> 3) * MT_PITCH + (w & 7)] = g < n_r ? words[tbeg + g] : 0ull;
+    }
+
+    const int b_begin = blockIdx.y * qblocks_per_group;
+    const int b_end = min(n_qblocks, b_begin + qblocks_per_group);
+    for (int b = b_begin; b < b_end; ++b) {
+        const int k_eff = min(qb_k[b], n_r);       // storage.h:34-38: the query is truncated to a shorter reference
+        const int last_valid = n_r - k_eff;        // last valid start offset (>= 0)
+        if (tile_start > last_valid) continue;     // CTA-uniform
+        __syncthreads();                           // ref_s staged / previous q_s consumed
+#pragma unroll
+        for (int qq = 0; qq < QB; ++qq) {
+            const uint64_t *qsrc = qwords + qstart[qb_idx[b * QB + qq]];
+            for (int j = tid; j < k_eff; j += MT_THREADS) q_s[j * QB + qq] = qsrc[j];
+        }
+        if (tid < QB) red_s[tid] = 0xFFFFFFFFu;
+        __syncthreads();
+
+        uint32_t acc[QB][8];
+#pragma unroll
+        for (int qq = 0; qq < QB; ++qq)
+#pragma unroll
+            for (int t = 0; t < 8; ++t) acc[qq][t] = 0;
+
+        const int warp_first = tile_start + (tid & ~31) * MT_T;
+        if (warp_first <= last_valid) {            // warp-uniform: skip warps that own no valid offset
+            const uint64_t *rp = ref_s + tid * MT_PITCH;
+            uint2 cur[8], nxt[8];
+            lds_block8(rp, cur);
+            const int nfull = k_eff >> 3;
+            const uint64_t *qs = q_s;
+            for (int jj = 0; jj < nfull; ++jj) {
+                rp += MT_PITCH;
+                lds_block8(rp, nxt);
+                step8<QB>(qs, cur, nxt, acc, 8);
+                qs += 8 * QB;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) cur[t] = nxt[t];
+            }
+            const int rem = k_eff & 7;
+            if (rem) {
+                rp += MT_PITCH;
+                lds_block8(rp, nxt);
+                step8<QB>(qs, cur, nxt, acc, rem);
+            }
+            const int lane = tid & 31;
+#pragma unroll
+            for (int qq = 0; qq < QB; ++qq) {
+                uint32_t bk = 0xFFFFFFFFu;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int loc = tid * MT_T + t;
+                    const uint32_t key = (acc[qq][t] << MT_LOCAL_BITS) | uint32_t(loc);
+                    if (tile_start + loc <= last_valid) bk = min(bk, key);
+                }
+                bk = __reduce_min_sync(0xFFFFFFFFu, bk);
+                if (lane == 0 && bk != 0xFFFFFFFFu) atomicMin(&red_s[qq], bk);
+            }
+        }
+        __syncthreads();
+        if (tid < QB) {
+            const uint32_t r = red_s[tid];
+            if (r != 0xFFFFFFFFu) {
+                const unsigned long long dist = r >> MT_LOCAL_BITS;
+                const unsigned long long off = (unsigned long long)(tile_start + int(r & (MT_TILE - 1)));
+                atomicMin(best + size_t(qb_idx[b * QB + tid]) * size_t(n_tracks) + size_t(tile.track),
+                          (dist << HPFW_KEY_OFFSET_BITS) | off);
+            }
+        }
+    }
+}
+
+// One CTA per query: the topk smallest keys (dist<<40 | track<<20 | offset) among its n_tracks per-track minima.
+__global__ void __launch_bounds__(256)
+topk_kernel(const unsigned long long *__restrict__ best, int n_tracks, long long track_base, int topk,
+            unsigned long long *__restrict__ keys_out) {
+    __shared__ unsigned long long wmin[8];
+    __shared__ unsigned long long prev_s;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const unsigned long long *row = best + size_t(q) * size_t(n_tracks);
+    unsigned long long prev = 0;
+    for (int r = 0; r < topk; ++r) {
+        unsigned long long loc = ~0ull;
+        for (int i = tid; i < n_tracks; i += 256) {
+            const unsigned long long v = row[i];
+            if (v == ~0ull) continue;
+            const unsigned long long key = ((v >> HPFW_KEY_OFFSET_BITS) << HPFW_KEY_DIST_SHIFT) |
+                                           ((unsigned long long)(track_base + i) << HPFW_KEY_OFFSET_BITS) |
+                                           (v & ((1ull << HPFW_KEY_OFFSET_BITS) - 1));
+            if ((r == 0 || key > prev) && key < loc) loc = key;
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, loc, s);
+            loc = o < loc ? o : loc;
+        }
+        if ((tid & 31) == 0) wmin[tid >> 5] = loc;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long m = wmin[0];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) m = wmin[w] < m ? wmin[w] : m;
+            prev_s = m;
+            keys_out[size_t(q) * topk + r] = m;
+        }
+        __syncthreads();
+        prev = prev_s;
+        if (prev == ~0ull) {   // exhausted: fill the rest
+            for (int rr = r + 1 + tid; rr < topk; rr += 256) keys_out[size_t(q) * topk + rr] = ~0ull;
+            break;
+        }
+    }
+}
+
+// in[n_ranks][n_queries][topk] -> out[n_queries][topk]; one thread per query (n_ranks*topk is tiny).
+__global__ void merge_kernel(const unsigned long long *__restrict__ in, int n_ranks, int n_queries, int topk,
+                             unsigned long long *__restrict__ out) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_queries) return;
+    unsigned long long prev = 0;
+    for (int r = 0; r < topk; ++r) {
+        unsigned long long m = ~0ull;
+        for (int g = 0; g < n_ranks; ++g) {
+            const unsigned long long *p = in + (size_t(g) * n_queries + q) * topk;
+            for (int i = 0; i < topk; ++i) {
+                const unsigned long long v = p[i];
+                if ((r == 0 || v > prev) && v < m) m = v;
+            }
+        }
+        out[size_t(q) * topk + r] = m;
+        prev = m;
+        if (m == ~0ull) {
+            for (int rr = r + 1; rr < topk; ++rr) out[size_t(q) * topk + rr] = ~0ull;
+            break;
+        }
+    }
+}
+
+}  // namespace hpfw_b200
+
+using namespace hpfw_b200;
+
+struct hpfw_db {
+    hpfw_ctx *ctx = nullptr;
+    int n_tracks = 0;
+    int64_t total_words = 0;
+    int64_t track_base = 0;
+    uint64_t *d_words = nullptr;
+    int64_t *d_track_start = nullptr;
+    MatchTile *d_tiles = nullptr;
+    int n_tiles = 0;
+    std::vector<int64_t> offsets;  // host copy
+};
+
+static int db_alloc_common(hpfw_ctx *ctx, const int64_t *offsets, int n_tracks, int64_t track_base, hpfw_db **out) {
+    if (!ctx || !out || (n_tracks > 0 && !offsets)) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_build: NULL argument");
+    if (n_tracks < 0) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_build: n_tracks < 0");
+    if (track_base < 0 || track_base + n_tracks > HPFW_MAX_TRACKS)
+        HPFW_FAIL(HPFW_ERR_LIMIT, "hpfw_db_build: track index %lld exceeds the %d-bit key field",
+                  (long long)(track_base + n_tracks), HPFW_KEY_TRACK_BITS);
+    std::vector<MatchTile> tiles;
+    for (int r = 0; r < n_tracks; ++r) {
+        const int64_t n = offsets[r + 1] - offsets[r];
+        if (n < 0) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_build: offsets not monotone at track %d", r);
+        if (n > HPFW_MAX_TRACK_WORDS)
+            HPFW_FAIL(HPFW_ERR_LIMIT, "hpfw_db_build: track %d has %lld words; limit %d (key offset field)", r,
+                      (long long)n, HPFW_MAX_TRACK_WORDS);
+        const int nt = std::max<int64_t>(1, (n + MT_TILE - 1) / MT_TILE);  // >= 1: an empty track still matches at 0
+        for (int t = 0; t < nt; ++t) tiles.push_back({r, t * MT_TILE});
+    }
+    hpfw_db *db = new hpfw_db();
+    db->ctx = ctx;
+    db->n_tracks = n_tracks;
+    db->track_base = track_base;
+    db->total_words = n_tracks ? offsets[n_tracks] - offsets[0] : 0;
+    db->offsets.resize(size_t(n_tracks) + 1);
+    for (int r = 0; r <= n_tracks; ++r) db->offsets[r] = (n_tracks ? offsets[r] - offsets[0] : 0);
+    db->n_tiles = int(tiles.size());
+    cudaError_t e = cudaMalloc(&db->d_words, sizeof(uint64_t) * size_t(db->total_words + 16));
+    if (e == cudaSuccess) e = cudaMalloc(&db->d_track_start, sizeof(int64_t) * (size_t(n_tracks) + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&db->d_tiles, sizeof(MatchTile) * std::max<size_t>(1, tiles.size()));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(db->d_track_start, db->offsets.data(), sizeof(int64_t) * (size_t(n_tracks) + 1),
+                       cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !tiles.empty())
+        e = cudaMemcpy(db->d_tiles, tiles.data(), sizeof(MatchTile) * tiles.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        hpfw_db_destroy(db);
+        HPFW_FAIL(HPFW_ERR_CUDA, "hpfw_db_build: %s", cudaGetErrorString(e));
+    }
+    *out = db;
+    return HPFW_OK;
+}
+
+extern "C" {
+
+int hpfw_db_build(hpfw_ctx *ctx, const uint64_t *words, const int64_t *offsets, int n_tracks, int64_t track_base,
+                  hpfw_db **out) {
+    if (!ctx) HPFW_FAIL(HPFW_ERR_ARG, "ctx is NULL");
+    DeviceGuard g(ctx->device);
+    hpfw_db *db = nullptr;
+    HPFW_TRY(db_alloc_common(ctx, offsets, n_tracks, track_base, &db));
+    if (db->total_words > 0) {
+        if (!words) {
+            hpfw_db_destroy(db);
+            HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_build: words is NULL");
+        }
+        cudaError_t e = cudaMemcpy(db->d_words, words + offsets[0], sizeof(uint64_t) * size_t(db->total_words),
+                                   cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            hpfw_db_destroy(db);
+            HPFW_FAIL(HPFW_ERR_CUDA, "hpfw_db_build: H2D copy failed: %s", cudaGetErrorString(e));
+        }
+    }
+    *out = db;
+    return HPFW_OK;
+}
+
+int hpfw_db_build_device(hpfw_ctx *ctx, const uint64_t *d_words, const int64_t *offsets, int n_tracks,
+                         int64_t track_base, void *stream, hpfw_db **out) {
+    if (!ctx) HPFW_FAIL(HPFW_ERR_ARG, "ctx is NULL");
+    DeviceGuard g(ctx->device);
+    hpfw_db *db = nullptr;
+    HPFW_TRY(db_alloc_common(ctx, offsets, n_tracks, track_base, &db));
+    if (db->total_words > 0) {
+        cudaError_t e = cudaMemcpyAsync(db->d_words, d_words + offsets[0], sizeof(uint64_t) * size_t(db->total_words),
+                                        cudaMemcpyDeviceToDevice, ctx->pick(stream));
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->pick(stream));
+        if (e != cudaSuccess) {
+            hpfw_db_destroy(db);
+            HPFW_FAIL(HPFW_ERR_CUDA, "hpfw_db_build_device: D2D copy failed: %s", cudaGetErrorString(e));
+        }
+    }
+    *out = db;
+    return HPFW_OK;
+}
+
+void hpfw_db_destroy(hpfw_db *db) {
+    if (!db) return;
+    DeviceGuard g(db->ctx->device);
+    cudaDeviceSynchronize();
+    if (db->d_words) cudaFree(db->d_words);
+    if (db->d_track_start) cudaFree(db->d_track_start);
+    if (db->d_tiles) cudaFree(db->d_tiles);
+    delete db;
+}
+
+int hpfw_db_tracks(const hpfw_db *db) { return db ? db->n_tracks : 0; }
+int64_t hpfw_db_words(const hpfw_db *db) { return db ? db->total_words : 0; }
+
+double hpfw_db_word_ops(const hpfw_db *db, const int64_t *qoffsets, int n_queries) {
+    if (!db || !qoffsets) return 0.0;
+    // group tracks by length once
+    double total = 0.0;
+    for (int q = 0; q < n_queries; ++q) {
+        const int64_t kq = qoffsets[q + 1] - qoffsets[q];
+        for (int r = 0; r < db->n_tracks; ++r) {
+            const int64_t n = db->offsets[r + 1] - db->offsets[r];
+            const int64_t k = std::min(kq, n);
+            total += double(n - k + 1) * double(k);
+        }
+    }
+    return total;
+}
+
+void hpfw_keys_decode(const uint64_t *keys, int n, hpfw_match *out) {
+    for (int i = 0; i < n; ++i) {
+        const uint64_t k = keys[i];
+        if (k == HPFW_KEY_NONE) {
+            out[i].track = -1;
+            out[i].cnt = SIZE_MAX;
+            out[i].offset = 0;
+        } else {
+            out[i].cnt = k >> HPFW_KEY_DIST_SHIFT;
+            out[i].track = int64_t((k >> HPFW_KEY_OFFSET_BITS) & ((1ull << HPFW_KEY_TRACK_BITS) - 1));
+            out[i].offset = int64_t(k & ((1ull << HPFW_KEY_OFFSET_BITS) - 1));
+        }
+    }
+}
+
+int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *qoffsets, int n_queries, int topk,
+                         uint64_t *d_keys_out, void *stream_) {
+    if (!db || !qoffsets || !d_keys_out) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_match_device: NULL argument");
+    if (n_queries < 0 || topk < 1 || topk > 1024) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_match_device: bad n_queries/topk");
+    if (n_queries == 0) return HPFW_OK;
+    hpfw_ctx *ctx = db->ctx;
+    DeviceGuard g(ctx->device);
+    cudaStream_t stream = ctx->pick(stream_);
+    const int R = db->n_tracks;
+
+    int kmax = 0;
+    for (int q = 0; q < n_queries; ++q) {
+        const int64_t k = qoffsets[q + 1] - qoffsets[q];
+        if (k < 0) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_match_device: qoffsets not monotone at query %d", q);
+        if (k > HPFW_MAX_QUERY_WORDS)
+            HPFW_FAIL(HPFW_ERR_LIMIT, "hpfw_db_match_device: query %d has %lld words; limit %d", q, (long long)k,
+                      HPFW_MAX_QUERY_WORDS);
+        kmax = std::max<int>(kmax, int(k));
+    }
+    if (!d_qwords && qoffsets[n_queries] > qoffsets[0]) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_match_device: d_qwords is NULL");
+
+    // queries per chunk: bound the best[] scratch to ~1 GiB
+    const size_t row_bytes = sizeof(uint64_t) * std::max<size_t>(1, size_t(R));
+    int qchunk = int(std::min<size_t>(size_t(n_queries), std::max<size_t>(1, (size_t(1) << 30) / row_bytes)));
+    qchunk = std::min(qchunk, 1 << 20);  // keeps gridDim.y within 65535
+    const int n_chunks = (n_queries + qchunk - 1) / qchunk;
+
+    // host metadata: [qstart int64 (n_queries+1)] then per chunk [qb_idx int32 (nb*QB)] [qb_k int32 (nb)]
+    struct ChunkMeta { size_t idx_off, k_off; int nb, q0, nq; };
+    std::vector<ChunkMeta> cm(n_chunks);
+    size_t meta_bytes = sizeof(int64_t) * (size_t(n_queries) + 1);
+    std::vector<int32_t> tables;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int q0 = c * qchunk, nq = std::min(qchunk, n_queries - q0);
+        std::vector<int> order(nq);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            return (qoffsets[q0 + a + 1] - qoffsets[q0 + a]) < (qoffsets[q0 + b + 1] - qoffsets[q0 + b]);
+        });
+        std::vector<int32_t> idx, ks;
+        for (int i = 0; i < nq;) {
+            const int64_t k = qoffsets[q0 + order[i] + 1] - qoffsets[q0 + order[i]];
+            int32_t blk[MT_QB];
+            int got = 0;
+            while (got < MT_QB && i < nq && qoffsets[q0 + order[i] + 1] - qoffsets[q0 + order[i]] == k)
+                blk[got++] = order[i++];
+            for (int f = got; f < MT_QB; ++f) blk[f] = blk[got - 1];  // pad a short block by repeating a query
+            for (int f = 0; f < MT_QB; ++f) idx.push_back(blk[f]);
+            ks.push_back(int32_t(k));
+        }
+        cm[c].nb = int(ks.size());
+        cm[c].q0 = q0;
+        cm[c].nq = nq;
+        cm[c].idx_off = meta_bytes + tables.size() * sizeof(int32_t);
+        tables.insert(tables.end(), idx.begin(), idx.end());
+        cm[c].k_off = meta_bytes + tables.size() * sizeof(int32_t);
+        tables.insert(tables.end(), ks.begin(), ks.end());
+    }
+    const size_t total_meta = meta_bytes + tables.size() * sizeof(int32_t);
+
+    // the pinned staging buffer may still be feeding the previous call's copy
+    HPFW_CUDA_TRY(cudaEventSynchronize(ctx->pin_in_free));
+    HPFW_TRY(ctx->pin_in.reserve(total_meta));
+    HPFW_TRY(ctx->qmeta.reserve(total_meta));
+    HPFW_TRY(ctx->best.reserve(row_bytes * size_t(qchunk)));
+    {
+        int64_t *qs = ctx->pin_in.as<int64_t>();
+        for (int q = 0; q <= n_queries; ++q) qs[q] = qoffsets[q] - qoffsets[0];
+        if (!tables.empty())
+            memcpy(ctx->pin_in.as<char>() + meta_bytes, tables.data(), tables.size() * sizeof(int32_t));
+    }
+    HPFW_CUDA_TRY(cudaMemcpyAsync(ctx->qmeta.ptr, ctx->pin_in.ptr, total_meta, cudaMemcpyHostToDevice, stream));
+    HPFW_CUDA_TRY(cudaEventRecord(ctx->pin_in_free, stream));
+
+    const int kpad = (kmax + 7) & ~7;
+    const int nload = MT_TILE + kpad + 8;
+    const size_t smem = sizeof(uint64_t) * (size_t(nload / 8) * MT_PITCH + size_t(kpad) * MT_QB);
+    if (smem > size_t(ctx->max_smem_optin))
+        HPFW_FAIL(HPFW_ERR_LIMIT, "hpfw_db_match_device: query of %d words needs %zu B shared memory (> %d)", kmax, smem,
+                  ctx->max_smem_optin);
+    HPFW_CUDA_TRY(cudaFuncSetAttribute(match_kernel<MT_QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+
+    const char *meta = ctx->qmeta.as<char>();
+    const int64_t *d_qstart = reinterpret_cast<const int64_t *>(meta);
+    const uint64_t *d_q = d_qwords ? d_qwords + qoffsets[0] : nullptr;
+    for (int c = 0; c < n_chunks; ++c) {
+        unsigned long long *best = ctx->best.as<unsigned long long>();
+        HPFW_CUDA_TRY(cudaMemsetAsync(best, 0xFF, row_bytes * size_t(cm[c].nq), stream));
+        if (db->n_tiles > 0 && cm[c].nb > 0) {
+            // a CTA = one reference tile x up to MT_BLOCKS_PER_CTA register blocks of queries: the staged tile is reused
+            // 16x, and a CTA stays a few ms of work so the last partial wave is a small tail
+            const int per_group = std::min(cm[c].nb, MT_BLOCKS_PER_CTA);
+            const int groups = (cm[c].nb + per_group - 1) / per_group;
+            dim3 grid(db->n_tiles, groups);
+            match_kernel<MT_QB><<<grid, MT_THREADS, smem, stream>>>(
+                db->d_words, db->d_track_start, db->d_tiles, d_q, d_qstart + cm[c].q0,
+                reinterpret_cast<const int32_t *>(meta + cm[c].idx_off),
+                reinterpret_cast<const int32_t *>(meta + cm[c].k_off), cm[c].nb, per_group, R, kpad, best);
+            HPFW_CUDA_TRY(cudaGetLastError());
+            ctx->launches++;
+        }
+        topk_kernel<<<cm[c].nq, 256, 0, stream>>>(best, R, (long long)db->track_base, topk,
+                                                    reinterpret_cast<unsigned long long *>(d_keys_out) + size_t(cm[c].q0) * topk);
+        HPFW_CUDA_TRY(cudaGetLastError());
+        ctx->launches++;
+    }
+    return HPFW_OK;
+}
+
+int hpfw_topk_merge_device(hpfw_ctx *ctx, const uint64_t *d_keys_in, int n_ranks, int n_queries, int topk,
+                           uint64_t *d_keys_out, void *stream) {
+    if (!ctx || !d_keys_in || !d_keys_out) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_topk_merge_device: NULL argument");
+    if (n_ranks < 1 || n_queries < 0 || topk < 1) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_topk_merge_device: bad sizes");
+    if (n_queries == 0) return HPFW_OK;
+    DeviceGuard g(ctx->device);
+    merge_kernel<<<(n_queries + 127) / 128, 128, 0, ctx->pick(stream)>>>(
+        reinterpret_cast<const unsigned long long *>(d_keys_in), n_ranks, n_queries, topk,
+        reinterpret_cast<unsigned long long *>(d_keys_out));
+    HPFW_CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    return HPFW_OK;
+}
+
+int hpfw_db_find_topk(hpfw_db *db, const uint64_t *qwords, const int64_t *qoffsets, int n_queries, int topk,
+                      hpfw_match *out) {
+    if (!db || !qoffsets || !out) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_find_topk: NULL argument");
+    if (n_queries <= 0) return n_queries == 0 ? HPFW_OK : HPFW_ERR_ARG;
+    if (topk < 1) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_find_topk: topk < 1");
+    hpfw_ctx *ctx = db->ctx;
+    DeviceGuard g(ctx->device);
+    const size_t nw = size_t(qoffsets[n_queries] - qoffsets[0]);
+    const size_t nkeys = size_t(n_queries) * size_t(topk);
+    HPFW_TRY(ctx->qwords.reserve(sizeof(uint64_t) * std::max<size_t>(1, nw)));
+    HPFW_TRY(ctx->keys.reserve(sizeof(uint64_t) * nkeys));
+    HPFW_TRY(ctx->pin_out.reserve(sizeof(uint64_t) * nkeys));
+    if (nw) {
+        if (!qwords) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_find_topk: qwords is NULL");
+        HPFW_CUDA_TRY(cudaMemcpyAsync(ctx->qwords.ptr, qwords + qoffsets[0], sizeof(uint64_t) * nw,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+    }
+    std::vector<int64_t> rel(size_t(n_queries) + 1);
+    for (int q = 0; q <= n_queries; ++q) rel[q] = qoffsets[q] - qoffsets[0];
+    HPFW_TRY(hpfw_db_match_device(db, ctx->qwords.as<uint64_t>(), rel.data(), n_queries, topk, ctx->keys.as<uint64_t>(),
+                                  ctx->stream));
+    HPFW_CUDA_TRY(cudaMemcpyAsync(ctx->pin_out.ptr, ctx->keys.ptr, sizeof(uint64_t) * nkeys, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    HPFW_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    hpfw_keys_decode(ctx->pin_out.as<uint64_t>(), int(nkeys), out);
+    return HPFW_OK;
+}
+
+int hpfw_db_find(hpfw_db *db, const uint64_t *q, int k, hpfw_match *out) {
+    if (k < 0) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_find: k < 0");
+    const int64_t qo[2] = {0, k};
+    return hpfw_db_find_topk(db, q, qo, 1, 1, out);
+}
+
+}  // extern "C"

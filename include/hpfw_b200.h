@@ -1,0 +1,159 @@
+/* include/hpfw_b200.h — C ABI of the B200-native hashprint feature-to-match path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, int status codes, no C++/torch types. Everything above it
+ * (include/hpfw/ C++ headers with the reference's class names, the ctypes mirror in hpfw_b200/, bench.py) calls only
+ * these symbols; everything below it is hand-written sm_100a CUDA in hpfw_b200/csrc/.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference):
+ *   hpfw_db_build / hpfw_db_find*            <- db::MemoryStorage::build / find
+ *                                               include/hpfw/audioproblems/live-song-id/storage.h:21-25, 27-64
+ *   hpfw_db_find_topk*                       <- notebook top-10 ranking, examples/python/liveid.ipynb:98-116, 909-927
+ *   hpfw_set_filters / hpfw_get_filters      <- ParallelCollector::filters (load/save),
+ *                                               include/hpfw/core/parallel_collector.h:61-73, 78
+ *   hpfw_hashprint_from_spectrogram*         <- HashprintHandle::calc_frames, `filters * frames`, calc_fingerprint,
+ *                                               fingerprint_to_hashprint
+ *                                               include/hpfw/core/hashprint_handle.h:79-93, 115-142;
+ *                                               include/hpfw/core/parallel_collector.h:56-58, 126-128
+ *   hpfw_cqt_spectrogram*                    <- spectrum::CQT::spectrogram after decoding (NSGConstantQ + abs/decimate +
+ *                                               amplitude_to_db), include/hpfw/spectrum/cqt.h:54-84,
+ *                                               include/hpfw/spectrum/convert.h:7-25
+ *   hpfw_calc_hashprint_audio*               <- ParallelCollector::calc_hashprint on a decoded buffer,
+ *                                               include/hpfw/core/parallel_collector.h:54-59
+ *   par_collector_* / *_result_free          <- the reference's own C ABI, modules/python/parallel_collector_wrapper.hpp:12-38
+ *                                               (declared in include/hpfw_b200_pyhpfw.h)
+ *
+ * Conventions
+ *   - every function returns HPFW_OK (0) or a negative error code; hpfw_last_error() gives the thread-local message.
+ *   - "host" entry points take host pointers and do their own H2D/D2H copies (what the reference-facing classes call);
+ *     "_device" entry points take device pointers (payload already in HBM) plus host metadata, enqueue on `stream`
+ *     (a cudaStream_t cast to void*; NULL = the context's own stream) and do not synchronise.
+ *   - there is NO CPU fallback: without a CUDA device every entry point fails with HPFW_ERR_CUDA.
+ *   - layouts follow the reference: spectrogram = column-major float[121 x cols] (time-major in memory),
+ *     filters = column-major float[64 x 2420] with row index band*20+context, hashprint word bit (63-f) = filter f.
+ */
+#ifndef HPFW_B200_H
+#define HPFW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HPFW_OK 0
+#define HPFW_ERR_CUDA (-1)      /* CUDA runtime / no device */
+#define HPFW_ERR_ARG (-2)       /* bad argument */
+#define HPFW_ERR_LIMIT (-3)     /* input exceeds a documented limit (key field widths, shared memory) */
+#define HPFW_ERR_STATE (-4)     /* e.g. filters not set */
+#define HPFW_ERR_SHORT (-5)     /* audio / spectrogram too short to yield a hashprint (reference: size_t underflow) */
+
+/* geometry of the default instantiation HashprintHandle<uint64_t, spectrum::CQT<44100,96,24,121,3>, 20, 80>
+ * (include/hpfw/audioproblems/live-song-id/live_song_id.h:16) */
+#define HPFW_BINS 121
+#define HPFW_CONTEXT 20
+#define HPFW_LAG 80
+#define HPFW_NFILTERS 64
+#define HPFW_FRAME_SIZE (HPFW_BINS * HPFW_CONTEXT)
+
+/* Packed match key: (distance << 40) | (track << 20) | offset. Integer '<' on keys is exactly the reference's
+ * strict-'<' ordering: smaller distance, then earlier DB index, then lower offset (storage.h:50-60). */
+#define HPFW_KEY_OFFSET_BITS 20
+#define HPFW_KEY_TRACK_BITS 20
+#define HPFW_KEY_DIST_SHIFT 40
+#define HPFW_KEY_NONE UINT64_MAX
+#define HPFW_MAX_TRACK_WORDS ((1 << HPFW_KEY_OFFSET_BITS) - 1)
+#define HPFW_MAX_TRACKS ((1 << HPFW_KEY_TRACK_BITS) - 1)
+#define HPFW_MAX_QUERY_WORDS 4096
+
+typedef struct hpfw_ctx hpfw_ctx; /* one per GPU */
+typedef struct hpfw_db hpfw_db;   /* a (shard of a) hashprint database resident in HBM */
+
+/* = db::MemoryStorage::SearchResult (storage.h:11-15) with the filename replaced by the DB index.
+ * No match (empty DB): track = -1, cnt = SIZE_MAX, offset = 0, as the reference's initial value (storage.h:28). */
+typedef struct hpfw_match {
+    int64_t track;
+    uint64_t cnt;
+    int64_t offset;
+} hpfw_match;
+
+const char *hpfw_last_error(void);
+const char *hpfw_version(void);
+
+int hpfw_ctx_create(int device, hpfw_ctx **out);
+void hpfw_ctx_destroy(hpfw_ctx *ctx);
+int hpfw_ctx_device(const hpfw_ctx *ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+uint64_t hpfw_ctx_launch_count(const hpfw_ctx *ctx);
+int hpfw_ctx_synchronize(hpfw_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------------------ matcher (stage 4) */
+/* words: concatenated hashprints of n_tracks tracks, offsets[n_tracks+1]; track_base = global index of the first
+ * track of this shard (0 for an unsharded DB). Host buffers; copied to HBM. */
+int hpfw_db_build(hpfw_ctx *ctx, const uint64_t *words, const int64_t *offsets, int n_tracks, int64_t track_base,
+                  hpfw_db **out);
+/* same, words already on the device (copied device-to-device into the DB's own layout); offsets on the host */
+int hpfw_db_build_device(hpfw_ctx *ctx, const uint64_t *d_words, const int64_t *offsets, int n_tracks,
+                         int64_t track_base, void *stream, hpfw_db **out);
+void hpfw_db_destroy(hpfw_db *db);
+int hpfw_db_tracks(const hpfw_db *db);
+int64_t hpfw_db_words(const hpfw_db *db);
+
+/* MemoryStorage::find: one query, top-1. Host buffers. */
+int hpfw_db_find(hpfw_db *db, const uint64_t *q, int k, hpfw_match *out);
+/* n_queries queries (concatenated words + qoffsets[n_queries+1]); out[n_queries * topk], ranked by key. Host buffers. */
+int hpfw_db_find_topk(hpfw_db *db, const uint64_t *qwords, const int64_t *qoffsets, int n_queries, int topk,
+                      hpfw_match *out);
+/* Device path: d_qwords on the device, qoffsets on the host (metadata); d_keys_out[n_queries * topk] packed keys. */
+int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *qoffsets, int n_queries, int topk,
+                         uint64_t *d_keys_out, void *stream);
+/* Multi-GPU merge after an all-gather: d_keys_in[n_ranks][n_queries][topk] -> d_keys_out[n_queries][topk]. */
+int hpfw_topk_merge_device(hpfw_ctx *ctx, const uint64_t *d_keys_in, int n_ranks, int n_queries, int topk,
+                           uint64_t *d_keys_out, void *stream);
+/* Host helper: unpack keys into hpfw_match records. */
+void hpfw_keys_decode(const uint64_t *keys, int n, hpfw_match *out);
+/* Algorithmic word-ops (one XOR64 + popcount64 each) of matching these queries against this DB:
+ * sum over queries and tracks of (n_r - k + 1) * k with k = min(k_q, n_r). */
+double hpfw_db_word_ops(const hpfw_db *db, const int64_t *qoffsets, int n_queries);
+
+/* -------------------------------------------------------------------------- projection / threshold / pack (stages 2,3) */
+int hpfw_set_filters(hpfw_ctx *ctx, const float *filters_colmajor_64x2420);
+int hpfw_get_filters(hpfw_ctx *ctx, float *filters_colmajor_64x2420);
+/* words produced for a spectrogram of `cols` columns: cols - 99 (<= 0: too short) */
+int hpfw_hashprint_words_for_cols(int cols);
+/* host: spectrogram[121 x cols] col-major -> hp_out[cols-99]; *n_out = words written */
+int hpfw_hashprint_from_spectrogram(hpfw_ctx *ctx, const float *spectrogram, int cols, uint64_t *hp_out, int *n_out);
+/* device, batched: n spectrograms concatenated in d_spectrograms, col_offsets[n+1] (host, in columns);
+ * d_hp_out receives track i's words at hp_offsets[i] = sum_{j<i} max(cols_j - 99, 0). */
+int hpfw_hashprint_from_spectrogram_device(hpfw_ctx *ctx, const float *d_spectrograms, const int64_t *col_offsets,
+                                           int n, uint64_t *d_hp_out, void *stream);
+/* diagnostic: the projection y = filters * frames itself (column-major float[64 x (cols-19)]), host buffers */
+int hpfw_project(hpfw_ctx *ctx, const float *spectrogram, int cols, float *y_out);
+
+/* ------------------------------------------------------------------------------------------------- CQT (stage 1) */
+/* spectrogram columns for an n_samples-long buffer: M/3 + 1 (cqt.h:73); 0 if the design is degenerate */
+int hpfw_cqt_cols(int64_t n_samples);
+/* host: mono float audio (already at the analysis rate) -> dB spectrogram[121 x cols] col-major */
+int hpfw_cqt_spectrogram(hpfw_ctx *ctx, const float *audio, int64_t n_samples, float *spectrogram_out, int *cols_out);
+/* device: same, buffers in HBM; d_spectrogram_out must hold 121 * hpfw_cqt_cols(n_samples) floats */
+int hpfw_cqt_spectrogram_device(hpfw_ctx *ctx, const float *d_audio, int64_t n_samples, float *d_spectrogram_out,
+                                void *stream);
+/* diagnostic: linear magnitudes |c_j[3i]| before the dB step */
+int hpfw_cqt_magnitude(hpfw_ctx *ctx, const float *audio, int64_t n_samples, float *mag_out, int *cols_out);
+
+/* ------------------------------------------------------------------------------ whole query path (stages 1-3, a8) */
+int hpfw_hashprint_words_for_samples(int64_t n_samples);
+int hpfw_calc_hashprint_audio(hpfw_ctx *ctx, const float *audio, int64_t n_samples, uint64_t *hp_out, int *n_out);
+int hpfw_calc_hashprint_audio_device(hpfw_ctx *ctx, const float *d_audio, int64_t n_samples, uint64_t *d_hp_out,
+                                     void *stream);
+
+/* ------------------------------------------------------------------------------------------------ measurement aids */
+/* Pipe microbenchmark used to pin the matcher's roofline denominator: runs register-only loops and reports
+ * lane-instructions per clock per SM for (0) POPC alone, (1) LOP3 alone, (2) the matcher's XOR/POPC/IADD3 mix,
+ * expressed as 64-bit word-ops per clock per SM for (2). out[3]; sm_clock_mhz_out = clock observed during the run. */
+int hpfw_microbench_pipes(hpfw_ctx *ctx, double *out, double *sm_clock_mhz_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPFW_B200_H */
