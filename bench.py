@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py — live-ID queries/s against a 10k-track hashprint DB (BASELINE.json metric), B200 vs the reference CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]             # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] --steps K --warmup W # the reference's MemoryStorage::find on host cores
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ... # N>1: one rank per GPU, DB sharded by track
+
+Workload (config.workload): DB = 10,000 tracks x 14,411 hashprint words (3-min tracks), synthetic iid words;
+one STEP = one batch of 128*N queries of 385 words (6 s), each a DB slice with 25 % of its bits flipped, matched at every
+alignment offset of every track (Hamming cross-correlation), top-10 per query. The DB is sharded by track over the N
+GPUs, queries are replicated, per-rank top-k keys are all-gathered (NCCL) and merged. Per-GPU work per step is constant
+in N ("weak").
+
+  value   device-resident: query words already in HBM when the timed region starts
+  e2e     through the host API (ShardedMemoryStorage.search_host): pinned host query words -> H2D -> match -> (allgather,
+          merge) -> D2H of the top-k records, every step
+  roofline  the match kernel against the POPC-pipe roof; duration from CUDA events around every launch
+  cpu_baseline  the reference's own MemoryStorage::find (oracle/_ref, compiled from /root/reference headers) on all host
+          cores over a bounded sample, on rank 0 at N=1 only
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TRACKS = 10_000
+TRACK_WORDS = 14_411        # 3 min @ 44.1 kHz
+QUERY_WORDS = 385           # 6 s
+QUERIES_PER_GPU = 128
+TOPK = 10
+FLIP = 0.25
+METRIC = "live_id_queries_per_sec_vs_10k_track_db"
+UNIT = "queries/s"
+POPC32_PER_CLK_SM = 16      # CUDA programming guide arithmetic-throughput table (population count); checked by the microbenchmark
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def word_ops_per_query(tracks=TRACKS, n=TRACK_WORDS, k=QUERY_WORDS) -> float:
+    return float(tracks) * float(n - k + 1) * float(k)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                          "200", "-i", str(self.device)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------ reference arm
+def host_db(seed: int, tracks: int):
+    rng = np.random.default_rng(seed)
+    words = rng.integers(0, 1 << 64, size=tracks * TRACK_WORDS, dtype=np.uint64)
+    offs = np.arange(tracks + 1, dtype=np.int64) * TRACK_WORDS
+    return words, offs
+
+
+def host_queries(seed: int, words, offs, nq: int):
+    rng = np.random.default_rng(seed)
+    tracks = len(offs) - 1
+    tr = rng.integers(0, tracks, size=nq)
+    off = rng.integers(0, TRACK_WORDS - QUERY_WORDS + 1, size=nq)
+    q = np.empty(nq * QUERY_WORDS, dtype=np.uint64)
+    for i in range(nq):
+        sl = words[offs[tr[i]] + off[i]: offs[tr[i]] + off[i] + QUERY_WORDS].copy()
+        noise = np.zeros(QUERY_WORDS, dtype=np.uint64)
+        for b in range(64):
+            noise |= (rng.random(QUERY_WORDS) < FLIP).astype(np.uint64) << np.uint64(b)
+        q[i * QUERY_WORDS:(i + 1) * QUERY_WORDS] = sl ^ noise
+    qoffs = np.arange(nq + 1, dtype=np.int64) * QUERY_WORDS
+    return q, qoffs, np.stack([tr, off], axis=1)
+
+
+def cpu_find_batch(words, offs, q, qoffs, cores):
+    """The reference's MemoryStorage::find over host threads (oracle/_ref) or, if that library is absent, the C port."""
+    import oracle
+    if oracle.ref_available():
+        tr, d, o = oracle.ref_find_batch(words, offs, q, qoffs, cores)
+        return "reference", tr, d, o
+    tr, d, o = oracle.find_topk_batch(words, offs, q, qoffs, 1, cores)
+    return "port", tr[:, 0], d[:, 0], o[:, 0]
+
+
+def cpu_sample(cores: int, sample_tracks: int, nq: int, seed: int = 7):
+    """Time one bounded sample: nq queries x sample_tracks tracks; returns (kind, seconds, queries/s scaled to 10k tracks)."""
+    words, offs = host_db(seed, sample_tracks)
+    q, qoffs, truth = host_queries(seed + 1, words, offs, nq)
+    t0 = time.perf_counter()
+    kind, tr, d, o = cpu_find_batch(words, offs, q, qoffs, cores)
+    dt = time.perf_counter() - t0
+    assert np.array_equal(tr, truth[:, 0]) and np.array_equal(o, truth[:, 1]), "CPU baseline returned wrong matches"
+    qps = nq / dt * (sample_tracks / TRACKS)       # find() is linear in the number of reference tracks
+    return kind, dt, qps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = host_cores()
+    sample_tracks = 1000
+    nq = max(cores, 8)
+    times = []
+    kind = "reference"
+    for i in range(args.warmup + args.steps):
+        kind, dt, qps = cpu_sample(cores, sample_tracks, nq, seed=11 + i)
+        if i >= args.warmup:
+            times.append((dt, qps))
+    dt = float(np.mean([t[0] for t in times]))
+    qps = float(np.mean([t[1] for t in times]))
+    sample = (f"each step: {nq} queries x {sample_tracks}-track subset of the DB on {cores} host threads, "
+              f"scaled x{sample_tracks}/{TRACKS} (find is linear in tracks); MemoryStorage::find compiled from the "
+              f"reference headers with -Ofast -march=native (no MKL involved in this path)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(n_gpus: int):
+    return {"workload": f"live-id search: {TRACKS}-track DB x {TRACK_WORDS} words (3-min tracks), "
+                        f"{QUERIES_PER_GPU}*N x {QUERY_WORDS}-word (6 s) queries per step, full-offset Hamming "
+                        f"cross-correlation, top-{TOPK}",
+            "tracks": TRACKS, "track_words": TRACK_WORDS, "query_words": QUERY_WORDS,
+            "queries_per_step": QUERIES_PER_GPU * n_gpus, "topk": TOPK,
+            "parallelism": f"db-shard x{n_gpus} (tracks), queries replicated, NCCL allgather of top-k keys",
+            "l2": "DB shard per GPU (>=144 MB) exceeds the 126 MB L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------------ CUDA arm
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    import hpfw_b200
+    from hpfw_b200 import _lib, synth
+    from hpfw_b200.sharded import ShardedMemoryStorage
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun --nproc-per-node {args.gpus} (one rank per GPU)")
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = hpfw_b200.Context(local_rank)
+
+    # ---- synthetic DB shard in HBM + planted queries (setup, untimed)
+    n = args.gpus
+    tracks = args.tracks
+    lo, hi = rank * tracks // n, (rank + 1) * tracks // n
+    d_words, offs = synth.device_hashprint_db(torch, dev, 1234 + rank, hi - lo, TRACK_WORDS)
+    qpg = args.queries_per_gpu
+    d_q_local, _, truth_local = synth.device_hashprint_queries(torch, d_words, offs, 99 + rank, qpg, QUERY_WORDS, FLIP)
+    truth_local[:, 0] += lo
+    if world > 1:
+        d_q = torch.empty((world, qpg * QUERY_WORDS), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(d_q.view(-1), d_q_local.contiguous())
+        d_q = d_q.view(-1)
+        t_all = torch.empty((world, qpg, 2), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(t_all.view(-1), torch.from_numpy(truth_local).to(dev).view(-1))
+        truth = t_all.view(-1, 2).cpu().numpy()
+    else:
+        d_q, truth = d_q_local, truth_local
+    nq = qpg * n
+    qoffs = np.arange(nq + 1, dtype=np.int64) * QUERY_WORDS
+    st = ShardedMemoryStorage(ctx, rank, world)
+    stream = torch.cuda.current_stream().cuda_stream
+    st.build_local_device(d_words.data_ptr(), offs, track_base=lo, stream=stream)
+    del d_words
+    h_q = torch.empty(d_q.shape, dtype=torch.int64, pin_memory=True)
+    h_q.copy_(d_q)
+    h_out = torch.empty((nq, TOPK), dtype=torch.int64, pin_memory=True)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- pipe microbenchmark (rank 0, untimed): pins the POPC roof
+    micro = ctx.microbench_pipes() if rank == 0 else None
+
+    # ---- device-resident arm
+    for _ in range(args.warmup):
+        keys = st.search_device(d_q, qoffs, TOPK)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.timing_read(_lib.K_MATCH, reset=True)
+    ctx.timing_read(_lib.K_TOPK, reset=True)
+    ctx.timing_enable(True)
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        keys = st.search_device(d_q, qoffs, TOPK)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    launches = ctx.launch_count() - launches0
+    match_ms, match_n = ctx.timing_read(_lib.K_MATCH, reset=True)
+    topk_ms, topk_n = ctx.timing_read(_lib.K_TOPK, reset=True)
+    ctx.timing_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    value = nq / (ms * 1e-3)
+
+    # correctness of what was just timed: planted queries must come back at their true (track, offset)
+    got = hpfw_b200.api.decode_keys(keys.cpu().numpy().view(np.uint64))
+    top1_ok = float(np.mean((got["track"][:, 0] == truth[:, 0]) & (got["offset"][:, 0] == truth[:, 1])))
+
+    # ---- end-to-end arm: host buffers in, host records out, every step
+    st.search_host(h_q, qoffs, TOPK, h_out)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        res = st.search_host(h_q, qoffs, TOPK, h_out)
+    e1.record()
+    barrier()
+    wall = (time.perf_counter() - t0) / args.steps
+    # host work (argument packing, key decoding) sits between the launches: take the larger of device and wall time
+    ms_e2e = max(max_over_ranks(e0.elapsed_time(e1)) / args.steps, max_over_ranks(wall * 1e3))
+    e2e_ok = float(np.mean((res["track"][:, 0] == truth[:, 0]) & (res["offset"][:, 0] == truth[:, 1])))
+    e2e_value = nq / (ms_e2e * 1e-3)
+
+    if world > 1:
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+
+    if rank == 0:
+        sm_max = None
+        peaks_src = "B200_PROFILING.md nominal clocks.max.sm 1965 MHz"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                sm_max = float(json.load(f)["sm_max_mhz"])
+                peaks_src = "MEASURED_PEAKS.json sm_max_mhz"
+        except (OSError, KeyError, ValueError):
+            sm_max = 1965.0
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        peak = sms * (POPC32_PER_CLK_SM / 2.0) * sm_max * 1e6 / 1e9          # Gword-op/s
+        ops_per_launch = word_ops_per_query(hi - lo) * nq / max(1, match_n / args.steps)
+        avg_ms = match_ms / max(1, match_n)
+        achieved = ops_per_launch / (avg_ms * 1e-3) / 1e9
+        roof = {"bound": "popc", "achieved": achieved, "peak": peak, "unit": "Gwordop/s", "frac": achieved / peak,
+                "traffic": None,
+                "kernel": "match_kernel", "avg_launch_ms": avg_ms, "launches": match_n,
+                "kernel_share_of_step": match_ms / args.steps / ms,
+                "peak_how": f"{sms} SMs x {POPC32_PER_CLK_SM} POPC.32/clk/SM / 2 per 64-bit word x {sm_max:.0f} MHz "
+                            f"({peaks_src}); 1 word-op = XOR64 + popcount64",
+                "microbench": micro,
+                "hbm_view": {"algorithmic_bytes_per_launch": 8.0 * (hi - lo) * TRACK_WORDS + 8.0 * nq * QUERY_WORDS,
+                             "note": "compute-bound: AI = k word-ops per 8 B of reference, HBM need is <1 % of peak"}}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "config": workload_config(n) | {"tracks": tracks, "queries_per_step": nq},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_q.numel() * 8),
+                    "d2h_bytes_per_step": int(h_out.numel() * 8), "ms_per_step": ms_e2e, "top1_ok": e2e_ok},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "top1_ok": top1_ok,
+            "topk_ms_per_step": topk_ms / args.steps,
+        }
+        if n == 1 and not args.no_cpu_baseline:
+            cores = host_cores()
+            nqc = max(cores, 8)
+            sample_tracks = 2000
+            kind, dt, qps = cpu_sample(cores, sample_tracks, nqc)
+            line["cpu_baseline"] = {
+                "value": qps, "unit": UNIT, "cores": cores, "kind": kind,
+                "sample": f"{nqc} queries x {sample_tracks}-track subset ({dt:.1f} s on {cores} host threads), scaled "
+                          f"x{sample_tracks}/{TRACKS} to the 10k-track DB; reference MemoryStorage::find, "
+                          f"-Ofast -march=native"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--tracks", type=int, default=TRACKS)
+    ap.add_argument("--queries-per-gpu", type=int, default=QUERIES_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_cuda(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -19,6 +19,7 @@ class Match(C.Structure):
     _fields_ = [("track", C.c_int64), ("cnt", C.c_uint64), ("offset", C.c_int64)]
 
 
+K_MATCH, K_TOPK, K_PROJECT, K_CQT, K_OTHER = range(5)
 OK, ERR_CUDA, ERR_ARG, ERR_LIMIT, ERR_STATE, ERR_SHORT = 0, -1, -2, -3, -4, -5
 
 _SIGS = {
@@ -30,6 +31,8 @@ _SIGS = {
     "hpfw_ctx_device": (C.c_int, [C.c_void_p]),
     "hpfw_ctx_launch_count": (C.c_uint64, [C.c_void_p]),
     "hpfw_ctx_synchronize": (C.c_int, [C.c_void_p]),
+    "hpfw_ctx_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "hpfw_ctx_timing_read": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
     "hpfw_db_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
     "hpfw_db_build_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
                                        C.POINTER(C.c_void_p)]),

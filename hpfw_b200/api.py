@@ -43,6 +43,15 @@ class Context:
     def synchronize(self) -> None:
         check(self._lib.hpfw_ctx_synchronize(self._h))
 
+    def timing_enable(self, on: bool = True) -> None:
+        check(self._lib.hpfw_ctx_timing_enable(self._h, 1 if on else 0))
+
+    def timing_read(self, kernel: int, reset: bool = True):
+        """(total device ms, launches) of a kernel class (_lib.K_MATCH, ...) since the last reset."""
+        ms, n = C.c_double(), C.c_uint64()
+        check(self._lib.hpfw_ctx_timing_read(self._h, kernel, C.byref(ms), C.byref(n), 1 if reset else 0))
+        return ms.value, int(n.value)
+
     def microbench_pipes(self):
         out = (C.c_double * 3)()
         clk = C.c_double()

@@ -110,6 +110,14 @@ struct hpfw_ctx {
     hpfw_b200::CqtPlanCache *cqt = nullptr;
     hpfw_b200::DeviceBuffer audio;
 
+    // optional per-kernel device timing (CUDA events on the launching stream); see hpfw_ctx_timing_*
+    bool timing = false;
+    struct TimingRec { int kernel; cudaEvent_t a, b; };
+    std::vector<TimingRec> timing_pending;
+    std::vector<cudaEvent_t> timing_pool;
+    double timing_ms[HPFW_K_COUNT] = {};
+    uint64_t timing_n[HPFW_K_COUNT] = {};
+
     cudaStream_t pick(void *s) const { return s ? static_cast<cudaStream_t>(s) : stream; }
 };
 
@@ -127,4 +135,36 @@ struct DeviceGuard {
     }
 };
 void cqt_cache_destroy(CqtPlanCache *);
+
+// Scope guard around ONE kernel launch: counts it and, when timing is enabled, brackets it with two events.
+struct KernelScope {
+    hpfw_ctx *ctx;
+    cudaStream_t stream;
+    int kernel;
+    cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t get(hpfw_ctx *c) {
+        cudaEvent_t e = nullptr;
+        if (!c->timing_pool.empty()) {
+            e = c->timing_pool.back();
+            c->timing_pool.pop_back();
+        } else {
+            cudaEventCreate(&e);
+        }
+        return e;
+    }
+    KernelScope(hpfw_ctx *c, int k, cudaStream_t s) : ctx(c), stream(s), kernel(k) {
+        ctx->launches++;
+        if (ctx->timing) {
+            a = get(ctx);
+            b = get(ctx);
+            cudaEventRecord(a, stream);
+        }
+    }
+    ~KernelScope() {
+        if (a) {
+            cudaEventRecord(b, stream);
+            ctx->timing_pending.push_back({kernel, a, b});
+        }
+    }
+};
 }  // namespace hpfw_b200

@@ -65,6 +65,11 @@ void hpfw_ctx_destroy(hpfw_ctx *c) {
     c->colmeta.release();
     c->audio.release();
     hpfw_b200::cqt_cache_destroy(c->cqt);
+    for (auto &r : c->timing_pending) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    for (auto e : c->timing_pool) cudaEventDestroy(e);
     if (c->pin_in_free) cudaEventDestroy(c->pin_in_free);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -72,6 +77,34 @@ void hpfw_ctx_destroy(hpfw_ctx *c) {
 
 int hpfw_ctx_device(const hpfw_ctx *c) { return c ? c->device : -1; }
 uint64_t hpfw_ctx_launch_count(const hpfw_ctx *c) { return c ? c->launches : 0; }
+
+int hpfw_ctx_timing_enable(hpfw_ctx *c, int on) {
+    if (!c) HPFW_FAIL(HPFW_ERR_ARG, "ctx is NULL");
+    c->timing = on != 0;
+    return HPFW_OK;
+}
+
+int hpfw_ctx_timing_read(hpfw_ctx *c, int kernel, double *total_ms, uint64_t *launches, int reset) {
+    if (!c || kernel < 0 || kernel >= HPFW_K_COUNT) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_ctx_timing_read: bad argument");
+    hpfw_b200::DeviceGuard g(c->device);
+    for (auto &r : c->timing_pending) {
+        HPFW_CUDA_TRY(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        HPFW_CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+        c->timing_ms[r.kernel] += double(ms);
+        c->timing_n[r.kernel] += 1;
+        c->timing_pool.push_back(r.a);
+        c->timing_pool.push_back(r.b);
+    }
+    c->timing_pending.clear();
+    if (total_ms) *total_ms = c->timing_ms[kernel];
+    if (launches) *launches = c->timing_n[kernel];
+    if (reset) {
+        c->timing_ms[kernel] = 0.0;
+        c->timing_n[kernel] = 0;
+    }
+    return HPFW_OK;
+}
 
 int hpfw_ctx_synchronize(hpfw_ctx *c) {
     if (!c) HPFW_FAIL(HPFW_ERR_ARG, "ctx is NULL");

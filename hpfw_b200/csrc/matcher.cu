@@ -473,17 +473,17 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
             const int per_group = std::min(cm[c].nb, MT_BLOCKS_PER_CTA);
             const int groups = (cm[c].nb + per_group - 1) / per_group;
             dim3 grid(db->n_tiles, groups);
+            KernelScope ks(ctx, HPFW_K_MATCH, stream);
             match_kernel<MT_QB><<<grid, MT_THREADS, smem, stream>>>(
                 db->d_words, db->d_track_start, db->d_tiles, d_q, d_qstart + cm[c].q0,
                 reinterpret_cast<const int32_t *>(meta + cm[c].idx_off),
                 reinterpret_cast<const int32_t *>(meta + cm[c].k_off), cm[c].nb, per_group, R, kpad, best);
             HPFW_CUDA_TRY(cudaGetLastError());
-            ctx->launches++;
         }
+        KernelScope ks(ctx, HPFW_K_TOPK, stream);
         topk_kernel<<<cm[c].nq, 256, 0, stream>>>(best, R, (long long)db->track_base, topk,
                                                     reinterpret_cast<unsigned long long *>(d_keys_out) + size_t(cm[c].q0) * topk);
         HPFW_CUDA_TRY(cudaGetLastError());
-        ctx->launches++;
     }
     return HPFW_OK;
 }
@@ -494,11 +494,11 @@ int hpfw_topk_merge_device(hpfw_ctx *ctx, const uint64_t *d_keys_in, int n_ranks
     if (n_ranks < 1 || n_queries < 0 || topk < 1) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_topk_merge_device: bad sizes");
     if (n_queries == 0) return HPFW_OK;
     DeviceGuard g(ctx->device);
+    KernelScope ks(ctx, HPFW_K_TOPK, ctx->pick(stream));
     merge_kernel<<<(n_queries + 127) / 128, 128, 0, ctx->pick(stream)>>>(
         reinterpret_cast<const unsigned long long *>(d_keys_in), n_ranks, n_queries, topk,
         reinterpret_cast<unsigned long long *>(d_keys_out));
     HPFW_CUDA_TRY(cudaGetLastError());
-    ctx->launches++;
     return HPFW_OK;
 }
 

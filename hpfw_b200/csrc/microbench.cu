@@ -69,7 +69,7 @@ extern "C" int hpfw_microbench_pipes(hpfw_ctx *ctx, double *out, double *sm_cloc
             if (mode == 1) pipe_kernel<1><<<grid, 256, 0, ctx->stream>>>(sink, iters, cyc);
             if (mode == 2) pipe_kernel<2><<<grid, 256, 0, ctx->stream>>>(sink, iters, cyc);
             HPFW_CUDA_TRY(cudaGetLastError());
-            ctx->launches++;
+            ctx->launches++;  // (not a product kernel class: counted, never event-timed by KernelScope)
             HPFW_CUDA_TRY(cudaEventRecord(e1, ctx->stream));
             HPFW_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         }

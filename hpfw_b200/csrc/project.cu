@@ -194,6 +194,7 @@ static int run_project(hpfw_ctx *ctx, int mode, const float *d_spectro, const in
     HPFW_CUDA_TRY(cudaEventRecord(ctx->pin_in_free, stream));
     const ProjTrack *d_tracks = ctx->colmeta.as<ProjTrack>();
     const ProjTile *d_tiles = reinterpret_cast<const ProjTile *>(ctx->colmeta.as<char>() + tb);
+    KernelScope ks(ctx, HPFW_K_PROJECT, stream);
     if (mode == 0) {
         HPFW_CUDA_TRY(cudaFuncSetAttribute(project_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(PJ_SMEM)));
         project_kernel<0><<<unsigned(tiles.size()), PJ_THREADS, PJ_SMEM, stream>>>(
@@ -204,7 +205,6 @@ static int run_project(hpfw_ctx *ctx, int mode, const float *d_spectro, const in
             d_spectro, ctx->filters_perm.as<float>(), d_tiles, d_tracks, nullptr, d_y);
     }
     HPFW_CUDA_TRY(cudaGetLastError());
-    ctx->launches++;
     return HPFW_OK;
 }
 

@@ -1,0 +1,116 @@
+"""Multi-GPU matcher: the reference database sharded by track across ranks (one process per GPU), queries replicated, one
+all-gather of the per-rank top-k keys, one merge kernel.
+
+The reference has no multi-device path (storage.h:29 "TODO: maybe parallelize search"); semantics are those of the single
+MemoryStorage: because a packed key (dist<<40 | global_track<<20 | offset) orders exactly like the reference's strict '<'
+scan, the merged result is bit-identical for any number of shards.
+
+torch / torch.distributed are plumbing here: device buffers, the NCCL process group and the all-gather call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+from ._lib import check
+from .api import Context, MemoryStorage, decode_keys
+
+KEY_OFFSET_BITS = 20
+KEY_TRACK_BITS = 20
+KEY_DIST_SHIFT = 40
+KEY_NONE = np.uint64((1 << 64) - 1)
+
+
+def pack_key(dist: int, track: int, offset: int) -> int:
+    """= the kernels' key layout (include/hpfw_b200.h HPFW_KEY_*)."""
+    return (int(dist) << KEY_DIST_SHIFT) | (int(track) << KEY_OFFSET_BITS) | int(offset)
+
+
+def plan_shards(track_words: Sequence[int], n_shards: int, query_words: int = 385) -> List[Tuple[int, int]]:
+    """Contiguous track ranges [begin, end) per shard, balanced by matcher work sum (n_r - k + 1) * k (clamped at n_r >= 1
+    offset). Contiguous ranges keep the global track index = DB order, which the tie rule (earliest track) relies on."""
+    lens = np.asarray(track_words, dtype=np.int64)
+    k = np.minimum(lens, query_words)
+    work = (lens - k + 1) * np.maximum(k, 1)
+    total = float(work.sum())
+    csum = np.concatenate([[0], np.cumsum(work)]).astype(np.float64)
+    bounds = [0]
+    for s in range(1, n_shards):
+        target = total * s / n_shards
+        b = int(np.searchsorted(csum, target, side="left"))
+        # pick the closer of b-1 / b, never before the previous bound
+        if b > 0 and abs(csum[b - 1] - target) <= abs(csum[min(b, len(lens))] - target):
+            b -= 1
+        bounds.append(min(max(b, bounds[-1]), len(lens)))
+    bounds.append(len(lens))
+    return [(bounds[i], bounds[i + 1]) for i in range(n_shards)]
+
+
+def allgather_keys(local, group=None):
+    """local: int64 tensor [Q, topk] (packed keys viewed as int64) -> [world, Q, topk] on the same device. One collective
+    per query batch: NCCL over NVLink on GPUs, gloo in the CPU tests."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+    if world == 1:
+        out[0].copy_(local)
+    else:
+        dist.all_gather_into_tensor(out.view(-1), local.contiguous().view(-1), group=group)
+    return out
+
+
+class ShardedMemoryStorage:
+    """MemoryStorage semantics over a DB sharded across the ranks of a torch.distributed group (1 rank = 1 GPU)."""
+
+    def __init__(self, ctx: Context, rank: int = 0, world: int = 1, group=None):
+        self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
+        self.local = MemoryStorage(ctx)
+        self.track_base = 0
+        self._keys_local = None
+        self._keys_all = None
+        self._keys_merged = None
+
+    def build_local(self, words: np.ndarray, offsets: np.ndarray, track_base: int) -> "ShardedMemoryStorage":
+        """This rank's shard (host buffers); track_base = global index of its first track."""
+        self.local.build_packed(words, offsets, track_base=track_base)
+        self.track_base = track_base
+        return self
+
+    def build_local_device(self, d_words_ptr: int, offsets: np.ndarray, track_base: int, stream: int = 0):
+        self.local.build_device(d_words_ptr, offsets, stream=stream, track_base=track_base)
+        self.track_base = track_base
+        return self
+
+    def search_device(self, d_qwords, qoffs: np.ndarray, topk: int):
+        """d_qwords: int64 CUDA tensor of the (replicated) query words. Returns the merged keys, int64 CUDA tensor
+        [Q, topk], identical on every rank. Everything is enqueued on torch's current stream; no host sync."""
+        import torch
+        nq = len(qoffs) - 1
+        dev = d_qwords.device
+        if self._keys_local is None or tuple(self._keys_local.shape) != (nq, topk):
+            self._keys_local = torch.empty((nq, topk), dtype=torch.int64, device=dev)
+            self._keys_merged = torch.empty((nq, topk), dtype=torch.int64, device=dev)
+        s = torch.cuda.current_stream(dev).cuda_stream
+        self.local.match_device(d_qwords.data_ptr(), qoffs, topk, self._keys_local.data_ptr(), s)
+        if self.world == 1:
+            return self._keys_local
+        allk = allgather_keys(self._keys_local, self.group)
+        check(self.ctx._lib.hpfw_topk_merge_device(self.ctx.handle, C.c_void_p(allk.data_ptr()), self.world, nq, topk,
+                                                   C.c_void_p(self._keys_merged.data_ptr()), C.c_void_p(s)))
+        self._keys_all = allk     # keep alive until the stream has consumed it
+        return self._keys_merged
+
+    def search_host(self, qwords_pinned, qoffs: np.ndarray, topk: int, out_pinned=None):
+        """End-to-end call with HOST buffers: qwords_pinned = pinned int64 CPU tensor; returns a structured numpy array
+        [Q, topk] (track, cnt, offset). Includes the H2D copy of the queries and the D2H copy of the result."""
+        import torch
+        dq = qwords_pinned.to(f"cuda:{self.ctx.device}", non_blocking=True)
+        keys = self.search_device(dq, qoffs, topk)
+        if out_pinned is None:
+            out_pinned = torch.empty(keys.shape, dtype=torch.int64, pin_memory=True)
+        out_pinned.copy_(keys, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return decode_keys(out_pinned.numpy().view(np.uint64))

@@ -86,6 +86,17 @@ int hpfw_ctx_device(const hpfw_ctx *ctx);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 uint64_t hpfw_ctx_launch_count(const hpfw_ctx *ctx);
 int hpfw_ctx_synchronize(hpfw_ctx *ctx);
+/* Per-kernel device timing for the roofline report: when enabled, every launch of a product kernel is bracketed by CUDA
+ * events on the stream it is launched on. hpfw_ctx_timing_read waits for the recorded events, returns the accumulated
+ * device time and launch count of kernel class `kernel`, and clears the accumulators of that class when reset != 0. */
+#define HPFW_K_MATCH 0    /* match_kernel (stage 4) */
+#define HPFW_K_TOPK 1     /* topk_kernel / merge_kernel */
+#define HPFW_K_PROJECT 2  /* project_kernel (stages 2-3) */
+#define HPFW_K_CQT 3      /* all CQT kernels (stage 1) */
+#define HPFW_K_OTHER 4
+#define HPFW_K_COUNT 5
+int hpfw_ctx_timing_enable(hpfw_ctx *ctx, int on);
+int hpfw_ctx_timing_read(hpfw_ctx *ctx, int kernel, double *total_ms, uint64_t *launches, int reset);
 
 /* ------------------------------------------------------------------------------------------------ matcher (stage 4) */
 /* words: concatenated hashprints of n_tracks tracks, offsets[n_tracks+1]; track_base = global index of the first

@@ -1,0 +1,148 @@
+"""Parity of the CUDA matcher (hpfw_b200/csrc/matcher.cu, through the C ABI) with the oracle / the reference-generated
+golden vectors. Integer work: every comparison is bit-exact."""
+import numpy as np
+import pytest
+
+import oracle
+from hpfw_b200 import MemoryStorage, synth
+from hpfw_b200.api import SIZE_MAX
+
+pytestmark = pytest.mark.gpu
+
+
+def _triple(r):
+    return (r.track, -1 if r.cnt >= (1 << 63) else r.cnt, r.offset)
+
+
+def test_find_golden(ctx, matcher_golden):
+    """MemoryStorage::find on every golden case (ragged, short refs, empty track, ties, empty DB, empty query)."""
+    for name, c in matcher_golden.items():
+        st = MemoryStorage(ctx).build_packed(c["words"], c["offs"])
+        qo = c["qoffs"]
+        for i in range(len(qo) - 1):
+            got = _triple(st.find(c["qwords"][qo[i]:qo[i + 1]]))
+            assert got == tuple(int(x) for x in c["res"][i]), (name, i)
+
+
+def test_find_returns_filenames(ctx, collector_golden):
+    c = collector_golden
+    offs = c["offs"]
+    pairs = [(str(n), c["words"][offs[i]:offs[i + 1]]) for i, n in enumerate(c["names"])]
+    st = MemoryStorage(ctx).build(pairs)
+    r = st.find(c["hpq"])
+    assert (r.track, r.cnt, r.offset) == tuple(int(x) for x in c["res"])
+    assert r.filename == str(c["names"][r.track])
+
+
+def test_topk_batched_vs_oracle(ctx, matcher_golden):
+    for name, c in matcher_golden.items():
+        R = len(c["offs"]) - 1
+        topk = R + 2
+        st = MemoryStorage(ctx).build_packed(c["words"], c["offs"])
+        out = st.find_topk_packed(c["qwords"], c["qoffs"], topk)
+        qo = c["qoffs"]
+        for i in range(len(qo) - 1):
+            tr, d, o = oracle.find_topk(c["words"], c["offs"], c["qwords"][qo[i]:qo[i + 1]], topk)
+            assert np.array_equal(out["track"][i], tr), (name, i)
+            assert np.array_equal(out["cnt"][i], d), (name, i)
+            assert np.array_equal(out["offset"][i], o), (name, i)
+
+
+@pytest.mark.parametrize("seed,n_tracks,max_len,ks", [
+    (1, 37, 700, (1, 7, 8, 9, 63, 143, 385)),
+    (2, 5, 5000, (385, 1514, 2047, 2048, 2049)),
+    (3, 64, 2100, (16, 385)),
+])
+def test_random_ragged_vs_oracle(ctx, seed, n_tracks, max_len, ks):
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(0, max_len, size=n_tracks)
+    lens[rng.integers(0, n_tracks)] = max_len          # at least one long track
+    words, offs = synth.synth_hashprint_db(seed, n_tracks, lens)
+    kk = np.array([ks[i % len(ks)] for i in range(3 * len(ks) + 1)], dtype=np.int64)
+    kk = np.minimum(kk, max_len)
+    qw, qo, truth = synth.synth_hashprint_queries(seed + 100, words, offs, len(kk), kk)
+    st = MemoryStorage(ctx).build_packed(words, offs)
+    topk = 5
+    out = st.find_topk_packed(qw, qo, topk)
+    tr, d, o = oracle.find_topk_batch(words, offs, qw, qo, topk, 8)
+    assert np.array_equal(out["track"], tr)
+    assert np.array_equal(out["cnt"], d)
+    assert np.array_equal(out["offset"], o)
+    # noisy sub-sequences at 25 % bit flips are found at their true position whenever the query is long enough
+    long_q = kk >= 63
+    assert np.array_equal(out["track"][long_q, 0], truth[long_q, 0])
+    assert np.array_equal(out["offset"][long_q, 0], truth[long_q, 1])
+
+
+def test_random_queries_unrelated_to_db(ctx):
+    """Random (non-planted) queries: near-ties everywhere, the strict-'<' tie rules decide."""
+    rng = np.random.default_rng(9)
+    words, offs = synth.synth_hashprint_db(9, 20, rng.integers(1, 900, size=20))
+    ks = np.array([1, 2, 3, 4, 5, 8, 16, 33], dtype=np.int64)
+    qo = np.zeros(len(ks) + 1, dtype=np.int64)
+    np.cumsum(ks, out=qo[1:])
+    qw = rng.integers(0, 1 << 64, size=int(qo[-1]), dtype=np.uint64)
+    st = MemoryStorage(ctx).build_packed(words, offs)
+    out = st.find_topk_packed(qw, qo, 20)
+    tr, d, o = oracle.find_topk_batch(words, offs, qw, qo, 20, 8)
+    assert np.array_equal(out["track"], tr) and np.array_equal(out["cnt"], d) and np.array_equal(out["offset"], o)
+
+
+def test_sharded_merge_equals_unsharded(ctx):
+    """DB split into shards with track_base, per-shard top-k keys merged by the merge kernel == unsharded result
+    (the single-process version of the multi-GPU path)."""
+    import torch
+    from hpfw_b200.api import decode_keys
+    rng = np.random.default_rng(11)
+    n_tracks, topk = 41, 7
+    words, offs = synth.synth_hashprint_db(11, n_tracks, rng.integers(50, 1500, size=n_tracks))
+    qw, qo, _ = synth.synth_hashprint_queries(12, words, offs, 23, 50)
+    whole = MemoryStorage(ctx).build_packed(words, offs).find_topk_packed(qw, qo, topk)
+    dq = torch.from_numpy(qw.view(np.int64)).cuda()
+    n_shards = 4
+    bounds = np.linspace(0, n_tracks, n_shards + 1).astype(int)
+    keys = torch.empty((n_shards, 23, topk), dtype=torch.int64, device="cuda")
+    shards = []
+    s = torch.cuda.current_stream().cuda_stream
+    for g in range(n_shards):
+        a, b = bounds[g], bounds[g + 1]
+        st = MemoryStorage(ctx).build_packed(words[offs[a]:offs[b]], offs[a:b + 1] - offs[a], track_base=int(a))
+        st.match_device(dq.data_ptr(), qo, topk, keys[g].data_ptr(), s)
+        shards.append(st)
+    merged = torch.empty((23, topk), dtype=torch.int64, device="cuda")
+    import ctypes as C
+    from hpfw_b200._lib import check
+    check(ctx._lib.hpfw_topk_merge_device(ctx.handle, C.c_void_p(keys.data_ptr()), n_shards, 23, topk,
+                                          C.c_void_p(merged.data_ptr()), C.c_void_p(s)))
+    torch.cuda.synchronize()
+    got = decode_keys(merged.cpu().numpy().view(np.uint64))
+    for f in ("track", "cnt", "offset"):
+        assert np.array_equal(got[f], whole[f]), f
+
+
+def test_full_size_properties(ctx):
+    """BASELINE config sizes (1000 x 14,411-word DB, 385-word queries): too big for the scalar oracle on every query, so
+    check (i) planted queries are found at their true (track, offset) with the exact planted distance, (ii) a sample
+    against the oracle, (iii) idempotence."""
+    words, offs = synth.synth_hashprint_db(21, 1000, 14411)
+    qw, qo, truth = synth.synth_hashprint_queries(22, words, offs, 64, 385)
+    st = MemoryStorage(ctx).build_packed(words, offs)
+    out = st.find_topk_packed(qw, qo, 10)
+    assert np.array_equal(out["track"][:, 0], truth[:, 0])
+    assert np.array_equal(out["offset"][:, 0], truth[:, 1])
+    for i in range(64):
+        a = offs[truth[i, 0]] + truth[i, 1]
+        planted = int(np.unpackbits((words[a:a + 385] ^ qw[qo[i]:qo[i + 1]]).view(np.uint8)).sum())
+        assert int(out["cnt"][i, 0]) == planted
+    tr, d, o = oracle.find_topk_batch(words, offs, qw[:qo[4]], qo[:5], 10, 8)
+    assert np.array_equal(out["track"][:4], tr) and np.array_equal(out["cnt"][:4], d) and np.array_equal(out["offset"][:4], o)
+    again = st.find_topk_packed(qw, qo, 10)
+    assert np.array_equal(again, out)
+
+
+def test_limits_reported(ctx):
+    from hpfw_b200 import HpfwError
+    words, offs = synth.synth_hashprint_db(31, 2, 100)
+    st = MemoryStorage(ctx).build_packed(words, offs)
+    with pytest.raises(HpfwError):
+        st.find(np.zeros(5000, dtype=np.uint64))      # > HPFW_MAX_QUERY_WORDS
