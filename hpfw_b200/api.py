@@ -23,6 +23,12 @@ def _ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def stream_arg(stream: int):
+    """cudaStream_t for the C ABI. The ABI reads NULL as "the context's own stream", so the CUDA legacy default stream
+    (handle 0, e.g. torch.cuda.current_stream().cuda_stream when no stream is set) is passed as cudaStreamLegacy (0x1)."""
+    return C.c_void_p(int(stream) if stream else 1)
+
+
 class Context:
     """One CUDA device. There is no CPU fallback: construction fails without a B200-class GPU."""
 
@@ -134,7 +140,7 @@ class MemoryStorage:
         self.track_base = track_base
         h = C.c_void_p()
         check(self._lib.hpfw_db_build_device(self.ctx.handle, C.c_void_p(d_words_ptr), _ptr(offsets), n, track_base,
-                                             C.c_void_p(stream), C.byref(h)))
+                                             stream_arg(stream), C.byref(h)))
         self._db = h
         self._offsets = offsets
         return self
@@ -170,7 +176,7 @@ class MemoryStorage:
         """Device path: query words and the key output live in HBM; enqueues on `stream` without synchronising."""
         qoffs = np.ascontiguousarray(qoffs, dtype=np.int64)
         check(self._lib.hpfw_db_match_device(self._require(), C.c_void_p(d_qwords_ptr), _ptr(qoffs), len(qoffs) - 1,
-                                             topk, C.c_void_p(d_keys_out_ptr), C.c_void_p(stream)))
+                                             topk, C.c_void_p(d_keys_out_ptr), stream_arg(stream)))
 
     def word_ops(self, qoffs: np.ndarray) -> float:
         qoffs = np.ascontiguousarray(qoffs, dtype=np.int64)

@@ -58,19 +58,60 @@ __device__ __forceinline__ void load_q(const uint64_t *p, uint2 (&q)[QB]) {
     }
 }
 
+// 3-input majority / parity: one LOP3 each.
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+// One block of up to 8 query words against the 16-word register window, for 8 offsets x QB queries.
+// POPC issues on the XU pipe at 16 lanes/clk/SM and is the bound of a plain XOR+POPC loop (ncu: xu 97 %, alu 37 %), so
+// consecutive query words are first combined by a carry-save adder on the ALU pipe: for x_a = q[j]^r[i+j] and
+// x_b = q[j+1]^r[i+j+1], ones' = ones^x_a^x_b keeps the weight-1 bits and only maj(ones,x_a,x_b) (weight 2) is POPC'd.
+// That halves the POPC count; the distance is 2*twos + popc(ones) at the end. Exact integer arithmetic.
 template <int QB>
 __device__ __forceinline__ void step8(const uint64_t *qs, const uint2 (&cur)[8], const uint2 (&nxt)[8],
-                                      uint32_t (&acc)[QB][8], int nsteps) {
+                                      uint2 (&ones)[QB][8], uint32_t (&twos)[QB][8], int nsteps) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        if (u < nsteps) {
-            uint2 q[QB];
-            load_q<QB>(qs + u * QB, q);
+    for (int u = 0; u < 8; u += 2) {
+        if (u + 1 < nsteps) {
+            uint2 q0[QB], q1[QB];
+            load_q<QB>(qs + u * QB, q0);
+            load_q<QB>(qs + (u + 1) * QB, q1);
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-                const uint2 x = (t + u < 8) ? cur[(t + u) & 7] : nxt[(t + u) & 7];
+                const uint2 xa = (t + u < 8) ? cur[(t + u) & 7] : nxt[(t + u) & 7];
+                const uint2 xb = (t + u + 1 < 8) ? cur[(t + u + 1) & 7] : nxt[(t + u + 1) & 7];
 #pragma unroll
-                for (int qq = 0; qq < QB; ++qq) acc[qq][t] += __popc(q[qq].x ^ x.x) + __popc(q[qq].y ^ x.y);
+                for (int qq = 0; qq < QB; ++qq) {
+                    const uint32_t alo = q0[qq].x ^ xa.x, ahi = q0[qq].y ^ xa.y;
+                    const uint32_t blo = q1[qq].x ^ xb.x, bhi = q1[qq].y ^ xb.y;
+                    const uint32_t clo = maj3(ones[qq][t].x, alo, blo), chi = maj3(ones[qq][t].y, ahi, bhi);
+                    ones[qq][t].x = xor3(ones[qq][t].x, alo, blo);
+                    ones[qq][t].y = xor3(ones[qq][t].y, ahi, bhi);
+                    twos[qq][t] += __popc(clo) + __popc(chi);
+                }
+            }
+        } else if (u < nsteps) {   // odd tail word: CSA with x_b = 0
+            uint2 q0[QB];
+            load_q<QB>(qs + u * QB, q0);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const uint2 xa = (t + u < 8) ? cur[(t + u) & 7] : nxt[(t + u) & 7];
+#pragma unroll
+                for (int qq = 0; qq < QB; ++qq) {
+                    const uint32_t alo = q0[qq].x ^ xa.x, ahi = q0[qq].y ^ xa.y;
+                    const uint32_t clo = ones[qq][t].x & alo, chi = ones[qq][t].y & ahi;
+                    ones[qq][t].x ^= alo;
+                    ones[qq][t].y ^= ahi;
+                    twos[qq][t] += __popc(clo) + __popc(chi);
+                }
             }
         }
     }
@@ -117,11 +158,15 @@ match_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ tra
         if (tid < QB) red_s[tid] = 0xFFFFFFFFu;
         __syncthreads();
 
-        uint32_t acc[QB][8];
+        uint2 ones[QB][8];
+        uint32_t twos[QB][8];
 #pragma unroll
         for (int qq = 0; qq < QB; ++qq)
 #pragma unroll
-            for (int t = 0; t < 8; ++t) acc[qq][t] = 0;
+            for (int t = 0; t < 8; ++t) {
+                ones[qq][t] = make_uint2(0u, 0u);
+                twos[qq][t] = 0;
+            }
 
         const int warp_first = tile_start + (tid & ~31) * MT_T;
         if (warp_first <= last_valid) {            // warp-uniform: skip warps that own no valid offset
@@ -133,7 +178,7 @@ match_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ tra
             for (int jj = 0; jj < nfull; ++jj) {
                 rp += MT_PITCH;
                 lds_block8(rp, nxt);
-                step8<QB>(qs, cur, nxt, acc, 8);
+                step8<QB>(qs, cur, nxt, ones, twos, 8);
                 qs += 8 * QB;
 #pragma unroll
                 for (int t = 0; t < 8; ++t) cur[t] = nxt[t];
@@ -142,7 +187,7 @@ match_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ tra
             if (rem) {
                 rp += MT_PITCH;
                 lds_block8(rp, nxt);
-                step8<QB>(qs, cur, nxt, acc, rem);
+                step8<QB>(qs, cur, nxt, ones, twos, rem);
             }
             const int lane = tid & 31;
 #pragma unroll
@@ -151,7 +196,8 @@ match_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ tra
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
                     const int loc = tid * MT_T + t;
-                    const uint32_t key = (acc[qq][t] << MT_LOCAL_BITS) | uint32_t(loc);
+                    const uint32_t dist = 2u * twos[qq][t] + __popc(ones[qq][t].x) + __popc(ones[qq][t].y);
+                    const uint32_t key = (dist << MT_LOCAL_BITS) | uint32_t(loc);
                     if (tile_start + loc <= last_valid) bk = min(bk, key);
                 }
                 bk = __reduce_min_sync(0xFFFFFFFFu, bk);

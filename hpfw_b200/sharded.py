@@ -15,7 +15,7 @@ from typing import List, Sequence, Tuple
 import numpy as np
 
 from ._lib import check
-from .api import Context, MemoryStorage, decode_keys
+from .api import Context, MemoryStorage, decode_keys, stream_arg
 
 KEY_OFFSET_BITS = 20
 KEY_TRACK_BITS = 20
@@ -99,7 +99,7 @@ class ShardedMemoryStorage:
             return self._keys_local
         allk = allgather_keys(self._keys_local, self.group)
         check(self.ctx._lib.hpfw_topk_merge_device(self.ctx.handle, C.c_void_p(allk.data_ptr()), self.world, nq, topk,
-                                                   C.c_void_p(self._keys_merged.data_ptr()), C.c_void_p(s)))
+                                                   C.c_void_p(self._keys_merged.data_ptr()), stream_arg(s)))
         self._keys_all = allk     # keep alive until the stream has consumed it
         return self._keys_merged
 

@@ -26,7 +26,8 @@
  *   - every function returns HPFW_OK (0) or a negative error code; hpfw_last_error() gives the thread-local message.
  *   - "host" entry points take host pointers and do their own H2D/D2H copies (what the reference-facing classes call);
  *     "_device" entry points take device pointers (payload already in HBM) plus host metadata, enqueue on `stream`
- *     (a cudaStream_t cast to void*; NULL = the context's own stream) and do not synchronise.
+ *     (a cudaStream_t cast to void*; NULL = the context's own non-blocking stream; name the CUDA legacy default stream
+ *     as cudaStreamLegacy, (void*)1) and do not synchronise.
  *   - there is NO CPU fallback: without a CUDA device every entry point fails with HPFW_ERR_CUDA.
  *   - layouts follow the reference: spectrogram = column-major float[121 x cols] (time-major in memory),
  *     filters = column-major float[64 x 2420] with row index band*20+context, hashprint word bit (63-f) = filter f.

@@ -8,6 +8,7 @@ import pytest
 
 import oracle
 from hpfw_b200._lib import check
+from hpfw_b200.api import stream_arg
 
 pytestmark = pytest.mark.gpu
 
@@ -122,7 +123,7 @@ def test_batched_device_entry_equals_single(ctx, hashprint_golden):
     d_hp = torch.zeros(sum(n_words), dtype=torch.int64, device="cuda")
     check(ctx._lib.hpfw_hashprint_from_spectrogram_device(
         ctx.handle, C.c_void_p(d_spec.data_ptr()), col_offs.ctypes.data_as(C.c_void_p), len(specs),
-        C.c_void_p(d_hp.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        C.c_void_p(d_hp.data_ptr()), stream_arg(torch.cuda.current_stream().cuda_stream)))
     torch.cuda.synchronize()
     got = d_hp.cpu().numpy().view(np.uint64)
     pos = 0
