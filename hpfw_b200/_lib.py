@@ -56,6 +56,8 @@ _SIGS = {
     "hpfw_cqt_spectrogram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int)]),
     "hpfw_cqt_spectrogram_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "hpfw_cqt_magnitude": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int)]),
+    "hpfw_cqt_design": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
+    "hpfw_fft_c2c": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "hpfw_hashprint_words_for_samples": (C.c_int, [C.c_int64]),
     "hpfw_calc_hashprint_audio": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int)]),
     "hpfw_calc_hashprint_audio_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

@@ -9,9 +9,6 @@ void set_error(const char *fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
-#ifndef HPFW_HAVE_CQT
-void cqt_cache_destroy(CqtPlanCache *) {}
-#endif
 }  // namespace hpfw_b200
 
 extern "C" {

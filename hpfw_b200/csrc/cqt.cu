@@ -1,23 +1,976 @@
-// hpfw_b200/csrc/cqt.cu — stage 1 (CQT front end). PLACEHOLDER while the kernels are being written: every entry point
-// reports HPFW_ERR_STATE (it does NOT fall back to any CPU path).
+// hpfw_b200/csrc/cqt.cu — stage 1: the constant-Q front end.
+//
+// Replaces spectrum::CQT::spectrogram after decoding (/root/reference/include/hpfw/spectrum/cqt.h:54-84: essentia
+// NSGConstantQ over the whole track, abs, keep every 3rd coefficient) and amplitude_to_db
+// (/root/reference/include/hpfw/spectrum/convert.h:7-25). The arithmetic of NSGConstantQ lives in essentia (absent from the
+// reference tree); the algorithm restated here is the one in oracle/nsgcq.py's header ("parity unpinned").
+//
+//   X = FFT_N(x);  per band j: buf[k] = X[pos_j + k] * hann_j[k], k in [-Lg_j/2, Lg_j/2);  c_j = IFFT_M(buf);
+//   S[j, i] = 20 log10 |c_j[3 i]|  relative to the track maximum, floored at -80 dB.
+//
+// B200 formulation (no library FFT; every transform below is a kernel in this file):
+//   (1) N real samples are packed to H = N/2 complex points and transformed by a two-pass ("four-step") FFT, H = n1 * n2
+//       with n1, n2 <= 8192 products of 2,3,5,7: pass A = length-n1 column FFTs + inter-pass twiddle, pass B = length-n2
+//       row FFTs whose transposed store keeps only the two bin ranges the 121 bands need (~19 % of the half spectrum).
+//       Each small FFT is a mixed-radix Stockham autosort in shared memory.
+//   (2) per band, only every 3rd of the M IFFT outputs is wanted and M is in general not smooth (43,528 = 8 * 5441), so
+//       c_j[3 i] is evaluated as a chirp-z transform: |c_j[3i]| = |sum_k a[k] e^{2 pi i 3 i k / M}| =
+//       |IFFT_L( FFT_L(a .* chirp) .* FFT_L(chirp_filter) )[i]|, L = 2^p >= Lg_j + F - 1. FFT_L is again four-step,
+//       L = 16 * L2: a radix-16 register FFT down the columns (fused with the half-spectrum untangle, the Hann window and
+//       the chirp), one shared-memory kernel per row doing FFT_L2 -> multiply -> IFFT_L2, and a radix-16 register IFFT
+//       fused with |.|^2, the 1/(L M) scale and the per-track maximum.
+//   (3) dB conversion + transpose to the reference's column-major [121 x cols] layout.
+// Everything for one track stays L2-resident (32 MB half spectrum, 38 MB CZT work area at 3 minutes).
 #include "common.cuh"
 
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+
+namespace hpfw_b200 {
+
+constexpr int CQ_BINS = HPFW_BINS;
+constexpr double CQ_SR = 44100.0;     // essentia NSGConstantQ default sampleRate: cqt.h:54-61 never forwards SampleRate
+constexpr double CQ_FMIN = 130.81;    // cqt.h:59
+constexpr int CQ_BPO = 24;            // cqt.h:20,56
+constexpr int CQ_MINWIN = 96;         // cqt.h:19,57
+constexpr int CQ_DOWN = 3;            // cqt.h:22
+constexpr int CQ_L1 = 16;             // CZT column radix
+constexpr int CQ_MAX_ROW = 8192;      // longest shared-memory FFT (2 x 64 KB ping-pong)
+constexpr int CQ_MAXRAD = 14;
+constexpr int CQ_TW_S = 1024;         // two-level twiddle: W^m = hi[m / S] * lo[m % S]
+constexpr int CQ_THREADS = 256;
+
+struct FftDesc {
+    int n;
+    int nrad;
+    int rad[CQ_MAXRAD];
+};
+
+struct BandMeta {
+    int first_bin;        // pos_j - floor(Lg_j / 2)
+    int lg;               // Lg_j
+    int half;             // floor(Lg_j / 2)
+    int L;                // CZT length
+    int L2;               // L / 16
+    int btab;             // index of the chirp-filter spectrum table for this L
+    long long work_off;   // offset (complex elements) of this band's L-point work area
+};
+
+// ------------------------------------------------------------------------------------------------ complex helpers
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+// multiply by -i (sign < 0) or +i (sign > 0)
+__device__ __forceinline__ float2 mul_i(float2 a, int sign) {
+    return sign < 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
+}
+__device__ __forceinline__ float2 twiddle2(const float2 *__restrict__ hi, const float2 *__restrict__ lo, long long m,
+                                           int sign) {
+    float2 w = cmul(hi[m / CQ_TW_S], lo[m % CQ_TW_S]);
+    return sign < 0 ? w : cconj(w);    // tables hold e^{-2 pi i m / P}
+}
+
+// ------------------------------------------------------------------------------------------------ small DFTs
+// cos / sin of 2 pi i / R for the odd radices (compile-time constants once the butterfly loops are unrolled)
+template <int R> __host__ __device__ constexpr float odd_cos(int i) {
+    if (R == 3) return i == 0 ? 1.f : -0.5f;
+    if (R == 5) return i == 0 ? 1.f : ((i == 1 || i == 4) ? 0.30901699437494745f : -0.8090169943749473f);
+    return i == 0 ? 1.f
+                  : ((i == 1 || i == 6) ? 0.6234898018587336f
+                                        : ((i == 2 || i == 5) ? -0.2225209339563144f : -0.9009688679024191f));
+}
+template <int R> __host__ __device__ constexpr float odd_sin(int i) {
+    if (R == 3) return i == 0 ? 0.f : (i == 1 ? 0.8660254037844386f : -0.8660254037844386f);
+    if (R == 5)
+        return i == 0 ? 0.f
+                      : (i == 1 ? 0.9510565162951535f
+                                : (i == 2 ? 0.5877852522924732f : (i == 3 ? -0.5877852522924732f : -0.9510565162951535f)));
+    return i == 0 ? 0.f
+                  : (i == 1 ? 0.7818314824680298f
+                            : (i == 2 ? 0.9749279121818236f
+                                      : (i == 3 ? 0.4338837391175581f
+                                                : (i == 4 ? -0.4338837391175581f
+                                                          : (i == 5 ? -0.9749279121818236f : -0.7818314824680298f)))));
+}
+
+// X_k = sum_m v_m e^{sign 2 pi i k m / R}, in place. Odd R through the symmetric pairs (v_m +- v_{R-m}).
+template <int R> __device__ __forceinline__ void dft_odd(float2 (&v)[R], int sign) {
+    constexpr int Hh = (R - 1) / 2;
+    float2 sm[Hh], df[Hh];
+#pragma unroll
+    for (int m = 1; m <= Hh; ++m) {
+        sm[m - 1] = cadd(v[m], v[R - m]);
+        df[m - 1] = csub(v[m], v[R - m]);
+    }
+    float2 x0 = v[0];
+    float2 out0 = x0;
+#pragma unroll
+    for (int m = 0; m < Hh; ++m) out0 = cadd(out0, sm[m]);
+#pragma unroll
+    for (int k = 1; k <= Hh; ++k) {
+        float2 A = x0, B = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int m = 1; m <= Hh; ++m) {
+            const float c = odd_cos<R>((k * m) % R), s = odd_sin<R>((k * m) % R);
+            A.x = fmaf(sm[m - 1].x, c, A.x);
+            A.y = fmaf(sm[m - 1].y, c, A.y);
+            B.x = fmaf(df[m - 1].x, s, B.x);
+            B.y = fmaf(df[m - 1].y, s, B.y);
+        }
+        const float2 iB = mul_i(B, sign);    // sign<0: -i B
+        v[k] = cadd(A, iB);
+        v[R - k] = csub(A, iB);
+    }
+    v[0] = out0;
+}
+
+__device__ __forceinline__ void dft2(float2 (&v)[2]) {
+    const float2 a = v[0], b = v[1];
+    v[0] = cadd(a, b);
+    v[1] = csub(a, b);
+}
+__device__ __forceinline__ void dft4(float2 &v0, float2 &v1, float2 &v2, float2 &v3, int sign) {
+    const float2 t0 = cadd(v0, v2), t1 = csub(v0, v2), t2 = cadd(v1, v3), t3 = mul_i(csub(v1, v3), sign);
+    v0 = cadd(t0, t2);
+    v1 = cadd(t1, t3);
+    v2 = csub(t0, t2);
+    v3 = csub(t1, t3);
+}
+__device__ __forceinline__ void dft8(float2 (&v)[8], int sign) {
+    float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+    float2 o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
+    dft4(e0, e1, e2, e3, sign);
+    dft4(o0, o1, o2, o3, sign);
+    const float r = 0.7071067811865476f;
+    // w8^k = e^{sign 2 pi i k / 8}
+    const float2 w1 = make_float2(r, sign < 0 ? -r : r), w3 = make_float2(-r, sign < 0 ? -r : r);
+    o1 = cmul(o1, w1);
+    o2 = mul_i(o2, sign);
+    o3 = cmul(o3, w3);
+    v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+    v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+    v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+    v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+}
+// 16-point DFT in registers: a = 4 a1 + a0 -> c = c0 + 4 c1 (see file header of the derivation in DESIGN.md)
+__device__ __forceinline__ void dft16(float2 (&v)[16], int sign) {
+    constexpr float C[4] = {1.f, 0.9238795325112867f, 0.7071067811865476f, 0.3826834323650898f};   // cos(2 pi m/16)
+    constexpr float S[4] = {0.f, 0.3826834323650898f, 0.7071067811865476f, 0.9238795325112867f};   // sin(2 pi m/16)
+    float2 y[4][4];   // y[a0][c0]
+#pragma unroll
+    for (int a0 = 0; a0 < 4; ++a0) {
+        float2 t0 = v[a0], t1 = v[4 + a0], t2 = v[8 + a0], t3 = v[12 + a0];
+        dft4(t0, t1, t2, t3, sign);
+        y[a0][0] = t0; y[a0][1] = t1; y[a0][2] = t2; y[a0][3] = t3;
+    }
+#pragma unroll
+    for (int a0 = 1; a0 < 4; ++a0)
+#pragma unroll
+        for (int c0 = 1; c0 < 4; ++c0) {
+            const int m = a0 * c0;   // 1,2,3,4,6,9
+            float c, s;
+            if (m <= 3) { c = C[m]; s = S[m]; }
+            else if (m == 4) { c = 0.f; s = 1.f; }
+            else if (m == 6) { c = -C[2]; s = S[2]; }
+            else { c = -C[1]; s = -S[1]; }     // m == 9: cos(9 pi/8) = -cos(pi/8), sin(9 pi/8) = -sin(pi/8)
+            const float2 w = make_float2(c, sign < 0 ? -s : s);
+            y[a0][c0] = cmul(y[a0][c0], w);
+        }
+#pragma unroll
+    for (int c0 = 0; c0 < 4; ++c0) {
+        float2 t0 = y[0][c0], t1 = y[1][c0], t2 = y[2][c0], t3 = y[3][c0];
+        dft4(t0, t1, t2, t3, sign);
+        v[c0] = t0; v[c0 + 4] = t1; v[c0 + 8] = t2; v[c0 + 12] = t3;
+    }
+}
+
+template <int R> __device__ __forceinline__ void dft_r(float2 (&v)[R], int sign);
+template <> __device__ __forceinline__ void dft_r<2>(float2 (&v)[2], int) { dft2(v); }
+template <> __device__ __forceinline__ void dft_r<3>(float2 (&v)[3], int sign) { dft_odd<3>(v, sign); }
+template <> __device__ __forceinline__ void dft_r<4>(float2 (&v)[4], int sign) { dft4(v[0], v[1], v[2], v[3], sign); }
+template <> __device__ __forceinline__ void dft_r<5>(float2 (&v)[5], int sign) { dft_odd<5>(v, sign); }
+template <> __device__ __forceinline__ void dft_r<7>(float2 (&v)[7], int sign) { dft_odd<7>(v, sign); }
+template <> __device__ __forceinline__ void dft_r<8>(float2 (&v)[8], int sign) { dft8(v, sign); }
+
+// ------------------------------------------------------------------------------------------------ shared-memory FFT
+// One Stockham autosort stage of radix R over G interleaved-by-sequence arrays of length n (sequence g at g*n).
+template <int R>
+__device__ __forceinline__ void stockham_stage(const float2 *in, float2 *out, int n, int G, int Ns,
+                                               const float2 *__restrict__ tw, int sign) {
+    const int m = n / R;
+    const int tws = n / (Ns * R);
+    for (int idx = threadIdx.x; idx < G * m; idx += blockDim.x) {
+        const int g = idx / m, j = idx - g * m;
+        const int blk = j / Ns, k = j - blk * Ns;
+        float2 v[R];
+#pragma unroll
+        for (int t = 0; t < R; ++t) v[t] = in[g * n + j + t * m];
+        if (Ns > 1) {
+#pragma unroll
+            for (int t = 1; t < R; ++t) {
+                float2 w = tw[k * t * tws];          // e^{-2 pi i k t / (Ns R)}
+                if (sign > 0) w = cconj(w);
+                v[t] = cmul(v[t], w);
+            }
+        }
+        dft_r<R>(v, sign);
+        const int base = g * n + blk * Ns * R + k;
+#pragma unroll
+        for (int t = 0; t < R; ++t) out[base + t * Ns] = v[t];
+    }
+}
+
+// FFT of G sequences of length d.n held in `a`; `b` is scratch of the same size. Returns the buffer holding the result
+// (natural order). All threads of the CTA must call it; the data in `a` must be visible (caller syncs before).
+__device__ float2 *smem_fft(float2 *a, float2 *b, const FftDesc &d, int G, const float2 *__restrict__ tw, int sign) {
+    int Ns = 1;
+    for (int s = 0; s < d.nrad; ++s) {
+        const int r = d.rad[s];
+        switch (r) {
+            case 2: stockham_stage<2>(a, b, d.n, G, Ns, tw, sign); break;
+            case 3: stockham_stage<3>(a, b, d.n, G, Ns, tw, sign); break;
+            case 4: stockham_stage<4>(a, b, d.n, G, Ns, tw, sign); break;
+            case 5: stockham_stage<5>(a, b, d.n, G, Ns, tw, sign); break;
+            case 7: stockham_stage<7>(a, b, d.n, G, Ns, tw, sign); break;
+            default: stockham_stage<8>(a, b, d.n, G, Ns, tw, sign); break;
+        }
+        __syncthreads();
+        float2 *t = a; a = b; b = t;
+        Ns *= r;
+    }
+    return a;
+}
+
+// ------------------------------------------------------------------------------------------------ main FFT, pass A
+// Column FFTs of the n1 x n2 row-major matrix `in` (element (a,b) at a*n2+b): for G adjacent columns per CTA,
+// out[c*n2 + b] = W_H^{b c} * sum_a in[a*n2 + b] e^{-2 pi i a c / n1}.
+__global__ void __launch_bounds__(CQ_THREADS)
+fft_cols_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, FftDesc d1, int n2, int G,
+                const float2 *__restrict__ tw1, const float2 *__restrict__ twH_hi, const float2 *__restrict__ twH_lo,
+                int sign) {
+    extern __shared__ __align__(16) float2 fsm[];
+    const int n1 = d1.n;
+    const int b0 = blockIdx.x * G;
+    const int g_here = min(G, n2 - b0);
+    float2 *A = fsm, *B = fsm + G * n1;
+    for (int idx = threadIdx.x; idx < n1 * G; idx += blockDim.x) {
+        const int a = idx / G, g = idx - a * G;
+        A[g * n1 + a] = g < g_here ? in[(long long)a * n2 + b0 + g] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    float2 *R = smem_fft(A, B, d1, G, tw1, sign);
+    for (int idx = threadIdx.x; idx < n1 * G; idx += blockDim.x) {
+        const int c = idx / G, g = idx - c * G;
+        if (g < g_here) {
+            const float2 w = twiddle2(twH_hi, twH_lo, (long long)(b0 + g) * c, sign);
+            out[(long long)c * n2 + b0 + g] = cmul(R[g * n1 + c], w);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ main FFT, pass B
+// Row FFTs: Z[c + n1*d] = sum_b in[c*n2 + b] e^{-2 pi i b d / n2}. Keeps only k in [klo, khi] (-> out_lo[k - klo]) and
+// k in [H - khi, H - klo] (-> out_hi[k - (H - khi)]); with keep_all != 0 stores the whole spectrum to out_lo[k].
+__global__ void __launch_bounds__(CQ_THREADS)
+fft_rows_kernel(const float2 *__restrict__ in, float2 *__restrict__ out_lo, float2 *__restrict__ out_hi, FftDesc d2,
+                int n1, int G, const float2 *__restrict__ tw2, int klo, int khi, int H, int keep_all, int sign) {
+    extern __shared__ __align__(16) float2 fsm[];
+    const int n2 = d2.n;
+    const int c0 = blockIdx.x * G;
+    const int g_here = min(G, n1 - c0);
+    float2 *A = fsm, *B = fsm + G * n2;
+    for (int idx = threadIdx.x; idx < n2 * G; idx += blockDim.x) {
+        const int g = idx / n2, b = idx - g * n2;
+        A[idx] = g < g_here ? in[(long long)(c0 + g) * n2 + b] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    float2 *R = smem_fft(A, B, d2, G, tw2, sign);
+    const int mlo = H - khi, mhi = H - klo;
+    for (int idx = threadIdx.x; idx < n2 * G; idx += blockDim.x) {
+        const int dd = idx / G, g = idx - dd * G;
+        if (g >= g_here) continue;
+        const int k = c0 + g + n1 * dd;
+        const float2 v = R[g * n2 + dd];
+        if (keep_all) {
+            out_lo[k] = v;
+        } else {
+            if (k >= klo && k <= khi) out_lo[k - klo] = v;
+            if (k >= mlo && k <= mhi) out_hi[k - mlo] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ CZT column pass
+// MODE 0: band input a[k'] = X[first_bin + k'] * hann * chirp from the packed half spectrum (untangled on the fly).
+// MODE 1: chirp filter b[n] = e^{-i pi 3 n^2 / M}, n = k' (k' < F) or k' - L (k' >= F), for plan creation.
+// Then 16-point FFT down the columns (k' = L2*a + b), twiddle W_L^{b c}, store work[c*L2 + b].
+template <int MODE>
+__global__ void __launch_bounds__(CQ_THREADS)
+czt_cols_kernel(const BandMeta *__restrict__ bands, const float2 *__restrict__ z_lo, const float2 *__restrict__ z_hi,
+                int klo, int khi, const float2 *__restrict__ twN_hi, const float2 *__restrict__ twN_lo, int M, int F,
+                float2 *__restrict__ work) {
+    const BandMeta bm = bands[blockIdx.y];
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= bm.L2) return;
+    const unsigned long long twoM = 2ull * (unsigned long long)M;
+    float2 v[16];
+#pragma unroll
+    for (int a = 0; a < 16; ++a) {
+        const int kp = bm.L2 * a + b;
+        float2 val = make_float2(0.f, 0.f);
+        if (MODE == 0) {
+            if (kp < bm.lg) {
+                const int k = bm.first_bin + kp;
+                const float2 zk = z_lo[k - klo];
+                const float2 zm = cconj(z_hi[khi - k]);             // conj(Z[H - k])
+                const float2 w = twiddle2(twN_hi, twN_lo, k, -1);   // e^{-2 pi i k / N}
+                const float2 se = cadd(zk, zm), so = cmul(w, csub(zk, zm));
+                // X[k] = (Zk + conj Zm)/2 - (i/2) W (Zk - conj Zm)
+                const float2 X = make_float2(0.5f * (se.x + so.y), 0.5f * (se.y - so.x));
+                const float hann = 0.5f + 0.5f * cospif(2.0f * (float)(kp - bm.half) / (float)bm.lg);
+                const unsigned long long ph = (3ull * (unsigned long long)kp * (unsigned long long)kp) % twoM;
+                float s, c;
+                sincospif((float)((double)ph / (double)M), &s, &c);
+                val = cmul(make_float2(X.x * hann, X.y * hann), make_float2(c, s));
+            }
+        } else {
+            const long long n = kp < F ? kp : (long long)kp - bm.L;
+            const unsigned long long ph = (3ull * (unsigned long long)(n * n)) % twoM;
+            float s, c;
+            sincospif((float)((double)ph / (double)M), &s, &c);
+            val = make_float2(c, -s);
+        }
+        v[a] = val;
+    }
+    dft16(v, -1);
+    float2 *dst = work + bm.work_off;
+    const float invL = 1.0f / (float)bm.L;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        float s, co;
+        sincospif(-2.0f * (float)(b * c) * invL, &s, &co);     // b*c < 2^20: exact in float; L is a power of two
+        dst[c * bm.L2 + b] = cmul(v[c], make_float2(co, s));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ CZT row pass
+// One CTA per (row c, band): FFT_L2 along the row (spectrum index k = c + 16 d at position d), multiply by the chirp-filter
+// spectrum, inverse FFT_L2 (-> b'), inverse inter-pass twiddle e^{+2 pi i b' c / L}. MODE 1 (plan creation) stops after
+// the forward FFT and stores the spectrum.
+template <int MODE>
+__global__ void __launch_bounds__(CQ_THREADS)
+czt_rows_kernel(const BandMeta *__restrict__ bands, float2 *__restrict__ work, const float2 *const *__restrict__ btabs,
+                const FftDesc *__restrict__ descs, const float2 *const *__restrict__ tws) {
+    extern __shared__ __align__(16) float2 fsm[];
+    const BandMeta bm = bands[blockIdx.y];
+    const int c = blockIdx.x;
+    __shared__ FftDesc d;
+    if (threadIdx.x == 0) d = descs[bm.btab];
+    const float2 *tw = tws[bm.btab];
+    float2 *row = work + bm.work_off + (long long)c * bm.L2;
+    float2 *A = fsm, *B = fsm + bm.L2;
+    for (int i = threadIdx.x; i < bm.L2; i += blockDim.x) A[i] = row[i];
+    __syncthreads();
+    float2 *R = smem_fft(A, B, d, 1, tw, -1);
+    if (MODE == 1) {
+        for (int i = threadIdx.x; i < bm.L2; i += blockDim.x) row[i] = R[i];
+        return;
+    }
+    const float2 *bt = btabs[bm.btab] + (long long)c * bm.L2;
+    for (int i = threadIdx.x; i < bm.L2; i += blockDim.x) R[i] = cmul(R[i], bt[i]);
+    __syncthreads();
+    float2 *O = (R == A) ? B : A;
+    float2 *R2 = smem_fft(R, O, d, 1, tw, +1);
+    const float invL = 1.0f / (float)bm.L;
+    for (int i = threadIdx.x; i < bm.L2; i += blockDim.x) {
+        float s, co;
+        sincospif(2.0f * (float)(i * c) * invL, &s, &co);
+        row[i] = cmul(R2[i], make_float2(co, s));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ CZT output pass
+// 16-point inverse FFT up the columns (-> a'), output index i = L2*a' + b'; power[band][i] = |c|^2 / (L M)^2 for i < F,
+// plus the per-track maximum (atomicMax on the bit pattern of a non-negative float).
+__global__ void __launch_bounds__(CQ_THREADS)
+czt_out_kernel(const BandMeta *__restrict__ bands, const float2 *__restrict__ work, int M, int F, int fpitch,
+               float *__restrict__ power, unsigned int *__restrict__ pmax) {
+    const BandMeta bm = bands[blockIdx.y];
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    float best = 0.f;
+    if (b < bm.L2 && b < F) {
+        const float2 *src = work + bm.work_off;
+        float2 v[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = src[c * bm.L2 + b];
+        dft16(v, +1);
+        const float scale = 1.0f / ((float)bm.L * (float)M);
+        float *dst = power + (long long)blockIdx.y * fpitch;
+#pragma unroll
+        for (int a = 0; a < 16; ++a) {
+            const int i = bm.L2 * a + b;
+            if (i < F) {
+                const float re = v[a].x * scale, im = v[a].y * scale;
+                const float p = fmaf(re, re, im * im);
+                dst[i] = p;
+                best = fmaxf(best, p);
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) best = fmaxf(best, __shfl_xor_sync(0xFFFFFFFFu, best, s));
+    if ((threadIdx.x & 31) == 0 && best > 0.f) atomicMax(pmax, __float_as_uint(best));
+}
+
+// ------------------------------------------------------------------------------------------------ dB + transpose
+// power[band][i] (band-major, pitch fpitch) -> out[col][band] (the reference's column-major 121 x cols).
+// MODE 0: amplitude_to_db (convert.h:7-25): 10 log10(max(p,1e-10)) - 10 log10(max(1e-10, pmax)), floored at -80 below the
+// maximum (which is 0 dB by construction). MODE 1: linear magnitude sqrt(p). Columns >= F (the one the reference leaves
+// unwritten when M % 3 == 0, cqt.h:73-81) are amplitude 0.
+template <int MODE>
+__global__ void __launch_bounds__(CQ_THREADS)
+db_kernel(const float *__restrict__ power, const unsigned int *__restrict__ pmax, int F, int cols, int fpitch,
+          float *__restrict__ out) {
+    __shared__ float tile[32][CQ_BINS + 2];
+    const int col0 = blockIdx.x * 32;
+    for (int idx = threadIdx.x; idx < 32 * CQ_BINS; idx += blockDim.x) {
+        const int band = idx / 32, cc = idx - band * 32;
+        const int col = col0 + cc;
+        tile[cc][band] = (col < F) ? power[(long long)band * fpitch + col] : 0.f;
+    }
+    __syncthreads();
+    const float mx = fmaxf(1e-10f, __uint_as_float(*pmax));
+    const float ref = 10.0f * log10f(mx);
+    for (int idx = threadIdx.x; idx < 32 * CQ_BINS; idx += blockDim.x) {
+        const int cc = idx / CQ_BINS, band = idx - cc * CQ_BINS;
+        const int col = col0 + cc;
+        if (col < cols) {
+            const float p = tile[cc][band];
+            float r;
+            if (MODE == 0) r = fmaxf(10.0f * log10f(fmaxf(p, 1e-10f)) - ref, -80.0f);
+            else r = sqrtf(p);
+            out[(long long)col * CQ_BINS + band] = r;
+        }
+    }
+}
+
+// ================================================================================================ host side: design + plan
+struct CqtDesign {
+    int pos[CQ_BINS], lg[CQ_BINS];
+    int M = 0, F = 0, cols = 0;
+};
+
+// oracle/nsgcq.py nsg_design, same double arithmetic (libm pow / floor)
+static bool cqt_design(int64_t n_samples, CqtDesign &d) {
+    if (n_samples < 2) return false;
+    const double q = std::pow(2.0, 1.0 / CQ_BPO) - std::pow(2.0, -1.0 / CQ_BPO);
+    const double fftres = CQ_SR / (double)n_samples;
+    for (int j = 0; j < CQ_BINS; ++j) {
+        const double f = CQ_FMIN * std::pow(2.0, (double)j / CQ_BPO);
+        const double bw = q * f;
+        d.pos[j] = (int)std::floor(f / fftres);
+        const long long r = (long long)std::floor(bw / fftres + 0.5);
+        d.lg[j] = (int)std::max<long long>(r, CQ_MINWIN);
+    }
+    d.M = d.lg[CQ_BINS - 1];
+    d.F = (d.M + CQ_DOWN - 1) / CQ_DOWN;
+    d.cols = d.M / CQ_DOWN + 1;
+    return true;
+}
+
+static bool factor_smooth(int n, FftDesc &d) {
+    d.n = n;
+    d.nrad = 0;
+    const int order[6] = {8, 4, 2, 3, 5, 7};
+    // odd radices first would give long strides early; powers of two first keeps the first (Ns = 1) stages twiddle-free
+    for (int r : order)
+        while (n % r == 0 && n > 1) {
+            if (d.nrad >= CQ_MAXRAD) return false;
+            d.rad[d.nrad++] = r;
+            n /= r;
+        }
+    return n == 1;
+}
+
+static std::vector<float2> twiddle_table(int n) {
+    std::vector<float2> t((size_t)n);
+    for (int m = 0; m < n; ++m) {
+        const double a = -2.0 * M_PI * (double)m / (double)n;
+        t[(size_t)m] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    return t;
+}
+
+struct TwoLevel {
+    DeviceBuffer hi, lo;
+    int upload(long long P) {
+        const long long nhi = P / CQ_TW_S + 2;
+        std::vector<float2> h((size_t)nhi), l((size_t)CQ_TW_S);
+        for (long long i = 0; i < nhi; ++i) {
+            const double a = -2.0 * M_PI * (double)((i * CQ_TW_S) % P) / (double)P;
+            h[(size_t)i] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+        for (int i = 0; i < CQ_TW_S; ++i) {
+            const double a = -2.0 * M_PI * (double)i / (double)P;
+            l[(size_t)i] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+        HPFW_TRY(hi.reserve(sizeof(float2) * h.size()));
+        HPFW_TRY(lo.reserve(sizeof(float2) * l.size()));
+        HPFW_CUDA_TRY(cudaMemcpy(hi.ptr, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice));
+        HPFW_CUDA_TRY(cudaMemcpy(lo.ptr, l.data(), sizeof(float2) * l.size(), cudaMemcpyHostToDevice));
+        return HPFW_OK;
+    }
+    void release() { hi.release(); lo.release(); }
+};
+
+struct CqtPlan {
+    int64_t N = 0;
+    int H = 0;
+    CqtDesign des;
+    int klo = 0, khi = 0;
+    FftDesc d1{}, d2{};
+    int G1 = 1, G2 = 1;
+    size_t smem1 = 0, smem2 = 0;
+    DeviceBuffer tw1, tw2;
+    TwoLevel twH, twN;
+    // CZT
+    std::vector<BandMeta> bands;
+    DeviceBuffer d_bands, d_btab_ptrs, d_descs, d_tw_ptrs;
+    std::vector<std::unique_ptr<DeviceBuffer>> btabs, rowtws;
+    int max_L2 = 0;
+    long long work_elems = 0;
+    int fpitch = 0;
+    // per-track scratch
+    DeviceBuffer zbuf, zlo, zhi, work, power, pmax;
+    uint64_t last_use = 0;
+
+    void release() {
+        tw1.release(); tw2.release(); twH.release(); twN.release();
+        d_bands.release(); d_btab_ptrs.release(); d_descs.release(); d_tw_ptrs.release();
+        for (auto &b : btabs) b->release();
+        for (auto &b : rowtws) b->release();
+        zbuf.release(); zlo.release(); zhi.release(); work.release(); power.release(); pmax.release();
+    }
+};
+
+struct CqtPlanCache {
+    std::map<int64_t, std::unique_ptr<CqtPlan>> plans;
+    uint64_t tick = 0;
+};
+
+void cqt_cache_destroy(CqtPlanCache *c) {
+    if (!c) return;
+    for (auto &kv : c->plans) kv.second->release();
+    delete c;
+}
+
+static int next_pow2(long long n) {
+    int p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+// best split H = n1 * n2 (n1 <= n2 <= CQ_MAX_ROW), both {2,3,5,7}-smooth; returns false if there is none
+static bool split_smooth(int H, int &n1, int &n2) {
+    int rest = H;
+    int e[4] = {0, 0, 0, 0};
+    const int p[4] = {2, 3, 5, 7};
+    for (int i = 0; i < 4; ++i)
+        while (rest % p[i] == 0) { rest /= p[i]; e[i]++; }
+    if (rest != 1) return false;
+    long long best = -1;
+    for (int a = 0; a <= e[0]; ++a)
+        for (int b = 0; b <= e[1]; ++b)
+            for (int c = 0; c <= e[2]; ++c)
+                for (int d = 0; d <= e[3]; ++d) {
+                    long long v = 1;
+                    for (int i = 0; i < a; ++i) v *= 2;
+                    for (int i = 0; i < b; ++i) v *= 3;
+                    for (int i = 0; i < c; ++i) v *= 5;
+                    for (int i = 0; i < d; ++i) v *= 7;
+                    const long long w = H / v;
+                    if (v <= w && w <= CQ_MAX_ROW && v > best) best = v;
+                }
+    if (best < 2) return false;
+    n1 = (int)best;
+    n2 = (int)(H / best);
+    return true;
+}
+
+// every FFT kernel may use up to the device's opt-in shared memory (plans of different sizes share the kernels)
+static int set_smem_limits(hpfw_ctx *ctx) {
+    const int lim = ctx->max_smem_optin;
+    HPFW_CUDA_TRY(cudaFuncSetAttribute(czt_rows_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    HPFW_CUDA_TRY(cudaFuncSetAttribute(czt_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    HPFW_CUDA_TRY(cudaFuncSetAttribute(fft_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    HPFW_CUDA_TRY(cudaFuncSetAttribute(fft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    return HPFW_OK;
+}
+
+static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t stream) {
+    pl.N = N;
+    if (N < 2 || (N & 1))
+        HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: audio length %lld is odd or empty; this build packs the real FFT into N/2 complex "
+                  "points and needs an even length", (long long)N);
+    if (N > (int64_t(1) << 27)) HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: audio length %lld exceeds 2^27 samples", (long long)N);
+    if (!cqt_design(N, pl.des)) HPFW_FAIL(HPFW_ERR_ARG, "CQT: bad length");
+    const CqtDesign &d = pl.des;
+    pl.H = (int)(N / 2);
+    int n1 = 0, n2 = 0;
+    if (!split_smooth(pl.H, n1, n2))
+        HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: N/2 = %d has no split n1*n2 with both factors {2,3,5,7}-smooth and <= %d; "
+                  "non-smooth audio lengths are not supported by this build", pl.H, CQ_MAX_ROW);
+    if (!factor_smooth(n1, pl.d1) || !factor_smooth(n2, pl.d2)) HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: too many FFT stages");
+    pl.klo = 1 << 30;
+    pl.khi = 0;
+    for (int j = 0; j < CQ_BINS; ++j) {
+        const int fb = d.pos[j] - d.lg[j] / 2;
+        pl.klo = std::min(pl.klo, fb);
+        pl.khi = std::max(pl.khi, fb + d.lg[j] - 1);
+    }
+    if (pl.klo < 1 || pl.khi >= pl.H)
+        HPFW_FAIL(HPFW_ERR_SHORT, "CQT: audio of %lld samples is too short for the 121-band design", (long long)N);
+    // shared-memory budgets: 2 (ping-pong) * G * n * 8 B
+    const size_t budget = std::min<size_t>((size_t)ctx->max_smem_optin, 200 * 1024);
+    pl.G1 = (int)std::max<size_t>(1, std::min<size_t>(8, budget / (16 * (size_t)n1)));
+    pl.G2 = (int)std::max<size_t>(1, std::min<size_t>(4, budget / (16 * (size_t)n2)));
+    pl.smem1 = 16 * (size_t)n1 * pl.G1;
+    pl.smem2 = 16 * (size_t)n2 * pl.G2;
+    {
+        auto t1 = twiddle_table(n1), t2 = twiddle_table(n2);
+        HPFW_TRY(pl.tw1.reserve(sizeof(float2) * t1.size()));
+        HPFW_TRY(pl.tw2.reserve(sizeof(float2) * t2.size()));
+        HPFW_CUDA_TRY(cudaMemcpy(pl.tw1.ptr, t1.data(), sizeof(float2) * t1.size(), cudaMemcpyHostToDevice));
+        HPFW_CUDA_TRY(cudaMemcpy(pl.tw2.ptr, t2.data(), sizeof(float2) * t2.size(), cudaMemcpyHostToDevice));
+    }
+    HPFW_TRY(pl.twH.upload(pl.H));
+    HPFW_TRY(pl.twN.upload(N));
+
+    // CZT layout
+    pl.bands.resize(CQ_BINS);
+    std::vector<int> Ls;
+    long long off = 0;
+    for (int j = 0; j < CQ_BINS; ++j) {
+        BandMeta &b = pl.bands[j];
+        b.lg = d.lg[j];
+        b.half = d.lg[j] / 2;
+        b.first_bin = d.pos[j] - b.half;
+        b.L = std::max(1024, next_pow2((long long)d.lg[j] + d.F - 1));
+        b.L2 = b.L / CQ_L1;
+        if (b.L2 > CQ_MAX_ROW)
+            HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: audio of %lld samples needs a %d-point chirp-z transform; limit %d "
+                      "(about 6.7 minutes at 44.1 kHz)", (long long)N, b.L, CQ_L1 * CQ_MAX_ROW);
+        auto it = std::find(Ls.begin(), Ls.end(), b.L);
+        if (it == Ls.end()) { Ls.push_back(b.L); b.btab = (int)Ls.size() - 1; }
+        else b.btab = (int)(it - Ls.begin());
+        b.work_off = off;
+        off += b.L;
+        pl.max_L2 = std::max(pl.max_L2, b.L2);
+    }
+    pl.work_elems = off;
+    pl.fpitch = (d.F + 31) & ~31;
+    HPFW_TRY(pl.d_bands.reserve(sizeof(BandMeta) * CQ_BINS));
+    HPFW_CUDA_TRY(cudaMemcpy(pl.d_bands.ptr, pl.bands.data(), sizeof(BandMeta) * CQ_BINS, cudaMemcpyHostToDevice));
+
+    // per distinct L: row-FFT descriptor + twiddles, chirp-filter spectrum (computed below with the same kernels)
+    std::vector<FftDesc> descs(Ls.size());
+    std::vector<const float2 *> twp(Ls.size()), btp(Ls.size());
+    for (size_t i = 0; i < Ls.size(); ++i) {
+        if (!factor_smooth(Ls[i] / CQ_L1, descs[i])) HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: too many FFT stages");
+        auto t = twiddle_table(Ls[i] / CQ_L1);
+        pl.rowtws.emplace_back(new DeviceBuffer());
+        HPFW_TRY(pl.rowtws.back()->reserve(sizeof(float2) * t.size()));
+        HPFW_CUDA_TRY(cudaMemcpy(pl.rowtws.back()->ptr, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice));
+        twp[i] = pl.rowtws.back()->as<float2>();
+        pl.btabs.emplace_back(new DeviceBuffer());
+        HPFW_TRY(pl.btabs.back()->reserve(sizeof(float2) * (size_t)Ls[i]));
+        btp[i] = pl.btabs.back()->as<float2>();
+    }
+    HPFW_TRY(pl.d_descs.reserve(sizeof(FftDesc) * descs.size()));
+    HPFW_TRY(pl.d_tw_ptrs.reserve(sizeof(void *) * twp.size()));
+    HPFW_TRY(pl.d_btab_ptrs.reserve(sizeof(void *) * btp.size()));
+    HPFW_CUDA_TRY(cudaMemcpy(pl.d_descs.ptr, descs.data(), sizeof(FftDesc) * descs.size(), cudaMemcpyHostToDevice));
+    HPFW_CUDA_TRY(cudaMemcpy(pl.d_tw_ptrs.ptr, twp.data(), sizeof(void *) * twp.size(), cudaMemcpyHostToDevice));
+    HPFW_CUDA_TRY(cudaMemcpy(pl.d_btab_ptrs.ptr, btp.data(), sizeof(void *) * btp.size(), cudaMemcpyHostToDevice));
+
+    HPFW_TRY(set_smem_limits(ctx));
+
+    // chirp-filter spectra: one pseudo-band per distinct L whose work area IS the table
+    {
+        std::vector<BandMeta> fb(Ls.size());
+        DeviceBuffer d_fb;
+        // the kernels address work + work_off: express each table as an offset from table 0 is not possible (separate
+        // allocations), so run one launch per table with work = that table and work_off = 0
+        for (size_t i = 0; i < Ls.size(); ++i) {
+            fb[i] = BandMeta{0, 0, 0, Ls[i], Ls[i] / CQ_L1, (int)i, 0};
+        }
+        HPFW_TRY(d_fb.reserve(sizeof(BandMeta) * fb.size()));
+        HPFW_CUDA_TRY(cudaMemcpy(d_fb.ptr, fb.data(), sizeof(BandMeta) * fb.size(), cudaMemcpyHostToDevice));
+        for (size_t i = 0; i < Ls.size(); ++i) {
+            const BandMeta *dbm = d_fb.as<BandMeta>() + i;
+            float2 *tab = pl.btabs[i]->as<float2>();
+            dim3 g1((fb[i].L2 + CQ_THREADS - 1) / CQ_THREADS, 1);
+            {
+                KernelScope ks(ctx, HPFW_K_CQT, stream);
+                czt_cols_kernel<1><<<g1, CQ_THREADS, 0, stream>>>(dbm, nullptr, nullptr, 0, 0, nullptr, nullptr, d.M, d.F,
+                                                                   tab);
+            }
+            {
+                KernelScope ks(ctx, HPFW_K_CQT, stream);
+                czt_rows_kernel<1><<<dim3(CQ_L1, 1), CQ_THREADS, 16 * (size_t)fb[i].L2, stream>>>(
+                    dbm, tab, pl.d_btab_ptrs.as<const float2 *>(), pl.d_descs.as<FftDesc>(),
+                    pl.d_tw_ptrs.as<const float2 *>());
+            }
+        }
+        HPFW_CUDA_TRY(cudaGetLastError());
+        HPFW_CUDA_TRY(cudaStreamSynchronize(stream));
+        d_fb.release();
+    }
+
+    // per-track scratch
+    const size_t nkeep = (size_t)(pl.khi - pl.klo + 1);
+    HPFW_TRY(pl.zbuf.reserve(sizeof(float2) * (size_t)pl.H));
+    HPFW_TRY(pl.zlo.reserve(sizeof(float2) * nkeep));
+    HPFW_TRY(pl.zhi.reserve(sizeof(float2) * nkeep));
+    HPFW_TRY(pl.work.reserve(sizeof(float2) * (size_t)pl.work_elems));
+    HPFW_TRY(pl.power.reserve(sizeof(float) * (size_t)CQ_BINS * pl.fpitch));
+    HPFW_TRY(pl.pmax.reserve(sizeof(unsigned int)));
+    return HPFW_OK;
+}
+
+static int plan_get(hpfw_ctx *ctx, int64_t N, CqtPlan **out, cudaStream_t stream) {
+    if (!ctx->cqt) ctx->cqt = new CqtPlanCache();
+    CqtPlanCache *c = ctx->cqt;
+    auto it = c->plans.find(N);
+    if (it == c->plans.end()) {
+        if (c->plans.size() >= 6) {   // evict the least recently used plan (each holds ~3x the track in scratch)
+            auto victim = c->plans.begin();
+            for (auto k = c->plans.begin(); k != c->plans.end(); ++k)
+                if (k->second->last_use < victim->second->last_use) victim = k;
+            HPFW_CUDA_TRY(cudaDeviceSynchronize());
+            victim->second->release();
+            c->plans.erase(victim);
+        }
+        std::unique_ptr<CqtPlan> p(new CqtPlan());
+        int st = plan_create(ctx, N, *p, stream);
+        if (st != HPFW_OK) {
+            p->release();
+            return st;
+        }
+        it = c->plans.emplace(N, std::move(p)).first;
+    }
+    it->second->last_use = ++c->tick;
+    *out = it->second.get();
+    return HPFW_OK;
+}
+
+// mode 0: dB spectrogram; mode 1: linear magnitudes. d_audio must be 8-byte aligned.
+static int cqt_run(hpfw_ctx *ctx, const float *d_audio, int64_t N, float *d_out, int mode, cudaStream_t stream) {
+    if ((reinterpret_cast<uintptr_t>(d_audio) & 7) != 0)
+        HPFW_FAIL(HPFW_ERR_ARG, "CQT: the audio buffer must be 8-byte aligned");
+    CqtPlan *pl = nullptr;
+    HPFW_TRY(plan_get(ctx, N, &pl, stream));
+    const CqtDesign &d = pl->des;
+    const int n1 = pl->d1.n, n2 = pl->d2.n;
+    const float2 *z_in = reinterpret_cast<const float2 *>(d_audio);
+    {
+        KernelScope ks(ctx, HPFW_K_CQT, stream);
+        fft_cols_kernel<<<(n2 + pl->G1 - 1) / pl->G1, CQ_THREADS, pl->smem1, stream>>>(
+            z_in, pl->zbuf.as<float2>(), pl->d1, n2, pl->G1, pl->tw1.as<float2>(), pl->twH.hi.as<float2>(),
+            pl->twH.lo.as<float2>(), -1);
+    }
+    {
+        KernelScope ks(ctx, HPFW_K_CQT, stream);
+        fft_rows_kernel<<<(n1 + pl->G2 - 1) / pl->G2, CQ_THREADS, pl->smem2, stream>>>(
+            pl->zbuf.as<float2>(), pl->zlo.as<float2>(), pl->zhi.as<float2>(), pl->d2, n1, pl->G2, pl->tw2.as<float2>(),
+            pl->klo, pl->khi, pl->H, 0, -1);
+    }
+    HPFW_CUDA_TRY(cudaMemsetAsync(pl->pmax.ptr, 0, sizeof(unsigned int), stream));
+    const dim3 gcol((pl->max_L2 + CQ_THREADS - 1) / CQ_THREADS, CQ_BINS);
+    {
+        KernelScope ks(ctx, HPFW_K_CQT, stream);
+        czt_cols_kernel<0><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands.as<BandMeta>(), pl->zlo.as<float2>(),
+                                                             pl->zhi.as<float2>(), pl->klo, pl->khi,
+                                                             pl->twN.hi.as<float2>(), pl->twN.lo.as<float2>(), d.M, d.F,
+                                                             pl->work.as<float2>());
+    }
+    {
+        KernelScope ks(ctx, HPFW_K_CQT, stream);
+        czt_rows_kernel<0><<<dim3(CQ_L1, CQ_BINS), CQ_THREADS, 16 * (size_t)pl->max_L2, stream>>>(
+            pl->d_bands.as<BandMeta>(), pl->work.as<float2>(), pl->d_btab_ptrs.as<const float2 *>(),
+            pl->d_descs.as<FftDesc>(), pl->d_tw_ptrs.as<const float2 *>());
+    }
+    {
+        KernelScope ks(ctx, HPFW_K_CQT, stream);
+        czt_out_kernel<<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands.as<BandMeta>(), pl->work.as<float2>(), d.M, d.F,
+                                                         pl->fpitch, pl->power.as<float>(),
+                                                         pl->pmax.as<unsigned int>());
+    }
+    {
+        KernelScope ks(ctx, HPFW_K_CQT, stream);
+        const int gb = (d.cols + 31) / 32;
+        if (mode == 0)
+            db_kernel<0><<<gb, CQ_THREADS, 0, stream>>>(pl->power.as<float>(), pl->pmax.as<unsigned int>(), d.F, d.cols,
+                                                         pl->fpitch, d_out);
+        else
+            db_kernel<1><<<gb, CQ_THREADS, 0, stream>>>(pl->power.as<float>(), pl->pmax.as<unsigned int>(), d.F, d.cols,
+                                                         pl->fpitch, d_out);
+    }
+    HPFW_CUDA_TRY(cudaGetLastError());
+    return HPFW_OK;
+}
+
+// Diagnostic / unit-test entry: forward or inverse complex FFT of a smooth length through the same two-pass kernels.
+static int fft_c2c_device(hpfw_ctx *ctx, const float2 *d_in, float2 *d_out, int n, int inverse, cudaStream_t stream) {
+    int n1 = 0, n2 = 0;
+    FftDesc d1{}, d2{};
+    if (!split_smooth(n, n1, n2) || !factor_smooth(n1, d1) || !factor_smooth(n2, d2))
+        HPFW_FAIL(HPFW_ERR_LIMIT, "hpfw_fft_c2c: %d is not a product n1*n2 of {2,3,5,7}-smooth factors <= %d", n,
+                  CQ_MAX_ROW);
+    const size_t budget = std::min<size_t>((size_t)ctx->max_smem_optin, 200 * 1024);
+    const int G1 = (int)std::max<size_t>(1, std::min<size_t>(8, budget / (16 * (size_t)n1)));
+    const int G2 = (int)std::max<size_t>(1, std::min<size_t>(4, budget / (16 * (size_t)n2)));
+    DeviceBuffer tw1, tw2, tmp;
+    TwoLevel twP;
+    auto t1 = twiddle_table(n1), t2 = twiddle_table(n2);
+    HPFW_TRY(tw1.reserve(sizeof(float2) * t1.size()));
+    HPFW_TRY(tw2.reserve(sizeof(float2) * t2.size()));
+    HPFW_TRY(tmp.reserve(sizeof(float2) * (size_t)n));
+    HPFW_CUDA_TRY(cudaMemcpy(tw1.ptr, t1.data(), sizeof(float2) * t1.size(), cudaMemcpyHostToDevice));
+    HPFW_CUDA_TRY(cudaMemcpy(tw2.ptr, t2.data(), sizeof(float2) * t2.size(), cudaMemcpyHostToDevice));
+    HPFW_TRY(twP.upload(n));
+    HPFW_TRY(set_smem_limits(ctx));
+    const int sign = inverse ? +1 : -1;
+    {
+        KernelScope ks(ctx, HPFW_K_CQT, stream);
+        fft_cols_kernel<<<(n2 + G1 - 1) / G1, CQ_THREADS, 16 * (size_t)n1 * G1, stream>>>(
+            d_in, tmp.as<float2>(), d1, n2, G1, tw1.as<float2>(), twP.hi.as<float2>(), twP.lo.as<float2>(), sign);
+    }
+    {
+        KernelScope ks(ctx, HPFW_K_CQT, stream);
+        fft_rows_kernel<<<(n1 + G2 - 1) / G2, CQ_THREADS, 16 * (size_t)n2 * G2, stream>>>(
+            tmp.as<float2>(), d_out, nullptr, d2, n1, G2, tw2.as<float2>(), 0, 0, n, 1, sign);
+    }
+    HPFW_CUDA_TRY(cudaGetLastError());
+    HPFW_CUDA_TRY(cudaStreamSynchronize(stream));
+    tw1.release(); tw2.release(); tmp.release(); twP.release();
+    return HPFW_OK;
+}
+
+}  // namespace hpfw_b200
+
+using namespace hpfw_b200;
+
 extern "C" {
-int hpfw_cqt_cols(int64_t) { return 0; }
-int hpfw_cqt_spectrogram(hpfw_ctx *, const float *, int64_t, float *, int *) {
-    HPFW_FAIL(HPFW_ERR_STATE, "CQT kernels not built into this library yet");
+
+int hpfw_cqt_design(int64_t n_samples, int *pos_out, int *lg_out, int *m_out) {
+    CqtDesign d;
+    if (!cqt_design(n_samples, d)) return HPFW_ERR_ARG;
+    if (pos_out) memcpy(pos_out, d.pos, sizeof(d.pos));
+    if (lg_out) memcpy(lg_out, d.lg, sizeof(d.lg));
+    if (m_out) *m_out = d.M;
+    return HPFW_OK;
 }
-int hpfw_cqt_spectrogram_device(hpfw_ctx *, const float *, int64_t, float *, void *) {
-    HPFW_FAIL(HPFW_ERR_STATE, "CQT kernels not built into this library yet");
+
+int hpfw_cqt_cols(int64_t n_samples) {
+    CqtDesign d;
+    if (!cqt_design(n_samples, d)) return 0;
+    return d.cols;
 }
-int hpfw_cqt_magnitude(hpfw_ctx *, const float *, int64_t, float *, int *) {
-    HPFW_FAIL(HPFW_ERR_STATE, "CQT kernels not built into this library yet");
+
+int hpfw_hashprint_words_for_samples(int64_t n_samples) {
+    const int cols = hpfw_cqt_cols(n_samples);
+    return std::max(0, hpfw_hashprint_words_for_cols(cols));
 }
-int hpfw_hashprint_words_for_samples(int64_t) { return 0; }
-int hpfw_calc_hashprint_audio(hpfw_ctx *, const float *, int64_t, uint64_t *, int *) {
-    HPFW_FAIL(HPFW_ERR_STATE, "CQT kernels not built into this library yet");
+
+int hpfw_cqt_spectrogram_device(hpfw_ctx *ctx, const float *d_audio, int64_t n_samples, float *d_out, void *stream) {
+    if (!ctx || !d_audio || !d_out) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_cqt_spectrogram_device: NULL argument");
+    DeviceGuard g(ctx->device);
+    return cqt_run(ctx, d_audio, n_samples, d_out, 0, ctx->pick(stream));
 }
-int hpfw_calc_hashprint_audio_device(hpfw_ctx *, const float *, int64_t, uint64_t *, void *) {
-    HPFW_FAIL(HPFW_ERR_STATE, "CQT kernels not built into this library yet");
+
+static int cqt_host(hpfw_ctx *ctx, const float *audio, int64_t n_samples, float *out, int *cols_out, int mode) {
+    if (!ctx || !audio || !out) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_cqt: NULL argument");
+    DeviceGuard g(ctx->device);
+    const int cols = hpfw_cqt_cols(n_samples);
+    if (cols <= 0) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_cqt: bad length");
+    HPFW_TRY(ctx->audio.reserve(sizeof(float) * (size_t)n_samples));
+    HPFW_TRY(ctx->spectro.reserve(sizeof(float) * (size_t)cols * CQ_BINS));
+    HPFW_CUDA_TRY(cudaMemcpyAsync(ctx->audio.ptr, audio, sizeof(float) * (size_t)n_samples, cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    HPFW_TRY(cqt_run(ctx, ctx->audio.as<float>(), n_samples, ctx->spectro.as<float>(), mode, ctx->stream));
+    HPFW_CUDA_TRY(cudaMemcpyAsync(out, ctx->spectro.ptr, sizeof(float) * (size_t)cols * CQ_BINS, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    HPFW_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (cols_out) *cols_out = cols;
+    return HPFW_OK;
 }
+
+int hpfw_cqt_spectrogram(hpfw_ctx *ctx, const float *audio, int64_t n_samples, float *out, int *cols_out) {
+    return cqt_host(ctx, audio, n_samples, out, cols_out, 0);
 }
+
+int hpfw_cqt_magnitude(hpfw_ctx *ctx, const float *audio, int64_t n_samples, float *out, int *cols_out) {
+    return cqt_host(ctx, audio, n_samples, out, cols_out, 1);
+}
+
+int hpfw_calc_hashprint_audio_device(hpfw_ctx *ctx, const float *d_audio, int64_t n_samples, uint64_t *d_hp_out,
+                                     void *stream) {
+    if (!ctx || !d_audio || !d_hp_out) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_calc_hashprint_audio_device: NULL argument");
+    DeviceGuard g(ctx->device);
+    const int cols = hpfw_cqt_cols(n_samples);
+    if (hpfw_hashprint_words_for_cols(cols) <= 0)
+        HPFW_FAIL(HPFW_ERR_SHORT, "audio of %lld samples gives %d spectrogram columns; at least 100 are needed",
+                  (long long)n_samples, cols);
+    HPFW_TRY(ctx->spectro.reserve(sizeof(float) * (size_t)cols * CQ_BINS));
+    cudaStream_t s = ctx->pick(stream);
+    HPFW_TRY(cqt_run(ctx, d_audio, n_samples, ctx->spectro.as<float>(), 0, s));
+    const int64_t co[2] = {0, cols};
+    return hpfw_hashprint_from_spectrogram_device(ctx, ctx->spectro.as<float>(), co, 1, d_hp_out, s);
+}
+
+int hpfw_calc_hashprint_audio(hpfw_ctx *ctx, const float *audio, int64_t n_samples, uint64_t *hp_out, int *n_out) {
+    if (!ctx || !audio || !hp_out || !n_out) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_calc_hashprint_audio: NULL argument");
+    *n_out = 0;
+    DeviceGuard g(ctx->device);
+    const int n = hpfw_hashprint_words_for_samples(n_samples);
+    if (n <= 0)
+        HPFW_FAIL(HPFW_ERR_SHORT, "audio of %lld samples is too short for one hashprint word", (long long)n_samples);
+    HPFW_TRY(ctx->audio.reserve(sizeof(float) * (size_t)n_samples));
+    HPFW_TRY(ctx->hp.reserve(sizeof(uint64_t) * (size_t)n));
+    HPFW_CUDA_TRY(cudaMemcpyAsync(ctx->audio.ptr, audio, sizeof(float) * (size_t)n_samples, cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    HPFW_TRY(hpfw_calc_hashprint_audio_device(ctx, ctx->audio.as<float>(), n_samples, ctx->hp.as<uint64_t>(), ctx->stream));
+    HPFW_CUDA_TRY(cudaMemcpyAsync(hp_out, ctx->hp.ptr, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    HPFW_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *n_out = n;
+    return HPFW_OK;
+}
+
+int hpfw_fft_c2c(hpfw_ctx *ctx, const float *in_interleaved, float *out_interleaved, int n, int inverse) {
+    if (!ctx || !in_interleaved || !out_interleaved || n < 4) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_fft_c2c: bad argument");
+    DeviceGuard g(ctx->device);
+    DeviceBuffer a, b;
+    HPFW_TRY(a.reserve(sizeof(float2) * (size_t)n));
+    HPFW_TRY(b.reserve(sizeof(float2) * (size_t)n));
+    HPFW_CUDA_TRY(cudaMemcpy(a.ptr, in_interleaved, sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice));
+    int st = fft_c2c_device(ctx, a.as<float2>(), b.as<float2>(), n, inverse, ctx->stream);
+    if (st == HPFW_OK) {
+        cudaError_t e = cudaMemcpy(out_interleaved, b.ptr, sizeof(float2) * (size_t)n, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            set_error("hpfw_fft_c2c: D2H failed: %s", cudaGetErrorString(e));
+            st = HPFW_ERR_CUDA;
+        }
+    }
+    a.release();
+    b.release();
+    return st;
+}
+
+}  // extern "C"

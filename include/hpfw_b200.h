@@ -152,6 +152,12 @@ int hpfw_cqt_spectrogram_device(hpfw_ctx *ctx, const float *d_audio, int64_t n_s
                                 void *stream);
 /* diagnostic: linear magnitudes |c_j[3i]| before the dB step */
 int hpfw_cqt_magnitude(hpfw_ctx *ctx, const float *audio, int64_t n_samples, float *mag_out, int *cols_out);
+/* host-only: the band layout of the NSG design for an n_samples-long input (FFT-bin units): pos[121], lg[121], M.
+ * Needs no device. */
+int hpfw_cqt_design(int64_t n_samples, int *pos_out, int *lg_out, int *m_out);
+/* diagnostic: complex FFT (inverse != 0: unnormalised inverse) of n interleaved (re,im) floats through the same
+ * two-pass mixed-radix kernels the CQT uses; n must split into two {2,3,5,7}-smooth factors <= 8192. Host buffers. */
+int hpfw_fft_c2c(hpfw_ctx *ctx, const float *in_interleaved, float *out_interleaved, int n, int inverse);
 
 /* ------------------------------------------------------------------------------ whole query path (stages 1-3, a8) */
 int hpfw_hashprint_words_for_samples(int64_t n_samples);

@@ -48,9 +48,9 @@ def _cround(x):
 def nsg_design(n_samples: int):
     """Band layout for an n_samples-long input: (pos[121], Lg[121], M). All in FFT-bin units (fftres = sr/N)."""
     b = int(math.floor(BINS_PER_OCTAVE * math.log2(F_MAX / F_MIN)))
-    j = np.arange(b + 1, dtype=np.float64)
-    f = F_MIN * np.power(2.0, j / BINS_PER_OCTAVE)
-    q = 2.0 ** (1.0 / BINS_PER_OCTAVE) - 2.0 ** (-1.0 / BINS_PER_OCTAVE)
+    # libm pow per band (math.pow), so the product's host-side design (std::pow) sees bit-identical doubles
+    f = np.array([F_MIN * math.pow(2.0, j / BINS_PER_OCTAVE) for j in range(b + 1)], dtype=np.float64)
+    q = math.pow(2.0, 1.0 / BINS_PER_OCTAVE) - math.pow(2.0, -1.0 / BINS_PER_OCTAVE)
     bw = q * f                                     # gamma = 0
     fftres = NSG_SR / float(n_samples)
     pos = np.floor(f / fftres).astype(np.int64)
