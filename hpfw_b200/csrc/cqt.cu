@@ -446,14 +446,14 @@ db_kernel(const float *__restrict__ power, const unsigned int *__restrict__ pmax
     }
     __syncthreads();
     const float mx = fmaxf(1e-10f, __uint_as_float(*pmax));
-    const float ref = 10.0f * log10f(mx);
+    const float ref = __fmul_rn(10.0f, log10f(mx));   // _rn: no FMA contraction, so the maximum maps to exactly 0 dB
     for (int idx = threadIdx.x; idx < 32 * CQ_BINS; idx += blockDim.x) {
         const int cc = idx / CQ_BINS, band = idx - cc * CQ_BINS;
         const int col = col0 + cc;
         if (col < cols) {
             const float p = tile[cc][band];
             float r;
-            if (MODE == 0) r = fmaxf(10.0f * log10f(fmaxf(p, 1e-10f)) - ref, -80.0f);
+            if (MODE == 0) r = fmaxf(__fsub_rn(__fmul_rn(10.0f, log10f(fmaxf(p, 1e-10f))), ref), -80.0f);
             else r = sqrtf(p);
             out[(long long)col * CQ_BINS + band] = r;
         }
@@ -605,7 +605,7 @@ static bool split_smooth(int H, int &n1, int &n2) {
 
 // every FFT kernel may use up to the device's opt-in shared memory (plans of different sizes share the kernels)
 static int set_smem_limits(hpfw_ctx *ctx) {
-    const int lim = ctx->max_smem_optin;
+    const int lim = ctx->max_smem_optin - 2048;   // dynamic + static shared memory must stay within the opt-in limit
     HPFW_CUDA_TRY(cudaFuncSetAttribute(czt_rows_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     HPFW_CUDA_TRY(cudaFuncSetAttribute(czt_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     HPFW_CUDA_TRY(cudaFuncSetAttribute(fft_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
@@ -637,7 +637,7 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
     if (pl.klo < 1 || pl.khi >= pl.H)
         HPFW_FAIL(HPFW_ERR_SHORT, "CQT: audio of %lld samples is too short for the 121-band design", (long long)N);
     // shared-memory budgets: 2 (ping-pong) * G * n * 8 B
-    const size_t budget = std::min<size_t>((size_t)ctx->max_smem_optin, 200 * 1024);
+    const size_t budget = std::min<size_t>((size_t)ctx->max_smem_optin - 2048, 200 * 1024);
     pl.G1 = (int)std::max<size_t>(1, std::min<size_t>(8, budget / (16 * (size_t)n1)));
     pl.G2 = (int)std::max<size_t>(1, std::min<size_t>(4, budget / (16 * (size_t)n2)));
     pl.smem1 = 16 * (size_t)n1 * pl.G1;
@@ -833,7 +833,7 @@ static int fft_c2c_device(hpfw_ctx *ctx, const float2 *d_in, float2 *d_out, int 
     if (!split_smooth(n, n1, n2) || !factor_smooth(n1, d1) || !factor_smooth(n2, d2))
         HPFW_FAIL(HPFW_ERR_LIMIT, "hpfw_fft_c2c: %d is not a product n1*n2 of {2,3,5,7}-smooth factors <= %d", n,
                   CQ_MAX_ROW);
-    const size_t budget = std::min<size_t>((size_t)ctx->max_smem_optin, 200 * 1024);
+    const size_t budget = std::min<size_t>((size_t)ctx->max_smem_optin - 2048, 200 * 1024);
     const int G1 = (int)std::max<size_t>(1, std::min<size_t>(8, budget / (16 * (size_t)n1)));
     const int G2 = (int)std::max<size_t>(1, std::min<size_t>(4, budget / (16 * (size_t)n2)));
     DeviceBuffer tw1, tw2, tmp;

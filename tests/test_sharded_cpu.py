@@ -1,0 +1,92 @@
+"""Host-side logic of the multi-GPU matcher under a real 2-process rendezvous (gloo, CPU): shard planning, global track
+indices, packed-key ordering and the all-gather plumbing. The per-shard top-k lists come from the oracle here (there is
+no GPU); the device merge kernel itself is covered by tests/test_matcher_gpu.py::test_sharded_merge_equals_unsharded."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import oracle
+from hpfw_b200 import synth
+from hpfw_b200.sharded import KEY_NONE, allgather_keys, pack_key, plan_shards
+
+
+def test_plan_shards_contiguous_and_balanced():
+    rng = np.random.default_rng(0)
+    lens = rng.integers(0, 20000, size=1000)
+    for n in (1, 2, 3, 4, 8):
+        sh = plan_shards(lens, n)
+        assert sh[0][0] == 0 and sh[-1][1] == 1000
+        assert all(sh[i][1] == sh[i + 1][0] for i in range(n - 1))
+        k = np.minimum(lens, 385)
+        work = (lens - k + 1) * np.maximum(k, 1)
+        per = np.array([work[a:b].sum() for a, b in sh], dtype=np.float64)
+        assert per.max() <= 1.1 * per.mean() + work.max()
+    assert plan_shards([5, 5], 4) [-1][1] == 2      # more shards than tracks: trailing shards are empty, none lost
+    assert sum(b - a for a, b in plan_shards([5, 5], 4)) == 2
+
+
+def test_pack_key_orders_like_the_reference_scan():
+    # smaller distance first, then earlier track, then lower offset (storage.h:50-60)
+    keys = [pack_key(5, 3, 7), pack_key(5, 3, 6), pack_key(5, 2, 900), pack_key(4, 1000, 1 << 19), pack_key(6, 0, 0)]
+    assert sorted(keys) == [keys[3], keys[2], keys[1], keys[0], keys[4]]
+    # largest legal key (HPFW_MAX_TRACKS, HPFW_MAX_TRACK_WORDS bound track and offset below 2^20 - 1) stays below KEY_NONE
+    assert pack_key((1 << 24) - 1, (1 << 20) - 2, (1 << 20) - 2) < int(KEY_NONE)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, seed, topk, ret):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(seed)
+        lens = rng.integers(1, 600, size=23)
+        words, offs = synth.synth_hashprint_db(seed, len(lens), lens)
+        qw, qo, _ = synth.synth_hashprint_queries(seed + 1, words, offs, 9, 40)
+        a, b = plan_shards(lens, world, query_words=40)[rank]
+        local = np.full((9, topk), KEY_NONE, dtype=np.uint64)
+        for q in range(9):
+            tr, d, o = oracle.find_topk(words[offs[a]:offs[b]], offs[a:b + 1] - offs[a], qw[qo[q]:qo[q + 1]], topk)
+            for r in range(topk):
+                if tr[r] >= 0:
+                    local[q, r] = pack_key(int(d[r]), int(tr[r]) + a, int(o[r]))      # global track index
+        allk = allgather_keys(torch.from_numpy(local.view(np.int64)))
+        assert tuple(allk.shape) == (world, 9, topk)
+        merged = np.sort(allk.numpy().view(np.uint64).transpose(1, 0, 2).reshape(9, -1), axis=1)[:, :topk]
+        # unsharded oracle
+        exp = np.full((9, topk), KEY_NONE, dtype=np.uint64)
+        for q in range(9):
+            tr, d, o = oracle.find_topk(words, offs, qw[qo[q]:qo[q + 1]], topk)
+            for r in range(topk):
+                if tr[r] >= 0:
+                    exp[q, r] = pack_key(int(d[r]), int(tr[r]), int(o[r]))
+        ret[rank] = bool(np.array_equal(merged, exp))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_allgather_merge_equals_unsharded_gloo(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    mgr = ctx.Manager()
+    ret = mgr.dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 5, 6, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert all(ret.get(r) for r in range(world)), dict(ret)
