@@ -5,6 +5,6 @@ LiveSongIdentification) over the C ABI in include/hpfw_b200.h. All compute is in
 CUDA); importing this package without that library raises.
 """
 from ._lib import HpfwError, Match, load  # noqa: F401
-from .api import Context, MemoryStorage, SearchResult  # noqa: F401
+from .api import Context, HashprintExtractor, MemoryStorage, SearchResult  # noqa: F401
 
-__all__ = ["Context", "MemoryStorage", "SearchResult", "HpfwError", "Match", "load"]
+__all__ = ["Context", "HashprintExtractor", "MemoryStorage", "SearchResult", "HpfwError", "Match", "load"]

@@ -61,6 +61,8 @@ _SIGS = {
     "hpfw_hashprint_words_for_samples": (C.c_int, [C.c_int64]),
     "hpfw_calc_hashprint_audio": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int)]),
     "hpfw_calc_hashprint_audio_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "hpfw_calc_hashprint_audio_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                                         C.c_void_p]),
     "hpfw_microbench_pipes": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

@@ -217,3 +217,55 @@ def decode_keys(keys: np.ndarray) -> np.ndarray:
     out = np.zeros(keys.shape, dtype=np.dtype([("track", "<i8"), ("cnt", "<u8"), ("offset", "<i8")]))
     L.hpfw_keys_decode(_ptr(keys), keys.size, out.ctypes.data_as(C.POINTER(Match)))
     return out
+
+
+class HashprintExtractor:
+    """Stages 1-3 on one GPU: the decoded-buffer side of ParallelCollector (parallel_collector.h:54-59, 115-137)."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self._lib = ctx._lib
+
+    def set_filters(self, filters_cm: np.ndarray) -> None:
+        """filters_cm: float32 memory of the reference's column-major 64 x 2420 Filters, i.e. numpy shape [2420, 64]."""
+        f = np.ascontiguousarray(filters_cm, dtype=np.float32)
+        if f.size != 64 * 2420:
+            raise ValueError("filters must hold 64 x 2420 floats")
+        check(self._lib.hpfw_set_filters(self.ctx.handle, _ptr(f)))
+
+    def cols(self, n_samples: int) -> int:
+        return int(self._lib.hpfw_cqt_cols(n_samples))
+
+    def words(self, n_samples: int) -> int:
+        return int(self._lib.hpfw_hashprint_words_for_samples(n_samples))
+
+    def spectrogram(self, audio: np.ndarray, magnitude: bool = False) -> np.ndarray:
+        """spectrum::CQT::spectrogram on a decoded mono buffer -> float32 [cols, 121] (dB, or linear magnitudes)."""
+        a = np.ascontiguousarray(audio, dtype=np.float32)
+        out = np.zeros((self.cols(len(a)), 121), dtype=np.float32)
+        got = C.c_int()
+        fn = self._lib.hpfw_cqt_magnitude if magnitude else self._lib.hpfw_cqt_spectrogram
+        check(fn(self.ctx.handle, _ptr(a), len(a), _ptr(out), C.byref(got)))
+        return out
+
+    def hashprint_from_spectrogram(self, spec_tm: np.ndarray) -> np.ndarray:
+        s = np.ascontiguousarray(spec_tm, dtype=np.float32)
+        hp = np.zeros(max(s.shape[0] - 99, 1), dtype=np.uint64)
+        n = C.c_int()
+        check(self._lib.hpfw_hashprint_from_spectrogram(self.ctx.handle, _ptr(s), s.shape[0], _ptr(hp), C.byref(n)))
+        return hp[:n.value]
+
+    def calc_hashprint(self, audio: np.ndarray) -> np.ndarray:
+        """ParallelCollector::calc_hashprint on a decoded buffer (host in, host out)."""
+        a = np.ascontiguousarray(audio, dtype=np.float32)
+        hp = np.zeros(max(self.words(len(a)), 1), dtype=np.uint64)
+        n = C.c_int()
+        check(self._lib.hpfw_calc_hashprint_audio(self.ctx.handle, _ptr(a), len(a), _ptr(hp), C.byref(n)))
+        return hp[:n.value]
+
+    def calc_hashprint_batch_device(self, d_audio_ptr: int, sample_offsets: np.ndarray, d_hp_out_ptr: int,
+                                    stream: int = 0) -> None:
+        """Many tracks already in HBM (concatenated, even offsets) -> concatenated hashprints in HBM; no host sync."""
+        so = np.ascontiguousarray(sample_offsets, dtype=np.int64)
+        check(self._lib.hpfw_calc_hashprint_audio_batch_device(self.ctx.handle, C.c_void_p(d_audio_ptr), _ptr(so),
+                                                               len(so) - 1, C.c_void_p(d_hp_out_ptr), stream_arg(stream)))

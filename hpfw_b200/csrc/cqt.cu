@@ -953,6 +953,41 @@ int hpfw_calc_hashprint_audio(hpfw_ctx *ctx, const float *audio, int64_t n_sampl
     return HPFW_OK;
 }
 
+int hpfw_calc_hashprint_audio_batch_device(hpfw_ctx *ctx, const float *d_audio, const int64_t *sample_offsets, int n,
+                                           uint64_t *d_hp_out, void *stream) {
+    if (!ctx || !sample_offsets || n < 0) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_calc_hashprint_audio_batch_device: bad argument");
+    if (n == 0) return HPFW_OK;
+    if (!d_audio || !d_hp_out) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_calc_hashprint_audio_batch_device: NULL buffer");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = ctx->pick(stream);
+    // chunks of tracks: CQT per track into one spectrogram buffer, then ONE projection launch for the chunk
+    const size_t chunk_bytes = size_t(512) << 20;
+    int i = 0;
+    int64_t hp_off = 0;
+    while (i < n) {
+        std::vector<int64_t> co{0};
+        int j = i;
+        while (j < n) {
+            const int64_t ns = sample_offsets[j + 1] - sample_offsets[j];
+            if (ns < 0 || (sample_offsets[j] & 1)) HPFW_FAIL(HPFW_ERR_ARG, "track %d: offsets must be monotone and even", j);
+            const int cols = hpfw_cqt_cols(ns);
+            if (hpfw_hashprint_words_for_cols(cols) <= 0)
+                HPFW_FAIL(HPFW_ERR_SHORT, "track %d (%lld samples) is too short for one hashprint word", j, (long long)ns);
+            if (j > i && sizeof(float) * size_t(co.back() + cols) * CQ_BINS > chunk_bytes) break;
+            co.push_back(co.back() + cols);
+            ++j;
+        }
+        HPFW_TRY(ctx->spectro.reserve(sizeof(float) * size_t(co.back()) * CQ_BINS));
+        for (int t = i; t < j; ++t)
+            HPFW_TRY(cqt_run(ctx, d_audio + sample_offsets[t], sample_offsets[t + 1] - sample_offsets[t],
+                             ctx->spectro.as<float>() + size_t(co[t - i]) * CQ_BINS, 0, s));
+        HPFW_TRY(hpfw_hashprint_from_spectrogram_device(ctx, ctx->spectro.as<float>(), co.data(), j - i, d_hp_out + hp_off, s));
+        for (int t = i; t < j; ++t) hp_off += hpfw_hashprint_words_for_cols(int(co[t - i + 1] - co[t - i]));
+        i = j;
+    }
+    return HPFW_OK;
+}
+
 int hpfw_fft_c2c(hpfw_ctx *ctx, const float *in_interleaved, float *out_interleaved, int n, int inverse) {
     if (!ctx || !in_interleaved || !out_interleaved || n < 4) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_fft_c2c: bad argument");
     DeviceGuard g(ctx->device);

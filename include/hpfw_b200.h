@@ -165,6 +165,12 @@ int hpfw_calc_hashprint_audio(hpfw_ctx *ctx, const float *audio, int64_t n_sampl
 int hpfw_calc_hashprint_audio_device(hpfw_ctx *ctx, const float *d_audio, int64_t n_samples, uint64_t *d_hp_out,
                                      void *stream);
 
+/* batched extraction (ParallelCollector::collect_fingerprints over many tracks, parallel_collector.h:115-137): n tracks
+ * concatenated in d_audio, sample_offsets[n+1] (host; every offset even so that each track is 8-byte aligned);
+ * d_hp_out receives track i's words at sum_{j<i} hpfw_hashprint_words_for_samples(len_j). */
+int hpfw_calc_hashprint_audio_batch_device(hpfw_ctx *ctx, const float *d_audio, const int64_t *sample_offsets, int n,
+                                           uint64_t *d_hp_out, void *stream);
+
 /* ------------------------------------------------------------------------------------------------ measurement aids */
 /* Pipe microbenchmark used to pin the matcher's roofline denominator: runs register-only loops and reports
  * lane-instructions per clock per SM for (0) POPC alone, (1) LOP3 alone, (2) the matcher's XOR/POPC/IADD3 mix,
