@@ -52,6 +52,12 @@ _SIGS = {
     "hpfw_hashprint_from_spectrogram_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                                          C.c_void_p]),
     "hpfw_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "hpfw_cov_reset": (C.c_int, [C.c_void_p]),
+    "hpfw_cov_set": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hpfw_cov_get": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hpfw_cov_add_spectrogram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "hpfw_cov_add_spectrogram_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "hpfw_calc_filters": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hpfw_cqt_cols": (C.c_int, [C.c_int64]),
     "hpfw_cqt_spectrogram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int)]),
     "hpfw_cqt_spectrogram_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

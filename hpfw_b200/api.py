@@ -263,6 +263,37 @@ class HashprintExtractor:
         check(self._lib.hpfw_calc_hashprint_audio(self.ctx.handle, _ptr(a), len(a), _ptr(hp), C.byref(n)))
         return hp[:n.value]
 
+    # ---- index-time filter learning (HashprintHandle::calc_cov / calc_filters, hashprint_handle.h:96-112) ----
+    def cov_reset(self) -> None:
+        check(self._lib.hpfw_cov_reset(self.ctx.handle))
+
+    def cov_add_spectrogram(self, spec_tm: np.ndarray) -> None:
+        """accum_cov += calc_cov(calc_frames(spectrogram)^T) (parallel_collector.h:92-97), accumulator resident in HBM."""
+        s = np.ascontiguousarray(spec_tm, dtype=np.float32)
+        check(self._lib.hpfw_cov_add_spectrogram(self.ctx.handle, _ptr(s), s.shape[0]))
+
+    def cov_get(self) -> np.ndarray:
+        out = np.zeros((2420, 2420), dtype=np.float32)
+        check(self._lib.hpfw_cov_get(self.ctx.handle, _ptr(out)))
+        return out
+
+    def cov_set(self, accum: np.ndarray) -> None:
+        a = np.ascontiguousarray(accum, dtype=np.float32)
+        if a.shape != (2420, 2420):
+            raise ValueError("accum_cov must be 2420 x 2420")
+        check(self._lib.hpfw_cov_set(self.ctx.handle, _ptr(a)))
+
+    def calc_filters(self, cov: np.ndarray | None = None, install: bool = True):
+        """Top-64 eigenvectors of `cov` (or of the context's accumulator) -> (filters [2420, 64] = memory of the
+        column-major 64 x 2420 Filters, eigenvalues[64]). Sign: largest-|component| of each filter positive."""
+        f = np.zeros((2420, 64), dtype=np.float32)
+        w = np.zeros(64, dtype=np.float32)
+        c = None if cov is None else np.ascontiguousarray(cov, dtype=np.float32)
+        check(self._lib.hpfw_calc_filters(self.ctx.handle, None if c is None else _ptr(c), _ptr(f), _ptr(w)))
+        if install:
+            self.set_filters(f)
+        return f, w
+
     def calc_hashprint_batch_device(self, d_audio_ptr: int, sample_offsets: np.ndarray, d_hp_out_ptr: int,
                                     stream: int = 0) -> None:
         """Many tracks already in HBM (concatenated, even offsets) -> concatenated hashprints in HBM; no host sync."""

@@ -106,6 +106,10 @@ struct hpfw_ctx {
     bool have_filters = false;
     hpfw_b200::DeviceBuffer spectro, hp, yproj, colmeta;
 
+    // filter learning (learn.cu): device-resident covariance accumulator (2420 x 2420) and scratch
+    hpfw_b200::DeviceBuffer cov_accum, cov_scratch;
+    uint64_t cov_tracks = 0;
+
     // cqt state
     hpfw_b200::CqtPlanCache *cqt = nullptr;
     hpfw_b200::DeviceBuffer audio;

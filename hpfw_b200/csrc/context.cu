@@ -61,6 +61,8 @@ void hpfw_ctx_destroy(hpfw_ctx *c) {
     c->yproj.release();
     c->colmeta.release();
     c->audio.release();
+    c->cov_accum.release();
+    c->cov_scratch.release();
     hpfw_b200::cqt_cache_destroy(c->cqt);
     for (auto &r : c->timing_pending) {
         cudaEventDestroy(r.a);

@@ -42,6 +42,7 @@ constexpr int CQ_MAX_ROW = 8192;      // longest shared-memory FFT (2 x 64 KB pi
 constexpr int CQ_MAXRAD = 14;
 constexpr int CQ_TW_S = 1024;         // two-level twiddle: W^m = hi[m / S] * lo[m % S]
 constexpr int CQ_THREADS = 256;
+constexpr int CQ_FFT_THREADS = 512;   // shared-memory FFT kernels: 2 CTAs x 16 warps per SM
 
 struct FftDesc {
     int n;
@@ -250,15 +251,16 @@ __device__ float2 *smem_fft(float2 *a, float2 *b, const FftDesc &d, int G, const
 // ------------------------------------------------------------------------------------------------ main FFT, pass A
 // Column FFTs of the n1 x n2 row-major matrix `in` (element (a,b) at a*n2+b): for G adjacent columns per CTA,
 // out[c*n2 + b] = W_H^{b c} * sum_a in[a*n2 + b] e^{-2 pi i a c / n1}.
-__global__ void __launch_bounds__(CQ_THREADS)
+__global__ void __launch_bounds__(CQ_FFT_THREADS, 2)
 fft_cols_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, FftDesc d1, int n2, int G,
-                const float2 *__restrict__ tw1, const float2 *__restrict__ twH_hi, const float2 *__restrict__ twH_lo,
+                const float2 *__restrict__ tw1_g, const float2 *__restrict__ twH_hi, const float2 *__restrict__ twH_lo,
                 int sign) {
     extern __shared__ __align__(16) float2 fsm[];
     const int n1 = d1.n;
     const int b0 = blockIdx.x * G;
     const int g_here = min(G, n2 - b0);
-    float2 *A = fsm, *B = fsm + G * n1;
+    float2 *tw1 = fsm, *A = fsm + n1, *B = A + G * n1;
+    for (int idx = threadIdx.x; idx < n1; idx += blockDim.x) tw1[idx] = tw1_g[idx];   // stage twiddles: no L1 gathers in the stages
     for (int idx = threadIdx.x; idx < n1 * G; idx += blockDim.x) {
         const int a = idx / G, g = idx - a * G;
         A[g * n1 + a] = g < g_here ? in[(long long)a * n2 + b0 + g] : make_float2(0.f, 0.f);
@@ -277,14 +279,15 @@ fft_cols_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, FftDesc
 // ------------------------------------------------------------------------------------------------ main FFT, pass B
 // Row FFTs: Z[c + n1*d] = sum_b in[c*n2 + b] e^{-2 pi i b d / n2}. Keeps only k in [klo, khi] (-> out_lo[k - klo]) and
 // k in [H - khi, H - klo] (-> out_hi[k - (H - khi)]); with keep_all != 0 stores the whole spectrum to out_lo[k].
-__global__ void __launch_bounds__(CQ_THREADS)
+__global__ void __launch_bounds__(CQ_FFT_THREADS, 2)
 fft_rows_kernel(const float2 *__restrict__ in, float2 *__restrict__ out_lo, float2 *__restrict__ out_hi, FftDesc d2,
-                int n1, int G, const float2 *__restrict__ tw2, int klo, int khi, int H, int keep_all, int sign) {
+                int n1, int G, const float2 *__restrict__ tw2_g, int klo, int khi, int H, int keep_all, int sign) {
     extern __shared__ __align__(16) float2 fsm[];
     const int n2 = d2.n;
     const int c0 = blockIdx.x * G;
     const int g_here = min(G, n1 - c0);
-    float2 *A = fsm, *B = fsm + G * n2;
+    float2 *tw2 = fsm, *A = fsm + n2, *B = A + G * n2;
+    for (int idx = threadIdx.x; idx < n2; idx += blockDim.x) tw2[idx] = tw2_g[idx];
     for (int idx = threadIdx.x; idx < n2 * G; idx += blockDim.x) {
         const int g = idx / n2, b = idx - g * n2;
         A[idx] = g < g_here ? in[(long long)(c0 + g) * n2 + b] : make_float2(0.f, 0.f);
@@ -372,10 +375,13 @@ czt_rows_kernel(const BandMeta *__restrict__ bands, float2 *__restrict__ work, c
     const int c = blockIdx.x;
     __shared__ FftDesc d;
     if (threadIdx.x == 0) d = descs[bm.btab];
-    const float2 *tw = tws[bm.btab];
+    const float2 *tw_g = tws[bm.btab];
     float2 *row = work + bm.work_off + (long long)c * bm.L2;
-    float2 *A = fsm, *B = fsm + bm.L2;
-    for (int i = threadIdx.x; i < bm.L2; i += blockDim.x) A[i] = row[i];
+    float2 *tw = fsm, *A = fsm + bm.L2, *B = A + bm.L2;
+    for (int i = threadIdx.x; i < bm.L2; i += blockDim.x) {
+        tw[i] = tw_g[i];
+        A[i] = row[i];
+    }
     __syncthreads();
     float2 *R = smem_fft(A, B, d, 1, tw, -1);
     if (MODE == 1) {
@@ -603,6 +609,21 @@ static bool split_smooth(int H, int &n1, int &n2) {
     return true;
 }
 
+// Shared memory of the two-pass FFT kernels: twiddles (n) + ping-pong (2 * G * n) complex values. G columns / rows per CTA
+// is sized for two resident CTAs per SM (~110 KB each) when the transform allows it, one CTA otherwise.
+static void fft_group_sizes(hpfw_ctx *ctx, int n1, int n2, int &G1, int &G2, size_t &smem1, size_t &smem2) {
+    const size_t two_cta = 110 * 1024, one_cta = (size_t)ctx->max_smem_optin - 2048;
+    auto pick = [&](int n, int gmax) {
+        size_t g = two_cta > 8 * (size_t)n ? (two_cta - 8 * (size_t)n) / (16 * (size_t)n) : 0;
+        if (g < 2) g = one_cta > 8 * (size_t)n ? (one_cta - 8 * (size_t)n) / (16 * (size_t)n) : 0;
+        return (int)std::max<size_t>(1, std::min<size_t>((size_t)gmax, g));
+    };
+    G1 = pick(n1, 8);
+    G2 = pick(n2, 4);
+    smem1 = 8 * (size_t)n1 * (1 + 2 * (size_t)G1);
+    smem2 = 8 * (size_t)n2 * (1 + 2 * (size_t)G2);
+}
+
 // every FFT kernel may use up to the device's opt-in shared memory (plans of different sizes share the kernels)
 static int set_smem_limits(hpfw_ctx *ctx) {
     const int lim = ctx->max_smem_optin - 2048;   // dynamic + static shared memory must stay within the opt-in limit
@@ -636,12 +657,7 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
     }
     if (pl.klo < 1 || pl.khi >= pl.H)
         HPFW_FAIL(HPFW_ERR_SHORT, "CQT: audio of %lld samples is too short for the 121-band design", (long long)N);
-    // shared-memory budgets: 2 (ping-pong) * G * n * 8 B
-    const size_t budget = std::min<size_t>((size_t)ctx->max_smem_optin - 2048, 200 * 1024);
-    pl.G1 = (int)std::max<size_t>(1, std::min<size_t>(8, budget / (16 * (size_t)n1)));
-    pl.G2 = (int)std::max<size_t>(1, std::min<size_t>(4, budget / (16 * (size_t)n2)));
-    pl.smem1 = 16 * (size_t)n1 * pl.G1;
-    pl.smem2 = 16 * (size_t)n2 * pl.G2;
+    fft_group_sizes(ctx, n1, n2, pl.G1, pl.G2, pl.smem1, pl.smem2);
     {
         auto t1 = twiddle_table(n1), t2 = twiddle_table(n2);
         HPFW_TRY(pl.tw1.reserve(sizeof(float2) * t1.size()));
@@ -723,7 +739,7 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
             }
             {
                 KernelScope ks(ctx, HPFW_K_CQT, stream);
-                czt_rows_kernel<1><<<dim3(CQ_L1, 1), CQ_THREADS, 16 * (size_t)fb[i].L2, stream>>>(
+                czt_rows_kernel<1><<<dim3(CQ_L1, 1), CQ_THREADS, 24 * (size_t)fb[i].L2, stream>>>(
                     dbm, tab, pl.d_btab_ptrs.as<const float2 *>(), pl.d_descs.as<FftDesc>(),
                     pl.d_tw_ptrs.as<const float2 *>());
             }
@@ -781,13 +797,13 @@ static int cqt_run(hpfw_ctx *ctx, const float *d_audio, int64_t N, float *d_out,
     const float2 *z_in = reinterpret_cast<const float2 *>(d_audio);
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
-        fft_cols_kernel<<<(n2 + pl->G1 - 1) / pl->G1, CQ_THREADS, pl->smem1, stream>>>(
+        fft_cols_kernel<<<(n2 + pl->G1 - 1) / pl->G1, CQ_FFT_THREADS, pl->smem1, stream>>>(
             z_in, pl->zbuf.as<float2>(), pl->d1, n2, pl->G1, pl->tw1.as<float2>(), pl->twH.hi.as<float2>(),
             pl->twH.lo.as<float2>(), -1);
     }
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
-        fft_rows_kernel<<<(n1 + pl->G2 - 1) / pl->G2, CQ_THREADS, pl->smem2, stream>>>(
+        fft_rows_kernel<<<(n1 + pl->G2 - 1) / pl->G2, CQ_FFT_THREADS, pl->smem2, stream>>>(
             pl->zbuf.as<float2>(), pl->zlo.as<float2>(), pl->zhi.as<float2>(), pl->d2, n1, pl->G2, pl->tw2.as<float2>(),
             pl->klo, pl->khi, pl->H, 0, -1);
     }
@@ -800,11 +816,15 @@ static int cqt_run(hpfw_ctx *ctx, const float *d_audio, int64_t N, float *d_out,
                                                              pl->twN.hi.as<float2>(), pl->twN.lo.as<float2>(), d.M, d.F,
                                                              pl->work.as<float2>());
     }
-    {
+    // one launch per run of bands with the same chirp length, so that short rows do not reserve the longest row's shared memory
+    for (int j0 = 0; j0 < CQ_BINS;) {
+        int j1 = j0;
+        while (j1 < CQ_BINS && pl->bands[j1].L == pl->bands[j0].L) ++j1;
         KernelScope ks(ctx, HPFW_K_CQT, stream);
-        czt_rows_kernel<0><<<dim3(CQ_L1, CQ_BINS), CQ_THREADS, 16 * (size_t)pl->max_L2, stream>>>(
-            pl->d_bands.as<BandMeta>(), pl->work.as<float2>(), pl->d_btab_ptrs.as<const float2 *>(),
+        czt_rows_kernel<0><<<dim3(CQ_L1, j1 - j0), CQ_THREADS, 24 * (size_t)pl->bands[j0].L2, stream>>>(
+            pl->d_bands.as<BandMeta>() + j0, pl->work.as<float2>(), pl->d_btab_ptrs.as<const float2 *>(),
             pl->d_descs.as<FftDesc>(), pl->d_tw_ptrs.as<const float2 *>());
+        j0 = j1;
     }
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
@@ -833,9 +853,9 @@ static int fft_c2c_device(hpfw_ctx *ctx, const float2 *d_in, float2 *d_out, int 
     if (!split_smooth(n, n1, n2) || !factor_smooth(n1, d1) || !factor_smooth(n2, d2))
         HPFW_FAIL(HPFW_ERR_LIMIT, "hpfw_fft_c2c: %d is not a product n1*n2 of {2,3,5,7}-smooth factors <= %d", n,
                   CQ_MAX_ROW);
-    const size_t budget = std::min<size_t>((size_t)ctx->max_smem_optin - 2048, 200 * 1024);
-    const int G1 = (int)std::max<size_t>(1, std::min<size_t>(8, budget / (16 * (size_t)n1)));
-    const int G2 = (int)std::max<size_t>(1, std::min<size_t>(4, budget / (16 * (size_t)n2)));
+    int G1 = 1, G2 = 1;
+    size_t smem1 = 0, smem2 = 0;
+    fft_group_sizes(ctx, n1, n2, G1, G2, smem1, smem2);
     DeviceBuffer tw1, tw2, tmp;
     TwoLevel twP;
     auto t1 = twiddle_table(n1), t2 = twiddle_table(n2);
@@ -849,12 +869,12 @@ static int fft_c2c_device(hpfw_ctx *ctx, const float2 *d_in, float2 *d_out, int 
     const int sign = inverse ? +1 : -1;
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
-        fft_cols_kernel<<<(n2 + G1 - 1) / G1, CQ_THREADS, 16 * (size_t)n1 * G1, stream>>>(
+        fft_cols_kernel<<<(n2 + G1 - 1) / G1, CQ_FFT_THREADS, smem1, stream>>>(
             d_in, tmp.as<float2>(), d1, n2, G1, tw1.as<float2>(), twP.hi.as<float2>(), twP.lo.as<float2>(), sign);
     }
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
-        fft_rows_kernel<<<(n1 + G2 - 1) / G2, CQ_THREADS, 16 * (size_t)n2 * G2, stream>>>(
+        fft_rows_kernel<<<(n1 + G2 - 1) / G2, CQ_FFT_THREADS, smem2, stream>>>(
             tmp.as<float2>(), d_out, nullptr, d2, n1, G2, tw2.as<float2>(), 0, 0, n, 1, sign);
     }
     HPFW_CUDA_TRY(cudaGetLastError());

@@ -1,0 +1,433 @@
+// hpfw_b200/csrc/learn.cu — index-time filter learning.
+//
+// Replaces HashprintHandle::calc_cov and calc_filters (/root/reference/include/hpfw/core/hashprint_handle.h:96-112) and the
+// mutex-protected accumulate of ParallelCollector::preprocess (/root/reference/include/hpfw/core/parallel_collector.h:92-97,111).
+//
+// calc_cov(frames^T) is a 2420 x 2420 x frames SYRK in the reference (170 GFLOP per 3-minute track). The context frames are
+// a sliding window over the spectrogram, X[t,(b,c)] = S[b,t+c], so with P_d[u] = S[b,u] S[b',u+d]
+//     G[(b,c),(b',c+d)] = sum_{u=c}^{c+nf-1} P_d[u] = T0_d[b,b'] - sum_{u<c} P_d[u] + sum_{u=nf}^{nf+c-1} P_d[u],
+//     T0_d[b,b'] = sum_{u<nf} P_d[u]:
+// twenty 121 x 121 x nf GEMMs (4.2 GFLOP) plus <= 19-term edge corrections give the same matrix as the SYRK, 40x cheaper.
+// The per-band mean is removed first (it cancels in the covariance) so that G - nf mu mu' does not cancel catastrophically
+// in fp32. cov = (G - nf mu_i mu_j) / (nf - 1) is added to the device-resident accumulator of the context.
+//
+// calc_filters: only the top 64 eigenvectors are needed, so instead of a dense eigen-solve the GPU runs block subspace
+// iteration (Z = A V, one 2420 x 2420 x 128 GEMM per step) while the host orthonormalises the 2420 x 128 block
+// (modified Gram-Schmidt, double) and does the 128 x 128 Rayleigh-Ritz step (cyclic Jacobi, double). Eigenvector signs are
+// arbitrary in any solver (MKL ssyev vs Eigen's QL differ too); they are normalised so that the largest-magnitude component is
+// positive. Hamming distances do not depend on the sign as long as DB and queries use the same filters.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace hpfw_b200 {
+
+constexpr int LN_BINS = HPFW_BINS;          // 121
+constexpr int LN_CTX = HPFW_CONTEXT;        // 20
+constexpr int LN_FS = HPFW_FRAME_SIZE;      // 2420
+constexpr int LN_KS = 16;                   // split-K factor of the T0 GEMMs
+constexpr int LN_P = 128;                   // subspace block size (64 wanted + 64 guard vectors)
+
+// ---- per-band mean over all columns; centred copy Sc[t][b] = S[t][b] - mean_b ------------------------------------------
+__global__ void __launch_bounds__(256) band_mean_kernel(const float *__restrict__ S, int cols, float *__restrict__ mean) {
+    // one CTA per band; double accumulation (cols up to ~3e4)
+    __shared__ double red[256];
+    const int b = blockIdx.x;
+    double acc = 0.0;
+    for (int t = threadIdx.x; t < cols; t += blockDim.x) acc += (double)S[(size_t)t * LN_BINS + b];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) mean[b] = (float)(red[0] / (double)cols);
+}
+
+__global__ void __launch_bounds__(256) center_kernel(const float *__restrict__ S, int cols, const float *__restrict__ mean,
+                                                     float *__restrict__ Sc) {
+    const size_t n = (size_t)cols * LN_BINS;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        Sc[i] = S[i] - mean[i % LN_BINS];
+}
+
+// ---- T0 partials: part[ks][d][b][b'] = sum_{u in chunk ks} Sc[u][b] * Sc[u+d][b'] ------------------------------------------
+// grid (2, 2, 20 * LN_KS), 256 threads, 64 x 64 output tile, 4 x 4 per thread, K-chunks of 16 rows.
+__global__ void __launch_bounds__(256)
+t0_gemm_kernel(const float *__restrict__ Sc, int nf, float *__restrict__ part) {
+    __shared__ float As[16][64 + 4], Bs[16][64 + 4];
+    const int d = blockIdx.z / LN_KS, ks = blockIdx.z % LN_KS;
+    const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+    const int per = (nf + LN_KS - 1) / LN_KS;
+    const int u_begin = ks * per, u_end = min(nf, u_begin + per);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4] = {};
+    for (int u0 = u_begin; u0 < u_end; u0 += 16) {
+        for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+            const int kk = e >> 6, col = e & 63;
+            const int u = u0 + kk;
+            const bool ok = u < u_end;
+            As[kk][col] = (ok && m0 + col < LN_BINS) ? Sc[(size_t)u * LN_BINS + m0 + col] : 0.f;
+            Bs[kk][col] = (ok && n0 + col < LN_BINS) ? Sc[(size_t)(u + d) * LN_BINS + n0 + col] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float *dst = part + ((size_t)ks * LN_CTX + d) * (128 * 128);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[(m0 + ty * 4 + i) * 128 + n0 + tx * 4 + j] = acc[i][j];
+}
+
+// ---- column sums over [0, nf) of the centred spectrogram, for the frame means ------------------------------------------
+__global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ Sc, int nf, float *__restrict__ sum0) {
+    __shared__ double red[256];
+    const int b = blockIdx.x;
+    double acc = 0.0;
+    for (int t = threadIdx.x; t < nf; t += blockDim.x) acc += (double)Sc[(size_t)t * LN_BINS + b];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sum0[b] = (float)red[0];
+}
+
+// ---- edge corrections, means, normalisation, accumulate --------------------------------------------------------------------
+// one thread per (d, b, b'): entries (i = b*20+c, j = b'*20+c+d), c = 0 .. 19-d, plus the mirrored entry when d > 0.
+__global__ void __launch_bounds__(256)
+cov_finish_kernel(const float *__restrict__ Sc, int nf, const float *__restrict__ part, const float *__restrict__ sum0,
+                  float *__restrict__ accum) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= LN_CTX * LN_BINS * LN_BINS) return;
+    const int bp = idx % LN_BINS, b = (idx / LN_BINS) % LN_BINS, d = idx / (LN_BINS * LN_BINS);
+    float t0 = 0.f;
+    for (int ks = 0; ks < LN_KS; ++ks) t0 += part[((size_t)ks * LN_CTX + d) * (128 * 128) + b * 128 + bp];
+    // running sums for the means of rows (b,c) and (b',c+d): sum_{u=c}^{c+nf-1} Sc[u][b] = sum0[b] - head + tail
+    float g = t0;
+    float si = sum0[b];                 // row (b, c) with c = 0
+    float sj = sum0[bp];                // row (b', c') with c' = d: shift d times first
+    for (int c = 0; c < d; ++c) sj += Sc[(size_t)(nf + c) * LN_BINS + bp] - Sc[(size_t)c * LN_BINS + bp];
+    const float inv_nf = 1.0f / (float)nf, inv_nm1 = 1.0f / (float)(nf - 1);
+    for (int c = 0; c + d < LN_CTX; ++c) {
+        const float mi = si * inv_nf, mj = sj * inv_nf;
+        const float cov = (g - (float)nf * mi * mj) * inv_nm1;
+        const int i = b * LN_CTX + c, j = bp * LN_CTX + c + d;
+        accum[(size_t)i + (size_t)LN_FS * j] += cov;
+        if (d > 0) accum[(size_t)j + (size_t)LN_FS * i] += cov;
+        if (c + d + 1 >= LN_CTX) break;   // last entry of this diagonal: the next window would read past the last column
+        // advance c -> c+1: drop u = c, add u = nf + c (both factors shifted by d in the second operand)
+        g += Sc[(size_t)(nf + c) * LN_BINS + b] * Sc[(size_t)(nf + c + d) * LN_BINS + bp] -
+             Sc[(size_t)c * LN_BINS + b] * Sc[(size_t)(c + d) * LN_BINS + bp];
+        si += Sc[(size_t)(nf + c) * LN_BINS + b] - Sc[(size_t)c * LN_BINS + b];
+        sj += Sc[(size_t)(nf + c + d) * LN_BINS + bp] - Sc[(size_t)(c + d) * LN_BINS + bp];
+    }
+}
+
+// ---- Z = A V for the subspace iteration: A symmetric n x n, V and Z column-major n x p ----------------------------------------
+__global__ void __launch_bounds__(256)
+symm_block_mul_kernel(const float *__restrict__ A, const float *__restrict__ V, float *__restrict__ Z, int n, int p) {
+    __shared__ float As[16][64 + 4], Vs[16][64 + 4];
+    const int m0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < n; k0 += 16) {
+        for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+            const int kk = e >> 6, col = e & 63;
+            const int k = k0 + kk;
+            // A(m, k) = A(k, m): read row k of the column-major matrix as a contiguous run over m
+            As[kk][col] = (k < n && m0 + col < n) ? A[(size_t)k * n + m0 + col] : 0.f;
+        }
+        for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+            const int col = e >> 4, kk = e & 15;
+            const int k = k0 + kk;
+            Vs[kk][col] = (k < n && c0 + col < p) ? V[(size_t)(c0 + col) * n + k] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Vs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = m0 + ty * 4 + i, c = c0 + tx * 4 + j;
+            if (m < n && c < p) Z[(size_t)c * n + m] = acc[i][j];
+        }
+}
+
+// ================================================================================================ host numerics (double)
+// modified Gram-Schmidt with one re-orthogonalisation pass; V is column-major n x p
+static void orthonormalise(std::vector<double> &V, int n, int p) {
+    for (int j = 0; j < p; ++j) {
+        double *vj = &V[(size_t)j * n];
+        for (int pass = 0; pass < 2; ++pass)
+            for (int i = 0; i < j; ++i) {
+                const double *vi = &V[(size_t)i * n];
+                double dot = 0.0;
+                for (int k = 0; k < n; ++k) dot += vi[k] * vj[k];
+                for (int k = 0; k < n; ++k) vj[k] -= dot * vi[k];
+            }
+        double nrm = 0.0;
+        for (int k = 0; k < n; ++k) nrm += vj[k] * vj[k];
+        nrm = std::sqrt(nrm);
+        if (nrm < 1e-300) {   // degenerate direction: replace by a unit vector not yet used
+            for (int k = 0; k < n; ++k) vj[k] = (k == j) ? 1.0 : 0.0;
+            nrm = 1.0;
+        }
+        for (int k = 0; k < n; ++k) vj[k] /= nrm;
+    }
+}
+
+// cyclic Jacobi eigen-decomposition of the symmetric p x p matrix H (row-major); eigenvectors in the columns of Q
+static void jacobi_eigh(std::vector<double> &H, int p, std::vector<double> &w, std::vector<double> &Q) {
+    Q.assign((size_t)p * p, 0.0);
+    for (int i = 0; i < p; ++i) Q[(size_t)i * p + i] = 1.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < p; ++i)
+            for (int j = 0; j < p; ++j) (i == j ? diag : off) += H[(size_t)i * p + j] * H[(size_t)i * p + j];
+        if (off <= 1e-30 * diag) break;
+        for (int a = 0; a < p - 1; ++a)
+            for (int b = a + 1; b < p; ++b) {
+                const double hab = H[(size_t)a * p + b];
+                if (std::fabs(hab) < 1e-300) continue;
+                const double haa = H[(size_t)a * p + a], hbb = H[(size_t)b * p + b];
+                const double theta = (hbb - haa) / (2.0 * hab);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < p; ++k) {
+                    const double hka = H[(size_t)k * p + a], hkb = H[(size_t)k * p + b];
+                    H[(size_t)k * p + a] = c * hka - s * hkb;
+                    H[(size_t)k * p + b] = s * hka + c * hkb;
+                }
+                for (int k = 0; k < p; ++k) {
+                    const double hak = H[(size_t)a * p + k], hbk = H[(size_t)b * p + k];
+                    H[(size_t)a * p + k] = c * hak - s * hbk;
+                    H[(size_t)b * p + k] = s * hak + c * hbk;
+                }
+                for (int k = 0; k < p; ++k) {
+                    const double qka = Q[(size_t)k * p + a], qkb = Q[(size_t)k * p + b];
+                    Q[(size_t)k * p + a] = c * qka - s * qkb;
+                    Q[(size_t)k * p + b] = s * qka + c * qkb;
+                }
+            }
+    }
+    w.resize(p);
+    for (int i = 0; i < p; ++i) w[i] = H[(size_t)i * p + i];
+}
+
+}  // namespace hpfw_b200
+
+using namespace hpfw_b200;
+
+static int cov_add_device(hpfw_ctx *ctx, const float *d_spec, int cols, cudaStream_t s) {
+    const int nf = cols - (LN_CTX - 1);
+    if (nf < 2) HPFW_FAIL(HPFW_ERR_SHORT, "covariance needs at least 21 spectrogram columns (got %d)", cols);
+    if (!ctx->cov_accum.ptr) {
+        HPFW_TRY(ctx->cov_accum.reserve(sizeof(float) * (size_t)LN_FS * LN_FS));
+        HPFW_CUDA_TRY(cudaMemsetAsync(ctx->cov_accum.ptr, 0, sizeof(float) * (size_t)LN_FS * LN_FS, s));
+    }
+    HPFW_TRY(ctx->cov_scratch.reserve(sizeof(float) * ((size_t)cols * LN_BINS + 2 * 128 + (size_t)LN_KS * LN_CTX * 128 * 128)));
+    float *Sc = ctx->cov_scratch.as<float>();
+    float *mean = Sc + (size_t)cols * LN_BINS;
+    float *sum0 = mean + 128;
+    float *part = sum0 + 128;
+    {
+        KernelScope ks(ctx, HPFW_K_OTHER, s);
+        band_mean_kernel<<<LN_BINS, 256, 0, s>>>(d_spec, cols, mean);
+    }
+    {
+        KernelScope ks(ctx, HPFW_K_OTHER, s);
+        center_kernel<<<ctx->sm_count * 4, 256, 0, s>>>(d_spec, cols, mean, Sc);
+    }
+    {
+        KernelScope ks(ctx, HPFW_K_OTHER, s);
+        colsum_kernel<<<LN_BINS, 256, 0, s>>>(Sc, nf, sum0);
+    }
+    {
+        KernelScope ks(ctx, HPFW_K_OTHER, s);
+        t0_gemm_kernel<<<dim3(2, 2, LN_CTX * LN_KS), 256, 0, s>>>(Sc, nf, part);
+    }
+    {
+        KernelScope ks(ctx, HPFW_K_OTHER, s);
+        const int total = LN_CTX * LN_BINS * LN_BINS;
+        cov_finish_kernel<<<(total + 255) / 256, 256, 0, s>>>(Sc, nf, part, sum0, ctx->cov_accum.as<float>());
+    }
+    HPFW_CUDA_TRY(cudaGetLastError());
+    ctx->cov_tracks++;
+    return HPFW_OK;
+}
+
+extern "C" {
+
+int hpfw_cov_reset(hpfw_ctx *ctx) {
+    if (!ctx) HPFW_FAIL(HPFW_ERR_ARG, "ctx is NULL");
+    DeviceGuard g(ctx->device);
+    HPFW_TRY(ctx->cov_accum.reserve(sizeof(float) * (size_t)LN_FS * LN_FS));
+    HPFW_CUDA_TRY(cudaMemsetAsync(ctx->cov_accum.ptr, 0, sizeof(float) * (size_t)LN_FS * LN_FS, ctx->stream));
+    ctx->cov_tracks = 0;
+    return HPFW_OK;
+}
+
+int hpfw_cov_set(hpfw_ctx *ctx, const float *accum_2420x2420) {
+    if (!ctx || !accum_2420x2420) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_cov_set: NULL argument");
+    DeviceGuard g(ctx->device);
+    HPFW_TRY(ctx->cov_accum.reserve(sizeof(float) * (size_t)LN_FS * LN_FS));
+    HPFW_CUDA_TRY(cudaMemcpyAsync(ctx->cov_accum.ptr, accum_2420x2420, sizeof(float) * (size_t)LN_FS * LN_FS,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    HPFW_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return HPFW_OK;
+}
+
+int hpfw_cov_get(hpfw_ctx *ctx, float *accum_2420x2420) {
+    if (!ctx || !accum_2420x2420) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_cov_get: NULL argument");
+    DeviceGuard g(ctx->device);
+    if (!ctx->cov_accum.ptr) HPFW_TRY(hpfw_cov_reset(ctx));
+    HPFW_CUDA_TRY(cudaMemcpyAsync(accum_2420x2420, ctx->cov_accum.ptr, sizeof(float) * (size_t)LN_FS * LN_FS,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    HPFW_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return HPFW_OK;
+}
+
+int hpfw_cov_add_spectrogram_device(hpfw_ctx *ctx, const float *d_spectrogram, int cols, void *stream) {
+    if (!ctx || !d_spectrogram) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_cov_add_spectrogram_device: NULL argument");
+    DeviceGuard g(ctx->device);
+    return cov_add_device(ctx, d_spectrogram, cols, ctx->pick(stream));
+}
+
+int hpfw_cov_add_spectrogram(hpfw_ctx *ctx, const float *spectrogram, int cols) {
+    if (!ctx || !spectrogram) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_cov_add_spectrogram: NULL argument");
+    if (cols < LN_CTX + 1) HPFW_FAIL(HPFW_ERR_SHORT, "covariance needs at least 21 spectrogram columns (got %d)", cols);
+    DeviceGuard g(ctx->device);
+    const size_t sb = sizeof(float) * (size_t)cols * LN_BINS;
+    HPFW_TRY(ctx->spectro.reserve(sb));
+    HPFW_CUDA_TRY(cudaMemcpyAsync(ctx->spectro.ptr, spectrogram, sb, cudaMemcpyHostToDevice, ctx->stream));
+    HPFW_TRY(cov_add_device(ctx, ctx->spectro.as<float>(), cols, ctx->stream));
+    HPFW_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return HPFW_OK;
+}
+
+int hpfw_calc_filters(hpfw_ctx *ctx, const float *cov, float *filters_out, float *eigenvalues_out) {
+    if (!ctx || !filters_out) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_calc_filters: NULL argument");
+    DeviceGuard g(ctx->device);
+    const int n = LN_FS, p = LN_P, want = HPFW_NFILTERS;
+    DeviceBuffer dA, dV, dZ;
+    const float *A = nullptr;
+    if (cov) {
+        HPFW_TRY(dA.reserve(sizeof(float) * (size_t)n * n));
+        HPFW_CUDA_TRY(cudaMemcpy(dA.ptr, cov, sizeof(float) * (size_t)n * n, cudaMemcpyHostToDevice));
+        A = dA.as<float>();
+    } else {
+        if (!ctx->cov_accum.ptr) HPFW_FAIL(HPFW_ERR_STATE, "hpfw_calc_filters: no covariance accumulated");
+        A = ctx->cov_accum.as<float>();
+    }
+    HPFW_TRY(dV.reserve(sizeof(float) * (size_t)n * p));
+    HPFW_TRY(dZ.reserve(sizeof(float) * (size_t)n * p));
+    std::vector<double> V((size_t)n * p), Z((size_t)n * p);
+    std::vector<float> Vf((size_t)n * p), Zf((size_t)n * p);
+    uint64_t lcg = 0x9E3779B97F4A7C15ull;
+    for (auto &v : V) {
+        lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+        v = (double)((lcg >> 11) & 0xFFFFFF) / 16777216.0 - 0.5;
+    }
+    orthonormalise(V, n, p);
+    std::vector<double> H, w, Q, prev(want, 0.0);
+    const dim3 grid((n + 63) / 64, (p + 63) / 64);
+    int status = HPFW_OK;
+    for (int it = 0; it < 300; ++it) {
+        for (size_t i = 0; i < V.size(); ++i) Vf[i] = (float)V[i];
+        cudaError_t e = cudaMemcpyAsync(dV.ptr, Vf.data(), sizeof(float) * Vf.size(), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) {
+            KernelScope ks(ctx, HPFW_K_OTHER, ctx->stream);
+            symm_block_mul_kernel<<<grid, 256, 0, ctx->stream>>>(A, dV.as<float>(), dZ.as<float>(), n, p);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(Zf.data(), dZ.ptr, sizeof(float) * Zf.size(), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            set_error("hpfw_calc_filters: %s", cudaGetErrorString(e));
+            status = HPFW_ERR_CUDA;
+            break;
+        }
+        // Rayleigh-Ritz: H = V^T (A V), rotate, then the power step V <- orth(A V Q)
+        H.assign((size_t)p * p, 0.0);
+        for (int i = 0; i < p; ++i)
+            for (int j = i; j < p; ++j) {
+                double dot = 0.0;
+                const double *vi = &V[(size_t)i * n];
+                const float *zj = &Zf[(size_t)j * n];
+                for (int k = 0; k < n; ++k) dot += vi[k] * (double)zj[k];
+                H[(size_t)i * p + j] = H[(size_t)j * p + i] = dot;
+            }
+        jacobi_eigh(H, p, w, Q);
+        std::vector<int> order(p);
+        for (int i = 0; i < p; ++i) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return w[a] > w[b]; });
+        // Z' = (A V) Q_sorted ; these are A * (Ritz vectors): use them as the next block (one power step)
+        for (int c = 0; c < p; ++c) {
+            double *zc = &Z[(size_t)c * n];
+            std::fill(zc, zc + n, 0.0);
+            for (int j = 0; j < p; ++j) {
+                const double q = Q[(size_t)j * p + order[c]];
+                if (q == 0.0) continue;
+                const float *zj = &Zf[(size_t)j * n];
+                for (int k = 0; k < n; ++k) zc[k] += q * (double)zj[k];
+            }
+        }
+        double change = 0.0, top = std::fabs(w[order[0]]) + 1e-300;
+        for (int i = 0; i < want; ++i) {
+            change = std::max(change, std::fabs(w[order[i]] - prev[i]) / top);
+            prev[i] = w[order[i]];
+        }
+        V.swap(Z);
+        orthonormalise(V, n, p);
+        if (it >= 3 && change < 1e-9) break;
+    }
+    if (status == HPFW_OK) {
+        // V now holds orth(A * Ritz vectors), converged to the eigenvectors in descending eigenvalue order.
+        // filters(f, i) = eigenvector_f[i], column-major 64 x 2420; sign: largest-|component| positive.
+        for (int f = 0; f < want; ++f) {
+            const double *v = &V[(size_t)f * n];
+            int arg = 0;
+            for (int k = 1; k < n; ++k)
+                if (std::fabs(v[k]) > std::fabs(v[arg])) arg = k;
+            const double sgn = v[arg] < 0 ? -1.0 : 1.0;
+            for (int k = 0; k < n; ++k) filters_out[(size_t)f + (size_t)want * k] = (float)(sgn * v[k]);
+            if (eigenvalues_out) eigenvalues_out[f] = (float)prev[f];
+        }
+    }
+    dA.release();
+    dV.release();
+    dZ.release();
+    return status;
+}
+
+}  // extern "C"

@@ -48,6 +48,17 @@ public:
         return hp;
     }
 
+    /// calc_filters (hashprint_handle.h:105-112): the 64 leading eigenvectors of `cov` as rows, descending eigenvalue.
+    /// Sign convention: the largest-magnitude component of every filter is positive (solvers differ in sign anyway).
+    static Filters calc_filters(device::Context &ctx, const CovarianceMatrix &cov) {
+        if (cov.rows() != static_cast<std::ptrdiff_t>(FrameSize) || cov.cols() != static_cast<std::ptrdiff_t>(FrameSize))
+            throw Error(HPFW_ERR_ARG, "covariance must be 2420 x 2420");
+        Filters f(NumOfFilters, FrameSize);
+        std::scoped_lock l(ctx.mutex());
+        device::check(hpfw_calc_filters(ctx.get(), cov.data(), f.data(), nullptr));
+        return f;
+    }
+
     /// Upload the learned filters (64 x 2420 column-major, as Filters stores them) to the device context.
     static void set_filters(device::Context &ctx, const Filters &filters) {
         if (filters.rows() != static_cast<std::ptrdiff_t>(NumOfFilters) ||

@@ -6,9 +6,11 @@
 //   prepare(files)        = per file: spectrogram (GPU), cache it (Cache::set_spectro, like :99), then hashprints of EVERY
 //                           cached spectrogram (collect_fingerprints, :115-137). Per-file errors are caught and logged and
 //                           the file is skipped (:101-103).
-// Filter learning (calc_cov / calc_filters, :92-97,:111) is index-time work outside this round's kernels:
-// prepare() uses the filters that load() found in the cache (cache/filters.cereal written by hpfw itself or by
-// set_filters()) and throws hpfw::Error(HPFW_ERR_STATE) when there are none.
+// Filter learning follows the reference too (:92-97,:111): every preprocessed spectrogram adds its frame covariance to
+// accum_cov (kept in HBM while prepare() runs; structured GEMM in learn.cu instead of the 2420 x 2420 x frames SYRK) and
+// filters = calc_filters(accum_cov) afterwards (GPU subspace iteration). As in the reference, accum_cov persists through
+// save()/load(), so it is cumulative across runs. calc_hashprint() before any filters exist throws
+// hpfw::Error(HPFW_ERR_STATE) (the reference would multiply by uninitialised memory).
 #pragma once
 
 #include <filesystem>
@@ -43,14 +45,7 @@ public:
 
     /// Process audio files and return {stem, hashprint} for every spectrogram in the cache (reference :48-52).
     std::vector<FilenameFingerprintPair> prepare(const std::vector<std::string> &filenames) {
-        require_filters();
-        for (const auto &filename : filenames) {
-            try {
-                cache.set_spectro(filename, algo.sh.spectrogram(filename));
-            } catch (const std::exception &e) {
-                std::cerr << "[hpfw] Error preprocessing '" << filename << "': " << e.what() << std::endl;
-            }
-        }
+        preprocess(filenames);
         save();
         return collect_fingerprints();
     }
@@ -100,11 +95,48 @@ private:
     std::shared_ptr<device::Context> ctx;
     bool have_filters = false, have_cov = false;
 
+    /// Spectrograms, covariance accumulation, filters (reference :82-112).
+    void preprocess(const std::vector<std::string> &filenames) {
+        size_t added = 0;
+        {
+            std::scoped_lock l(ctx->mutex());
+            if (have_cov) device::check(hpfw_cov_set(ctx->get(), accum_cov.data()));
+            else device::check(hpfw_cov_reset(ctx->get()));
+        }
+        for (const auto &filename : filenames) {
+            try {
+                const Spectrogram spectro = algo.sh.spectrogram(filename);
+                {
+                    std::scoped_lock l(ctx->mutex());
+                    device::check(hpfw_cov_add_spectrogram(ctx->get(), spectro.data(), static_cast<int>(spectro.cols())));
+                }
+                cache.set_spectro(filename, spectro);
+                ++added;
+            } catch (const std::exception &e) {
+                std::cerr << "[hpfw] Error preprocessing '" << filename << "': " << e.what() << std::endl;
+            }
+        }
+        if (added == 0 && !have_cov) {
+            if (have_filters) return;      // nothing new to learn from: keep the loaded filters
+            throw Error(HPFW_ERR_STATE, "prepare(): no readable audio file and no cached covariance to learn filters from");
+        }
+        accum_cov.resize(Algo::FrameSize, Algo::FrameSize);
+        Filters f(Algo::NumOfFilters, Algo::FrameSize);
+        {
+            std::scoped_lock l(ctx->mutex());
+            device::check(hpfw_cov_get(ctx->get(), accum_cov.data()));
+            // the reference divides by cache.size()+1 first (:111); a positive scale does not change the eigenvectors
+            device::check(hpfw_calc_filters(ctx->get(), nullptr, f.data(), nullptr));
+        }
+        have_cov = true;
+        set_filters(f);
+    }
+
     void require_filters() const {
         if (!have_filters)
             throw Error(HPFW_ERR_STATE,
-                        "no filters: load() found no cache/filters.cereal and set_filters() was not called "
-                        "(GPU filter learning is not part of this build)");
+                        "no filters: prepare() has not run, load() found no cache/filters.cereal and set_filters() was "
+                        "not called");
         // another collector may have re-programmed the shared context
         Algo::set_filters(*ctx, filters);
     }

@@ -142,6 +142,21 @@ int hpfw_hashprint_from_spectrogram_device(hpfw_ctx *ctx, const float *d_spectro
 /* diagnostic: the projection y = filters * frames itself (column-major float[64 x (cols-19)]), host buffers */
 int hpfw_project(hpfw_ctx *ctx, const float *spectrogram, int cols, float *y_out);
 
+/* ------------------------------------------------------------------------------ filter learning (index time, row a10) */
+/* HashprintHandle::calc_cov + the accumulate of ParallelCollector::preprocess (hashprint_handle.h:96-102,
+ * parallel_collector.h:92-97): the context keeps accum_cov (2420 x 2420 float) in HBM; each call adds the sample
+ * covariance of one spectrogram's context frames. */
+int hpfw_cov_reset(hpfw_ctx *ctx);
+int hpfw_cov_set(hpfw_ctx *ctx, const float *accum_2420x2420);     /* e.g. cache/accum_cov.cereal payload */
+int hpfw_cov_get(hpfw_ctx *ctx, float *accum_2420x2420);
+int hpfw_cov_add_spectrogram(hpfw_ctx *ctx, const float *spectrogram, int cols);                       /* host buffer */
+int hpfw_cov_add_spectrogram_device(hpfw_ctx *ctx, const float *d_spectrogram, int cols, void *stream);
+/* HashprintHandle::calc_filters (hashprint_handle.h:105-112): the 64 eigenvectors of the largest eigenvalues as rows of
+ * a column-major 64 x 2420 matrix, descending eigenvalue. cov = host 2420 x 2420 symmetric matrix, or NULL for the
+ * context's accumulator (any positive scale gives the same filters). Sign convention: the largest-magnitude component of
+ * every filter is positive. eigenvalues_out (64 floats) may be NULL. */
+int hpfw_calc_filters(hpfw_ctx *ctx, const float *cov, float *filters_out, float *eigenvalues_out);
+
 /* ------------------------------------------------------------------------------------------------- CQT (stage 1) */
 /* spectrogram columns for an n_samples-long buffer: M/3 + 1 (cqt.h:73); 0 if the design is degenerate */
 int hpfw_cqt_cols(int64_t n_samples);
