@@ -117,6 +117,13 @@ def test_live_id_example_config0(tmp_path, hashprint_golden):
     lines = [ln[3:].split() for ln in p.stdout.splitlines() if ln.startswith("=> ") and not ln.startswith("=> Finding")]
     results, summary = lines[:-1], lines[-1]
     assert len(results) == 10
+    # index() re-learns the filters from the indexed tracks, as the reference's prepare() does (parallel_collector.h:111):
+    # the oracle chain below uses the filters the run left in cache/filters.cereal
+    hdr = np.fromfile(tmp_path / "cache" / "filters.cereal", dtype=np.int32, count=2)
+    assert tuple(hdr) == (64, 2420)
+    learned = np.fromfile(tmp_path / "cache" / "filters.cereal", dtype=np.float32, offset=8).reshape(2420, 64)
+    assert not np.array_equal(learned, filt)
+    filt = learned
     # oracle chain on the same audio
     hps = [oracle.hashprint_from_spectrogram(nsgcq.spectrogram(t), filt) for t in tracks]
     words, offs = oracle.pack_db(hps)
