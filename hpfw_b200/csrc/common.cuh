@@ -82,6 +82,9 @@ struct PinnedBuffer {
 };
 
 struct CqtPlanCache;  // cqt.cu
+}  // namespace hpfw_b200
+#define HPFW_CTX_LANES 4
+namespace hpfw_b200 {
 
 }  // namespace hpfw_b200
 
@@ -112,6 +115,9 @@ struct hpfw_ctx {
 
     // cqt state
     hpfw_b200::CqtPlanCache *cqt = nullptr;
+    cudaStream_t lane_stream[HPFW_CTX_LANES] = {};   // batched extraction: concurrent tracks
+    cudaEvent_t lane_join[HPFW_CTX_LANES] = {};
+    cudaEvent_t lane_fork = nullptr;
     hpfw_b200::DeviceBuffer audio;
 
     // optional per-kernel device timing (CUDA events on the launching stream); see hpfw_ctx_timing_*

@@ -69,6 +69,11 @@ void hpfw_ctx_destroy(hpfw_ctx *c) {
         cudaEventDestroy(r.b);
     }
     for (auto e : c->timing_pool) cudaEventDestroy(e);
+    for (int l = 0; l < HPFW_CTX_LANES; ++l) {
+        if (c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]);
+        if (c->lane_join[l]) cudaEventDestroy(c->lane_join[l]);
+    }
+    if (c->lane_fork) cudaEventDestroy(c->lane_fork);
     if (c->pin_in_free) cudaEventDestroy(c->pin_in_free);
     cudaStreamDestroy(c->stream);
     delete c;

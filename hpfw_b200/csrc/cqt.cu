@@ -42,6 +42,7 @@ constexpr int CQ_MAX_ROW = 8192;      // longest shared-memory FFT (2 x 64 KB pi
 constexpr int CQ_MAXRAD = 14;
 constexpr int CQ_TW_S = 1024;         // two-level twiddle: W^m = hi[m / S] * lo[m % S]
 constexpr int CQ_THREADS = 256;
+constexpr int CQ_LANES = HPFW_CTX_LANES;   // concurrent tracks of a batch (streams + scratch sets)
 constexpr int CQ_FFT_THREADS = 512;   // shared-memory FFT kernels: 2 CTAs x 16 warps per SM
 
 struct FftDesc {
@@ -552,16 +553,36 @@ struct CqtPlan {
     int max_L2 = 0;
     long long work_elems = 0;
     int fpitch = 0;
-    // per-track scratch
-    DeviceBuffer zbuf, zlo, zhi, work, power, pmax;
+    // per-track scratch, one set per lane (tracks of a batch run concurrently on CQ_LANES streams)
+    struct Scratch {
+        DeviceBuffer zbuf, zlo, zhi, work, power, pmax;
+        bool ready = false;
+    } lanes[CQ_LANES];
     uint64_t last_use = 0;
+
+    int lane_reserve(int lane) {
+        Scratch &sc = lanes[lane];
+        if (sc.ready) return HPFW_OK;
+        const size_t nkeep = (size_t)(khi - klo + 1);
+        HPFW_TRY(sc.zbuf.reserve(sizeof(float2) * (size_t)H));
+        HPFW_TRY(sc.zlo.reserve(sizeof(float2) * nkeep));
+        HPFW_TRY(sc.zhi.reserve(sizeof(float2) * nkeep));
+        HPFW_TRY(sc.work.reserve(sizeof(float2) * (size_t)work_elems));
+        HPFW_TRY(sc.power.reserve(sizeof(float) * (size_t)CQ_BINS * fpitch));
+        HPFW_TRY(sc.pmax.reserve(sizeof(unsigned int)));
+        sc.ready = true;
+        return HPFW_OK;
+    }
 
     void release() {
         tw1.release(); tw2.release(); twH.release(); twN.release();
         d_bands.release(); d_btab_ptrs.release(); d_descs.release(); d_tw_ptrs.release();
         for (auto &b : btabs) b->release();
         for (auto &b : rowtws) b->release();
-        zbuf.release(); zlo.release(); zhi.release(); work.release(); power.release(); pmax.release();
+        for (auto &sc : lanes) {
+            sc.zbuf.release(); sc.zlo.release(); sc.zhi.release(); sc.work.release(); sc.power.release(); sc.pmax.release();
+            sc.ready = false;
+        }
     }
 };
 
@@ -749,15 +770,7 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
         d_fb.release();
     }
 
-    // per-track scratch
-    const size_t nkeep = (size_t)(pl.khi - pl.klo + 1);
-    HPFW_TRY(pl.zbuf.reserve(sizeof(float2) * (size_t)pl.H));
-    HPFW_TRY(pl.zlo.reserve(sizeof(float2) * nkeep));
-    HPFW_TRY(pl.zhi.reserve(sizeof(float2) * nkeep));
-    HPFW_TRY(pl.work.reserve(sizeof(float2) * (size_t)pl.work_elems));
-    HPFW_TRY(pl.power.reserve(sizeof(float) * (size_t)CQ_BINS * pl.fpitch));
-    HPFW_TRY(pl.pmax.reserve(sizeof(unsigned int)));
-    return HPFW_OK;
+    return pl.lane_reserve(0);
 }
 
 static int plan_get(hpfw_ctx *ctx, int64_t N, CqtPlan **out, cudaStream_t stream) {
@@ -787,34 +800,37 @@ static int plan_get(hpfw_ctx *ctx, int64_t N, CqtPlan **out, cudaStream_t stream
 }
 
 // mode 0: dB spectrogram; mode 1: linear magnitudes. d_audio must be 8-byte aligned.
-static int cqt_run(hpfw_ctx *ctx, const float *d_audio, int64_t N, float *d_out, int mode, cudaStream_t stream) {
+static int cqt_run(hpfw_ctx *ctx, const float *d_audio, int64_t N, float *d_out, int mode, cudaStream_t stream,
+                   int lane = 0) {
     if ((reinterpret_cast<uintptr_t>(d_audio) & 7) != 0)
         HPFW_FAIL(HPFW_ERR_ARG, "CQT: the audio buffer must be 8-byte aligned");
     CqtPlan *pl = nullptr;
     HPFW_TRY(plan_get(ctx, N, &pl, stream));
+    HPFW_TRY(pl->lane_reserve(lane));
+    CqtPlan::Scratch *sc = &pl->lanes[lane];
     const CqtDesign &d = pl->des;
     const int n1 = pl->d1.n, n2 = pl->d2.n;
     const float2 *z_in = reinterpret_cast<const float2 *>(d_audio);
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
         fft_cols_kernel<<<(n2 + pl->G1 - 1) / pl->G1, CQ_FFT_THREADS, pl->smem1, stream>>>(
-            z_in, pl->zbuf.as<float2>(), pl->d1, n2, pl->G1, pl->tw1.as<float2>(), pl->twH.hi.as<float2>(),
+            z_in, sc->zbuf.as<float2>(), pl->d1, n2, pl->G1, pl->tw1.as<float2>(), pl->twH.hi.as<float2>(),
             pl->twH.lo.as<float2>(), -1);
     }
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
         fft_rows_kernel<<<(n1 + pl->G2 - 1) / pl->G2, CQ_FFT_THREADS, pl->smem2, stream>>>(
-            pl->zbuf.as<float2>(), pl->zlo.as<float2>(), pl->zhi.as<float2>(), pl->d2, n1, pl->G2, pl->tw2.as<float2>(),
+            sc->zbuf.as<float2>(), sc->zlo.as<float2>(), sc->zhi.as<float2>(), pl->d2, n1, pl->G2, pl->tw2.as<float2>(),
             pl->klo, pl->khi, pl->H, 0, -1);
     }
-    HPFW_CUDA_TRY(cudaMemsetAsync(pl->pmax.ptr, 0, sizeof(unsigned int), stream));
+    HPFW_CUDA_TRY(cudaMemsetAsync(sc->pmax.ptr, 0, sizeof(unsigned int), stream));
     const dim3 gcol((pl->max_L2 + CQ_THREADS - 1) / CQ_THREADS, CQ_BINS);
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
-        czt_cols_kernel<0><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands.as<BandMeta>(), pl->zlo.as<float2>(),
-                                                             pl->zhi.as<float2>(), pl->klo, pl->khi,
+        czt_cols_kernel<0><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands.as<BandMeta>(), sc->zlo.as<float2>(),
+                                                             sc->zhi.as<float2>(), pl->klo, pl->khi,
                                                              pl->twN.hi.as<float2>(), pl->twN.lo.as<float2>(), d.M, d.F,
-                                                             pl->work.as<float2>());
+                                                             sc->work.as<float2>());
     }
     // one launch per run of bands with the same chirp length, so that short rows do not reserve the longest row's shared memory
     for (int j0 = 0; j0 < CQ_BINS;) {
@@ -822,24 +838,24 @@ static int cqt_run(hpfw_ctx *ctx, const float *d_audio, int64_t N, float *d_out,
         while (j1 < CQ_BINS && pl->bands[j1].L == pl->bands[j0].L) ++j1;
         KernelScope ks(ctx, HPFW_K_CQT, stream);
         czt_rows_kernel<0><<<dim3(CQ_L1, j1 - j0), CQ_THREADS, 24 * (size_t)pl->bands[j0].L2, stream>>>(
-            pl->d_bands.as<BandMeta>() + j0, pl->work.as<float2>(), pl->d_btab_ptrs.as<const float2 *>(),
+            pl->d_bands.as<BandMeta>() + j0, sc->work.as<float2>(), pl->d_btab_ptrs.as<const float2 *>(),
             pl->d_descs.as<FftDesc>(), pl->d_tw_ptrs.as<const float2 *>());
         j0 = j1;
     }
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
-        czt_out_kernel<<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands.as<BandMeta>(), pl->work.as<float2>(), d.M, d.F,
-                                                         pl->fpitch, pl->power.as<float>(),
-                                                         pl->pmax.as<unsigned int>());
+        czt_out_kernel<<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands.as<BandMeta>(), sc->work.as<float2>(), d.M, d.F,
+                                                         pl->fpitch, sc->power.as<float>(),
+                                                         sc->pmax.as<unsigned int>());
     }
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
         const int gb = (d.cols + 31) / 32;
         if (mode == 0)
-            db_kernel<0><<<gb, CQ_THREADS, 0, stream>>>(pl->power.as<float>(), pl->pmax.as<unsigned int>(), d.F, d.cols,
+            db_kernel<0><<<gb, CQ_THREADS, 0, stream>>>(sc->power.as<float>(), sc->pmax.as<unsigned int>(), d.F, d.cols,
                                                          pl->fpitch, d_out);
         else
-            db_kernel<1><<<gb, CQ_THREADS, 0, stream>>>(pl->power.as<float>(), pl->pmax.as<unsigned int>(), d.F, d.cols,
+            db_kernel<1><<<gb, CQ_THREADS, 0, stream>>>(sc->power.as<float>(), sc->pmax.as<unsigned int>(), d.F, d.cols,
                                                          pl->fpitch, d_out);
     }
     HPFW_CUDA_TRY(cudaGetLastError());
@@ -886,6 +902,16 @@ static int fft_c2c_device(hpfw_ctx *ctx, const float2 *d_in, float2 *d_out, int 
 }  // namespace hpfw_b200
 
 using namespace hpfw_b200;
+
+static int lanes_init(hpfw_ctx *ctx) {
+    if (ctx->lane_fork) return HPFW_OK;
+    for (int l = 0; l < HPFW_CTX_LANES; ++l) {
+        HPFW_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking));
+        HPFW_CUDA_TRY(cudaEventCreateWithFlags(&ctx->lane_join[l], cudaEventDisableTiming));
+    }
+    HPFW_CUDA_TRY(cudaEventCreateWithFlags(&ctx->lane_fork, cudaEventDisableTiming));
+    return HPFW_OK;
+}
 
 extern "C" {
 
@@ -998,9 +1024,21 @@ int hpfw_calc_hashprint_audio_batch_device(hpfw_ctx *ctx, const float *d_audio, 
             ++j;
         }
         HPFW_TRY(ctx->spectro.reserve(sizeof(float) * size_t(co.back()) * CQ_BINS));
-        for (int t = i; t < j; ++t)
+        // fork: the tracks of the chunk run round-robin on CQ_LANES streams (own scratch each) so that the small tail waves
+        // of one track's kernels overlap another track's; join before the chunk's single projection launch
+        HPFW_TRY(lanes_init(ctx));
+        const int nl = std::min(CQ_LANES, j - i);
+        HPFW_CUDA_TRY(cudaEventRecord(ctx->lane_fork, s));
+        for (int l = 0; l < nl; ++l) HPFW_CUDA_TRY(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->lane_fork, 0));
+        for (int t = i; t < j; ++t) {
+            const int l = (t - i) % nl;
             HPFW_TRY(cqt_run(ctx, d_audio + sample_offsets[t], sample_offsets[t + 1] - sample_offsets[t],
-                             ctx->spectro.as<float>() + size_t(co[t - i]) * CQ_BINS, 0, s));
+                             ctx->spectro.as<float>() + size_t(co[t - i]) * CQ_BINS, 0, ctx->lane_stream[l], l));
+        }
+        for (int l = 0; l < nl; ++l) {
+            HPFW_CUDA_TRY(cudaEventRecord(ctx->lane_join[l], ctx->lane_stream[l]));
+            HPFW_CUDA_TRY(cudaStreamWaitEvent(s, ctx->lane_join[l], 0));
+        }
         HPFW_TRY(hpfw_hashprint_from_spectrogram_device(ctx, ctx->spectro.as<float>(), co.data(), j - i, d_hp_out + hp_off, s));
         for (int t = i; t < j; ++t) hp_off += hpfw_hashprint_words_for_cols(int(co[t - i + 1] - co[t - i]));
         i = j;
