@@ -127,7 +127,7 @@ cov_finish_kernel(const float *__restrict__ Sc, int nf, const float *__restrict_
     const float inv_nf = 1.0f / (float)nf, inv_nm1 = 1.0f / (float)(nf - 1);
     for (int c = 0; c + d < LN_CTX; ++c) {
         const float mi = si * inv_nf, mj = sj * inv_nf;
-        const float cov = (g - (float)nf * mi * mj) * inv_nm1;
+        const float cov = (g - (float)nf * (mi * mj)) * inv_nm1;   // (mi * mj) first: bit-identical for (i,j) and (j,i)
         const int i = b * LN_CTX + c, j = bp * LN_CTX + c + d;
         accum[(size_t)i + (size_t)LN_FS * j] += cov;
         if (d > 0) accum[(size_t)j + (size_t)LN_FS * i] += cov;

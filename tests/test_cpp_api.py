@@ -162,10 +162,16 @@ def test_pyhpfw_wrapper_matches_cpp_path(tmp_path, hashprint_golden):
     pc.load(cache)
     hp = pc.calc_hashprint(str(tmp_path / "a.wav"))
     assert hp.dtype == np.uint64 and len(hp) == 385
-    got = pc.prepare([str(tmp_path / "a.wav"), str(tmp_path / "missing.wav")])     # unreadable file is skipped
-    assert len(got) == 1 and got[0][0] == "a" and np.array_equal(got[0][1], hp)
     import oracle
     from oracle import nsgcq
     ref = oracle.hashprint_from_spectrogram(nsgcq.spectrogram(a), hashprint_golden["filters"])
     diff = int(np.unpackbits((hp ^ ref).view(np.uint8)).sum())
     assert diff <= 1e-3 * 64 * len(ref)
+    # prepare() re-learns the filters from the indexed files (parallel_collector.h:111) and saves them
+    got = pc.prepare([str(tmp_path / "a.wav"), str(tmp_path / "missing.wav")])     # unreadable file is skipped
+    assert len(got) == 1 and got[0][0] == "a" and len(got[0][1]) == 385
+    assert np.array_equal(pc.calc_hashprint(str(tmp_path / "a.wav")), got[0][1])
+    learned = np.fromfile(cache + "filters.cereal", dtype=np.float32, offset=8).reshape(2420, 64)
+    ref2 = oracle.hashprint_from_spectrogram(nsgcq.spectrogram(a), learned)
+    diff2 = int(np.unpackbits((got[0][1] ^ ref2).view(np.uint8)).sum())
+    assert diff2 <= 1e-3 * 64 * len(ref2)
