@@ -51,6 +51,7 @@ _SIGS = {
     "hpfw_hashprint_from_spectrogram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     "hpfw_hashprint_from_spectrogram_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                                          C.c_void_p]),
+    "hpfw_set_projection_impl": (C.c_int, [C.c_void_p, C.c_int]),
     "hpfw_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "hpfw_cov_reset": (C.c_int, [C.c_void_p]),
     "hpfw_cov_set": (C.c_int, [C.c_void_p, C.c_void_p]),

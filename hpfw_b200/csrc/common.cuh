@@ -108,6 +108,8 @@ struct hpfw_ctx {
     std::vector<float> filters_host;       // column-major 64 x 2420 as given
     bool have_filters = false;
     hpfw_b200::DeviceBuffer spectro, hp, yproj, colmeta;
+    hpfw_b200::DeviceBuffer filters_tc, delta_tc;   // project_tc.cu: tf32 filters [tap][filter][band], differenced spectrogram
+    int project_impl = 0;                           // 0 = CUDA-core kernel, 1 = tcgen05 (one A block), 2 = tcgen05 (A per tap)
 
     // filter learning (learn.cu): device-resident covariance accumulator (2420 x 2420) and scratch
     hpfw_b200::DeviceBuffer cov_accum, cov_scratch;
@@ -145,6 +147,9 @@ struct DeviceGuard {
     }
 };
 void cqt_cache_destroy(CqtPlanCache *);
+int project_tc_set_filters(hpfw_ctx *ctx, const float *filters_colmajor);
+int project_tc_run(hpfw_ctx *ctx, int impl, const float *d_spectro, const int64_t *col_offsets, int n, uint64_t *d_hp,
+                   cudaStream_t stream);
 
 // Scope guard around ONE kernel launch: counts it and, when timing is enabled, brackets it with two events.
 struct KernelScope {

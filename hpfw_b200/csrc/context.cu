@@ -60,6 +60,8 @@ void hpfw_ctx_destroy(hpfw_ctx *c) {
     c->hp.release();
     c->yproj.release();
     c->colmeta.release();
+    c->filters_tc.release();
+    c->delta_tc.release();
     c->audio.release();
     c->cov_accum.release();
     c->cov_scratch.release();

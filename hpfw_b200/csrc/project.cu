@@ -223,6 +223,7 @@ int hpfw_set_filters(hpfw_ctx *ctx, const float *f) {
                     perm[((size_t(b) * 4 + j) * 16 + fgi) * PJ_CTX + c] = f[(fgi * 4 + j) + size_t(PJ_NF) * (b * PJ_CTX + c)];
     HPFW_TRY(ctx->filters_perm.reserve(sizeof(float) * perm.size()));
     HPFW_CUDA_TRY(cudaMemcpy(ctx->filters_perm.ptr, perm.data(), sizeof(float) * perm.size(), cudaMemcpyHostToDevice));
+    HPFW_TRY(project_tc_set_filters(ctx, f));
     ctx->have_filters = true;
     return HPFW_OK;
 }
@@ -242,7 +243,16 @@ int hpfw_hashprint_from_spectrogram_device(hpfw_ctx *ctx, const float *d_spectro
     if (n == 0) return HPFW_OK;
     if (!d_spectrograms || !d_hp_out) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_hashprint_from_spectrogram_device: NULL buffer");
     DeviceGuard g(ctx->device);
+    if (!ctx->have_filters) HPFW_FAIL(HPFW_ERR_STATE, "filters not set: call hpfw_set_filters first");
+    if (ctx->project_impl != 0)
+        return project_tc_run(ctx, ctx->project_impl, d_spectrograms, col_offsets, n, d_hp_out, ctx->pick(stream));
     return run_project(ctx, 0, d_spectrograms, col_offsets, n, d_hp_out, nullptr, ctx->pick(stream));
+}
+
+int hpfw_set_projection_impl(hpfw_ctx *ctx, int impl) {
+    if (!ctx || impl < 0 || impl > 2) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_set_projection_impl: impl must be 0, 1 or 2");
+    ctx->project_impl = impl;
+    return HPFW_OK;
 }
 
 int hpfw_hashprint_from_spectrogram(hpfw_ctx *ctx, const float *spectrogram, int cols, uint64_t *hp_out, int *n_out) {
@@ -257,7 +267,7 @@ int hpfw_hashprint_from_spectrogram(hpfw_ctx *ctx, const float *spectrogram, int
     HPFW_TRY(ctx->hp.reserve(sizeof(uint64_t) * size_t(n)));
     HPFW_CUDA_TRY(cudaMemcpyAsync(ctx->spectro.ptr, spectrogram, sb, cudaMemcpyHostToDevice, ctx->stream));
     const int64_t co[2] = {0, cols};
-    HPFW_TRY(run_project(ctx, 0, ctx->spectro.as<float>(), co, 1, ctx->hp.as<uint64_t>(), nullptr, ctx->stream));
+    HPFW_TRY(hpfw_hashprint_from_spectrogram_device(ctx, ctx->spectro.as<float>(), co, 1, ctx->hp.as<uint64_t>(), ctx->stream));
     HPFW_CUDA_TRY(cudaMemcpyAsync(hp_out, ctx->hp.ptr, sizeof(uint64_t) * size_t(n), cudaMemcpyDeviceToHost, ctx->stream));
     HPFW_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     *n_out = n;

@@ -1,0 +1,356 @@
+// hpfw_b200/csrc/project_tc.cu — stages 2+3 on the 5th-generation tensor cores (tcgen05, TMEM accumulator, TMA-fed).
+//
+// Same computation as project.cu (HashprintHandle::calc_frames + `filters * frames` + calc_fingerprint +
+// fingerprint_to_hashprint, /root/reference/include/hpfw/core/hashprint_handle.h:79-142, parallel_collector.h:57):
+//
+//   hp[t] bit (63-f) = [ sum_{c<20} sum_{b<121} F[f, b*20+c] * (S[b,t+c] - S[b,t+80+c]) >= 0 ]
+//
+// as an implicit GEMM: per 128-frame tile D[128 x 64] = sum_c A_c[128 x 128] * B_c[64 x 128]^T with
+//   A_c[t, b] = Dd[t0+t+c][b]     Dd = tf32(S[t] - S[t+80]), bands padded 121 -> 128 (a pre-pass writes it once, 512 B/row)
+//   B_c[f, b] = tf32(F[f, b*20+c]) (permuted once in hpfw_set_filters)
+// K = 20 taps x 128 bands, split in 32-band (128-byte) swizzle atoms: 80 x 4 tcgen05.mma.kind::tf32 (M128 N64 K8) per tile.
+//
+// The context window makes the 20 A_c tiles overlapping row windows of ONE [147 x 128] block, so the block is loaded once by
+// TMA (4 boxes of 152 rows x 128 B, SWIZZLE_128B) and tap c is addressed by advancing the shared-memory descriptor's start
+// address by c rows (c * 128 B): TMA and the MMA both derive the 128-byte swizzle phase from the shared-memory address
+// bits, so a row-offset start stays consistent with how the block was written. (impl 2 = conservative variant that
+// reloads the [128 x 128] window per tap; both are tested against the CUDA-core kernel and the oracle.)
+// B_c streams through a 3-stage TMA/mbarrier ring. The epilogue reads the TMEM accumulator with tcgen05.ld (one frame per
+// thread, 64 filters in registers), thresholds and packs the 64-bit word.
+#include "common.cuh"
+
+#include <cuda.h>
+
+#include <cstring>
+
+namespace hpfw_b200 {
+
+constexpr int TC_BINS = HPFW_BINS;       // 121
+constexpr int TC_BPAD = 128;             // bands padded
+constexpr int TC_CTX = HPFW_CONTEXT;     // 20
+constexpr int TC_LAG = HPFW_LAG;         // 80
+constexpr int TC_NF = HPFW_NFILTERS;     // 64
+constexpr int TC_M = 128;                // frames per tile
+constexpr int TC_AROWS = 152;            // 128 + 19 rounded up to a multiple of 8
+constexpr int TC_KB = 4;                 // 32-band swizzle atoms per tap
+constexpr int TC_STAGES_1 = 3;          // B ring depth, impl 1
+constexpr int TC_STAGES_2 = 2;          // A+B ring depth, impl 2 (96 KB per stage)
+constexpr uint32_t TC_A_ATOM_BYTES = TC_AROWS * 128;        // 19,456
+constexpr uint32_t TC_A1_ATOM_BYTES = TC_M * 128;           // 16,384 (impl 2)
+constexpr uint32_t TC_B_ATOM_BYTES = TC_NF * 128;           // 8,192
+constexpr uint32_t TC_B_STAGE_BYTES = TC_KB * TC_B_ATOM_BYTES;   // 32,768
+constexpr uint32_t TC_TMEM_COLS = 64;
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=b=TF32 [7,10)/[10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_NF >> 3) << 17) | ((TC_M >> 4) << 24);
+
+struct TcTile {
+    int32_t track;
+    int32_t t0;
+};
+struct TcTrack {
+    int64_t row_base;    // first row of this track in the concatenated Dd matrix
+    int64_t out_start;
+    int32_t n_out;       // hashprint words
+    int32_t pad;
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug must surface as a launch failure (trap), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+        if (spin > (1u << 24)) __trap();
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30) = 1,
+// SBO>>4 [32,46) = 1024 B between 8-row groups, version 1 [46,48), layout type 2 [61,64)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ---- pre-pass: Dd[row][b] = tf32(S[t][b] - S[t+80][b]), bands 121..127 = 0 ------------------------------------------------
+__global__ void __launch_bounds__(256)
+tc_delta_kernel(const float *__restrict__ spectro, const int64_t *__restrict__ col_start, const int64_t *__restrict__ row_base,
+                const int32_t *__restrict__ rows, int n_tracks, float *__restrict__ dd) {
+    const int trk = blockIdx.y;
+    const int nr = rows[trk];
+    const float *S = spectro + col_start[trk] * TC_BINS;
+    float *D = dd + row_base[trk] * TC_BPAD;
+    const int64_t total = (int64_t)nr * TC_BPAD;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = i >> 7;
+        const int b = (int)(i & 127);
+        float v = 0.f;
+        if (b < TC_BINS) v = S[t * TC_BINS + b] - S[(t + TC_LAG) * TC_BINS + b];
+        uint32_t r;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+        D[i] = __uint_as_float(r);
+    }
+}
+
+// ---- main kernel ------------------------------------------------------------------------------------------------------------
+template <int IMPL>   // 1: one A block + row-offset descriptors; 2: A window reloaded per tap
+__global__ void __launch_bounds__(128, 1)
+project_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const TcTile *__restrict__ tiles, const TcTrack *__restrict__ tracks, uint64_t *__restrict__ hp_out) {
+    extern __shared__ uint8_t tsm_raw[];
+    // SWIZZLE_128B atoms must sit on 1024-byte boundaries: align the dynamic region by hand (1 KB of slack is allocated)
+    uint8_t *tsm = tsm_raw + ((1024u - (smem_u32(tsm_raw) & 1023u)) & 1023u);
+    // carve: [A region][B stages], every atom a multiple of 1024 bytes
+    constexpr int TC_STAGES = (IMPL == 1) ? TC_STAGES_1 : TC_STAGES_2;
+    constexpr uint32_t A_BYTES = (IMPL == 1) ? TC_KB * TC_A_ATOM_BYTES : TC_STAGES * TC_KB * TC_A1_ATOM_BYTES;
+    uint8_t *smA = tsm;
+    uint8_t *smB = tsm + A_BYTES;
+    __shared__ __align__(8) uint64_t bar_a, bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_acc;
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const TcTile tile = tiles[blockIdx.x];
+    const TcTrack trk = tracks[tile.track];
+    const int row0 = (int)(trk.row_base + tile.t0);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x == 32) {
+        mbar_init(&bar_a, 1);
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_empty[s], 1);
+        }
+        mbar_init(&bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        if (IMPL == 1) {
+            mbar_expect_tx(&bar_a, TC_KB * TC_A_ATOM_BYTES);
+            for (int kb = 0; kb < TC_KB; ++kb) tma_load_2d(&tmA, &bar_a, smA + kb * TC_A_ATOM_BYTES, kb * 32, row0);
+        }
+        for (int c = 0; c < TC_CTX; ++c) {
+            const int s = c % TC_STAGES;
+            if (c >= TC_STAGES) mbar_wait(&bar_empty[s], ((c / TC_STAGES) - 1) & 1);
+            mbar_expect_tx(&bar_full[s], TC_B_STAGE_BYTES + (IMPL == 2 ? TC_KB * TC_A1_ATOM_BYTES : 0));
+            for (int kb = 0; kb < TC_KB; ++kb)
+                tma_load_2d(&tmB, &bar_full[s], smB + s * TC_B_STAGE_BYTES + kb * TC_B_ATOM_BYTES, kb * 32, c * TC_NF);
+            if (IMPL == 2)
+                for (int kb = 0; kb < TC_KB; ++kb)
+                    tma_load_2d(&tmA, &bar_full[s], smA + (s * TC_KB + kb) * TC_A1_ATOM_BYTES, kb * 32, row0 + c);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        if (IMPL == 1) mbar_wait(&bar_a, 0);
+        uint32_t acc = 0;
+        for (int c = 0; c < TC_CTX; ++c) {
+            const int s = c % TC_STAGES;
+            mbar_wait(&bar_full[s], (c / TC_STAGES) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int kb = 0; kb < TC_KB; ++kb) {
+                const uint32_t a_addr = (IMPL == 1) ? smem_u32(smA + kb * TC_A_ATOM_BYTES) + c * 128
+                                                    : smem_u32(smA + (s * TC_KB + kb) * TC_A1_ATOM_BYTES);
+                const uint32_t b_addr = smem_u32(smB + s * TC_B_STAGE_BYTES + kb * TC_B_ATOM_BYTES);
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {     // 8 tf32 = 32 bytes per MMA along K inside the 128-byte atom
+                    tc_mma_tf32(tmem_base, smem_desc_sw128(a_addr + k4 * 32), smem_desc_sw128(b_addr + k4 * 32), TC_IDESC, acc);
+                    acc = 1;
+                }
+            }
+            tc_commit(&bar_empty[s]);     // arrives when the MMAs above have finished reading this stage
+        }
+        tc_commit(&bar_acc);              // accumulator complete
+    }
+
+    // ===== epilogue: all four warps; warp w owns TMEM lanes (= frames) 32w .. 32w+31 =====
+    mbar_wait(&bar_acc, 0);
+    tc_fence_after();
+    uint32_t v[64];
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]),
+          "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]),
+          "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]),
+          "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]),
+          "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    uint64_t word = 0;
+#pragma unroll
+    for (int f = 0; f < 64; ++f) word |= (uint64_t)(__uint_as_float(v[f]) >= 0.f ? 1u : 0u) << (63 - f);
+    const int t = tile.t0 + warp * 32 + lane;
+    if (t < trk.n_out) hp_out[trk.out_start + t] = word;
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+static int make_map_2d(CUtensorMap *map, const void *base, uint64_t rows, uint32_t box_rows) {
+    // row-major [rows][128] float: dim0 = 128 bands (contiguous), dim1 = rows, pitch 512 B; box = 32 bands x box_rows rows
+    const cuuint64_t dims[2] = {TC_BPAD, rows};
+    const cuuint64_t strides[1] = {TC_BPAD * sizeof(float)};
+    const cuuint32_t box[2] = {32, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    // the driver entry point is resolved through the runtime so that the library does not link libcuda.so (it must load,
+    // and fail loudly, on machines without a driver)
+    typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiled encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        HPFW_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) HPFW_FAIL(HPFW_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+        encode = reinterpret_cast<EncodeTiled>(fn);
+    }
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) HPFW_FAIL(HPFW_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return HPFW_OK;
+}
+
+// filters (column-major 64 x 2420, row index b*20+c) -> tf32 [c][f][b padded to 128]
+int project_tc_set_filters(hpfw_ctx *ctx, const float *f) {
+    std::vector<float> perm((size_t)TC_CTX * TC_NF * TC_BPAD, 0.f);
+    for (int c = 0; c < TC_CTX; ++c)
+        for (int fi = 0; fi < TC_NF; ++fi)
+            for (int b = 0; b < TC_BINS; ++b) {
+                float v = f[fi + (size_t)TC_NF * (b * TC_CTX + c)];
+                uint32_t u;
+                memcpy(&u, &v, 4);
+                // round to nearest, ties away (cvt.rna.tf32): keep 10 mantissa bits
+                if ((u & 0x7F800000u) != 0x7F800000u) u = (u + 0x1000u) & 0xFFFFE000u;
+                memcpy(&v, &u, 4);
+                perm[((size_t)c * TC_NF + fi) * TC_BPAD + b] = v;
+            }
+    HPFW_TRY(ctx->filters_tc.reserve(sizeof(float) * perm.size()));
+    HPFW_CUDA_TRY(cudaMemcpy(ctx->filters_tc.ptr, perm.data(), sizeof(float) * perm.size(), cudaMemcpyHostToDevice));
+    return HPFW_OK;
+}
+
+int project_tc_run(hpfw_ctx *ctx, int impl, const float *d_spectro, const int64_t *col_offsets, int n, uint64_t *d_hp,
+                   cudaStream_t stream) {
+    std::vector<TcTrack> tracks((size_t)std::max(n, 1));
+    std::vector<TcTile> tiles;
+    std::vector<int64_t> col_start((size_t)n), row_base((size_t)n);
+    std::vector<int32_t> rows((size_t)n);
+    int64_t out = 0, rb = 0;
+    int max_rows = 0;
+    for (int i = 0; i < n; ++i) {
+        const int64_t cols = col_offsets[i + 1] - col_offsets[i];
+        if (cols < 0 || cols > (int64_t(1) << 30)) HPFW_FAIL(HPFW_ERR_ARG, "bad column count for spectrogram %d", i);
+        const int64_t n_out = std::max<int64_t>(0, cols - (TC_CTX - 1) - TC_LAG);
+        const int64_t nr = n_out > 0 ? cols - TC_LAG : 0;       // rows of Dd this track needs: n_out + 19
+        col_start[i] = col_offsets[i];
+        row_base[i] = rb;
+        rows[i] = (int32_t)nr;
+        tracks[i] = {rb, out, (int32_t)n_out, 0};
+        for (int64_t t0 = 0; t0 < n_out; t0 += TC_M) tiles.push_back({i, (int32_t)t0});
+        out += n_out;
+        rb += nr;
+        max_rows = std::max<int>(max_rows, (int)nr);
+    }
+    if (tiles.empty()) return HPFW_OK;
+    // device metadata
+    const size_t b_tracks = sizeof(TcTrack) * tracks.size(), b_tiles = sizeof(TcTile) * tiles.size();
+    const size_t b_i64 = sizeof(int64_t) * (size_t)n, b_i32 = sizeof(int32_t) * (size_t)n;
+    const size_t o_tiles = b_tracks, o_cs = o_tiles + ((b_tiles + 7) & ~size_t(7)), o_rb = o_cs + b_i64, o_rows = o_rb + b_i64;
+    const size_t total = o_rows + b_i32;
+    HPFW_CUDA_TRY(cudaEventSynchronize(ctx->pin_in_free));
+    HPFW_TRY(ctx->pin_in.reserve(total));
+    HPFW_TRY(ctx->colmeta.reserve(total));
+    char *h = ctx->pin_in.as<char>();
+    memcpy(h, tracks.data(), b_tracks);
+    memcpy(h + o_tiles, tiles.data(), b_tiles);
+    memcpy(h + o_cs, col_start.data(), b_i64);
+    memcpy(h + o_rb, row_base.data(), b_i64);
+    memcpy(h + o_rows, rows.data(), b_i32);
+    HPFW_CUDA_TRY(cudaMemcpyAsync(ctx->colmeta.ptr, h, total, cudaMemcpyHostToDevice, stream));
+    HPFW_CUDA_TRY(cudaEventRecord(ctx->pin_in_free, stream));
+    const char *dm = ctx->colmeta.as<char>();
+    // at least one TMA box of rows (rows past the last track are never part of a stored frame)
+    const uint64_t map_rows = std::max<uint64_t>((uint64_t)rb, 256);
+    HPFW_TRY(ctx->delta_tc.reserve(sizeof(float) * (size_t)map_rows * TC_BPAD));
+    {
+        KernelScope ks(ctx, HPFW_K_PROJECT, stream);
+        const int gx = std::max(1, std::min(64, (max_rows * TC_BPAD + 256 * 8 - 1) / (256 * 8)));
+        tc_delta_kernel<<<dim3(gx, n), 256, 0, stream>>>(d_spectro, reinterpret_cast<const int64_t *>(dm + o_cs),
+                                                         reinterpret_cast<const int64_t *>(dm + o_rb),
+                                                         reinterpret_cast<const int32_t *>(dm + o_rows), n,
+                                                         ctx->delta_tc.as<float>());
+    }
+    CUtensorMap tmA, tmB;
+    HPFW_TRY(make_map_2d(&tmA, ctx->delta_tc.ptr, map_rows, impl == 1 ? TC_AROWS : TC_M));
+    HPFW_TRY(make_map_2d(&tmB, ctx->filters_tc.ptr, (uint64_t)TC_CTX * TC_NF, TC_NF));
+    const size_t smem1 = TC_KB * TC_A_ATOM_BYTES + TC_STAGES_1 * TC_B_STAGE_BYTES + 1024;
+    const size_t smem2 = TC_STAGES_2 * TC_KB * TC_A1_ATOM_BYTES + TC_STAGES_2 * TC_B_STAGE_BYTES + 1024;
+    {
+        KernelScope ks(ctx, HPFW_K_PROJECT, stream);
+        if (impl == 1) {
+            HPFW_CUDA_TRY(cudaFuncSetAttribute(project_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+            project_tc_kernel<1><<<(unsigned)tiles.size(), 128, smem1, stream>>>(
+                tmA, tmB, reinterpret_cast<const TcTile *>(dm + o_tiles), reinterpret_cast<const TcTrack *>(dm), d_hp);
+        } else {
+            HPFW_CUDA_TRY(cudaFuncSetAttribute(project_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            project_tc_kernel<2><<<(unsigned)tiles.size(), 128, smem2, stream>>>(
+                tmA, tmB, reinterpret_cast<const TcTile *>(dm + o_tiles), reinterpret_cast<const TcTrack *>(dm), d_hp);
+        }
+    }
+    HPFW_CUDA_TRY(cudaGetLastError());
+    return HPFW_OK;
+}
+
+}  // namespace hpfw_b200
