@@ -333,10 +333,13 @@ def run_extraction(args, ctx, rank, world, dev, max_over_ranks, barrier):
         hbm, sm_max, src = 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
     # tracks of a batch run concurrently on 4 streams, so the summed kernel durations overlap: the CQT stage time per track is
     # the step time minus the (serial) projection launches
+    try:
+        tf32_peak = float(pk["bf16_tflops_sustained"]) / 2.0
+        tf32_src = "half of the measured sustained bf16 cuBLAS rate (MEASURED_PEAKS.json): tf32 dense = bf16 / 2"
+    except (NameError, KeyError, ValueError):
+        tf32_peak, tf32_src = 1590.0 / 2.0, "half of the fallback bf16 rate (B200_PROFILING.md)"
     cq_per_track = max(1e-6, (ms * reps - pj_ms) / max(1, per_rank * reps))
     cq_kernel_sum_per_track = cq_ms / max(1, per_rank * reps)
-    pj_per_launch = pj_ms / max(1, pj_n)
-    tracks_per_pj = per_rank * reps / max(1, pj_n)
     cqt_bytes = 4.0 * n + 4.0 * 121 * cols
     out = {
         "metric": "hashprint_frames_per_sec", "value": value, "unit": "frames/s",
@@ -351,11 +354,11 @@ def run_extraction(args, ctx, rank, world, dev, max_over_ranks, barrier):
                      "ms_per_track": cq_per_track, "kernel_ms_sum_per_track_overlapped": cq_kernel_sum_per_track,
                      "peak_how": src,
                      "algorithmic_bytes_per_track": cqt_bytes},
-        "roofline_projection": {"bound": "fp32 fma (CUDA cores)", "kernel": "project_kernel<0>",
-                                "achieved": 2.0 * 64 * 2420 * frames * tracks_per_pj / (pj_per_launch * 1e-3) / 1e12,
-                                "peak": sms * 128 * 2 * sm_max * 1e6 / 1e12, "unit": "TFLOP/s",
-                                "avg_launch_ms": pj_per_launch,
-                                "peak_how": f"{sms} SMs x 128 FFMA/clk x 2 x {sm_max:.0f} MHz"},
+        "roofline_projection": {"bound": "tensor", "kernel": "project_tc_kernel<1> (tcgen05 kind::tf32, + tc_delta_kernel pre-pass)",
+                                "achieved": 2.0 * 64 * 2420 * frames * per_rank * reps / (pj_ms * 1e-3) / 1e12,
+                                "peak": tf32_peak, "unit": "TFLOP/s",
+                                "ms_per_track": pj_ms / max(1, per_rank * reps), "launches": pj_n,
+                                "peak_how": tf32_src},
     }
     out["roofline_projection"]["frac"] = out["roofline_projection"]["achieved"] / out["roofline_projection"]["peak"]
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

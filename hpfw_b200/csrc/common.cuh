@@ -109,7 +109,7 @@ struct hpfw_ctx {
     bool have_filters = false;
     hpfw_b200::DeviceBuffer spectro, hp, yproj, colmeta;
     hpfw_b200::DeviceBuffer filters_tc, delta_tc;   // project_tc.cu: tf32 filters [tap][filter][band], differenced spectrogram
-    int project_impl = 0;                           // 0 = CUDA-core kernel, 1 = tcgen05 (one A block), 2 = tcgen05 (A per tap)
+    int project_impl = 1;                           // 1 = tcgen05 (one A block, default), 2 = tcgen05 (A per tap), 0 = CUDA-core kernel
 
     // filter learning (learn.cu): device-resident covariance accumulator (2420 x 2420) and scratch
     hpfw_b200::DeviceBuffer cov_accum, cov_scratch;

@@ -13,6 +13,14 @@ from hpfw_b200.api import stream_arg
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _cuda_core_kernel(ctx):
+    """This file pins the fp32 CUDA-core kernel (impl 0); the default tcgen05 kernel is covered by test_project_tc_gpu.py."""
+    check(ctx._lib.hpfw_set_projection_impl(ctx.handle, 0))
+    yield
+    check(ctx._lib.hpfw_set_projection_impl(ctx.handle, 1))
+
+
 def _set_filters(ctx, filt):
     f = np.ascontiguousarray(filt, dtype=np.float32)
     check(ctx._lib.hpfw_set_filters(ctx.handle, f.ctypes.data_as(C.c_void_p)))

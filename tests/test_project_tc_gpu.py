@@ -24,7 +24,7 @@ def ex(ctx, hashprint_golden):
     e = HashprintExtractor(ctx)
     e.set_filters(hashprint_golden["filters"])
     yield e
-    check(ctx._lib.hpfw_set_projection_impl(ctx.handle, 0))
+    check(ctx._lib.hpfw_set_projection_impl(ctx.handle, 1))
 
 
 @pytest.mark.parametrize("impl", [2, 1])
@@ -65,7 +65,7 @@ def test_tc_bit_order_single_tap_filters(ctx, impl):
     try:
         hp = e.hashprint_from_spectrogram(spec)
     finally:
-        check(ctx._lib.hpfw_set_projection_impl(ctx.handle, 0))
+        check(ctx._lib.hpfw_set_projection_impl(ctx.handle, 1))
     n = cols - 99
     exp = np.zeros(n, dtype=np.uint64)
     for f, (b, c) in enumerate(taps):
