@@ -83,7 +83,7 @@ struct PinnedBuffer {
 
 struct CqtPlanCache;  // cqt.cu
 }  // namespace hpfw_b200
-#define HPFW_CTX_LANES 4
+#define HPFW_CTX_LANES 8
 namespace hpfw_b200 {
 
 }  // namespace hpfw_b200

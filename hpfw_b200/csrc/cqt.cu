@@ -25,6 +25,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -605,6 +606,7 @@ static int next_pow2(long long n) {
 
 // best split H = n1 * n2 (n1 <= n2 <= CQ_MAX_ROW), both {2,3,5,7}-smooth; returns false if there is none
 static bool split_smooth(int H, int &n1, int &n2) {
+    const int n1max = env_int("HPFW_CQT_N1MAX", 1 << 30);   // tuning override: cap the column-FFT length
     int rest = H;
     int e[4] = {0, 0, 0, 0};
     const int p[4] = {2, 3, 5, 7};
@@ -622,7 +624,7 @@ static bool split_smooth(int H, int &n1, int &n2) {
                     for (int i = 0; i < c; ++i) v *= 5;
                     for (int i = 0; i < d; ++i) v *= 7;
                     const long long w = H / v;
-                    if (v <= w && w <= CQ_MAX_ROW && v > best) best = v;
+                    if (v <= w && w <= CQ_MAX_ROW && v > best && v <= n1max) best = v;
                 }
     if (best < 2) return false;
     n1 = (int)best;
@@ -632,6 +634,11 @@ static bool split_smooth(int H, int &n1, int &n2) {
 
 // Shared memory of the two-pass FFT kernels: twiddles (n) + ping-pong (2 * G * n) complex values. G columns / rows per CTA
 // is sized for two resident CTAs per SM (~110 KB each) when the transform allows it, one CTA otherwise.
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
 static void fft_group_sizes(hpfw_ctx *ctx, int n1, int n2, int &G1, int &G2, size_t &smem1, size_t &smem2) {
     const size_t two_cta = 110 * 1024, one_cta = (size_t)ctx->max_smem_optin - 2048;
     auto pick = [&](int n, int gmax) {
@@ -641,6 +648,11 @@ static void fft_group_sizes(hpfw_ctx *ctx, int n1, int n2, int &G1, int &G2, siz
     };
     G1 = pick(n1, 8);
     G2 = pick(n2, 4);
+    // tuning overrides (experiments only)
+    const size_t one = (size_t)ctx->max_smem_optin - 2048;
+    const int g1 = env_int("HPFW_CQT_G1", 0), g2 = env_int("HPFW_CQT_G2", 0);
+    if (g1 > 0 && 8 * (size_t)n1 * (1 + 2 * (size_t)g1) <= one) G1 = g1;
+    if (g2 > 0 && 8 * (size_t)n2 * (1 + 2 * (size_t)g2) <= one) G2 = g2;
     smem1 = 8 * (size_t)n1 * (1 + 2 * (size_t)G1);
     smem2 = 8 * (size_t)n2 * (1 + 2 * (size_t)G2);
 }
@@ -1027,7 +1039,7 @@ int hpfw_calc_hashprint_audio_batch_device(hpfw_ctx *ctx, const float *d_audio, 
         // fork: the tracks of the chunk run round-robin on CQ_LANES streams (own scratch each) so that the small tail waves
         // of one track's kernels overlap another track's; join before the chunk's single projection launch
         HPFW_TRY(lanes_init(ctx));
-        const int nl = std::min(CQ_LANES, j - i);
+        const int nl = std::max(1, std::min(std::min(CQ_LANES, env_int("HPFW_CQT_LANES", 4)), j - i));
         HPFW_CUDA_TRY(cudaEventRecord(ctx->lane_fork, s));
         for (int l = 0; l < nl; ++l) HPFW_CUDA_TRY(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->lane_fork, 0));
         for (int t = i; t < j; ++t) {

@@ -17,7 +17,8 @@ offs = np.arange(ntr + 1, dtype=np.int64) * cols
 words = cols - 99
 s = torch.cuda.current_stream().cuda_stream
 res = {}
-for impl in (0, 2, 1):
+impls = tuple(int(x) for x in sys.argv[2].split(",")) if len(sys.argv) > 2 else (0, 2, 1)
+for impl in impls:
     check(ctx._lib.hpfw_set_projection_impl(ctx.handle, impl))
     hp = torch.zeros(ntr * words, dtype=torch.int64, device="cuda")
     def run():
@@ -31,6 +32,6 @@ for impl in (0, 2, 1):
     res[impl] = hp.cpu().numpy().view(np.uint64)
     fl = 2.0 * 64 * 2420 * (cols - 19) * ntr
     print(f"impl {impl}: {ms:.3f} ms for {ntr} tracks = {ms/ntr*1e3:.1f} us/track, {fl/ms/1e9:.1f} TFLOP/s (algorithmic)")
-for impl in (1, 2):
+for impl in [i for i in impls if i != 0 and 0 in res]:
     d = int(np.unpackbits((res[impl] ^ res[0]).view(np.uint8)).sum())
     print(f"impl {impl} vs 0: {d} of {64*len(res[0])} bits differ ({100.0*d/(64*len(res[0])):.5f} %)")
