@@ -598,6 +598,11 @@ void cqt_cache_destroy(CqtPlanCache *c) {
     delete c;
 }
 
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
 static int next_pow2(long long n) {
     int p = 1;
     while (p < n) p <<= 1;
@@ -634,11 +639,6 @@ static bool split_smooth(int H, int &n1, int &n2) {
 
 // Shared memory of the two-pass FFT kernels: twiddles (n) + ping-pong (2 * G * n) complex values. G columns / rows per CTA
 // is sized for two resident CTAs per SM (~110 KB each) when the transform allows it, one CTA otherwise.
-static int env_int(const char *name, int dflt) {
-    const char *v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
-
 static void fft_group_sizes(hpfw_ctx *ctx, int n1, int n2, int &G1, int &G2, size_t &smem1, size_t &smem2) {
     const size_t two_cta = 110 * 1024, one_cta = (size_t)ctx->max_smem_optin - 2048;
     auto pick = [&](int n, int gmax) {
