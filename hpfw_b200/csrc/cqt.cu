@@ -50,7 +50,13 @@ struct FftDesc {
     int n;
     int nrad;
     int rad[CQ_MAXRAD];
+    int tw_off[CQ_MAXRAD];   // offset of stage s in the stage-twiddle table: entry [(t-1)*Ns + k] = e^{-2 pi i k t/(Ns R)}
 };
+
+// Shared-memory index padding: one extra element per 8. A radix-8 Stockham stage with Ns = 1 writes element 8j+t from
+// thread j (64-byte stride = 16-way bank conflict); padded, the stride is 72 bytes and a half-warp hits 16 distinct bank
+// pairs. The same map keeps the later stages and the contiguous reads conflict-free.
+#define CQ_PAD(i) ((i) + ((i) >> 3))
 
 struct BandMeta {
     int first_bin;        // pos_j - floor(Lg_j / 2)
@@ -202,22 +208,23 @@ template <> __device__ __forceinline__ void dft_r<7>(float2 (&v)[7], int sign) {
 template <> __device__ __forceinline__ void dft_r<8>(float2 (&v)[8], int sign) { dft8(v, sign); }
 
 // ------------------------------------------------------------------------------------------------ shared-memory FFT
-// One Stockham autosort stage of radix R over G interleaved-by-sequence arrays of length n (sequence g at g*n).
+// One Stockham autosort stage of radix R over G sequences of length n (sequence g at logical index g*n; every shared-memory
+// access goes through CQ_PAD). tws = this stage's twiddles, laid out [(t-1)*Ns + k] so that consecutive threads
+// (consecutive k) read consecutive entries.
 template <int R>
 __device__ __forceinline__ void stockham_stage(const float2 *in, float2 *out, int n, int G, int Ns,
-                                               const float2 *__restrict__ tw, int sign) {
+                                               const float2 *__restrict__ tws, int sign) {
     const int m = n / R;
-    const int tws = n / (Ns * R);
     for (int idx = threadIdx.x; idx < G * m; idx += blockDim.x) {
         const int g = idx / m, j = idx - g * m;
         const int blk = j / Ns, k = j - blk * Ns;
         float2 v[R];
 #pragma unroll
-        for (int t = 0; t < R; ++t) v[t] = in[g * n + j + t * m];
+        for (int t = 0; t < R; ++t) v[t] = in[CQ_PAD(g * n + j + t * m)];
         if (Ns > 1) {
 #pragma unroll
             for (int t = 1; t < R; ++t) {
-                float2 w = tw[k * t * tws];          // e^{-2 pi i k t / (Ns R)}
+                float2 w = tws[(t - 1) * Ns + k];          // e^{-2 pi i k t / (Ns R)}
                 if (sign > 0) w = cconj(w);
                 v[t] = cmul(v[t], w);
             }
@@ -225,23 +232,23 @@ __device__ __forceinline__ void stockham_stage(const float2 *in, float2 *out, in
         dft_r<R>(v, sign);
         const int base = g * n + blk * Ns * R + k;
 #pragma unroll
-        for (int t = 0; t < R; ++t) out[base + t * Ns] = v[t];
+        for (int t = 0; t < R; ++t) out[CQ_PAD(base + t * Ns)] = v[t];
     }
 }
 
-// FFT of G sequences of length d.n held in `a`; `b` is scratch of the same size. Returns the buffer holding the result
-// (natural order). All threads of the CTA must call it; the data in `a` must be visible (caller syncs before).
+// FFT of G sequences of length d.n held (CQ_PAD-indexed) in `a`; `b` is scratch of the same size; `tw` = the stage-twiddle
+// table of d (< d.n entries). Returns the buffer holding the result (natural order, CQ_PAD-indexed). All threads of the CTA must call it; the data in `a` must be visible (caller syncs before).
 __device__ float2 *smem_fft(float2 *a, float2 *b, const FftDesc &d, int G, const float2 *__restrict__ tw, int sign) {
     int Ns = 1;
     for (int s = 0; s < d.nrad; ++s) {
         const int r = d.rad[s];
         switch (r) {
-            case 2: stockham_stage<2>(a, b, d.n, G, Ns, tw, sign); break;
-            case 3: stockham_stage<3>(a, b, d.n, G, Ns, tw, sign); break;
-            case 4: stockham_stage<4>(a, b, d.n, G, Ns, tw, sign); break;
-            case 5: stockham_stage<5>(a, b, d.n, G, Ns, tw, sign); break;
-            case 7: stockham_stage<7>(a, b, d.n, G, Ns, tw, sign); break;
-            default: stockham_stage<8>(a, b, d.n, G, Ns, tw, sign); break;
+            case 2: stockham_stage<2>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign); break;
+            case 3: stockham_stage<3>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign); break;
+            case 4: stockham_stage<4>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign); break;
+            case 5: stockham_stage<5>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign); break;
+            case 7: stockham_stage<7>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign); break;
+            default: stockham_stage<8>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign); break;
         }
         __syncthreads();
         float2 *t = a; a = b; b = t;
@@ -261,11 +268,11 @@ fft_cols_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, FftDesc
     const int n1 = d1.n;
     const int b0 = blockIdx.x * G;
     const int g_here = min(G, n2 - b0);
-    float2 *tw1 = fsm, *A = fsm + n1, *B = A + G * n1;
+    float2 *tw1 = fsm, *A = fsm + n1, *B = A + CQ_PAD(G * n1) + 1;
     for (int idx = threadIdx.x; idx < n1; idx += blockDim.x) tw1[idx] = tw1_g[idx];   // stage twiddles: no L1 gathers in the stages
     for (int idx = threadIdx.x; idx < n1 * G; idx += blockDim.x) {
         const int a = idx / G, g = idx - a * G;
-        A[g * n1 + a] = g < g_here ? in[(long long)a * n2 + b0 + g] : make_float2(0.f, 0.f);
+        A[CQ_PAD(g * n1 + a)] = g < g_here ? in[(long long)a * n2 + b0 + g] : make_float2(0.f, 0.f);
     }
     __syncthreads();
     float2 *R = smem_fft(A, B, d1, G, tw1, sign);
@@ -273,7 +280,7 @@ fft_cols_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, FftDesc
         const int c = idx / G, g = idx - c * G;
         if (g < g_here) {
             const float2 w = twiddle2(twH_hi, twH_lo, (long long)(b0 + g) * c, sign);
-            out[(long long)c * n2 + b0 + g] = cmul(R[g * n1 + c], w);
+            out[(long long)c * n2 + b0 + g] = cmul(R[CQ_PAD(g * n1 + c)], w);
         }
     }
 }
@@ -288,11 +295,11 @@ fft_rows_kernel(const float2 *__restrict__ in, float2 *__restrict__ out_lo, floa
     const int n2 = d2.n;
     const int c0 = blockIdx.x * G;
     const int g_here = min(G, n1 - c0);
-    float2 *tw2 = fsm, *A = fsm + n2, *B = A + G * n2;
+    float2 *tw2 = fsm, *A = fsm + n2, *B = A + CQ_PAD(G * n2) + 1;
     for (int idx = threadIdx.x; idx < n2; idx += blockDim.x) tw2[idx] = tw2_g[idx];
     for (int idx = threadIdx.x; idx < n2 * G; idx += blockDim.x) {
         const int g = idx / n2, b = idx - g * n2;
-        A[idx] = g < g_here ? in[(long long)(c0 + g) * n2 + b] : make_float2(0.f, 0.f);
+        A[CQ_PAD(idx)] = g < g_here ? in[(long long)(c0 + g) * n2 + b] : make_float2(0.f, 0.f);
     }
     __syncthreads();
     float2 *R = smem_fft(A, B, d2, G, tw2, sign);
@@ -301,7 +308,7 @@ fft_rows_kernel(const float2 *__restrict__ in, float2 *__restrict__ out_lo, floa
         const int dd = idx / G, g = idx - dd * G;
         if (g >= g_here) continue;
         const int k = c0 + g + n1 * dd;
-        const float2 v = R[g * n2 + dd];
+        const float2 v = R[CQ_PAD(g * n2 + dd)];
         if (keep_all) {
             out_lo[k] = v;
         } else {
@@ -379,19 +386,19 @@ czt_rows_kernel(const BandMeta *__restrict__ bands, float2 *__restrict__ work, c
     if (threadIdx.x == 0) d = descs[bm.btab];
     const float2 *tw_g = tws[bm.btab];
     float2 *row = work + bm.work_off + (long long)c * bm.L2;
-    float2 *tw = fsm, *A = fsm + bm.L2, *B = A + bm.L2;
+    float2 *tw = fsm, *A = fsm + bm.L2, *B = A + CQ_PAD(bm.L2) + 1;
     for (int i = threadIdx.x; i < bm.L2; i += blockDim.x) {
         tw[i] = tw_g[i];
-        A[i] = row[i];
+        A[CQ_PAD(i)] = row[i];
     }
     __syncthreads();
     float2 *R = smem_fft(A, B, d, 1, tw, -1);
     if (MODE == 1) {
-        for (int i = threadIdx.x; i < bm.L2; i += blockDim.x) row[i] = R[i];
+        for (int i = threadIdx.x; i < bm.L2; i += blockDim.x) row[i] = R[CQ_PAD(i)];
         return;
     }
     const float2 *bt = btabs[bm.btab] + (long long)c * bm.L2;
-    for (int i = threadIdx.x; i < bm.L2; i += blockDim.x) R[i] = cmul(R[i], bt[i]);
+    for (int i = threadIdx.x; i < bm.L2; i += blockDim.x) R[CQ_PAD(i)] = cmul(R[CQ_PAD(i)], bt[i]);
     __syncthreads();
     float2 *O = (R == A) ? B : A;
     float2 *R2 = smem_fft(R, O, d, 1, tw, +1);
@@ -399,7 +406,7 @@ czt_rows_kernel(const BandMeta *__restrict__ bands, float2 *__restrict__ work, c
     for (int i = threadIdx.x; i < bm.L2; i += blockDim.x) {
         float s, co;
         sincospif(2.0f * (float)(i * c) * invL, &s, &co);
-        row[i] = cmul(R2[i], make_float2(co, s));
+        row[i] = cmul(R2[CQ_PAD(i)], make_float2(co, s));
     }
 }
 
@@ -503,14 +510,29 @@ static bool factor_smooth(int n, FftDesc &d) {
             d.rad[d.nrad++] = r;
             n /= r;
         }
+    int off = 0, Ns = 1;
+    for (int s = 0; s < d.nrad; ++s) {
+        d.tw_off[s] = off;
+        if (Ns > 1) off += (d.rad[s] - 1) * Ns;
+        Ns *= d.rad[s];
+    }
     return n == 1;
 }
 
-static std::vector<float2> twiddle_table(int n) {
-    std::vector<float2> t((size_t)n);
-    for (int m = 0; m < n; ++m) {
-        const double a = -2.0 * M_PI * (double)m / (double)n;
-        t[(size_t)m] = make_float2((float)std::cos(a), (float)std::sin(a));
+// stage-twiddle table of a descriptor: for every stage with Ns > 1, entries [(t-1)*Ns + k] = e^{-2 pi i k t / (Ns R)},
+// t = 1..R-1, k < Ns (n - 1 entries at most; padded to n)
+static std::vector<float2> twiddle_table(const FftDesc &d) {
+    std::vector<float2> t((size_t)d.n, make_float2(1.f, 0.f));
+    int Ns = 1;
+    for (int s = 0; s < d.nrad; ++s) {
+        const int R = d.rad[s];
+        if (Ns > 1)
+            for (int tt = 1; tt < R; ++tt)
+                for (int k = 0; k < Ns; ++k) {
+                    const double a = -2.0 * M_PI * (double)((long long)k * tt) / (double)((long long)Ns * R);
+                    t[(size_t)d.tw_off[s] + (size_t)(tt - 1) * Ns + k] = make_float2((float)std::cos(a), (float)std::sin(a));
+                }
+        Ns *= R;
     }
     return t;
 }
@@ -603,6 +625,9 @@ static int env_int(const char *name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
+static size_t czt_row_smem(int L2) { return 8 * ((size_t)L2 + 2 * ((size_t)CQ_PAD(L2) + 1)); }
+static size_t fft_pass_smem(int n, int G) { return 8 * ((size_t)n + 2 * ((size_t)CQ_PAD(G * n) + 1)); }
+
 static int next_pow2(long long n) {
     int p = 1;
     while (p < n) p <<= 1;
@@ -642,19 +667,23 @@ static bool split_smooth(int H, int &n1, int &n2) {
 static void fft_group_sizes(hpfw_ctx *ctx, int n1, int n2, int &G1, int &G2, size_t &smem1, size_t &smem2) {
     const size_t two_cta = 110 * 1024, one_cta = (size_t)ctx->max_smem_optin - 2048;
     auto pick = [&](int n, int gmax) {
-        size_t g = two_cta > 8 * (size_t)n ? (two_cta - 8 * (size_t)n) / (16 * (size_t)n) : 0;
-        if (g < 2) g = one_cta > 8 * (size_t)n ? (one_cta - 8 * (size_t)n) / (16 * (size_t)n) : 0;
-        return (int)std::max<size_t>(1, std::min<size_t>((size_t)gmax, g));
+        int g = gmax;
+        while (g > 1 && fft_pass_smem(n, g) > two_cta) --g;
+        if (g < 2) {
+            g = gmax;
+            while (g > 1 && fft_pass_smem(n, g) > one_cta) --g;
+        }
+        return g;
     };
     G1 = pick(n1, 8);
     G2 = pick(n2, 4);
     // tuning overrides (experiments only)
     const size_t one = (size_t)ctx->max_smem_optin - 2048;
     const int g1 = env_int("HPFW_CQT_G1", 0), g2 = env_int("HPFW_CQT_G2", 0);
-    if (g1 > 0 && 8 * (size_t)n1 * (1 + 2 * (size_t)g1) <= one) G1 = g1;
-    if (g2 > 0 && 8 * (size_t)n2 * (1 + 2 * (size_t)g2) <= one) G2 = g2;
-    smem1 = 8 * (size_t)n1 * (1 + 2 * (size_t)G1);
-    smem2 = 8 * (size_t)n2 * (1 + 2 * (size_t)G2);
+    if (g1 > 0 && fft_pass_smem(n1, g1) <= one) G1 = g1;
+    if (g2 > 0 && fft_pass_smem(n2, g2) <= one) G2 = g2;
+    smem1 = fft_pass_smem(n1, G1);
+    smem2 = fft_pass_smem(n2, G2);
 }
 
 // every FFT kernel may use up to the device's opt-in shared memory (plans of different sizes share the kernels)
@@ -692,7 +721,7 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
         HPFW_FAIL(HPFW_ERR_SHORT, "CQT: audio of %lld samples is too short for the 121-band design", (long long)N);
     fft_group_sizes(ctx, n1, n2, pl.G1, pl.G2, pl.smem1, pl.smem2);
     {
-        auto t1 = twiddle_table(n1), t2 = twiddle_table(n2);
+        auto t1 = twiddle_table(pl.d1), t2 = twiddle_table(pl.d2);
         HPFW_TRY(pl.tw1.reserve(sizeof(float2) * t1.size()));
         HPFW_TRY(pl.tw2.reserve(sizeof(float2) * t2.size()));
         HPFW_CUDA_TRY(cudaMemcpy(pl.tw1.ptr, t1.data(), sizeof(float2) * t1.size(), cudaMemcpyHostToDevice));
@@ -732,7 +761,7 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
     std::vector<const float2 *> twp(Ls.size()), btp(Ls.size());
     for (size_t i = 0; i < Ls.size(); ++i) {
         if (!factor_smooth(Ls[i] / CQ_L1, descs[i])) HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: too many FFT stages");
-        auto t = twiddle_table(Ls[i] / CQ_L1);
+        auto t = twiddle_table(descs[i]);
         pl.rowtws.emplace_back(new DeviceBuffer());
         HPFW_TRY(pl.rowtws.back()->reserve(sizeof(float2) * t.size()));
         HPFW_CUDA_TRY(cudaMemcpy(pl.rowtws.back()->ptr, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice));
@@ -772,7 +801,7 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
             }
             {
                 KernelScope ks(ctx, HPFW_K_CQT, stream);
-                czt_rows_kernel<1><<<dim3(CQ_L1, 1), CQ_THREADS, 24 * (size_t)fb[i].L2, stream>>>(
+                czt_rows_kernel<1><<<dim3(CQ_L1, 1), CQ_THREADS, czt_row_smem(fb[i].L2), stream>>>(
                     dbm, tab, pl.d_btab_ptrs.as<const float2 *>(), pl.d_descs.as<FftDesc>(),
                     pl.d_tw_ptrs.as<const float2 *>());
             }
@@ -849,7 +878,7 @@ static int cqt_run(hpfw_ctx *ctx, const float *d_audio, int64_t N, float *d_out,
         int j1 = j0;
         while (j1 < CQ_BINS && pl->bands[j1].L == pl->bands[j0].L) ++j1;
         KernelScope ks(ctx, HPFW_K_CQT, stream);
-        czt_rows_kernel<0><<<dim3(CQ_L1, j1 - j0), CQ_THREADS, 24 * (size_t)pl->bands[j0].L2, stream>>>(
+        czt_rows_kernel<0><<<dim3(CQ_L1, j1 - j0), CQ_THREADS, czt_row_smem(pl->bands[j0].L2), stream>>>(
             pl->d_bands.as<BandMeta>() + j0, sc->work.as<float2>(), pl->d_btab_ptrs.as<const float2 *>(),
             pl->d_descs.as<FftDesc>(), pl->d_tw_ptrs.as<const float2 *>());
         j0 = j1;
@@ -886,7 +915,7 @@ static int fft_c2c_device(hpfw_ctx *ctx, const float2 *d_in, float2 *d_out, int 
     fft_group_sizes(ctx, n1, n2, G1, G2, smem1, smem2);
     DeviceBuffer tw1, tw2, tmp;
     TwoLevel twP;
-    auto t1 = twiddle_table(n1), t2 = twiddle_table(n2);
+    auto t1 = twiddle_table(d1), t2 = twiddle_table(d2);
     HPFW_TRY(tw1.reserve(sizeof(float2) * t1.size()));
     HPFW_TRY(tw2.reserve(sizeof(float2) * t2.size()));
     HPFW_TRY(tmp.reserve(sizeof(float2) * (size_t)n));
