@@ -51,7 +51,12 @@ struct FftDesc {
     int nrad;
     int rad[CQ_MAXRAD];
     int tw_off[CQ_MAXRAD];   // offset of stage s in the stage-twiddle table: entry [(t-1)*Ns + k] = e^{-2 pi i k t/(Ns R)}
+    unsigned long long mg_m[CQ_MAXRAD];    // ceil(2^40 / (n / R_s)): x / m  = (x * mg_m) >> 40 for x < 2^20
+    unsigned long long mg_ns[CQ_MAXRAD];   // ceil(2^40 / Ns_s)
 };
+
+// exact x / d for x < 2^20, d < 2^20 with mg = ceil(2^40 / d): one 64-bit multiply instead of an integer division
+__device__ __forceinline__ int fastdiv(int x, unsigned long long mg) { return (int)(((unsigned long long)(unsigned)x * mg) >> 40); }
 
 // Shared-memory index padding: one extra element per 8. A radix-8 Stockham stage with Ns = 1 writes element 8j+t from
 // thread j (64-byte stride = 16-way bank conflict); padded, the stride is 72 bytes and a half-warp hits 16 distinct bank
@@ -213,11 +218,12 @@ template <> __device__ __forceinline__ void dft_r<8>(float2 (&v)[8], int sign) {
 // (consecutive k) read consecutive entries.
 template <int R>
 __device__ __forceinline__ void stockham_stage(const float2 *in, float2 *out, int n, int G, int Ns,
-                                               const float2 *__restrict__ tws, int sign) {
+                                               const float2 *__restrict__ tws, int sign, unsigned long long mg_m,
+                                               unsigned long long mg_ns) {
     const int m = n / R;
     for (int idx = threadIdx.x; idx < G * m; idx += blockDim.x) {
-        const int g = idx / m, j = idx - g * m;
-        const int blk = j / Ns, k = j - blk * Ns;
+        const int g = (G == 1) ? 0 : fastdiv(idx, mg_m), j = idx - g * m;
+        const int blk = fastdiv(j, mg_ns), k = j - blk * Ns;
         float2 v[R];
 #pragma unroll
         for (int t = 0; t < R; ++t) v[t] = in[CQ_PAD(g * n + j + t * m)];
@@ -243,12 +249,12 @@ __device__ float2 *smem_fft(float2 *a, float2 *b, const FftDesc &d, int G, const
     for (int s = 0; s < d.nrad; ++s) {
         const int r = d.rad[s];
         switch (r) {
-            case 2: stockham_stage<2>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign); break;
-            case 3: stockham_stage<3>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign); break;
-            case 4: stockham_stage<4>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign); break;
-            case 5: stockham_stage<5>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign); break;
-            case 7: stockham_stage<7>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign); break;
-            default: stockham_stage<8>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign); break;
+            case 2: stockham_stage<2>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign, d.mg_m[s], d.mg_ns[s]); break;
+            case 3: stockham_stage<3>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign, d.mg_m[s], d.mg_ns[s]); break;
+            case 4: stockham_stage<4>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign, d.mg_m[s], d.mg_ns[s]); break;
+            case 5: stockham_stage<5>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign, d.mg_m[s], d.mg_ns[s]); break;
+            case 7: stockham_stage<7>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign, d.mg_m[s], d.mg_ns[s]); break;
+            default: stockham_stage<8>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign, d.mg_m[s], d.mg_ns[s]); break;
         }
         __syncthreads();
         float2 *t = a; a = b; b = t;
@@ -269,13 +275,16 @@ fft_cols_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, FftDesc
     const int b0 = blockIdx.x * G;
     const int g_here = min(G, n2 - b0);
     float2 *tw1 = fsm, *A = fsm + n1, *B = A + CQ_PAD(G * n1) + 1;
+#pragma unroll 4
     for (int idx = threadIdx.x; idx < n1; idx += blockDim.x) tw1[idx] = tw1_g[idx];   // stage twiddles: no L1 gathers in the stages
+#pragma unroll 4
     for (int idx = threadIdx.x; idx < n1 * G; idx += blockDim.x) {
         const int a = idx / G, g = idx - a * G;
         A[CQ_PAD(g * n1 + a)] = g < g_here ? in[(long long)a * n2 + b0 + g] : make_float2(0.f, 0.f);
     }
     __syncthreads();
     float2 *R = smem_fft(A, B, d1, G, tw1, sign);
+#pragma unroll 4
     for (int idx = threadIdx.x; idx < n1 * G; idx += blockDim.x) {
         const int c = idx / G, g = idx - c * G;
         if (g < g_here) {
@@ -296,7 +305,9 @@ fft_rows_kernel(const float2 *__restrict__ in, float2 *__restrict__ out_lo, floa
     const int c0 = blockIdx.x * G;
     const int g_here = min(G, n1 - c0);
     float2 *tw2 = fsm, *A = fsm + n2, *B = A + CQ_PAD(G * n2) + 1;
+#pragma unroll 4
     for (int idx = threadIdx.x; idx < n2; idx += blockDim.x) tw2[idx] = tw2_g[idx];
+#pragma unroll 4
     for (int idx = threadIdx.x; idx < n2 * G; idx += blockDim.x) {
         const int g = idx / n2, b = idx - g * n2;
         A[CQ_PAD(idx)] = g < g_here ? in[(long long)(c0 + g) * n2 + b] : make_float2(0.f, 0.f);
@@ -387,6 +398,7 @@ czt_rows_kernel(const BandMeta *__restrict__ bands, float2 *__restrict__ work, c
     const float2 *tw_g = tws[bm.btab];
     float2 *row = work + bm.work_off + (long long)c * bm.L2;
     float2 *tw = fsm, *A = fsm + bm.L2, *B = A + CQ_PAD(bm.L2) + 1;
+#pragma unroll 4
     for (int i = threadIdx.x; i < bm.L2; i += blockDim.x) {
         tw[i] = tw_g[i];
         A[CQ_PAD(i)] = row[i];
@@ -398,6 +410,7 @@ czt_rows_kernel(const BandMeta *__restrict__ bands, float2 *__restrict__ work, c
         return;
     }
     const float2 *bt = btabs[bm.btab] + (long long)c * bm.L2;
+#pragma unroll 4
     for (int i = threadIdx.x; i < bm.L2; i += blockDim.x) R[CQ_PAD(i)] = cmul(R[CQ_PAD(i)], bt[i]);
     __syncthreads();
     float2 *O = (R == A) ? B : A;
@@ -511,8 +524,11 @@ static bool factor_smooth(int n, FftDesc &d) {
             n /= r;
         }
     int off = 0, Ns = 1;
+    auto magic = [](unsigned long long dv) { return ((1ull << 40) + dv - 1) / dv; };
     for (int s = 0; s < d.nrad; ++s) {
         d.tw_off[s] = off;
+        d.mg_m[s] = magic((unsigned long long)(d.n / d.rad[s]));
+        d.mg_ns[s] = magic((unsigned long long)Ns);
         if (Ns > 1) off += (d.rad[s] - 1) * Ns;
         Ns *= d.rad[s];
     }
