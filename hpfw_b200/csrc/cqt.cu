@@ -27,6 +27,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 
@@ -40,11 +41,12 @@ constexpr int CQ_MINWIN = 96;         // cqt.h:19,57
 constexpr int CQ_DOWN = 3;            // cqt.h:22
 constexpr int CQ_L1 = 16;             // CZT column radix
 constexpr int CQ_MAX_ROW = 8192;      // longest shared-memory FFT (2 x 64 KB ping-pong)
-constexpr int CQ_MAXRAD = 14;
+constexpr int CQ_MAXRAD = 14;      // stages per shared-memory FFT (8192 = 16*16*16*2 needs 4; 2^13 in radix 2 would need 13)
 constexpr int CQ_TW_S = 1024;         // two-level twiddle: W^m = hi[m / S] * lo[m % S]
 constexpr int CQ_THREADS = 256;
 constexpr int CQ_LANES = HPFW_CTX_LANES;   // concurrent tracks of a batch (streams + scratch sets)
-constexpr int CQ_FFT_THREADS = 512;   // shared-memory FFT kernels: 2 CTAs x 16 warps per SM
+constexpr int CQ_FFT_THREADS = 256;   // shared-memory FFT kernels: 2 CTAs per SM, <= 128 registers (radix-16 butterflies)
+constexpr int CQ_ROW_POINTS = 4096;   // CZT row pass: a CTA transforms G rows with G * L2 <= 4096 points
 
 struct FftDesc {
     int n;
@@ -70,7 +72,12 @@ struct BandMeta {
     int L;                // CZT length
     int L2;               // L / 16
     int btab;             // index of the chirp-filter spectrum table for this L
+    int r0;               // > 0: L2 = 256 * r0 and the row pass runs czt_rows3_kernel; 0: generic shared-memory FFT
     long long work_off;   // offset (complex elements) of this band's L-point work area
+};
+
+struct RowTile {          // CZT row pass: rows [c0, c0 + g) of one band (contiguous in the work area)
+    int band, c0, g;
 };
 
 // ------------------------------------------------------------------------------------------------ complex helpers
@@ -211,6 +218,110 @@ template <> __device__ __forceinline__ void dft_r<4>(float2 (&v)[4], int sign) {
 template <> __device__ __forceinline__ void dft_r<5>(float2 (&v)[5], int sign) { dft_odd<5>(v, sign); }
 template <> __device__ __forceinline__ void dft_r<7>(float2 (&v)[7], int sign) { dft_odd<7>(v, sign); }
 template <> __device__ __forceinline__ void dft_r<8>(float2 (&v)[8], int sign) { dft8(v, sign); }
+template <> __device__ __forceinline__ void dft_r<16>(float2 (&v)[16], int sign) { dft16(v, sign); }
+
+// cos / sin of 2 pi m / R for the composite radices (immediates once the butterfly loops are unrolled)
+template <int R> struct TwTab;
+template <> struct TwTab<6> {
+    static __device__ __forceinline__ float c(int m) {
+        constexpr float t[6] = {1.0f, 0.5f, -0.5f, -1.0f, -0.5f, 0.5f};
+        return t[m];
+    }
+    static __device__ __forceinline__ float s(int m) {
+        constexpr float t[6] = {0.0f, 0.8660254037844386f, 0.86602540378443871f, 0.0f, -0.86602540378443837f, -0.8660254037844386f};
+        return t[m];
+    }
+};
+template <> struct TwTab<9> {
+    static __device__ __forceinline__ float c(int m) {
+        constexpr float t[9] = {1.0f, 0.76604444311897801f, 0.17364817766693041f, -0.5f, -0.93969262078590832f, -0.93969262078590843f, -0.5f, 0.17364817766692997f, 0.76604444311897779f};
+        return t[m];
+    }
+    static __device__ __forceinline__ float s(int m) {
+        constexpr float t[9] = {0.0f, 0.64278760968653925f, 0.98480775301220802f, 0.86602540378443871f, 0.34202014332566888f, -0.34202014332566866f, -0.86602540378443837f, -0.98480775301220813f, -0.64278760968653958f};
+        return t[m];
+    }
+};
+template <> struct TwTab<10> {
+    static __device__ __forceinline__ float c(int m) {
+        constexpr float t[10] = {1.0f, 0.80901699437494745f, 0.30901699437494745f, -0.30901699437494734f, -0.80901699437494734f, -1.0f, -0.80901699437494756f, -0.30901699437494756f, 0.30901699437494723f, 0.80901699437494734f};
+        return t[m];
+    }
+    static __device__ __forceinline__ float s(int m) {
+        constexpr float t[10] = {0.0f, 0.58778525229247314f, 0.95105651629515353f, 0.95105651629515364f, 0.58778525229247325f, 0.0f, -0.58778525229247303f, -0.95105651629515353f, -0.95105651629515364f, -0.58778525229247336f};
+        return t[m];
+    }
+};
+template <> struct TwTab<12> {
+    static __device__ __forceinline__ float c(int m) {
+        constexpr float t[12] = {1.0f, 0.86602540378443871f, 0.5f, 0.0f, -0.5f, -0.86602540378443871f, -1.0f, -0.86602540378443882f, -0.5f, 0.0f, 0.5f, 0.86602540378443837f};
+        return t[m];
+    }
+    static __device__ __forceinline__ float s(int m) {
+        constexpr float t[12] = {0.0f, 0.5f, 0.8660254037844386f, 1.0f, 0.86602540378443871f, 0.5f, 0.0f, -0.5f, -0.86602540378443837f, -1.0f, -0.8660254037844386f, -0.5f};
+        return t[m];
+    }
+};
+template <> struct TwTab<14> {
+    static __device__ __forceinline__ float c(int m) {
+        constexpr float t[14] = {1.0f, 0.90096886790241915f, 0.62348980185873359f, 0.22252093395631445f, -0.22252093395631434f, -0.62348980185873348f, -0.90096886790241903f, -1.0f, -0.90096886790241915f, -0.62348980185873371f, -0.22252093395631459f, 0.22252093395631334f, 0.62348980185873337f, 0.90096886790241937f};
+        return t[m];
+    }
+    static __device__ __forceinline__ float s(int m) {
+        constexpr float t[14] = {0.0f, 0.43388373911755812f, 0.7818314824680298f, 0.97492791218182362f, 0.97492791218182362f, 0.78183148246802991f, 0.43388373911755823f, 0.0f, -0.43388373911755801f, -0.78183148246802969f, -0.97492791218182362f, -0.97492791218182384f, -0.78183148246802991f, -0.43388373911755751f};
+        return t[m];
+    }
+};
+template <> struct TwTab<15> {
+    static __device__ __forceinline__ float c(int m) {
+        constexpr float t[15] = {1.0f, 0.91354545764260087f, 0.66913060635885824f, 0.30901699437494745f, -0.10452846326765333f, -0.5f, -0.80901699437494734f, -0.97814760073380569f, -0.97814760073380569f, -0.80901699437494756f, -0.5f, -0.10452846326765423f, 0.30901699437494723f, 0.66913060635885846f, 0.91354545764260098f};
+        return t[m];
+    }
+    static __device__ __forceinline__ float s(int m) {
+        constexpr float t[15] = {0.0f, 0.40673664307580015f, 0.74314482547739413f, 0.95105651629515353f, 0.9945218953682734f, 0.86602540378443871f, 0.58778525229247325f, 0.20791169081775931f, -0.20791169081775907f, -0.58778525229247303f, -0.86602540378443837f, -0.99452189536827329f, -0.95105651629515364f, -0.74314482547739402f, -0.40673664307580015f};
+        return t[m];
+    }
+};
+
+// Composite radix R = R1 * R2 in registers (Cooley-Tukey inside the butterfly): input a = R2 a1 + a0, output
+// c = c0 + R1 c1:  X[c] = sum_a0 W_R2^{a0 c1} W_R^{a0 c0} sum_a1 v[R2 a1 + a0] W_R1^{a1 c0}. One Stockham stage of radix
+// 14 / 15 / 16 replaces two stages (and their shared-memory round trip and barrier) of radix 2x7 / 3x5 / 4x4.
+template <int R1, int R2> __device__ __forceinline__ void dft_comp(float2 (&v)[R1 * R2], int sign) {
+    constexpr int R = R1 * R2;
+    float2 y[R2][R1];
+#pragma unroll
+    for (int a0 = 0; a0 < R2; ++a0) {
+        float2 t[R1];
+#pragma unroll
+        for (int a1 = 0; a1 < R1; ++a1) t[a1] = v[R2 * a1 + a0];
+        dft_r<R1>(t, sign);
+#pragma unroll
+        for (int c0 = 0; c0 < R1; ++c0) y[a0][c0] = t[c0];
+    }
+#pragma unroll
+    for (int a0 = 1; a0 < R2; ++a0)
+#pragma unroll
+        for (int c0 = 1; c0 < R1; ++c0) {
+            const int m = (a0 * c0) % R;
+            const float c = TwTab<R>::c(m), sn = TwTab<R>::s(m);
+            y[a0][c0] = cmul(y[a0][c0], make_float2(c, sign < 0 ? -sn : sn));
+        }
+#pragma unroll
+    for (int c0 = 0; c0 < R1; ++c0) {
+        float2 t[R2];
+#pragma unroll
+        for (int a0 = 0; a0 < R2; ++a0) t[a0] = y[a0][c0];
+        dft_r<R2>(t, sign);
+#pragma unroll
+        for (int c1 = 0; c1 < R2; ++c1) v[c0 + R1 * c1] = t[c1];
+    }
+}
+template <> __device__ __forceinline__ void dft_r<6>(float2 (&v)[6], int sign) { dft_comp<3, 2>(v, sign); }
+template <> __device__ __forceinline__ void dft_r<9>(float2 (&v)[9], int sign) { dft_comp<3, 3>(v, sign); }
+template <> __device__ __forceinline__ void dft_r<10>(float2 (&v)[10], int sign) { dft_comp<5, 2>(v, sign); }
+template <> __device__ __forceinline__ void dft_r<12>(float2 (&v)[12], int sign) { dft_comp<4, 3>(v, sign); }
+template <> __device__ __forceinline__ void dft_r<14>(float2 (&v)[14], int sign) { dft_comp<7, 2>(v, sign); }
+template <> __device__ __forceinline__ void dft_r<15>(float2 (&v)[15], int sign) { dft_comp<5, 3>(v, sign); }
 
 // ------------------------------------------------------------------------------------------------ shared-memory FFT
 // One Stockham autosort stage of radix R over G sequences of length n (sequence g at logical index g*n; every shared-memory
@@ -254,6 +365,13 @@ __device__ float2 *smem_fft(float2 *a, float2 *b, const FftDesc &d, int G, const
             case 4: stockham_stage<4>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign, d.mg_m[s], d.mg_ns[s]); break;
             case 5: stockham_stage<5>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign, d.mg_m[s], d.mg_ns[s]); break;
             case 7: stockham_stage<7>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign, d.mg_m[s], d.mg_ns[s]); break;
+            case 6: stockham_stage<6>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign, d.mg_m[s], d.mg_ns[s]); break;
+            case 9: stockham_stage<9>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign, d.mg_m[s], d.mg_ns[s]); break;
+            case 10: stockham_stage<10>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign, d.mg_m[s], d.mg_ns[s]); break;
+            case 12: stockham_stage<12>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign, d.mg_m[s], d.mg_ns[s]); break;
+            case 14: stockham_stage<14>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign, d.mg_m[s], d.mg_ns[s]); break;
+            case 15: stockham_stage<15>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign, d.mg_m[s], d.mg_ns[s]); break;
+            case 16: stockham_stage<16>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign, d.mg_m[s], d.mg_ns[s]); break;
             default: stockham_stage<8>(a, b, d.n, G, Ns, tw + d.tw_off[s], sign, d.mg_m[s], d.mg_ns[s]); break;
         }
         __syncthreads();
@@ -263,68 +381,176 @@ __device__ float2 *smem_fft(float2 *a, float2 *b, const FftDesc &d, int G, const
     return a;
 }
 
-// ------------------------------------------------------------------------------------------------ main FFT, pass A
-// Column FFTs of the n1 x n2 row-major matrix `in` (element (a,b) at a*n2+b): for G adjacent columns per CTA,
-// out[c*n2 + b] = W_H^{b c} * sum_a in[a*n2 + b] e^{-2 pi i a c / n1}.
-__global__ void __launch_bounds__(CQ_FFT_THREADS, 2)
-fft_cols_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, FftDesc d1, int n2, int G,
-                const float2 *__restrict__ tw1_g, const float2 *__restrict__ twH_hi, const float2 *__restrict__ twH_lo,
-                int sign) {
-    extern __shared__ __align__(16) float2 fsm[];
-    const int n1 = d1.n;
-    const int b0 = blockIdx.x * G;
-    const int g_here = min(G, n2 - b0);
-    float2 *tw1 = fsm, *A = fsm + n1, *B = A + CQ_PAD(G * n1) + 1;
-#pragma unroll 4
-    for (int idx = threadIdx.x; idx < n1; idx += blockDim.x) tw1[idx] = tw1_g[idx];   // stage twiddles: no L1 gathers in the stages
-#pragma unroll 4
-    for (int idx = threadIdx.x; idx < n1 * G; idx += blockDim.x) {
-        const int a = idx / G, g = idx - a * G;
-        A[CQ_PAD(g * n1 + a)] = g < g_here ? in[(long long)a * n2 + b0 + g] : make_float2(0.f, 0.f);
+// ------------------------------------------------------------------------------------------------ register-FFT helpers
+// shared-memory index padding of the register kernels: one extra element per 16 (thread strides of 2..16 elements stay
+// conflict-free or 2-way)
+__device__ __forceinline__ int cr_pad(int i) { return i + (i >> 4); }
+__host__ __device__ constexpr int hibit(int u) { int h = 1; while (h * 2 <= u) h *= 2; return h; }
+
+// v[u] *= w^u, u = 1 .. R-1
+template <int R> __device__ __forceinline__ void apply_powers(float2 (&v)[R], float2 w) {
+    float2 p[R];
+    p[0] = make_float2(1.f, 0.f);
+    if (R > 1) p[1] = w;
+#pragma unroll
+    for (int u = 2; u < R; ++u) {
+        const int hi = hibit(u), lo = u - hi;
+        p[u] = lo == 0 ? cmul(p[hi / 2], p[hi / 2]) : cmul(p[hi], p[lo]);
     }
-    __syncthreads();
-    float2 *R = smem_fft(A, B, d1, G, tw1, sign);
-#pragma unroll 4
-    for (int idx = threadIdx.x; idx < n1 * G; idx += blockDim.x) {
-        const int c = idx / G, g = idx - c * G;
+#pragma unroll
+    for (int u = 1; u < R; ++u) v[u] = cmul(v[u], p[u]);
+}
+
+// ------------------------------------------------------------------------------------------------ main FFT passes
+// Two-pass ("four-step") FFT of H = n1 * n2 points, element (a, b) at a*n2 + b:
+//   MODE 0 (pass A): length-n1 FFTs down G adjacent columns per CTA, out[c*n2 + b] = W_H^{b c} * sum_a in[a*n2 + b] W_n1^{a c};
+//   MODE 1 (pass B): length-n2 FFTs along G rows per CTA, Z[c + n1*d] = sum_b in[c*n2 + b] W_n2^{b d}, keeping only
+//           k in [klo, khi] (-> out_lo[k - klo]) and k in [H - khi, H - klo] (-> out_hi[k - (H - khi)]); keep_all != 0
+//           stores the whole spectrum to out_lo[k].
+// Each length-n FFT is a Stockham autosort over the plan's radices (2..16, composite radices in registers). The first
+// stage reads global memory straight into its butterflies and the last stage applies the pass's output twiddle / bin
+// selection from registers, so an element makes (stages - 1) shared-memory round trips instead of (stages + 2). A
+// butterfly loads ONE twiddle W_n^{step k} (L1-resident table of n entries) and forms its powers by a product tree.
+__device__ __forceinline__ float2 tw_dir(float2 w, int sign) { return sign < 0 ? w : cconj(w); }   // tables hold e^{-2 pi i ./n}
+
+template <> __device__ __forceinline__ void dft_r<1>(float2 (&)[1], int) {}
+
+template <int R, int MODE>
+__device__ __forceinline__ void pass_first(const float2 *__restrict__ in, float2 *S, int n, int G, int g_here, int pitch,
+                                           int sign, unsigned long long mg_g, unsigned long long mg_m) {
+    const int m = n / R, tot = G * m;
+    for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
+        int g, j;
+        if (MODE == 0) { j = fastdiv(idx, mg_g); g = idx - j * G; }     // adjacent columns are adjacent in memory
+        else { g = fastdiv(idx, mg_m); j = idx - g * m; }
+        float2 v[R];
         if (g < g_here) {
-            const float2 w = twiddle2(twH_hi, twH_lo, (long long)(b0 + g) * c, sign);
-            out[(long long)c * n2 + b0 + g] = cmul(R[CQ_PAD(g * n1 + c)], w);
+#pragma unroll
+            for (int u = 0; u < R; ++u) v[u] = MODE == 0 ? in[(j + u * m) * pitch + g] : in[g * pitch + j + u * m];
+        } else {
+#pragma unroll
+            for (int u = 0; u < R; ++u) v[u] = make_float2(0.f, 0.f);
+        }
+        dft_r<R>(v, sign);
+#pragma unroll
+        for (int u = 0; u < R; ++u) S[cr_pad(g * n + j * R + u)] = v[u];
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void pass_mid(const float2 *Sin, float2 *Sout, int n, int G, int Ns, const float2 *__restrict__ T,
+                                         int sign, unsigned long long mg_m, unsigned long long mg_ns) {
+    const int m = n / R, tot = G * m, step = m / Ns;      // W_{Ns R}^k = W_n^{step k}
+    for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
+        const int g = fastdiv(idx, mg_m), j = idx - g * m;
+        const int blk = fastdiv(j, mg_ns), k = j - blk * Ns;
+        float2 v[R];
+#pragma unroll
+        for (int u = 0; u < R; ++u) v[u] = Sin[cr_pad(g * n + j + u * m)];
+        apply_powers<R>(v, tw_dir(T[step * k], sign));
+        dft_r<R>(v, sign);
+        const int base = g * n + blk * Ns * R + k;
+#pragma unroll
+        for (int u = 0; u < R; ++u) Sout[cr_pad(base + u * Ns)] = v[u];
+    }
+}
+
+struct PassOut {
+    float2 *lo, *hi;          // MODE 0: lo = out (+ b0); MODE 1: the two kept ranges
+    const float2 *tw_hi, *tw_lo;
+    int other;                // MODE 0: n2 (row pitch); MODE 1: n1
+    int first;                // MODE 0: b0; MODE 1: c0
+    int klo, khi, H, keep_all;
+};
+
+template <int R, int MODE>
+__device__ __forceinline__ void pass_last(const float2 *Sin, float2 *Sout, int n, int G, int g_here,
+                                          const float2 *__restrict__ T, int sign, unsigned long long mg_m,
+                                          const PassOut &po) {
+    const int m = n / R, tot = G * m;       // Ns = m: blk = 0, k = j; outputs d = j + u m
+    for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
+        const int g = fastdiv(idx, mg_m), j = idx - g * m;
+        float2 v[R];
+#pragma unroll
+        for (int u = 0; u < R; ++u) v[u] = Sin[cr_pad(g * n + j + u * m)];
+        if (R > 1) apply_powers<R>(v, tw_dir(T[j], sign));
+        dft_r<R>(v, sign);
+        if (MODE == 0) {
+            // inter-pass twiddle W_H^{b d} = W_H^{b j} (W_H^{b m})^u, then staged for the column-adjacent store
+            const int bcol = po.first + g;
+            const float2 wa = twiddle2(po.tw_hi, po.tw_lo, (long long)bcol * j, sign);
+            if (R > 1) apply_powers<R>(v, twiddle2(po.tw_hi, po.tw_lo, (long long)bcol * m, sign));
+#pragma unroll
+            for (int u = 0; u < R; ++u) Sout[cr_pad(g * n + j + u * m)] = cmul(v[u], wa);
+        } else if (g < g_here) {
+            const int c = po.first + g, mlo = po.H - po.khi, mhi = po.H - po.klo;
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                const int k = c + po.other * (j + u * m);
+                if (po.keep_all) {
+                    po.lo[k] = v[u];
+                } else {
+                    if (k >= po.klo && k <= po.khi) po.lo[k - po.klo] = v[u];
+                    if (k >= mlo && k <= mhi) po.hi[k - mlo] = v[u];
+                }
+            }
         }
     }
 }
 
-// ------------------------------------------------------------------------------------------------ main FFT, pass B
-// Row FFTs: Z[c + n1*d] = sum_b in[c*n2 + b] e^{-2 pi i b d / n2}. Keeps only k in [klo, khi] (-> out_lo[k - klo]) and
-// k in [H - khi, H - klo] (-> out_hi[k - (H - khi)]); with keep_all != 0 stores the whole spectrum to out_lo[k].
-__global__ void __launch_bounds__(CQ_FFT_THREADS, 2)
-fft_rows_kernel(const float2 *__restrict__ in, float2 *__restrict__ out_lo, float2 *__restrict__ out_hi, FftDesc d2,
-                int n1, int G, const float2 *__restrict__ tw2_g, int klo, int khi, int H, int keep_all, int sign) {
-    extern __shared__ __align__(16) float2 fsm[];
-    const int n2 = d2.n;
-    const int c0 = blockIdx.x * G;
-    const int g_here = min(G, n1 - c0);
-    float2 *tw2 = fsm, *A = fsm + n2, *B = A + CQ_PAD(G * n2) + 1;
-#pragma unroll 4
-    for (int idx = threadIdx.x; idx < n2; idx += blockDim.x) tw2[idx] = tw2_g[idx];
-#pragma unroll 4
-    for (int idx = threadIdx.x; idx < n2 * G; idx += blockDim.x) {
-        const int g = idx / n2, b = idx - g * n2;
-        A[CQ_PAD(idx)] = g < g_here ? in[(long long)(c0 + g) * n2 + b] : make_float2(0.f, 0.f);
+#define HPFW_RADIX_SWITCH(r, CALL)                                                                                      \
+    switch (r) {                                                                                                        \
+        case 2: { constexpr int R = 2; CALL; } break;                                                                   \
+        case 3: { constexpr int R = 3; CALL; } break;                                                                   \
+        case 4: { constexpr int R = 4; CALL; } break;                                                                   \
+        case 5: { constexpr int R = 5; CALL; } break;                                                                   \
+        case 6: { constexpr int R = 6; CALL; } break;                                                                   \
+        case 7: { constexpr int R = 7; CALL; } break;                                                                   \
+        case 8: { constexpr int R = 8; CALL; } break;                                                                   \
+        case 9: { constexpr int R = 9; CALL; } break;                                                                   \
+        case 10: { constexpr int R = 10; CALL; } break;                                                                 \
+        case 12: { constexpr int R = 12; CALL; } break;                                                                 \
+        case 14: { constexpr int R = 14; CALL; } break;                                                                 \
+        case 15: { constexpr int R = 15; CALL; } break;                                                                 \
+        case 16: { constexpr int R = 16; CALL; } break;                                                                 \
+        default: { constexpr int R = 1; CALL; } break;                                                                  \
     }
+
+template <int MODE>
+__global__ void __launch_bounds__(CQ_FFT_THREADS, 2)
+fft_pass_kernel(const float2 *__restrict__ in, float2 *__restrict__ out_lo, float2 *__restrict__ out_hi, FftDesc d,
+                int other, int G, unsigned long long mg_g, const float2 *__restrict__ T,
+                const float2 *__restrict__ twH_hi, const float2 *__restrict__ twH_lo, int klo, int khi, int H,
+                int keep_all, int sign) {
+    extern __shared__ __align__(16) float2 fsm[];
+    const int n = d.n;
+    const int first = blockIdx.x * G;
+    const int pitch = MODE == 0 ? other : n;                   // row pitch n2 of the n1 x n2 matrix
+    const int g_here = min(G, (MODE == 0 ? other : other) - first);   // MODE 0: columns left (n2); MODE 1: rows left (n1)
+    float2 *S0 = fsm, *S1 = fsm + cr_pad(G * n) + 16;
+    const float2 *src = MODE == 0 ? in + first : in + (long long)first * pitch;
+    PassOut po{MODE == 0 ? out_lo + first : out_lo, out_hi, twH_hi, twH_lo, other, first, klo, khi, H, keep_all};
+
+    HPFW_RADIX_SWITCH(d.rad[0], (pass_first<R, MODE>(src, S0, n, G, g_here, pitch, sign, mg_g, d.mg_m[0])));
     __syncthreads();
-    float2 *R = smem_fft(A, B, d2, G, tw2, sign);
-    const int mlo = H - khi, mhi = H - klo;
-    for (int idx = threadIdx.x; idx < n2 * G; idx += blockDim.x) {
-        const int dd = idx / G, g = idx - dd * G;
-        if (g >= g_here) continue;
-        const int k = c0 + g + n1 * dd;
-        const float2 v = R[CQ_PAD(g * n2 + dd)];
-        if (keep_all) {
-            out_lo[k] = v;
-        } else {
-            if (k >= klo && k <= khi) out_lo[k - klo] = v;
-            if (k >= mlo && k <= mhi) out_hi[k - mlo] = v;
+    int Ns = d.rad[0];
+    float2 *cur = S0, *nxt = S1;
+    for (int s = 1; s + 1 < d.nrad; ++s) {
+        HPFW_RADIX_SWITCH(d.rad[s], (pass_mid<R>(cur, nxt, n, G, Ns, T, sign, d.mg_m[s], d.mg_ns[s])));
+        __syncthreads();
+        float2 *t = cur; cur = nxt; nxt = t;
+        Ns *= d.rad[s];
+    }
+    const int sl = d.nrad - 1;
+    HPFW_RADIX_SWITCH(d.rad[sl], (pass_last<R, MODE>(cur, nxt, n, G, g_here, T, sign, d.mg_m[sl], po)));
+    if (MODE == 0) {
+        __syncthreads();
+        // nxt holds out-values at [g][c]; store with the G adjacent columns contiguous (32-byte runs for G = 4)
+        const int tot = G * n;
+#pragma unroll 4
+        for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
+            const int c = fastdiv(idx, mg_g), g = idx - c * G;
+            if (g < g_here) po.lo[c * pitch + g] = nxt[cr_pad(g * n + c)];
         }
     }
 }
@@ -377,7 +603,7 @@ czt_cols_kernel(const BandMeta *__restrict__ bands, const float2 *__restrict__ z
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
         float s, co;
-        sincospif(-2.0f * (float)(b * c) * invL, &s, &co);     // b*c < 2^20: exact in float; L is a power of two
+        sincospif(-2.0f * (float)(b * c) * invL, &s, &co);     // b*c < L <= 2^17: exact in float
         dst[c * bm.L2 + b] = cmul(v[c], make_float2(co, s));
     }
 }
@@ -387,39 +613,173 @@ czt_cols_kernel(const BandMeta *__restrict__ bands, const float2 *__restrict__ z
 // spectrum, inverse FFT_L2 (-> b'), inverse inter-pass twiddle e^{+2 pi i b' c / L}. MODE 1 (plan creation) stops after
 // the forward FFT and stores the spectrum.
 template <int MODE>
-__global__ void __launch_bounds__(CQ_THREADS)
-czt_rows_kernel(const BandMeta *__restrict__ bands, float2 *__restrict__ work, const float2 *const *__restrict__ btabs,
-                const FftDesc *__restrict__ descs, const float2 *const *__restrict__ tws) {
+__global__ void __launch_bounds__(CQ_FFT_THREADS, 2)
+czt_rows_kernel(const BandMeta *__restrict__ bands, const RowTile *__restrict__ tiles, float2 *__restrict__ work,
+                const float2 *const *__restrict__ btabs, const FftDesc *__restrict__ descs,
+                const float2 *const *__restrict__ tws) {
     extern __shared__ __align__(16) float2 fsm[];
-    const BandMeta bm = bands[blockIdx.y];
-    const int c = blockIdx.x;
+    const RowTile tl = tiles[blockIdx.x];
+    const BandMeta bm = bands[tl.band];
     __shared__ FftDesc d;
     if (threadIdx.x == 0) d = descs[bm.btab];
     const float2 *tw_g = tws[bm.btab];
-    float2 *row = work + bm.work_off + (long long)c * bm.L2;
-    float2 *tw = fsm, *A = fsm + bm.L2, *B = A + CQ_PAD(bm.L2) + 1;
+    const int L2 = bm.L2, G = tl.g, tot = G * L2;
+    float2 *rows = work + bm.work_off + (long long)tl.c0 * L2;
+    float2 *tw = fsm, *A = fsm + L2, *B = A + CQ_PAD(tot) + 1;
 #pragma unroll 4
-    for (int i = threadIdx.x; i < bm.L2; i += blockDim.x) {
-        tw[i] = tw_g[i];
-        A[CQ_PAD(i)] = row[i];
-    }
+    for (int i = threadIdx.x; i < L2; i += blockDim.x) tw[i] = tw_g[i];
+#pragma unroll 4
+    for (int i = threadIdx.x; i < tot; i += blockDim.x) A[CQ_PAD(i)] = rows[i];
     __syncthreads();
-    float2 *R = smem_fft(A, B, d, 1, tw, -1);
+    float2 *R = smem_fft(A, B, d, G, tw, -1);
     if (MODE == 1) {
-        for (int i = threadIdx.x; i < bm.L2; i += blockDim.x) row[i] = R[CQ_PAD(i)];
+        for (int i = threadIdx.x; i < tot; i += blockDim.x) rows[i] = R[CQ_PAD(i)];
         return;
     }
-    const float2 *bt = btabs[bm.btab] + (long long)c * bm.L2;
+    const float2 *bt = btabs[bm.btab] + (long long)tl.c0 * L2;
 #pragma unroll 4
-    for (int i = threadIdx.x; i < bm.L2; i += blockDim.x) R[CQ_PAD(i)] = cmul(R[CQ_PAD(i)], bt[i]);
+    for (int i = threadIdx.x; i < tot; i += blockDim.x) R[CQ_PAD(i)] = cmul(R[CQ_PAD(i)], bt[i]);
     __syncthreads();
     float2 *O = (R == A) ? B : A;
-    float2 *R2 = smem_fft(R, O, d, 1, tw, +1);
+    float2 *R2 = smem_fft(R, O, d, G, tw, +1);
     const float invL = 1.0f / (float)bm.L;
-    for (int i = threadIdx.x; i < bm.L2; i += blockDim.x) {
-        float s, co;
-        sincospif(2.0f * (float)(i * c) * invL, &s, &co);
-        row[i] = cmul(R2[CQ_PAD(i)], make_float2(co, s));
+    for (int g = 0; g < G; ++g) {
+        const int c = tl.c0 + g;
+#pragma unroll 4
+        for (int i = threadIdx.x; i < L2; i += blockDim.x) {
+            float s, co;
+            sincospif(2.0f * (float)(i * c) * invL, &s, &co);      // i * c < L <= 2^17: exact in float
+            rows[g * L2 + i] = cmul(R2[CQ_PAD(g * L2 + i)], make_float2(co, s));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ CZT row pass, L2 = 256 r0
+// The row transform for L2 = r0 * 16 * 16 (r0 in {2..10,12,14,15,16}) with every stage in registers:
+//   forward  Stockham (r0, 16, 16): stage 1 reads global memory, stage 3 leaves X[k + 16 r0 u] in the thread that, in the
+//   inverse  Stockham (16, 16, r0), owns exactly those inputs — the chirp-filter multiply happens in registers and the
+//   last stage stores to global memory with the inter-pass twiddle applied. Four shared-memory exchanges per element in
+//   all (ping-pong buffers, one barrier each) against eleven in the generic kernel. Per butterfly ONE twiddle W_N^m is
+//   loaded (L1-resident table) and its powers are formed by a depth-4 product tree on the otherwise idle FMA pipe.
+template <int R>
+__device__ __forceinline__ void rows3_first(const float2 *__restrict__ rows, float2 *S, int G, int N) {
+    const int j = threadIdx.x;
+    for (int g = 0; g < G; ++g) {
+        float2 v[R];
+#pragma unroll
+        for (int u = 0; u < R; ++u) v[u] = rows[g * N + j + 256 * u];
+        dft_r<R>(v, -1);
+#pragma unroll
+        for (int u = 0; u < R; ++u) S[cr_pad(g * N + j * R + u)] = v[u];
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void rows3_last(float2 *__restrict__ rows, const float2 *S, const float2 *__restrict__ T,
+                                           int G, int N, int c0, float invL, float inv16r) {
+    const int j = threadIdx.x;
+    const float2 wt = cconj(T[j]);
+    for (int g = 0; g < G; ++g) {
+        float2 v[R];
+#pragma unroll
+        for (int u = 0; u < R; ++u) v[u] = S[cr_pad(g * N + j + 256 * u)];
+        apply_powers<R>(v, wt);
+        dft_r<R>(v, +1);
+        // inter-pass twiddle e^{+2 pi i b' c / L}, b' = j + 256 u:  wa * wb^u
+        const int c = c0 + g;
+        float sa, ca, sb, cb;
+        sincospif(2.0f * (float)(j * c) * invL, &sa, &ca);
+        sincospif(2.0f * (float)c * inv16r, &sb, &cb);
+        apply_powers<R>(v, make_float2(cb, sb));
+        const float2 wa = make_float2(ca, sa);
+#pragma unroll
+        for (int u = 0; u < R; ++u) rows[g * N + j + 256 * u] = cmul(v[u], wa);
+    }
+}
+
+__global__ void __launch_bounds__(256, 2)
+czt_rows3_kernel(const BandMeta *__restrict__ bands, const RowTile *__restrict__ tiles, float2 *__restrict__ work,
+                 const float2 *const *__restrict__ btabs, const float2 *const *__restrict__ ttabs) {
+    extern __shared__ __align__(16) float2 fsm[];
+    const RowTile tl = tiles[blockIdx.x];
+    const BandMeta bm = bands[tl.band];
+    const int r0 = bm.r0, N = bm.L2, G = tl.g, m16 = 16 * r0;     // N = 256 r0; m16 = butterflies per row of a radix-16 stage
+    float2 *rows = work + bm.work_off + (long long)tl.c0 * N;
+    const float2 *__restrict__ T = ttabs[bm.btab];                  // T[m] = e^{-2 pi i m / N}
+    float2 *S0 = fsm, *S1 = fsm + cr_pad(CQ_ROW_POINTS) + 16;
+
+    switch (r0) {
+        case 2: rows3_first<2>(rows, S0, G, N); break;
+        case 3: rows3_first<3>(rows, S0, G, N); break;
+        case 4: rows3_first<4>(rows, S0, G, N); break;
+        case 5: rows3_first<5>(rows, S0, G, N); break;
+        case 6: rows3_first<6>(rows, S0, G, N); break;
+        case 7: rows3_first<7>(rows, S0, G, N); break;
+        case 8: rows3_first<8>(rows, S0, G, N); break;
+        case 9: rows3_first<9>(rows, S0, G, N); break;
+        case 10: rows3_first<10>(rows, S0, G, N); break;
+        case 12: rows3_first<12>(rows, S0, G, N); break;
+        case 14: rows3_first<14>(rows, S0, G, N); break;
+        case 15: rows3_first<15>(rows, S0, G, N); break;
+        default: rows3_first<16>(rows, S0, G, N); break;
+    }
+    __syncthreads();
+
+    // radix-16 stages: thread -> (row g, butterfly j2 < 16 r0); G * 16 r0 <= 256
+    const int idx = threadIdx.x;
+    const bool active = idx < G * m16;
+    const int g = __float2int_rz(((float)idx + 0.5f) / (float)m16);
+    const int j2 = idx - g * m16;
+    const int base = g * N;
+    float2 v[16];
+    if (active) {   // forward stage 2: Ns = r0
+        const int blk = __float2int_rz(((float)j2 + 0.5f) / (float)r0), k = j2 - blk * r0;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = S0[cr_pad(base + j2 + u * m16)];
+        apply_powers<16>(v, T[16 * k]);
+        dft16(v, -1);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) S1[cr_pad(base + blk * m16 + k + u * r0)] = v[u];
+    }
+    __syncthreads();
+    if (active) {   // forward stage 3: Ns = 16 r0; then the chirp-filter multiply and inverse stage 1 (Ns = 1), all in registers
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = S1[cr_pad(base + j2 + u * m16)];
+        apply_powers<16>(v, T[j2]);
+        dft16(v, -1);
+        const float2 *bt = btabs[bm.btab] + (long long)(tl.c0 + g) * N + j2;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = cmul(v[u], bt[u * m16]);
+        dft16(v, +1);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) S0[cr_pad(base + j2 * 16 + u)] = v[u];
+    }
+    __syncthreads();
+    if (active) {   // inverse stage 2: Ns = 16
+        const int blk = j2 >> 4, k = j2 & 15;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = S0[cr_pad(base + j2 + u * m16)];
+        apply_powers<16>(v, cconj(T[r0 * k]));
+        dft16(v, +1);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) S1[cr_pad(base + blk * 256 + k + 16 * u)] = v[u];
+    }
+    __syncthreads();
+    const float invL = 1.0f / (float)bm.L, inv16r = 1.0f / (float)m16;
+    switch (r0) {
+        case 2: rows3_last<2>(rows, S1, T, G, N, tl.c0, invL, inv16r); break;
+        case 3: rows3_last<3>(rows, S1, T, G, N, tl.c0, invL, inv16r); break;
+        case 4: rows3_last<4>(rows, S1, T, G, N, tl.c0, invL, inv16r); break;
+        case 5: rows3_last<5>(rows, S1, T, G, N, tl.c0, invL, inv16r); break;
+        case 6: rows3_last<6>(rows, S1, T, G, N, tl.c0, invL, inv16r); break;
+        case 7: rows3_last<7>(rows, S1, T, G, N, tl.c0, invL, inv16r); break;
+        case 8: rows3_last<8>(rows, S1, T, G, N, tl.c0, invL, inv16r); break;
+        case 9: rows3_last<9>(rows, S1, T, G, N, tl.c0, invL, inv16r); break;
+        case 10: rows3_last<10>(rows, S1, T, G, N, tl.c0, invL, inv16r); break;
+        case 12: rows3_last<12>(rows, S1, T, G, N, tl.c0, invL, inv16r); break;
+        case 14: rows3_last<14>(rows, S1, T, G, N, tl.c0, invL, inv16r); break;
+        case 15: rows3_last<15>(rows, S1, T, G, N, tl.c0, invL, inv16r); break;
+        default: rows3_last<16>(rows, S1, T, G, N, tl.c0, invL, inv16r); break;
     }
 }
 
@@ -512,17 +872,41 @@ static bool cqt_design(int64_t n_samples, CqtDesign &d) {
     return true;
 }
 
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// Radix sequence of a {2,3,5,7}-smooth n: the fewest Stockham stages over the butterflies this file has (every stage is
+// one shared-memory round trip + barrier), ties broken towards the smaller radix sum; stages run in ascending radix order
+// (the first stage, Ns = 1, is twiddle-free and its strided stores conflict least for a small radix).
 static bool factor_smooth(int n, FftDesc &d) {
     d.n = n;
     d.nrad = 0;
-    const int order[6] = {8, 4, 2, 3, 5, 7};
-    // odd radices first would give long strides early; powers of two first keeps the first (Ns = 1) stages twiddle-free
-    for (int r : order)
-        while (n % r == 0 && n > 1) {
-            if (d.nrad >= CQ_MAXRAD) return false;
-            d.rad[d.nrad++] = r;
-            n /= r;
+    const int maxrad = env_int("HPFW_CQT_MAXRADIX", 16);
+    const int all[13] = {16, 15, 14, 12, 10, 9, 8, 7, 6, 5, 4, 3, 2};
+    std::map<int, std::pair<int, int>> memo;   // n -> (stages * 1000 + radix sum, first radix)
+    std::function<int(int)> best = [&](int m) -> int {
+        if (m == 1) return 0;
+        auto it = memo.find(m);
+        if (it != memo.end()) return it->second.first;
+        int bc = 1 << 30, br = 0;
+        for (int r : all) {
+            if (r > maxrad || m % r) continue;
+            const int sub = best(m / r);
+            if (sub >= (1 << 29)) continue;
+            const int c = sub + 1000 + r;
+            if (c < bc) { bc = c; br = r; }
         }
+        memo[m] = {bc, br};
+        return bc;
+    };
+    if (best(n) >= (1 << 29)) return false;
+    std::vector<int> rads;
+    for (int m = n; m > 1; m /= memo[m].second) rads.push_back(memo[m].second);
+    std::sort(rads.begin(), rads.end());
+    if ((int)rads.size() > CQ_MAXRAD) return false;
+    for (int r : rads) d.rad[d.nrad++] = r;
     int off = 0, Ns = 1;
     auto magic = [](unsigned long long dv) { return ((1ull << 40) + dv - 1) / dv; };
     for (int s = 0; s < d.nrad; ++s) {
@@ -532,7 +916,7 @@ static bool factor_smooth(int n, FftDesc &d) {
         if (Ns > 1) off += (d.rad[s] - 1) * Ns;
         Ns *= d.rad[s];
     }
-    return n == 1;
+    return true;
 }
 
 // stage-twiddle table of a descriptor: for every stage with Ns > 1, entries [(t-1)*Ns + k] = e^{-2 pi i k t / (Ns R)},
@@ -587,8 +971,10 @@ struct CqtPlan {
     TwoLevel twH, twN;
     // CZT
     std::vector<BandMeta> bands;
-    DeviceBuffer d_bands, d_btab_ptrs, d_descs, d_tw_ptrs;
-    std::vector<std::unique_ptr<DeviceBuffer>> btabs, rowtws;
+    DeviceBuffer d_bands, d_btab_ptrs, d_descs, d_tw_ptrs, d_tt_ptrs, d_tiles, d_tiles3;
+    int n_tiles = 0, n_tiles3 = 0;
+    size_t smem_rows = 0;
+    std::vector<std::unique_ptr<DeviceBuffer>> btabs, rowtws, ttabs;
     int max_L2 = 0;
     long long work_elems = 0;
     int fpitch = 0;
@@ -615,7 +1001,9 @@ struct CqtPlan {
 
     void release() {
         tw1.release(); tw2.release(); twH.release(); twN.release();
-        d_bands.release(); d_btab_ptrs.release(); d_descs.release(); d_tw_ptrs.release();
+        d_bands.release(); d_btab_ptrs.release(); d_descs.release(); d_tw_ptrs.release(); d_tiles.release(); d_tt_ptrs.release();
+        d_tiles3.release();
+        for (auto &b : ttabs) b->release();
         for (auto &b : btabs) b->release();
         for (auto &b : rowtws) b->release();
         for (auto &sc : lanes) {
@@ -636,21 +1024,59 @@ void cqt_cache_destroy(CqtPlanCache *c) {
     delete c;
 }
 
-static int env_int(const char *name, int dflt) {
-    const char *v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
+static size_t czt_row_smem(int L2, int G) { return 8 * ((size_t)L2 + 2 * ((size_t)CQ_PAD(G * L2) + 1)); }
+static size_t rows3_smem() { return 2 * 8 * ((size_t)CQ_ROW_POINTS + CQ_ROW_POINTS / 16 + 16); }
+static size_t fft_pass_smem(int n, int G) { const size_t t = (size_t)G * n; return 2 * 8 * (t + t / 16 + 16); }
+static unsigned long long magic40(unsigned long long d) { return ((1ull << 40) + d - 1) / d; }
+// the pass kernels need a first and a last stage: a single-radix transform gets a pass-through radix-1 last stage
+static void pad_single_stage(FftDesc &d) {
+    if (d.nrad != 1) return;
+    d.rad[1] = 1;
+    d.tw_off[1] = 0;
+    d.mg_m[1] = magic40((unsigned long long)d.n);
+    d.mg_ns[1] = magic40((unsigned long long)d.n);
+    d.nrad = 2;
+}
+// T[m] = e^{-2 pi i m / n}, m < n: the one twiddle table of a register-FFT of length n
+static std::vector<float2> unit_table(int n) {
+    std::vector<float2> t((size_t)n);
+    for (int m = 0; m < n; ++m) {
+        const double a = -2.0 * M_PI * (double)m / (double)n;
+        t[(size_t)m] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    return t;
 }
 
-static size_t czt_row_smem(int L2) { return 8 * ((size_t)L2 + 2 * ((size_t)CQ_PAD(L2) + 1)); }
-static size_t fft_pass_smem(int n, int G) { return 8 * ((size_t)n + 2 * ((size_t)CQ_PAD(G * n) + 1)); }
-
-static int next_pow2(long long n) {
-    int p = 1;
-    while (p < n) p <<= 1;
-    return p;
+// CZT row length L2 (the chirp-z length is L = 16 * L2 >= need): the {2,3,5,7}-smooth size in [need2, 2 need2) with the
+// least row-pass work L2 * (stages + 1.5). Sizes are kept on a coarse grid (128 / 64 / 16) so that a plan has few distinct
+// chirp-filter tables and every row starts on a 128-byte boundary. HPFW_CQT_POW2L=1 restores power-of-two lengths.
+static int pick_row_len(long long need2) {
+    if (need2 < 64) need2 = 64;
+    if (env_int("HPFW_CQT_POW2L", 0)) {
+        long long p = 64;
+        while (p < need2) p <<= 1;
+        return (int)p;
+    }
+    if (need2 > 256 && need2 <= 4096 && !env_int("HPFW_CQT_ROWS_GENERIC", 0)) {   // L2 = 256 r0: czt_rows3_kernel
+        const int r0s[13] = {2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 15, 16};
+        for (int r0 : r0s)
+            if (256 * r0 >= need2) return 256 * r0;
+    }
+    double best = 1e300;
+    int best_n = 0;
+    for (long long c = need2; c < 2 * need2 && c <= CQ_MAX_ROW; ++c) {
+        const int grid = c >= 1024 ? 128 : (c >= 512 ? 64 : 16);
+        if (c % grid) continue;
+        FftDesc d{};
+        if (!factor_smooth((int)c, d)) continue;
+        const double cost = (double)c * (d.nrad + 1.5);
+        if (cost < best) { best = cost; best_n = (int)c; }
+    }
+    return best_n;   // 0: nothing fits under CQ_MAX_ROW
 }
 
-// best split H = n1 * n2 (n1 <= n2 <= CQ_MAX_ROW), both {2,3,5,7}-smooth; returns false if there is none
+// split H = n1 * n2 (n1 <= n2 <= CQ_MAX_ROW), both {2,3,5,7}-smooth: the fewest Stockham stages in total, then the most
+// balanced; returns false if there is none
 static bool split_smooth(int H, int &n1, int &n2) {
     const int n1max = env_int("HPFW_CQT_N1MAX", 1 << 30);   // tuning override: cap the column-FFT length
     int rest = H;
@@ -660,6 +1086,7 @@ static bool split_smooth(int H, int &n1, int &n2) {
         while (rest % p[i] == 0) { rest /= p[i]; e[i]++; }
     if (rest != 1) return false;
     long long best = -1;
+    int best_stages = 1 << 30;
     for (int a = 0; a <= e[0]; ++a)
         for (int b = 0; b <= e[1]; ++b)
             for (int c = 0; c <= e[2]; ++c)
@@ -670,7 +1097,11 @@ static bool split_smooth(int H, int &n1, int &n2) {
                     for (int i = 0; i < c; ++i) v *= 5;
                     for (int i = 0; i < d; ++i) v *= 7;
                     const long long w = H / v;
-                    if (v <= w && w <= CQ_MAX_ROW && v > best && v <= n1max) best = v;
+                    if (!(v <= w && w <= CQ_MAX_ROW && v >= 2 && v <= n1max)) continue;
+                    FftDesc da{}, db{};
+                    if (!factor_smooth((int)v, da) || !factor_smooth((int)w, db)) continue;
+                    const int st = da.nrad + db.nrad;
+                    if (st < best_stages || (st == best_stages && v > best)) { best_stages = st; best = v; }
                 }
     if (best < 2) return false;
     n1 = (int)best;
@@ -685,19 +1116,19 @@ static void fft_group_sizes(hpfw_ctx *ctx, int n1, int n2, int &G1, int &G2, siz
     auto pick = [&](int n, int gmax) {
         int g = gmax;
         while (g > 1 && fft_pass_smem(n, g) > two_cta) --g;
-        if (g < 2) {
+        if (fft_pass_smem(n, g) > two_cta) {
             g = gmax;
             while (g > 1 && fft_pass_smem(n, g) > one_cta) --g;
         }
         return g;
     };
     G1 = pick(n1, 8);
+    if (G1 > 4) G1 = 4 * (G1 / 4);       // whole 32-byte sectors
     G2 = pick(n2, 4);
     // tuning overrides (experiments only)
-    const size_t one = (size_t)ctx->max_smem_optin - 2048;
     const int g1 = env_int("HPFW_CQT_G1", 0), g2 = env_int("HPFW_CQT_G2", 0);
-    if (g1 > 0 && fft_pass_smem(n1, g1) <= one) G1 = g1;
-    if (g2 > 0 && fft_pass_smem(n2, g2) <= one) G2 = g2;
+    if (g1 > 0 && fft_pass_smem(n1, g1) <= one_cta) G1 = g1;
+    if (g2 > 0 && fft_pass_smem(n2, g2) <= one_cta) G2 = g2;
     smem1 = fft_pass_smem(n1, G1);
     smem2 = fft_pass_smem(n2, G2);
 }
@@ -707,8 +1138,9 @@ static int set_smem_limits(hpfw_ctx *ctx) {
     const int lim = ctx->max_smem_optin - 2048;   // dynamic + static shared memory must stay within the opt-in limit
     HPFW_CUDA_TRY(cudaFuncSetAttribute(czt_rows_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     HPFW_CUDA_TRY(cudaFuncSetAttribute(czt_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    HPFW_CUDA_TRY(cudaFuncSetAttribute(fft_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    HPFW_CUDA_TRY(cudaFuncSetAttribute(fft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    HPFW_CUDA_TRY(cudaFuncSetAttribute(fft_pass_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    HPFW_CUDA_TRY(cudaFuncSetAttribute(czt_rows3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows3_smem()));
+    HPFW_CUDA_TRY(cudaFuncSetAttribute(fft_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     return HPFW_OK;
 }
 
@@ -737,7 +1169,9 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
         HPFW_FAIL(HPFW_ERR_SHORT, "CQT: audio of %lld samples is too short for the 121-band design", (long long)N);
     fft_group_sizes(ctx, n1, n2, pl.G1, pl.G2, pl.smem1, pl.smem2);
     {
-        auto t1 = twiddle_table(pl.d1), t2 = twiddle_table(pl.d2);
+        pad_single_stage(pl.d1);
+        pad_single_stage(pl.d2);
+        auto t1 = unit_table(n1), t2 = unit_table(n2);
         HPFW_TRY(pl.tw1.reserve(sizeof(float2) * t1.size()));
         HPFW_TRY(pl.tw2.reserve(sizeof(float2) * t2.size()));
         HPFW_CUDA_TRY(cudaMemcpy(pl.tw1.ptr, t1.data(), sizeof(float2) * t1.size(), cudaMemcpyHostToDevice));
@@ -755,11 +1189,17 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
         b.lg = d.lg[j];
         b.half = d.lg[j] / 2;
         b.first_bin = d.pos[j] - b.half;
-        b.L = std::max(1024, next_pow2((long long)d.lg[j] + d.F - 1));
-        b.L2 = b.L / CQ_L1;
-        if (b.L2 > CQ_MAX_ROW)
-            HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: audio of %lld samples needs a %d-point chirp-z transform; limit %d "
-                      "(about 6.7 minutes at 44.1 kHz)", (long long)N, b.L, CQ_L1 * CQ_MAX_ROW);
+        const long long need = (long long)d.lg[j] + d.F - 1;
+        b.L2 = pick_row_len((need + CQ_L1 - 1) / CQ_L1);
+        b.L = b.L2 * CQ_L1;
+        b.r0 = 0;
+        if (b.L2 > 256 && b.L2 <= 4096 && b.L2 % 256 == 0 && !env_int("HPFW_CQT_ROWS_GENERIC", 0)) {
+            const int r0 = b.L2 / 256;
+            if ((r0 >= 2 && r0 <= 10) || r0 == 12 || r0 == 14 || r0 == 15 || r0 == 16) b.r0 = r0;
+        }
+        if (b.L2 <= 0)
+            HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: audio of %lld samples needs a %lld-point chirp-z transform; limit %d "
+                      "(about 6.7 minutes at 44.1 kHz)", (long long)N, need, CQ_L1 * CQ_MAX_ROW);
         auto it = std::find(Ls.begin(), Ls.end(), b.L);
         if (it == Ls.end()) { Ls.push_back(b.L); b.btab = (int)Ls.size() - 1; }
         else b.btab = (int)(it - Ls.begin());
@@ -771,10 +1211,38 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
     pl.fpitch = (d.F + 31) & ~31;
     HPFW_TRY(pl.d_bands.reserve(sizeof(BandMeta) * CQ_BINS));
     HPFW_CUDA_TRY(cudaMemcpy(pl.d_bands.ptr, pl.bands.data(), sizeof(BandMeta) * CQ_BINS, cudaMemcpyHostToDevice));
+    // row-pass tiles: G consecutive rows of a band per CTA (G * L2 <= CQ_ROW_POINTS; for the register kernel also
+    // G * 16 r0 <= 256), so that every CTA of a launch has about the same work and shared-memory footprint whatever the
+    // band's chirp length. One tile list per kernel.
+    {
+        std::vector<RowTile> tiles, tiles3;
+        for (int j = 0; j < CQ_BINS; ++j) {
+            const int L2 = pl.bands[j].L2, r0 = pl.bands[j].r0;
+            const int G = std::max(1, std::min(CQ_L1, r0 ? 16 / r0 : CQ_ROW_POINTS / L2));
+            for (int c0 = 0; c0 < CQ_L1; c0 += G) {
+                const int g = std::min(G, CQ_L1 - c0);
+                if (r0) {
+                    tiles3.push_back({j, c0, g});
+                } else {
+                    tiles.push_back({j, c0, g});
+                    pl.smem_rows = std::max(pl.smem_rows, czt_row_smem(L2, g));
+                }
+            }
+        }
+        pl.n_tiles = (int)tiles.size();
+        pl.n_tiles3 = (int)tiles3.size();
+        HPFW_TRY(pl.d_tiles.reserve(sizeof(RowTile) * std::max<size_t>(1, tiles.size())));
+        HPFW_TRY(pl.d_tiles3.reserve(sizeof(RowTile) * std::max<size_t>(1, tiles3.size())));
+        if (!tiles.empty())
+            HPFW_CUDA_TRY(cudaMemcpy(pl.d_tiles.ptr, tiles.data(), sizeof(RowTile) * tiles.size(), cudaMemcpyHostToDevice));
+        if (!tiles3.empty())
+            HPFW_CUDA_TRY(cudaMemcpy(pl.d_tiles3.ptr, tiles3.data(), sizeof(RowTile) * tiles3.size(),
+                                     cudaMemcpyHostToDevice));
+    }
 
     // per distinct L: row-FFT descriptor + twiddles, chirp-filter spectrum (computed below with the same kernels)
     std::vector<FftDesc> descs(Ls.size());
-    std::vector<const float2 *> twp(Ls.size()), btp(Ls.size());
+    std::vector<const float2 *> twp(Ls.size()), btp(Ls.size()), ttp(Ls.size());
     for (size_t i = 0; i < Ls.size(); ++i) {
         if (!factor_smooth(Ls[i] / CQ_L1, descs[i])) HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: too many FFT stages");
         auto t = twiddle_table(descs[i]);
@@ -785,7 +1253,20 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
         pl.btabs.emplace_back(new DeviceBuffer());
         HPFW_TRY(pl.btabs.back()->reserve(sizeof(float2) * (size_t)Ls[i]));
         btp[i] = pl.btabs.back()->as<float2>();
+        // T[m] = e^{-2 pi i m / L2}: the one twiddle table of czt_rows3_kernel
+        const int n2r = Ls[i] / CQ_L1;
+        std::vector<float2> tt((size_t)n2r);
+        for (int m = 0; m < n2r; ++m) {
+            const double a = -2.0 * M_PI * (double)m / (double)n2r;
+            tt[(size_t)m] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+        pl.ttabs.emplace_back(new DeviceBuffer());
+        HPFW_TRY(pl.ttabs.back()->reserve(sizeof(float2) * tt.size()));
+        HPFW_CUDA_TRY(cudaMemcpy(pl.ttabs.back()->ptr, tt.data(), sizeof(float2) * tt.size(), cudaMemcpyHostToDevice));
+        ttp[i] = pl.ttabs.back()->as<float2>();
     }
+    HPFW_TRY(pl.d_tt_ptrs.reserve(sizeof(void *) * ttp.size()));
+    HPFW_CUDA_TRY(cudaMemcpy(pl.d_tt_ptrs.ptr, ttp.data(), sizeof(void *) * ttp.size(), cudaMemcpyHostToDevice));
     HPFW_TRY(pl.d_descs.reserve(sizeof(FftDesc) * descs.size()));
     HPFW_TRY(pl.d_tw_ptrs.reserve(sizeof(void *) * twp.size()));
     HPFW_TRY(pl.d_btab_ptrs.reserve(sizeof(void *) * btp.size()));
@@ -798,11 +1279,15 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
     // chirp-filter spectra: one pseudo-band per distinct L whose work area IS the table
     {
         std::vector<BandMeta> fb(Ls.size());
-        DeviceBuffer d_fb;
+        DeviceBuffer d_fb, d_ft;
+        std::vector<RowTile> ft(CQ_L1);
+        for (int c = 0; c < CQ_L1; ++c) ft[c] = RowTile{0, c, 1};
+        HPFW_TRY(d_ft.reserve(sizeof(RowTile) * ft.size()));
+        HPFW_CUDA_TRY(cudaMemcpy(d_ft.ptr, ft.data(), sizeof(RowTile) * ft.size(), cudaMemcpyHostToDevice));
         // the kernels address work + work_off: express each table as an offset from table 0 is not possible (separate
         // allocations), so run one launch per table with work = that table and work_off = 0
         for (size_t i = 0; i < Ls.size(); ++i) {
-            fb[i] = BandMeta{0, 0, 0, Ls[i], Ls[i] / CQ_L1, (int)i, 0};
+            fb[i] = BandMeta{0, 0, 0, Ls[i], Ls[i] / CQ_L1, (int)i, 0, 0};
         }
         HPFW_TRY(d_fb.reserve(sizeof(BandMeta) * fb.size()));
         HPFW_CUDA_TRY(cudaMemcpy(d_fb.ptr, fb.data(), sizeof(BandMeta) * fb.size(), cudaMemcpyHostToDevice));
@@ -817,14 +1302,15 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
             }
             {
                 KernelScope ks(ctx, HPFW_K_CQT, stream);
-                czt_rows_kernel<1><<<dim3(CQ_L1, 1), CQ_THREADS, czt_row_smem(fb[i].L2), stream>>>(
-                    dbm, tab, pl.d_btab_ptrs.as<const float2 *>(), pl.d_descs.as<FftDesc>(),
+                czt_rows_kernel<1><<<CQ_L1, CQ_FFT_THREADS, czt_row_smem(fb[i].L2, 1), stream>>>(
+                    dbm, d_ft.as<RowTile>(), tab, pl.d_btab_ptrs.as<const float2 *>(), pl.d_descs.as<FftDesc>(),
                     pl.d_tw_ptrs.as<const float2 *>());
             }
         }
         HPFW_CUDA_TRY(cudaGetLastError());
         HPFW_CUDA_TRY(cudaStreamSynchronize(stream));
         d_fb.release();
+        d_ft.release();
     }
 
     return pl.lane_reserve(0);
@@ -870,15 +1356,15 @@ static int cqt_run(hpfw_ctx *ctx, const float *d_audio, int64_t N, float *d_out,
     const float2 *z_in = reinterpret_cast<const float2 *>(d_audio);
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
-        fft_cols_kernel<<<(n2 + pl->G1 - 1) / pl->G1, CQ_FFT_THREADS, pl->smem1, stream>>>(
-            z_in, sc->zbuf.as<float2>(), pl->d1, n2, pl->G1, pl->tw1.as<float2>(), pl->twH.hi.as<float2>(),
-            pl->twH.lo.as<float2>(), -1);
+        fft_pass_kernel<0><<<(n2 + pl->G1 - 1) / pl->G1, CQ_FFT_THREADS, pl->smem1, stream>>>(
+            z_in, sc->zbuf.as<float2>(), nullptr, pl->d1, n2, pl->G1, magic40((unsigned long long)pl->G1),
+            pl->tw1.as<float2>(), pl->twH.hi.as<float2>(), pl->twH.lo.as<float2>(), 0, 0, pl->H, 1, -1);
     }
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
-        fft_rows_kernel<<<(n1 + pl->G2 - 1) / pl->G2, CQ_FFT_THREADS, pl->smem2, stream>>>(
-            sc->zbuf.as<float2>(), sc->zlo.as<float2>(), sc->zhi.as<float2>(), pl->d2, n1, pl->G2, pl->tw2.as<float2>(),
-            pl->klo, pl->khi, pl->H, 0, -1);
+        fft_pass_kernel<1><<<(n1 + pl->G2 - 1) / pl->G2, CQ_FFT_THREADS, pl->smem2, stream>>>(
+            sc->zbuf.as<float2>(), sc->zlo.as<float2>(), sc->zhi.as<float2>(), pl->d2, n1, pl->G2,
+            magic40((unsigned long long)pl->G2), pl->tw2.as<float2>(), nullptr, nullptr, pl->klo, pl->khi, pl->H, 0, -1);
     }
     HPFW_CUDA_TRY(cudaMemsetAsync(sc->pmax.ptr, 0, sizeof(unsigned int), stream));
     const dim3 gcol((pl->max_L2 + CQ_THREADS - 1) / CQ_THREADS, CQ_BINS);
@@ -889,15 +1375,17 @@ static int cqt_run(hpfw_ctx *ctx, const float *d_audio, int64_t N, float *d_out,
                                                              pl->twN.hi.as<float2>(), pl->twN.lo.as<float2>(), d.M, d.F,
                                                              sc->work.as<float2>());
     }
-    // one launch per run of bands with the same chirp length, so that short rows do not reserve the longest row's shared memory
-    for (int j0 = 0; j0 < CQ_BINS;) {
-        int j1 = j0;
-        while (j1 < CQ_BINS && pl->bands[j1].L == pl->bands[j0].L) ++j1;
+    if (pl->n_tiles3 > 0) {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
-        czt_rows_kernel<0><<<dim3(CQ_L1, j1 - j0), CQ_THREADS, czt_row_smem(pl->bands[j0].L2), stream>>>(
-            pl->d_bands.as<BandMeta>() + j0, sc->work.as<float2>(), pl->d_btab_ptrs.as<const float2 *>(),
-            pl->d_descs.as<FftDesc>(), pl->d_tw_ptrs.as<const float2 *>());
-        j0 = j1;
+        czt_rows3_kernel<<<pl->n_tiles3, 256, rows3_smem(), stream>>>(
+            pl->d_bands.as<BandMeta>(), pl->d_tiles3.as<RowTile>(), sc->work.as<float2>(),
+            pl->d_btab_ptrs.as<const float2 *>(), pl->d_tt_ptrs.as<const float2 *>());
+    }
+    if (pl->n_tiles > 0) {
+        KernelScope ks(ctx, HPFW_K_CQT, stream);
+        czt_rows_kernel<0><<<pl->n_tiles, CQ_FFT_THREADS, pl->smem_rows, stream>>>(
+            pl->d_bands.as<BandMeta>(), pl->d_tiles.as<RowTile>(), sc->work.as<float2>(),
+            pl->d_btab_ptrs.as<const float2 *>(), pl->d_descs.as<FftDesc>(), pl->d_tw_ptrs.as<const float2 *>());
     }
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
@@ -931,7 +1419,9 @@ static int fft_c2c_device(hpfw_ctx *ctx, const float2 *d_in, float2 *d_out, int 
     fft_group_sizes(ctx, n1, n2, G1, G2, smem1, smem2);
     DeviceBuffer tw1, tw2, tmp;
     TwoLevel twP;
-    auto t1 = twiddle_table(d1), t2 = twiddle_table(d2);
+    pad_single_stage(d1);
+    pad_single_stage(d2);
+    auto t1 = unit_table(n1), t2 = unit_table(n2);
     HPFW_TRY(tw1.reserve(sizeof(float2) * t1.size()));
     HPFW_TRY(tw2.reserve(sizeof(float2) * t2.size()));
     HPFW_TRY(tmp.reserve(sizeof(float2) * (size_t)n));
@@ -942,13 +1432,15 @@ static int fft_c2c_device(hpfw_ctx *ctx, const float2 *d_in, float2 *d_out, int 
     const int sign = inverse ? +1 : -1;
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
-        fft_cols_kernel<<<(n2 + G1 - 1) / G1, CQ_FFT_THREADS, smem1, stream>>>(
-            d_in, tmp.as<float2>(), d1, n2, G1, tw1.as<float2>(), twP.hi.as<float2>(), twP.lo.as<float2>(), sign);
+        fft_pass_kernel<0><<<(n2 + G1 - 1) / G1, CQ_FFT_THREADS, smem1, stream>>>(
+            d_in, tmp.as<float2>(), nullptr, d1, n2, G1, magic40((unsigned long long)G1), tw1.as<float2>(),
+            twP.hi.as<float2>(), twP.lo.as<float2>(), 0, 0, n, 1, sign);
     }
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
-        fft_rows_kernel<<<(n1 + G2 - 1) / G2, CQ_FFT_THREADS, smem2, stream>>>(
-            tmp.as<float2>(), d_out, nullptr, d2, n1, G2, tw2.as<float2>(), 0, 0, n, 1, sign);
+        fft_pass_kernel<1><<<(n1 + G2 - 1) / G2, CQ_FFT_THREADS, smem2, stream>>>(
+            tmp.as<float2>(), d_out, nullptr, d2, n1, G2, magic40((unsigned long long)G2), tw2.as<float2>(), nullptr,
+            nullptr, 0, 0, n, 1, sign);
     }
     HPFW_CUDA_TRY(cudaGetLastError());
     HPFW_CUDA_TRY(cudaStreamSynchronize(stream));
