@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhpfw_b200.so")
+# HPFW_B200_LIB: A/B experiments with an alternative build of the same library (never a different implementation)
+LIB_PATH = os.environ.get("HPFW_B200_LIB") or os.path.join(HERE, "libhpfw_b200.so")
 
 
 class HpfwError(RuntimeError):

@@ -12,15 +12,19 @@
 //   (1) N real samples are packed to H = N/2 complex points and transformed by a two-pass ("four-step") FFT, H = n1 * n2
 //       with n1, n2 <= 8192 products of 2,3,5,7: pass A = length-n1 column FFTs + inter-pass twiddle, pass B = length-n2
 //       row FFTs whose transposed store keeps only the two bin ranges the 121 bands need (~19 % of the half spectrum).
-//       Each small FFT is a mixed-radix Stockham autosort in shared memory.
+//       Each small FFT is a Stockham autosort over radices 2..16 (composite radices 6,9,10,12,14,15,16 are evaluated in
+//       registers) whose first stage reads global memory and whose last stage writes it: fft_pass_kernel.
 //   (2) per band, only every 3rd of the M IFFT outputs is wanted and M is in general not smooth (43,528 = 8 * 5441), so
 //       c_j[3 i] is evaluated as a chirp-z transform: |c_j[3i]| = |sum_k a[k] e^{2 pi i 3 i k / M}| =
-//       |IFFT_L( FFT_L(a .* chirp) .* FFT_L(chirp_filter) )[i]|, L = 2^p >= Lg_j + F - 1. FFT_L is again four-step,
-//       L = 16 * L2: a radix-16 register FFT down the columns (fused with the half-spectrum untangle, the Hann window and
-//       the chirp), one shared-memory kernel per row doing FFT_L2 -> multiply -> IFFT_L2, and a radix-16 register IFFT
-//       fused with |.|^2, the 1/(L M) scale and the per-track maximum.
+//       |IFFT_L( FFT_L(a .* chirp) .* FFT_L(chirp_filter) )[i]|, L = 16 * L2 >= Lg_j + F - 1 with L2 = 256 r0 the
+//       smallest of r0 in {2..10,12,14,15,16} that fits (a power of two would waste 38 % of the work at 3 minutes).
+//       FFT_L is again four-step: a radix-16 register FFT down the columns (fused with the half-spectrum untangle, the
+//       Hann window and the chirp), czt_rows3_kernel doing FFT_L2 -> multiply -> IFFT_L2 per row with the data in
+//       registers between stages, and a radix-16 register IFFT fused with |.|^2, the 1/(L M) scale and the per-track
+//       maximum. Rows shorter than 512 or longer than 4096 points use the generic shared-memory kernel (czt_rows_kernel).
 //   (3) dB conversion + transpose to the reference's column-major [121 x cols] layout.
-// Everything for one track stays L2-resident (32 MB half spectrum, 38 MB CZT work area at 3 minutes).
+// Twiddles: one table W_n^m per transform length; a butterfly loads one entry and forms its powers by a depth-4 product
+// tree on the FMA pipe (error <= 5 ulp of a unit phasor) instead of R-1 table loads.
 #include "common.cuh"
 
 #include <algorithm>
@@ -45,7 +49,13 @@ constexpr int CQ_MAXRAD = 14;      // stages per shared-memory FFT (8192 = 16*16
 constexpr int CQ_TW_S = 1024;         // two-level twiddle: W^m = hi[m / S] * lo[m % S]
 constexpr int CQ_THREADS = 256;
 constexpr int CQ_LANES = HPFW_CTX_LANES;   // concurrent tracks of a batch (streams + scratch sets)
-constexpr int CQ_FFT_THREADS = 256;   // shared-memory FFT kernels: 2 CTAs per SM, <= 128 registers (radix-16 butterflies)
+constexpr int CQ_FFT_THREADS = 256;   // FFT kernels: 3 CTAs per SM (80 registers, <= 74 KB shared memory each)
+#ifndef CQ_ROWS3_CTAS
+#define CQ_ROWS3_CTAS 3
+#endif
+#ifndef CQ_PASS_CTAS
+#define CQ_PASS_CTAS 3
+#endif
 constexpr int CQ_ROW_POINTS = 4096;   // CZT row pass: a CTA transforms G rows with G * L2 <= 4096 points
 
 struct FftDesc {
@@ -433,25 +443,31 @@ __device__ __forceinline__ void pass_first(const float2 *__restrict__ in, float2
         }
         dft_r<R>(v, sign);
 #pragma unroll
-        for (int u = 0; u < R; ++u) S[cr_pad(g * n + j * R + u)] = v[u];
+        for (int u = 0; u < R; ++u) S[cr_pad(MODE == 0 ? (j * R + u) * G + g : g * n + j * R + u)] = v[u];
     }
 }
 
-template <int R>
+// Shared-memory layout of a pass: MODE 0 interleaves the G columns (position p of column g at p*G + g) and maps threads
+// with g fastest, so that a warp's accesses are linear in the thread index in every stage and the final column-adjacent
+// store reads shared memory linearly; MODE 1 keeps each row contiguous (g*n + p) with the butterfly index fastest.
+template <int R, int MODE>
 __device__ __forceinline__ void pass_mid(const float2 *Sin, float2 *Sout, int n, int G, int Ns, const float2 *__restrict__ T,
-                                         int sign, unsigned long long mg_m, unsigned long long mg_ns) {
+                                         int sign, unsigned long long mg_g, unsigned long long mg_m,
+                                         unsigned long long mg_ns) {
     const int m = n / R, tot = G * m, step = m / Ns;      // W_{Ns R}^k = W_n^{step k}
     for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
-        const int g = fastdiv(idx, mg_m), j = idx - g * m;
+        int g, j;
+        if (MODE == 0) { j = fastdiv(idx, mg_g); g = idx - j * G; }
+        else { g = fastdiv(idx, mg_m); j = idx - g * m; }
         const int blk = fastdiv(j, mg_ns), k = j - blk * Ns;
         float2 v[R];
 #pragma unroll
-        for (int u = 0; u < R; ++u) v[u] = Sin[cr_pad(g * n + j + u * m)];
+        for (int u = 0; u < R; ++u) v[u] = Sin[cr_pad(MODE == 0 ? idx + u * tot : g * n + j + u * m)];
         apply_powers<R>(v, tw_dir(T[step * k], sign));
         dft_r<R>(v, sign);
-        const int base = g * n + blk * Ns * R + k;
+        const int base = blk * Ns * R + k;
 #pragma unroll
-        for (int u = 0; u < R; ++u) Sout[cr_pad(base + u * Ns)] = v[u];
+        for (int u = 0; u < R; ++u) Sout[cr_pad(MODE == 0 ? (base + u * Ns) * G + g : g * n + base + u * Ns)] = v[u];
     }
 }
 
@@ -465,14 +481,16 @@ struct PassOut {
 
 template <int R, int MODE>
 __device__ __forceinline__ void pass_last(const float2 *Sin, float2 *Sout, int n, int G, int g_here,
-                                          const float2 *__restrict__ T, int sign, unsigned long long mg_m,
-                                          const PassOut &po) {
+                                          const float2 *__restrict__ T, int sign, unsigned long long mg_g,
+                                          unsigned long long mg_m, const PassOut &po) {
     const int m = n / R, tot = G * m;       // Ns = m: blk = 0, k = j; outputs d = j + u m
     for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
-        const int g = fastdiv(idx, mg_m), j = idx - g * m;
+        int g, j;
+        if (MODE == 0) { j = fastdiv(idx, mg_g); g = idx - j * G; }
+        else { g = fastdiv(idx, mg_m); j = idx - g * m; }
         float2 v[R];
 #pragma unroll
-        for (int u = 0; u < R; ++u) v[u] = Sin[cr_pad(g * n + j + u * m)];
+        for (int u = 0; u < R; ++u) v[u] = Sin[cr_pad(MODE == 0 ? idx + u * tot : g * n + j + u * m)];
         if (R > 1) apply_powers<R>(v, tw_dir(T[j], sign));
         dft_r<R>(v, sign);
         if (MODE == 0) {
@@ -481,7 +499,7 @@ __device__ __forceinline__ void pass_last(const float2 *Sin, float2 *Sout, int n
             const float2 wa = twiddle2(po.tw_hi, po.tw_lo, (long long)bcol * j, sign);
             if (R > 1) apply_powers<R>(v, twiddle2(po.tw_hi, po.tw_lo, (long long)bcol * m, sign));
 #pragma unroll
-            for (int u = 0; u < R; ++u) Sout[cr_pad(g * n + j + u * m)] = cmul(v[u], wa);
+            for (int u = 0; u < R; ++u) Sout[cr_pad(idx + u * tot)] = cmul(v[u], wa);
         } else if (g < g_here) {
             const int c = po.first + g, mlo = po.H - po.khi, mhi = po.H - po.klo;
 #pragma unroll
@@ -517,7 +535,7 @@ __device__ __forceinline__ void pass_last(const float2 *Sin, float2 *Sout, int n
     }
 
 template <int MODE>
-__global__ void __launch_bounds__(CQ_FFT_THREADS, 2)
+__global__ void __launch_bounds__(CQ_FFT_THREADS, CQ_PASS_CTAS)
 fft_pass_kernel(const float2 *__restrict__ in, float2 *__restrict__ out_lo, float2 *__restrict__ out_hi, FftDesc d,
                 int other, int G, unsigned long long mg_g, const float2 *__restrict__ T,
                 const float2 *__restrict__ twH_hi, const float2 *__restrict__ twH_lo, int klo, int khi, int H,
@@ -536,13 +554,13 @@ fft_pass_kernel(const float2 *__restrict__ in, float2 *__restrict__ out_lo, floa
     int Ns = d.rad[0];
     float2 *cur = S0, *nxt = S1;
     for (int s = 1; s + 1 < d.nrad; ++s) {
-        HPFW_RADIX_SWITCH(d.rad[s], (pass_mid<R>(cur, nxt, n, G, Ns, T, sign, d.mg_m[s], d.mg_ns[s])));
+        HPFW_RADIX_SWITCH(d.rad[s], (pass_mid<R, MODE>(cur, nxt, n, G, Ns, T, sign, mg_g, d.mg_m[s], d.mg_ns[s])));
         __syncthreads();
         float2 *t = cur; cur = nxt; nxt = t;
         Ns *= d.rad[s];
     }
     const int sl = d.nrad - 1;
-    HPFW_RADIX_SWITCH(d.rad[sl], (pass_last<R, MODE>(cur, nxt, n, G, g_here, T, sign, d.mg_m[sl], po)));
+    HPFW_RADIX_SWITCH(d.rad[sl], (pass_last<R, MODE>(cur, nxt, n, G, g_here, T, sign, mg_g, d.mg_m[sl], po)));
     if (MODE == 0) {
         __syncthreads();
         // nxt holds out-values at [g][c]; store with the G adjacent columns contiguous (32-byte runs for G = 4)
@@ -550,7 +568,7 @@ fft_pass_kernel(const float2 *__restrict__ in, float2 *__restrict__ out_lo, floa
 #pragma unroll 4
         for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
             const int c = fastdiv(idx, mg_g), g = idx - c * G;
-            if (g < g_here) po.lo[c * pitch + g] = nxt[cr_pad(g * n + c)];
+            if (g < g_here) po.lo[c * pitch + g] = nxt[cr_pad(idx)];
         }
     }
 }
@@ -562,8 +580,8 @@ fft_pass_kernel(const float2 *__restrict__ in, float2 *__restrict__ out_lo, floa
 template <int MODE>
 __global__ void __launch_bounds__(CQ_THREADS)
 czt_cols_kernel(const BandMeta *__restrict__ bands, const float2 *__restrict__ z_lo, const float2 *__restrict__ z_hi,
-                int klo, int khi, const float2 *__restrict__ twN_hi, const float2 *__restrict__ twN_lo, int M, int F,
-                float2 *__restrict__ work) {
+                int klo, int khi, const float2 *__restrict__ twN_hi, const float2 *__restrict__ twN_lo,
+                const float2 *__restrict__ chirp, int M, int F, float2 *__restrict__ work) {
     const BandMeta bm = bands[blockIdx.y];
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= bm.L2) return;
@@ -583,10 +601,7 @@ czt_cols_kernel(const BandMeta *__restrict__ bands, const float2 *__restrict__ z
                 // X[k] = (Zk + conj Zm)/2 - (i/2) W (Zk - conj Zm)
                 const float2 X = make_float2(0.5f * (se.x + so.y), 0.5f * (se.y - so.x));
                 const float hann = 0.5f + 0.5f * cospif(2.0f * (float)(kp - bm.half) / (float)bm.lg);
-                const unsigned long long ph = (3ull * (unsigned long long)kp * (unsigned long long)kp) % twoM;
-                float s, c;
-                sincospif((float)((double)ph / (double)M), &s, &c);
-                val = cmul(make_float2(X.x * hann, X.y * hann), make_float2(c, s));
+                val = cmul(make_float2(X.x * hann, X.y * hann), chirp[kp]);     // chirp[kp] = e^{+i pi 3 kp^2 / M}
             }
         } else {
             const long long n = kp < F ? kp : (long long)kp - bm.L;
@@ -599,13 +614,13 @@ czt_cols_kernel(const BandMeta *__restrict__ bands, const float2 *__restrict__ z
     }
     dft16(v, -1);
     float2 *dst = work + bm.work_off;
-    const float invL = 1.0f / (float)bm.L;
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
+    {   // inter-pass twiddle W_L^{b c}, c = 0..15: one sincospif, powers by product tree
         float s, co;
-        sincospif(-2.0f * (float)(b * c) * invL, &s, &co);     // b*c < L <= 2^17: exact in float
-        dst[c * bm.L2 + b] = cmul(v[c], make_float2(co, s));
+        sincospif(-2.0f * (float)b / (float)bm.L, &s, &co);
+        apply_powers<16>(v, make_float2(co, s));
     }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) dst[c * bm.L2 + b] = v[c];
 }
 
 // ------------------------------------------------------------------------------------------------ CZT row pass
@@ -697,7 +712,7 @@ __device__ __forceinline__ void rows3_last(float2 *__restrict__ rows, const floa
     }
 }
 
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, CQ_ROWS3_CTAS)
 czt_rows3_kernel(const BandMeta *__restrict__ bands, const RowTile *__restrict__ tiles, float2 *__restrict__ work,
                  const float2 *const *__restrict__ btabs, const float2 *const *__restrict__ ttabs) {
     extern __shared__ __align__(16) float2 fsm[];
@@ -967,7 +982,7 @@ struct CqtPlan {
     FftDesc d1{}, d2{};
     int G1 = 1, G2 = 1;
     size_t smem1 = 0, smem2 = 0;
-    DeviceBuffer tw1, tw2;
+    DeviceBuffer tw1, tw2, chirp;
     TwoLevel twH, twN;
     // CZT
     std::vector<BandMeta> bands;
@@ -1000,7 +1015,7 @@ struct CqtPlan {
     }
 
     void release() {
-        tw1.release(); tw2.release(); twH.release(); twN.release();
+        tw1.release(); tw2.release(); chirp.release(); twH.release(); twN.release();
         d_bands.release(); d_btab_ptrs.release(); d_descs.release(); d_tw_ptrs.release(); d_tiles.release(); d_tt_ptrs.release();
         d_tiles3.release();
         for (auto &b : ttabs) b->release();
@@ -1078,7 +1093,11 @@ static int pick_row_len(long long need2) {
 // split H = n1 * n2 (n1 <= n2 <= CQ_MAX_ROW), both {2,3,5,7}-smooth: the fewest Stockham stages in total, then the most
 // balanced; returns false if there is none
 static bool split_smooth(int H, int &n1, int &n2) {
-    const int n1max = env_int("HPFW_CQT_N1MAX", 1 << 30);   // tuning override: cap the column-FFT length
+    // column FFTs longer than ~1000 points push pass A to one CTA per SM (4 adjacent columns = one 32-byte sector is the
+    // least it should load): prefer a split with n1 <= 1024 when there is one. HPFW_CQT_N1MAX overrides (tuning).
+    int n1max = env_int("HPFW_CQT_N1MAX", 0);
+    const bool capped_default = n1max <= 0;
+    if (capped_default) n1max = 1024;
     int rest = H;
     int e[4] = {0, 0, 0, 0};
     const int p[4] = {2, 3, 5, 7};
@@ -1103,27 +1122,34 @@ static bool split_smooth(int H, int &n1, int &n2) {
                     const int st = da.nrad + db.nrad;
                     if (st < best_stages || (st == best_stages && v > best)) { best_stages = st; best = v; }
                 }
+    if (best < 2 && capped_default) {   // nothing under the default cap: any split
+        setenv("HPFW_CQT_N1MAX", "1073741824", 1);
+        const bool ok = split_smooth(H, n1, n2);
+        unsetenv("HPFW_CQT_N1MAX");
+        return ok;
+    }
     if (best < 2) return false;
     n1 = (int)best;
     n2 = (int)(H / best);
     return true;
 }
 
-// Shared memory of the two-pass FFT kernels: twiddles (n) + ping-pong (2 * G * n) complex values. G columns / rows per CTA
-// is sized for two resident CTAs per SM (~110 KB each) when the transform allows it, one CTA otherwise.
+// Shared memory of the two-pass FFT kernels: ping-pong buffers of G * n padded complex values. G (columns / rows per CTA)
+// is sized for three resident CTAs per SM (<= 74 KB each) when the transform allows it, one CTA otherwise.
 static void fft_group_sizes(hpfw_ctx *ctx, int n1, int n2, int &G1, int &G2, size_t &smem1, size_t &smem2) {
-    const size_t two_cta = 110 * 1024, one_cta = (size_t)ctx->max_smem_optin - 2048;
+    const size_t multi_cta = (size_t)env_int("HPFW_CQT_SMEM_KB", 74) * 1024, one_cta = (size_t)ctx->max_smem_optin - 2048;
     auto pick = [&](int n, int gmax) {
         int g = gmax;
-        while (g > 1 && fft_pass_smem(n, g) > two_cta) --g;
-        if (fft_pass_smem(n, g) > two_cta) {
+        while (g > 1 && fft_pass_smem(n, g) > multi_cta) --g;
+        if (fft_pass_smem(n, g) > multi_cta) {
             g = gmax;
             while (g > 1 && fft_pass_smem(n, g) > one_cta) --g;
         }
         return g;
     };
     G1 = pick(n1, 8);
-    if (G1 > 4) G1 = 4 * (G1 / 4);       // whole 32-byte sectors
+    G1 = G1 >= 8 ? 8 : (G1 >= 4 ? 4 : G1);   // whole 32-byte sectors (4 adjacent columns) wherever shared memory allows
+    if (G1 < 4 && fft_pass_smem(n1, 4) <= one_cta) G1 = 4;
     G2 = pick(n2, 4);
     // tuning overrides (experiments only)
     const int g1 = env_int("HPFW_CQT_G1", 0), g2 = env_int("HPFW_CQT_G2", 0);
@@ -1179,6 +1205,17 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
     }
     HPFW_TRY(pl.twH.upload(pl.H));
     HPFW_TRY(pl.twN.upload(N));
+    {   // input chirp e^{+i pi 3 k^2 / M}, k < M (the longest band window), phase reduced mod 2M in integers
+        std::vector<float2> ch((size_t)d.M);
+        const unsigned long long twoM = 2ull * (unsigned long long)d.M;
+        for (int k = 0; k < d.M; ++k) {
+            const unsigned long long ph = (3ull * (unsigned long long)k * (unsigned long long)k) % twoM;
+            const double a = M_PI * (double)ph / (double)d.M;
+            ch[(size_t)k] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+        HPFW_TRY(pl.chirp.reserve(sizeof(float2) * ch.size()));
+        HPFW_CUDA_TRY(cudaMemcpy(pl.chirp.ptr, ch.data(), sizeof(float2) * ch.size(), cudaMemcpyHostToDevice));
+    }
 
     // CZT layout
     pl.bands.resize(CQ_BINS);
@@ -1297,8 +1334,8 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
             dim3 g1((fb[i].L2 + CQ_THREADS - 1) / CQ_THREADS, 1);
             {
                 KernelScope ks(ctx, HPFW_K_CQT, stream);
-                czt_cols_kernel<1><<<g1, CQ_THREADS, 0, stream>>>(dbm, nullptr, nullptr, 0, 0, nullptr, nullptr, d.M, d.F,
-                                                                   tab);
+                czt_cols_kernel<1><<<g1, CQ_THREADS, 0, stream>>>(dbm, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr,
+                                                                   d.M, d.F, tab);
             }
             {
                 KernelScope ks(ctx, HPFW_K_CQT, stream);
@@ -1372,8 +1409,8 @@ static int cqt_run(hpfw_ctx *ctx, const float *d_audio, int64_t N, float *d_out,
         KernelScope ks(ctx, HPFW_K_CQT, stream);
         czt_cols_kernel<0><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands.as<BandMeta>(), sc->zlo.as<float2>(),
                                                              sc->zhi.as<float2>(), pl->klo, pl->khi,
-                                                             pl->twN.hi.as<float2>(), pl->twN.lo.as<float2>(), d.M, d.F,
-                                                             sc->work.as<float2>());
+                                                             pl->twN.hi.as<float2>(), pl->twN.lo.as<float2>(),
+                                                             pl->chirp.as<float2>(), d.M, d.F, sc->work.as<float2>());
     }
     if (pl->n_tiles3 > 0) {
         KernelScope ks(ctx, HPFW_K_CQT, stream);

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Run on the GPU box via gpurun: parity tests, smoke, bench, ncu launch list + one full capture of the match kernel.
-# Usage: scripts/gpu_check.sh [tag]
+# Usage: scripts/gpu_check.sh [tag]   (NCU=0 skips the profiler passes)
 set -u
 TAG=${1:-r01}
 OUT=gpurun_out/$TAG
