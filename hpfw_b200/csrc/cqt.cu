@@ -509,7 +509,7 @@ __device__ __forceinline__ void pass_last(const float2 *Sin, float2 *Sout, int n
                     po.lo[k] = v[u];
                 } else {
                     if (k >= po.klo && k <= po.khi) po.lo[k - po.klo] = v[u];
-                    if (k >= mlo && k <= mhi) po.hi[k - mlo] = v[u];
+                    if (po.hi != nullptr && k >= mlo && k <= mhi) po.hi[k - mlo] = v[u];
                 }
             }
         }
@@ -573,9 +573,58 @@ fft_pass_kernel(const float2 *__restrict__ in, float2 *__restrict__ out_lo, floa
     }
 }
 
+// ------------------------------------------------------------------------------------------------ Bluestein (any N)
+// Audio lengths whose half is not a product of 2,3,5,7 (or that are odd) cannot use the packed two-pass FFT. For those the
+// wanted bins X[klo..khi] of the length-N DFT are a chirp convolution, n k = (n^2 + k^2 - (k-n)^2) / 2:
+//   X[k] = c[k] * sum_n (x[n] c[n]) b[k - n],  c[m] = e^{-i pi m^2 / N},  b = conj(c),
+// evaluated by the same pass kernels on a smooth length P >= N + (khi - klo): FFT_P(a) .* FFT_P(b') -> IFFT_P, where b' is
+// b shifted by klo so that output index 0 is bin klo. Phases are reduced mod 2N in 64-bit integers before sincospi.
+__device__ __forceinline__ float2 bl_chirp(long long m, long long N, int sign) {     // e^{sign i pi m^2 / N}
+    const unsigned long long r = ((unsigned long long)(m * m)) % (2ull * (unsigned long long)N);
+    float s, c;
+    sincospif((float)((double)r / (double)N), &s, &c);
+    return make_float2(c, sign < 0 ? -s : s);
+}
+__global__ void __launch_bounds__(CQ_THREADS)
+bl_prep_kernel(const float *__restrict__ x, long long N, int P, float2 *__restrict__ a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    float2 v = make_float2(0.f, 0.f);
+    if (i < N) {
+        const float2 c = bl_chirp(i, N, -1);
+        const float xv = x[i];
+        v = make_float2(xv * c.x, xv * c.y);
+    }
+    a[i] = v;
+}
+__global__ void __launch_bounds__(CQ_THREADS)
+bl_filter_kernel(long long N, int P, int klo, int K, float2 *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    float2 v = make_float2(0.f, 0.f);
+    if (i < K) v = bl_chirp((long long)i + klo, N, +1);
+    else if ((long long)i > (long long)P - N) v = bl_chirp((long long)i - P + klo, N, +1);     // m' = i - P in (-N, 0)
+    out[i] = v;
+}
+__global__ void __launch_bounds__(CQ_THREADS)
+bl_mul_kernel(float2 *__restrict__ a, const float2 *__restrict__ b, int P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) a[i] = cmul(a[i], b[i]);
+}
+__global__ void __launch_bounds__(CQ_THREADS)
+bl_post_kernel(float2 *__restrict__ x, long long N, int P, int klo, int K) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K) return;
+    const float2 c = bl_chirp((long long)i + klo, N, -1);
+    const float inv = 1.0f / (float)P;
+    const float2 v = cmul(x[i], c);
+    x[i] = make_float2(v.x * inv, v.y * inv);
+}
+
 // ------------------------------------------------------------------------------------------------ CZT column pass
 // MODE 0: band input a[k'] = X[first_bin + k'] * hann * chirp from the packed half spectrum (untangled on the fly).
 // MODE 1: chirp filter b[n] = e^{-i pi 3 n^2 / M}, n = k' (k' < F) or k' - L (k' >= F), for plan creation.
+// MODE 2: as MODE 0 but X[k] is read as is (the Bluestein path already produced the full-spectrum bins).
 // Then 16-point FFT down the columns (k' = L2*a + b), twiddle W_L^{b c}, store work[c*L2 + b].
 template <int MODE>
 __global__ void __launch_bounds__(CQ_THREADS)
@@ -591,7 +640,13 @@ czt_cols_kernel(const BandMeta *__restrict__ bands, const float2 *__restrict__ z
     for (int a = 0; a < 16; ++a) {
         const int kp = bm.L2 * a + b;
         float2 val = make_float2(0.f, 0.f);
-        if (MODE == 0) {
+        if (MODE == 2) {          // Bluestein plans: z_lo holds X[klo ..] itself
+            if (kp < bm.lg) {
+                const float2 X = z_lo[bm.first_bin + kp - klo];
+                const float hann = 0.5f + 0.5f * cospif(2.0f * (float)(kp - bm.half) / (float)bm.lg);
+                val = cmul(make_float2(X.x * hann, X.y * hann), chirp[kp]);
+            }
+        } else if (MODE == 0) {
             if (kp < bm.lg) {
                 const int k = bm.first_bin + kp;
                 const float2 zk = z_lo[k - klo];
@@ -977,6 +1032,9 @@ struct TwoLevel {
 struct CqtPlan {
     int64_t N = 0;
     int H = 0;
+    bool bluestein = false;     // N odd or N/2 not {2,3,5,7}-smooth: chirp convolution on length P (d1, d2, tw1, tw2, twH are P's)
+    int P = 0;
+    DeviceBuffer bhat;          // FFT_P of the shifted chirp filter
     CqtDesign des;
     int klo = 0, khi = 0;
     FftDesc d1{}, d2{};
@@ -995,7 +1053,7 @@ struct CqtPlan {
     int fpitch = 0;
     // per-track scratch, one set per lane (tracks of a batch run concurrently on CQ_LANES streams)
     struct Scratch {
-        DeviceBuffer zbuf, zlo, zhi, work, power, pmax;
+        DeviceBuffer zbuf, zlo, zhi, work, power, pmax, bl_a;
         bool ready = false;
     } lanes[CQ_LANES];
     uint64_t last_use = 0;
@@ -1004,9 +1062,10 @@ struct CqtPlan {
         Scratch &sc = lanes[lane];
         if (sc.ready) return HPFW_OK;
         const size_t nkeep = (size_t)(khi - klo + 1);
-        HPFW_TRY(sc.zbuf.reserve(sizeof(float2) * (size_t)H));
+        HPFW_TRY(sc.zbuf.reserve(sizeof(float2) * (size_t)(bluestein ? P : H)));
         HPFW_TRY(sc.zlo.reserve(sizeof(float2) * nkeep));
-        HPFW_TRY(sc.zhi.reserve(sizeof(float2) * nkeep));
+        if (bluestein) HPFW_TRY(sc.bl_a.reserve(sizeof(float2) * (size_t)P));
+        else HPFW_TRY(sc.zhi.reserve(sizeof(float2) * nkeep));
         HPFW_TRY(sc.work.reserve(sizeof(float2) * (size_t)work_elems));
         HPFW_TRY(sc.power.reserve(sizeof(float) * (size_t)CQ_BINS * fpitch));
         HPFW_TRY(sc.pmax.reserve(sizeof(unsigned int)));
@@ -1015,7 +1074,7 @@ struct CqtPlan {
     }
 
     void release() {
-        tw1.release(); tw2.release(); chirp.release(); twH.release(); twN.release();
+        tw1.release(); tw2.release(); chirp.release(); twH.release(); twN.release(); bhat.release();
         d_bands.release(); d_btab_ptrs.release(); d_descs.release(); d_tw_ptrs.release(); d_tiles.release(); d_tt_ptrs.release();
         d_tiles3.release();
         for (auto &b : ttabs) b->release();
@@ -1023,6 +1082,7 @@ struct CqtPlan {
         for (auto &b : rowtws) b->release();
         for (auto &sc : lanes) {
             sc.zbuf.release(); sc.zlo.release(); sc.zhi.release(); sc.work.release(); sc.power.release(); sc.pmax.release();
+            sc.bl_a.release();
             sc.ready = false;
         }
     }
@@ -1170,20 +1230,32 @@ static int set_smem_limits(hpfw_ctx *ctx) {
     return HPFW_OK;
 }
 
+// the plan's two-pass FFT (H points for the packed path, P for Bluestein): in -> tmp -> out_lo / out_hi
+static int fft_two_pass(hpfw_ctx *ctx, const CqtPlan &pl, const float2 *in, float2 *tmp, float2 *out_lo, float2 *out_hi,
+                        int klo, int khi, int keep_all, int sign, cudaStream_t stream) {
+    const int n1 = pl.d1.n, n2 = pl.d2.n, len = pl.bluestein ? pl.P : pl.H;
+    {
+        KernelScope ks(ctx, HPFW_K_CQT, stream);
+        fft_pass_kernel<0><<<(n2 + pl.G1 - 1) / pl.G1, CQ_FFT_THREADS, pl.smem1, stream>>>(
+            in, tmp, nullptr, pl.d1, n2, pl.G1, magic40((unsigned long long)pl.G1), pl.tw1.as<float2>(),
+            pl.twH.hi.as<float2>(), pl.twH.lo.as<float2>(), 0, 0, len, 1, sign);
+    }
+    {
+        KernelScope ks(ctx, HPFW_K_CQT, stream);
+        fft_pass_kernel<1><<<(n1 + pl.G2 - 1) / pl.G2, CQ_FFT_THREADS, pl.smem2, stream>>>(
+            tmp, out_lo, out_hi, pl.d2, n1, pl.G2, magic40((unsigned long long)pl.G2), pl.tw2.as<float2>(), nullptr,
+            nullptr, klo, khi, len, keep_all, sign);
+    }
+    return HPFW_OK;
+}
+
 static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t stream) {
     pl.N = N;
-    if (N < 2 || (N & 1))
-        HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: audio length %lld is odd or empty; this build packs the real FFT into N/2 complex "
-                  "points and needs an even length", (long long)N);
+    if (N < 2) HPFW_FAIL(HPFW_ERR_ARG, "CQT: empty audio");
     if (N > (int64_t(1) << 27)) HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: audio length %lld exceeds 2^27 samples", (long long)N);
     if (!cqt_design(N, pl.des)) HPFW_FAIL(HPFW_ERR_ARG, "CQT: bad length");
     const CqtDesign &d = pl.des;
     pl.H = (int)(N / 2);
-    int n1 = 0, n2 = 0;
-    if (!split_smooth(pl.H, n1, n2))
-        HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: N/2 = %d has no split n1*n2 with both factors {2,3,5,7}-smooth and <= %d; "
-                  "non-smooth audio lengths are not supported by this build", pl.H, CQ_MAX_ROW);
-    if (!factor_smooth(n1, pl.d1) || !factor_smooth(n2, pl.d2)) HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: too many FFT stages");
     pl.klo = 1 << 30;
     pl.khi = 0;
     for (int j = 0; j < CQ_BINS; ++j) {
@@ -1193,6 +1265,25 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
     }
     if (pl.klo < 1 || pl.khi >= pl.H)
         HPFW_FAIL(HPFW_ERR_SHORT, "CQT: audio of %lld samples is too short for the 121-band design", (long long)N);
+    int n1 = 0, n2 = 0;
+    pl.bluestein = (N & 1) || !split_smooth(pl.H, n1, n2) || env_int("HPFW_CQT_BLUESTEIN", 0);
+    if (pl.bluestein) {
+        // smallest smooth P >= N + K - 1 that the two-pass engine can split; among the first few, the fewest stages
+        const long long need = N + (long long)(pl.khi - pl.klo);
+        int found = 0, best_st = 1 << 30;
+        for (long long c = need; c <= (1ll << 26) && found < 8; ++c) {
+            int a1 = 0, a2 = 0;
+            if (!split_smooth((int)c, a1, a2)) continue;
+            FftDesc da{}, db{};
+            if (!factor_smooth(a1, da) || !factor_smooth(a2, db)) continue;
+            ++found;
+            if (da.nrad + db.nrad < best_st) { best_st = da.nrad + db.nrad; pl.P = (int)c; n1 = a1; n2 = a2; }
+        }
+        if (!pl.P)
+            HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: audio of %lld samples needs a %lld-point chirp convolution; limit 2^26",
+                      (long long)N, need);
+    }
+    if (!factor_smooth(n1, pl.d1) || !factor_smooth(n2, pl.d2)) HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: too many FFT stages");
     fft_group_sizes(ctx, n1, n2, pl.G1, pl.G2, pl.smem1, pl.smem2);
     {
         pad_single_stage(pl.d1);
@@ -1203,8 +1294,8 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
         HPFW_CUDA_TRY(cudaMemcpy(pl.tw1.ptr, t1.data(), sizeof(float2) * t1.size(), cudaMemcpyHostToDevice));
         HPFW_CUDA_TRY(cudaMemcpy(pl.tw2.ptr, t2.data(), sizeof(float2) * t2.size(), cudaMemcpyHostToDevice));
     }
-    HPFW_TRY(pl.twH.upload(pl.H));
-    HPFW_TRY(pl.twN.upload(N));
+    HPFW_TRY(pl.twH.upload(pl.bluestein ? pl.P : pl.H));
+    if (!pl.bluestein) HPFW_TRY(pl.twN.upload(N));
     {   // input chirp e^{+i pi 3 k^2 / M}, k < M (the longest band window), phase reduced mod 2M in integers
         std::vector<float2> ch((size_t)d.M);
         const unsigned long long twoM = 2ull * (unsigned long long)d.M;
@@ -1350,7 +1441,21 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
         d_ft.release();
     }
 
-    return pl.lane_reserve(0);
+    HPFW_TRY(pl.lane_reserve(0));
+    if (pl.bluestein) {     // FFT_P of the shifted chirp filter, through lane 0's scratch
+        CqtPlan::Scratch &sc = pl.lanes[0];
+        const int P = pl.P, K = pl.khi - pl.klo + 1, gb = (P + CQ_THREADS - 1) / CQ_THREADS;
+        HPFW_TRY(pl.bhat.reserve(sizeof(float2) * (size_t)P));
+        {
+            KernelScope ks(ctx, HPFW_K_CQT, stream);
+            bl_filter_kernel<<<gb, CQ_THREADS, 0, stream>>>((long long)N, P, pl.klo, K, sc.bl_a.as<float2>());
+        }
+        HPFW_TRY(fft_two_pass(ctx, pl, sc.bl_a.as<float2>(), sc.zbuf.as<float2>(), pl.bhat.as<float2>(), nullptr, 0, 0, 1,
+                              -1, stream));
+        HPFW_CUDA_TRY(cudaGetLastError());
+        HPFW_CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    return HPFW_OK;
 }
 
 static int plan_get(hpfw_ctx *ctx, int64_t N, CqtPlan **out, cudaStream_t stream) {
@@ -1382,35 +1487,49 @@ static int plan_get(hpfw_ctx *ctx, int64_t N, CqtPlan **out, cudaStream_t stream
 // mode 0: dB spectrogram; mode 1: linear magnitudes. d_audio must be 8-byte aligned.
 static int cqt_run(hpfw_ctx *ctx, const float *d_audio, int64_t N, float *d_out, int mode, cudaStream_t stream,
                    int lane = 0) {
-    if ((reinterpret_cast<uintptr_t>(d_audio) & 7) != 0)
-        HPFW_FAIL(HPFW_ERR_ARG, "CQT: the audio buffer must be 8-byte aligned");
     CqtPlan *pl = nullptr;
     HPFW_TRY(plan_get(ctx, N, &pl, stream));
     HPFW_TRY(pl->lane_reserve(lane));
     CqtPlan::Scratch *sc = &pl->lanes[lane];
     const CqtDesign &d = pl->des;
-    const int n1 = pl->d1.n, n2 = pl->d2.n;
-    const float2 *z_in = reinterpret_cast<const float2 *>(d_audio);
-    {
-        KernelScope ks(ctx, HPFW_K_CQT, stream);
-        fft_pass_kernel<0><<<(n2 + pl->G1 - 1) / pl->G1, CQ_FFT_THREADS, pl->smem1, stream>>>(
-            z_in, sc->zbuf.as<float2>(), nullptr, pl->d1, n2, pl->G1, magic40((unsigned long long)pl->G1),
-            pl->tw1.as<float2>(), pl->twH.hi.as<float2>(), pl->twH.lo.as<float2>(), 0, 0, pl->H, 1, -1);
-    }
-    {
-        KernelScope ks(ctx, HPFW_K_CQT, stream);
-        fft_pass_kernel<1><<<(n1 + pl->G2 - 1) / pl->G2, CQ_FFT_THREADS, pl->smem2, stream>>>(
-            sc->zbuf.as<float2>(), sc->zlo.as<float2>(), sc->zhi.as<float2>(), pl->d2, n1, pl->G2,
-            magic40((unsigned long long)pl->G2), pl->tw2.as<float2>(), nullptr, nullptr, pl->klo, pl->khi, pl->H, 0, -1);
+    if (!pl->bluestein) {
+        if ((reinterpret_cast<uintptr_t>(d_audio) & 7) != 0)
+            HPFW_FAIL(HPFW_ERR_ARG, "CQT: the audio buffer must be 8-byte aligned");
+        HPFW_TRY(fft_two_pass(ctx, *pl, reinterpret_cast<const float2 *>(d_audio), sc->zbuf.as<float2>(),
+                              sc->zlo.as<float2>(), sc->zhi.as<float2>(), pl->klo, pl->khi, 0, -1, stream));
+    } else {
+        const int P = pl->P, K = pl->khi - pl->klo + 1, gb = (P + CQ_THREADS - 1) / CQ_THREADS;
+        {
+            KernelScope ks(ctx, HPFW_K_CQT, stream);
+            bl_prep_kernel<<<gb, CQ_THREADS, 0, stream>>>(d_audio, (long long)N, P, sc->bl_a.as<float2>());
+        }
+        HPFW_TRY(fft_two_pass(ctx, *pl, sc->bl_a.as<float2>(), sc->zbuf.as<float2>(), sc->bl_a.as<float2>(), nullptr, 0, 0,
+                              1, -1, stream));
+        {
+            KernelScope ks(ctx, HPFW_K_CQT, stream);
+            bl_mul_kernel<<<gb, CQ_THREADS, 0, stream>>>(sc->bl_a.as<float2>(), pl->bhat.as<float2>(), P);
+        }
+        HPFW_TRY(fft_two_pass(ctx, *pl, sc->bl_a.as<float2>(), sc->zbuf.as<float2>(), sc->zlo.as<float2>(), nullptr, 0,
+                              K - 1, 0, +1, stream));
+        {
+            KernelScope ks(ctx, HPFW_K_CQT, stream);
+            bl_post_kernel<<<(K + CQ_THREADS - 1) / CQ_THREADS, CQ_THREADS, 0, stream>>>(sc->zlo.as<float2>(), (long long)N,
+                                                                                         P, pl->klo, K);
+        }
     }
     HPFW_CUDA_TRY(cudaMemsetAsync(sc->pmax.ptr, 0, sizeof(unsigned int), stream));
     const dim3 gcol((pl->max_L2 + CQ_THREADS - 1) / CQ_THREADS, CQ_BINS);
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
-        czt_cols_kernel<0><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands.as<BandMeta>(), sc->zlo.as<float2>(),
-                                                             sc->zhi.as<float2>(), pl->klo, pl->khi,
-                                                             pl->twN.hi.as<float2>(), pl->twN.lo.as<float2>(),
-                                                             pl->chirp.as<float2>(), d.M, d.F, sc->work.as<float2>());
+        if (pl->bluestein)
+            czt_cols_kernel<2><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands.as<BandMeta>(), sc->zlo.as<float2>(), nullptr,
+                                                                 pl->klo, pl->khi, nullptr, nullptr,
+                                                                 pl->chirp.as<float2>(), d.M, d.F, sc->work.as<float2>());
+        else
+            czt_cols_kernel<0><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands.as<BandMeta>(), sc->zlo.as<float2>(),
+                                                                 sc->zhi.as<float2>(), pl->klo, pl->khi,
+                                                                 pl->twN.hi.as<float2>(), pl->twN.lo.as<float2>(),
+                                                                 pl->chirp.as<float2>(), d.M, d.F, sc->work.as<float2>());
     }
     if (pl->n_tiles3 > 0) {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
@@ -1601,7 +1720,7 @@ int hpfw_calc_hashprint_audio_batch_device(hpfw_ctx *ctx, const float *d_audio, 
         int j = i;
         while (j < n) {
             const int64_t ns = sample_offsets[j + 1] - sample_offsets[j];
-            if (ns < 0 || (sample_offsets[j] & 1)) HPFW_FAIL(HPFW_ERR_ARG, "track %d: offsets must be monotone and even", j);
+            if (ns < 0) HPFW_FAIL(HPFW_ERR_ARG, "track %d: offsets must be monotone", j);
             const int cols = hpfw_cqt_cols(ns);
             if (hpfw_hashprint_words_for_cols(cols) <= 0)
                 HPFW_FAIL(HPFW_ERR_SHORT, "track %d (%lld samples) is too short for one hashprint word", j, (long long)ns);
