@@ -1150,8 +1150,8 @@ static int pick_row_len(long long need2) {
     return best_n;   // 0: nothing fits under CQ_MAX_ROW
 }
 
-// split H = n1 * n2 (n1 <= n2 <= CQ_MAX_ROW), both {2,3,5,7}-smooth: the fewest Stockham stages in total, then the most
-// balanced; returns false if there is none
+// split H = n1 * n2 (n1 <= n2 <= CQ_MAX_ROW), both {2,3,5,7}-smooth: the fewest Stockham stages in total, then a row pitch
+// that keeps pass A's column groups sector-aligned, then the most balanced; returns false if there is none
 static bool split_smooth(int H, int &n1, int &n2) {
     // column FFTs longer than ~1000 points push pass A to one CTA per SM (4 adjacent columns = one 32-byte sector is the
     // least it should load): prefer a split with n1 <= 1024 when there is one. HPFW_CQT_N1MAX overrides (tuning).
@@ -1165,7 +1165,7 @@ static bool split_smooth(int H, int &n1, int &n2) {
         while (rest % p[i] == 0) { rest /= p[i]; e[i]++; }
     if (rest != 1) return false;
     long long best = -1;
-    int best_stages = 1 << 30;
+    int best_stages = 1 << 30, best_al = -1;
     for (int a = 0; a <= e[0]; ++a)
         for (int b = 0; b <= e[1]; ++b)
             for (int c = 0; c <= e[2]; ++c)
@@ -1180,7 +1180,11 @@ static bool split_smooth(int H, int &n1, int &n2) {
                     FftDesc da{}, db{};
                     if (!factor_smooth((int)v, da) || !factor_smooth((int)w, db)) continue;
                     const int st = da.nrad + db.nrad;
-                    if (st < best_stages || (st == best_stages && v > best)) { best_stages = st; best = v; }
+                    // pass A touches 4 adjacent columns = one 32-byte sector only if the row pitch n2 is a multiple of 4
+                    const int al = (w % 4 == 0) ? 1 : 0;
+                    if (st < best_stages || (st == best_stages && (al > best_al || (al == best_al && v > best)))) {
+                        best_stages = st; best_al = al; best = v;
+                    }
                 }
     if (best < 2 && capped_default) {   // nothing under the default cap: any split
         setenv("HPFW_CQT_N1MAX", "1073741824", 1);
