@@ -1152,12 +1152,7 @@ static int pick_row_len(long long need2) {
 
 // split H = n1 * n2 (n1 <= n2 <= CQ_MAX_ROW), both {2,3,5,7}-smooth: the fewest Stockham stages in total, then a row pitch
 // that keeps pass A's column groups sector-aligned, then the most balanced; returns false if there is none
-static bool split_smooth(int H, int &n1, int &n2) {
-    // column FFTs longer than ~1000 points push pass A to one CTA per SM (4 adjacent columns = one 32-byte sector is the
-    // least it should load): prefer a split with n1 <= 1024 when there is one. HPFW_CQT_N1MAX overrides (tuning).
-    int n1max = env_int("HPFW_CQT_N1MAX", 0);
-    const bool capped_default = n1max <= 0;
-    if (capped_default) n1max = 1024;
+static bool split_smooth_capped(int H, int n1max, int &n1, int &n2) {
     int rest = H;
     int e[4] = {0, 0, 0, 0};
     const int p[4] = {2, 3, 5, 7};
@@ -1186,16 +1181,18 @@ static bool split_smooth(int H, int &n1, int &n2) {
                         best_stages = st; best_al = al; best = v;
                     }
                 }
-    if (best < 2 && capped_default) {   // nothing under the default cap: any split
-        setenv("HPFW_CQT_N1MAX", "1073741824", 1);
-        const bool ok = split_smooth(H, n1, n2);
-        unsetenv("HPFW_CQT_N1MAX");
-        return ok;
-    }
     if (best < 2) return false;
     n1 = (int)best;
     n2 = (int)(H / best);
     return true;
+}
+
+// Column FFTs longer than ~1000 points push pass A to one CTA per SM (4 adjacent columns = one 32-byte sector is the least
+// it should load): prefer a split with n1 <= 1024 when there is one. HPFW_CQT_N1MAX overrides the cap (tuning).
+static bool split_smooth(int H, int &n1, int &n2) {
+    const int cap = env_int("HPFW_CQT_N1MAX", 0);
+    if (cap > 0) return split_smooth_capped(H, cap, n1, n2);
+    return split_smooth_capped(H, 1024, n1, n2) || split_smooth_capped(H, 1 << 30, n1, n2);
 }
 
 // Shared memory of the two-pass FFT kernels: ping-pong buffers of G * n padded complex values. G (columns / rows per CTA)
