@@ -34,6 +34,7 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <mutex>
 
 namespace hpfw_b200 {
 
@@ -918,6 +919,51 @@ db_kernel(const float *__restrict__ power, const unsigned int *__restrict__ pmax
     }
 }
 
+// ------------------------------------------------------------------------------------------------ plan tables
+// Fills every twiddle / chirp table of a plan in one launch (blockIdx.y = job): double-precision sincospi on the device,
+// rounded once to float.
+enum { TAB_UNIT = 0, TAB_HI = 1, TAB_LO = 2, TAB_CHIRP = 3, TAB_STAGE = 4 };
+struct TabJob {
+    int kind, count;
+    long long off;      // float2 offset from the arena base
+    long long p0;       // period (UNIT/HI/LO), M (CHIRP), index into the descriptor array (STAGE)
+};
+__device__ __forceinline__ float2 unit_phasor(double frac2) {      // e^{i pi frac2}
+    double s, c;
+    sincospi(frac2, &s, &c);
+    return make_float2((float)c, (float)s);
+}
+__global__ void __launch_bounds__(CQ_THREADS)
+table_fill_kernel(const TabJob *__restrict__ jobs, const FftDesc *__restrict__ descs, float2 *__restrict__ arena) {
+    const TabJob jb = jobs[blockIdx.y];
+    float2 *dst = arena + jb.off;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < jb.count; i += gridDim.x * blockDim.x) {
+        float2 v = make_float2(1.f, 0.f);
+        switch (jb.kind) {
+            case TAB_UNIT: v = unit_phasor(-2.0 * (double)i / (double)jb.p0); break;
+            case TAB_HI: v = unit_phasor(-2.0 * (double)(((long long)i * CQ_TW_S) % jb.p0) / (double)jb.p0); break;
+            case TAB_LO: v = unit_phasor(-2.0 * (double)i / (double)jb.p0); break;
+            case TAB_CHIRP: {   // e^{+i pi 3 k^2 / M}, phase reduced mod 2M in integers
+                const unsigned long long ph = (3ull * (unsigned long long)i * (unsigned long long)i) % (2ull * (unsigned long long)jb.p0);
+                v = unit_phasor((double)ph / (double)jb.p0);
+            } break;
+            default: {          // TAB_STAGE: stage twiddles of the generic shared-memory FFT, [(t-1)*Ns + k] = e^{-2 pi i k t/(Ns R)}
+                const FftDesc &d = descs[jb.p0];
+                int Ns = 1;
+                for (int s = 0; s < d.nrad; ++s) {
+                    const int R = d.rad[s];
+                    if (Ns > 1 && i >= d.tw_off[s] && i < d.tw_off[s] + (R - 1) * Ns) {
+                        const int e = i - d.tw_off[s], t = e / Ns + 1, k = e - (t - 1) * Ns;
+                        v = unit_phasor(-2.0 * (double)((long long)k * t) / (double)((long long)Ns * R));
+                    }
+                    Ns *= R;
+                }
+            } break;
+        }
+        dst[i] = v;
+    }
+}
+
 // ================================================================================================ host side: design + plan
 struct CqtDesign {
     int pos[CQ_BINS], lg[CQ_BINS];
@@ -950,10 +996,24 @@ static int env_int(const char *name, int dflt) {
 // Radix sequence of a {2,3,5,7}-smooth n: the fewest Stockham stages over the butterflies this file has (every stage is
 // one shared-memory round trip + barrier), ties broken towards the smaller radix sum; stages run in ascending radix order
 // (the first stage, Ns = 1, is twiddle-free and its strided stores conflict least for a small radix).
-static bool factor_smooth(int n, FftDesc &d) {
+static bool factor_smooth_uncached(int n, FftDesc &d, int maxrad);
+static bool factor_smooth(int n, FftDesc &d) {      // planning calls this thousands of times per new length: memoised
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, std::pair<bool, FftDesc>> cache;
+    const int maxrad = env_int("HPFW_CQT_MAXRADIX", 16);
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find({n, maxrad});
+    if (it == cache.end()) {
+        FftDesc t{};
+        const bool ok = factor_smooth_uncached(n, t, maxrad);
+        it = cache.emplace(std::make_pair(n, maxrad), std::make_pair(ok, t)).first;
+    }
+    d = it->second.second;
+    return it->second.first;
+}
+static bool factor_smooth_uncached(int n, FftDesc &d, int maxrad) {
     d.n = n;
     d.nrad = 0;
-    const int maxrad = env_int("HPFW_CQT_MAXRADIX", 16);
     const int all[13] = {16, 15, 14, 12, 10, 9, 8, 7, 6, 5, 4, 3, 2};
     std::map<int, std::pair<int, int>> memo;   // n -> (stages * 1000 + radix sum, first radix)
     std::function<int(int)> best = [&](int m) -> int {
@@ -989,24 +1049,6 @@ static bool factor_smooth(int n, FftDesc &d) {
     return true;
 }
 
-// stage-twiddle table of a descriptor: for every stage with Ns > 1, entries [(t-1)*Ns + k] = e^{-2 pi i k t / (Ns R)},
-// t = 1..R-1, k < Ns (n - 1 entries at most; padded to n)
-static std::vector<float2> twiddle_table(const FftDesc &d) {
-    std::vector<float2> t((size_t)d.n, make_float2(1.f, 0.f));
-    int Ns = 1;
-    for (int s = 0; s < d.nrad; ++s) {
-        const int R = d.rad[s];
-        if (Ns > 1)
-            for (int tt = 1; tt < R; ++tt)
-                for (int k = 0; k < Ns; ++k) {
-                    const double a = -2.0 * M_PI * (double)((long long)k * tt) / (double)((long long)Ns * R);
-                    t[(size_t)d.tw_off[s] + (size_t)(tt - 1) * Ns + k] = make_float2((float)std::cos(a), (float)std::sin(a));
-                }
-        Ns *= R;
-    }
-    return t;
-}
-
 struct TwoLevel {
     DeviceBuffer hi, lo;
     int upload(long long P) {
@@ -1029,74 +1071,130 @@ struct TwoLevel {
     void release() { hi.release(); lo.release(); }
 };
 
+// ---- plan memory ---------------------------------------------------------------------------------------------------
+// A plan = every table and index list one audio length needs, in ONE device allocation (the arena) filled by two kernels
+// (table_fill_kernel + the chirp-filter transforms) from ONE pinned metadata block; no host trigonometry, no synchronous
+// copy, no cudaMalloc in steady state (arenas and pinned blocks are recycled through free lists when a plan is evicted).
+// Music libraries have a different sample count for every track, so planning has to cost about as much as a kernel launch.
+struct PlanMem {
+    DeviceBuffer dev;
+    PinnedBuffer pin;
+};
+
 struct CqtPlan {
     int64_t N = 0;
     int H = 0;
     bool bluestein = false;     // N odd or N/2 not {2,3,5,7}-smooth: chirp convolution on length P (d1, d2, tw1, tw2, twH are P's)
     int P = 0;
-    DeviceBuffer bhat;          // FFT_P of the shifted chirp filter
     CqtDesign des;
     int klo = 0, khi = 0;
     FftDesc d1{}, d2{};
     int G1 = 1, G2 = 1;
     size_t smem1 = 0, smem2 = 0;
-    DeviceBuffer tw1, tw2, chirp;
-    TwoLevel twH, twN;
-    // CZT
-    std::vector<BandMeta> bands;
-    DeviceBuffer d_bands, d_btab_ptrs, d_descs, d_tw_ptrs, d_tt_ptrs, d_tiles, d_tiles3;
+    PlanMem mem;
+    DeviceBuffer bhat;          // Bluestein: FFT_P of the shifted chirp filter
+    // pointers into the arena
+    const float2 *tw1 = nullptr, *tw2 = nullptr, *twH_hi = nullptr, *twH_lo = nullptr, *twN_hi = nullptr, *twN_lo = nullptr,
+                 *chirp = nullptr;
+    const BandMeta *d_bands = nullptr;
+    const RowTile *d_tiles = nullptr, *d_tiles3 = nullptr;
+    const FftDesc *d_descs = nullptr;
+    const float2 *const *d_tw_ptrs = nullptr, *const *d_btab_ptrs = nullptr, *const *d_tt_ptrs = nullptr;
     int n_tiles = 0, n_tiles3 = 0;
     size_t smem_rows = 0;
-    std::vector<std::unique_ptr<DeviceBuffer>> btabs, rowtws, ttabs;
     int max_L2 = 0;
     long long work_elems = 0;
     int fpitch = 0;
-    // per-track scratch, one set per lane (tracks of a batch run concurrently on CQ_LANES streams)
-    struct Scratch {
-        DeviceBuffer zbuf, zlo, zhi, work, power, pmax, bl_a;
-        bool ready = false;
-    } lanes[CQ_LANES];
+    cudaEvent_t ready = nullptr;     // recorded on the creating stream after the tables are filled
+    cudaEvent_t last_done[CQ_LANES] = {};   // per lane: recorded after the latest transform that used this plan
+    cudaStream_t created_on = nullptr;
     uint64_t last_use = 0;
+};
 
-    int lane_reserve(int lane) {
-        Scratch &sc = lanes[lane];
-        if (sc.ready) return HPFW_OK;
-        const size_t nkeep = (size_t)(khi - klo + 1);
-        HPFW_TRY(sc.zbuf.reserve(sizeof(float2) * (size_t)(bluestein ? P : H)));
-        HPFW_TRY(sc.zlo.reserve(sizeof(float2) * nkeep));
-        if (bluestein) HPFW_TRY(sc.bl_a.reserve(sizeof(float2) * (size_t)P));
-        else HPFW_TRY(sc.zhi.reserve(sizeof(float2) * nkeep));
-        HPFW_TRY(sc.work.reserve(sizeof(float2) * (size_t)work_elems));
-        HPFW_TRY(sc.power.reserve(sizeof(float) * (size_t)CQ_BINS * fpitch));
-        HPFW_TRY(sc.pmax.reserve(sizeof(unsigned int)));
-        sc.ready = true;
-        return HPFW_OK;
-    }
-
-    void release() {
-        tw1.release(); tw2.release(); chirp.release(); twH.release(); twN.release(); bhat.release();
-        d_bands.release(); d_btab_ptrs.release(); d_descs.release(); d_tw_ptrs.release(); d_tiles.release(); d_tt_ptrs.release();
-        d_tiles3.release();
-        for (auto &b : ttabs) b->release();
-        for (auto &b : btabs) b->release();
-        for (auto &b : rowtws) b->release();
-        for (auto &sc : lanes) {
-            sc.zbuf.release(); sc.zlo.release(); sc.zhi.release(); sc.work.release(); sc.power.release(); sc.pmax.release();
-            sc.bl_a.release();
-            sc.ready = false;
-        }
-    }
+// per-lane scratch, shared by all plans (grow-only): tracks of a batch run concurrently on CQ_LANES streams
+struct CqtLane {
+    DeviceBuffer zbuf, zlo, zhi, work, power, pmax, bl_a;
 };
 
 struct CqtPlanCache {
     std::map<int64_t, std::unique_ptr<CqtPlan>> plans;
+    std::vector<PlanMem> free_mem;
+    std::vector<DeviceBuffer> free_big;
+    std::vector<cudaEvent_t> free_events;
+    CqtLane lanes[CQ_LANES];
+    bool smem_set = false;
     uint64_t tick = 0;
 };
 
+static void plan_release(CqtPlanCache *c, CqtPlan &p, bool recycle) {
+    if (recycle) {
+        if (p.mem.dev.ptr) c->free_mem.push_back(p.mem);
+        if (p.bhat.ptr) c->free_big.push_back(p.bhat);
+        if (p.ready) c->free_events.push_back(p.ready);
+        for (cudaEvent_t e : p.last_done)
+            if (e) c->free_events.push_back(e);
+    } else {
+        p.mem.dev.release();
+        p.mem.pin.release();
+        p.bhat.release();
+        if (p.ready) cudaEventDestroy(p.ready);
+        for (cudaEvent_t e : p.last_done)
+            if (e) cudaEventDestroy(e);
+    }
+    p.mem = PlanMem();
+    p.bhat = DeviceBuffer();
+    p.ready = nullptr;
+    for (cudaEvent_t &e : p.last_done) e = nullptr;
+}
+
 void cqt_cache_destroy(CqtPlanCache *c) {
     if (!c) return;
-    for (auto &kv : c->plans) kv.second->release();
+    for (auto &kv : c->plans) plan_release(c, *kv.second, false);
+    for (auto &m : c->free_mem) { m.dev.release(); m.pin.release(); }
+    for (auto &b : c->free_big) b.release();
+    for (auto e : c->free_events) cudaEventDestroy(e);
+    for (auto &l : c->lanes) {
+        l.zbuf.release(); l.zlo.release(); l.zhi.release(); l.work.release(); l.power.release(); l.pmax.release();
+        l.bl_a.release();
+    }
     delete c;
+}
+
+// A recycled buffer for a new plan: the smallest that is large enough, else the largest (reserve() regrows it), else none.
+static void take_mem(std::vector<PlanMem> &pool, size_t bytes, PlanMem &out) {
+    int best = -1;
+    for (size_t i = 0; i < pool.size(); ++i) {
+        if (best < 0) { best = (int)i; continue; }
+        const size_t cb = pool[(size_t)best].dev.cap, ci = pool[i].dev.cap;
+        if (cb >= bytes ? (ci >= bytes && ci < cb) : ci > cb) best = (int)i;
+    }
+    if (best < 0) return;
+    out = pool[(size_t)best];
+    pool.erase(pool.begin() + best);
+}
+static void take_big(std::vector<DeviceBuffer> &pool, size_t bytes, DeviceBuffer &out) {
+    int best = -1;
+    for (size_t i = 0; i < pool.size(); ++i) {
+        if (best < 0) { best = (int)i; continue; }
+        const size_t cb = pool[(size_t)best].cap, ci = pool[i].cap;
+        if (cb >= bytes ? (ci >= bytes && ci < cb) : ci > cb) best = (int)i;
+    }
+    if (best < 0) return;
+    out = pool[(size_t)best];
+    pool.erase(pool.begin() + best);
+}
+
+static int lane_reserve(CqtPlanCache *c, const CqtPlan &pl, int lane) {
+    CqtLane &sc = c->lanes[lane];
+    const size_t nkeep = (size_t)(pl.khi - pl.klo + 1);
+    HPFW_TRY(sc.zbuf.reserve(sizeof(float2) * (size_t)(pl.bluestein ? pl.P : pl.H)));
+    HPFW_TRY(sc.zlo.reserve(sizeof(float2) * nkeep));
+    if (pl.bluestein) HPFW_TRY(sc.bl_a.reserve(sizeof(float2) * (size_t)pl.P));
+    else HPFW_TRY(sc.zhi.reserve(sizeof(float2) * nkeep));
+    HPFW_TRY(sc.work.reserve(sizeof(float2) * (size_t)pl.work_elems));
+    HPFW_TRY(sc.power.reserve(sizeof(float) * (size_t)CQ_BINS * pl.fpitch));
+    HPFW_TRY(sc.pmax.reserve(sizeof(unsigned int)));
+    return HPFW_OK;
 }
 
 static size_t czt_row_smem(int L2, int G) { return 8 * ((size_t)L2 + 2 * ((size_t)CQ_PAD(G * L2) + 1)); }
@@ -1238,19 +1336,42 @@ static int fft_two_pass(hpfw_ctx *ctx, const CqtPlan &pl, const float2 *in, floa
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
         fft_pass_kernel<0><<<(n2 + pl.G1 - 1) / pl.G1, CQ_FFT_THREADS, pl.smem1, stream>>>(
-            in, tmp, nullptr, pl.d1, n2, pl.G1, magic40((unsigned long long)pl.G1), pl.tw1.as<float2>(),
-            pl.twH.hi.as<float2>(), pl.twH.lo.as<float2>(), 0, 0, len, 1, sign);
+            in, tmp, nullptr, pl.d1, n2, pl.G1, magic40((unsigned long long)pl.G1), pl.tw1, pl.twH_hi, pl.twH_lo, 0, 0, len,
+            1, sign);
     }
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
         fft_pass_kernel<1><<<(n1 + pl.G2 - 1) / pl.G2, CQ_FFT_THREADS, pl.smem2, stream>>>(
-            tmp, out_lo, out_hi, pl.d2, n1, pl.G2, magic40((unsigned long long)pl.G2), pl.tw2.as<float2>(), nullptr,
-            nullptr, klo, khi, len, keep_all, sign);
+            tmp, out_lo, out_hi, pl.d2, n1, pl.G2, magic40((unsigned long long)pl.G2), pl.tw2, nullptr, nullptr, klo, khi,
+            len, keep_all, sign);
     }
     return HPFW_OK;
 }
 
-static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t stream) {
+// {2,3,5,7}-smooth numbers in [lo, hi], ascending
+static std::vector<long long> smooth_in_range(long long lo, long long hi) {
+    std::vector<long long> out;
+    for (long long a = 1; a <= hi; a *= 2)
+        for (long long b = a; b <= hi; b *= 3)
+            for (long long c = b; c <= hi; c *= 5)
+                for (long long d = c; d <= hi; d *= 7)
+                    if (d >= lo) out.push_back(d);
+    std::sort(out.begin(), out.end());
+    return out;
+}
+
+static int event_get(CqtPlanCache *c, cudaEvent_t *e) {
+    if (!c->free_events.empty()) {
+        *e = c->free_events.back();
+        c->free_events.pop_back();
+        return HPFW_OK;
+    }
+    HPFW_CUDA_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    return HPFW_OK;
+}
+
+static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t stream, int lane) {
+    CqtPlanCache *cache = ctx->cqt;
     pl.N = N;
     if (N < 2) HPFW_FAIL(HPFW_ERR_ARG, "CQT: empty audio");
     if (N > (int64_t(1) << 27)) HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: audio length %lld exceeds 2^27 samples", (long long)N);
@@ -1269,16 +1390,16 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
     int n1 = 0, n2 = 0;
     pl.bluestein = (N & 1) || !split_smooth(pl.H, n1, n2) || env_int("HPFW_CQT_BLUESTEIN", 0);
     if (pl.bluestein) {
-        // smallest smooth P >= N + K - 1 that the two-pass engine can split; among the first few, the fewest stages
+        // smooth P >= N + K - 1 that the two-pass engine can split: among the 8 smallest, the fewest stages
         const long long need = N + (long long)(pl.khi - pl.klo);
         int found = 0, best_st = 1 << 30;
-        for (long long c = need; c <= (1ll << 26) && found < 8; ++c) {
+        for (long long c : smooth_in_range(need, std::min<long long>(1ll << 26, need + need / 4))) {
             int a1 = 0, a2 = 0;
             if (!split_smooth((int)c, a1, a2)) continue;
             FftDesc da{}, db{};
             if (!factor_smooth(a1, da) || !factor_smooth(a2, db)) continue;
-            ++found;
             if (da.nrad + db.nrad < best_st) { best_st = da.nrad + db.nrad; pl.P = (int)c; n1 = a1; n2 = a2; }
+            if (++found >= 8) break;
         }
         if (!pl.P)
             HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: audio of %lld samples needs a %lld-point chirp convolution; limit 2^26",
@@ -1286,35 +1407,15 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
     }
     if (!factor_smooth(n1, pl.d1) || !factor_smooth(n2, pl.d2)) HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: too many FFT stages");
     fft_group_sizes(ctx, n1, n2, pl.G1, pl.G2, pl.smem1, pl.smem2);
-    {
-        pad_single_stage(pl.d1);
-        pad_single_stage(pl.d2);
-        auto t1 = unit_table(n1), t2 = unit_table(n2);
-        HPFW_TRY(pl.tw1.reserve(sizeof(float2) * t1.size()));
-        HPFW_TRY(pl.tw2.reserve(sizeof(float2) * t2.size()));
-        HPFW_CUDA_TRY(cudaMemcpy(pl.tw1.ptr, t1.data(), sizeof(float2) * t1.size(), cudaMemcpyHostToDevice));
-        HPFW_CUDA_TRY(cudaMemcpy(pl.tw2.ptr, t2.data(), sizeof(float2) * t2.size(), cudaMemcpyHostToDevice));
-    }
-    HPFW_TRY(pl.twH.upload(pl.bluestein ? pl.P : pl.H));
-    if (!pl.bluestein) HPFW_TRY(pl.twN.upload(N));
-    {   // input chirp e^{+i pi 3 k^2 / M}, k < M (the longest band window), phase reduced mod 2M in integers
-        std::vector<float2> ch((size_t)d.M);
-        const unsigned long long twoM = 2ull * (unsigned long long)d.M;
-        for (int k = 0; k < d.M; ++k) {
-            const unsigned long long ph = (3ull * (unsigned long long)k * (unsigned long long)k) % twoM;
-            const double a = M_PI * (double)ph / (double)d.M;
-            ch[(size_t)k] = make_float2((float)std::cos(a), (float)std::sin(a));
-        }
-        HPFW_TRY(pl.chirp.reserve(sizeof(float2) * ch.size()));
-        HPFW_CUDA_TRY(cudaMemcpy(pl.chirp.ptr, ch.data(), sizeof(float2) * ch.size(), cudaMemcpyHostToDevice));
-    }
+    pad_single_stage(pl.d1);
+    pad_single_stage(pl.d2);
 
     // CZT layout
-    pl.bands.resize(CQ_BINS);
+    std::vector<BandMeta> bands(CQ_BINS);
     std::vector<int> Ls;
     long long off = 0;
     for (int j = 0; j < CQ_BINS; ++j) {
-        BandMeta &b = pl.bands[j];
+        BandMeta &b = bands[j];
         b.lg = d.lg[j];
         b.half = d.lg[j] / 2;
         b.first_bin = d.pos[j] - b.half;
@@ -1338,114 +1439,146 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
     }
     pl.work_elems = off;
     pl.fpitch = (d.F + 31) & ~31;
-    HPFW_TRY(pl.d_bands.reserve(sizeof(BandMeta) * CQ_BINS));
-    HPFW_CUDA_TRY(cudaMemcpy(pl.d_bands.ptr, pl.bands.data(), sizeof(BandMeta) * CQ_BINS, cudaMemcpyHostToDevice));
+    const int nL = (int)Ls.size();
+
     // row-pass tiles: G consecutive rows of a band per CTA (G * L2 <= CQ_ROW_POINTS; for the register kernel also
     // G * 16 r0 <= 256), so that every CTA of a launch has about the same work and shared-memory footprint whatever the
     // band's chirp length. One tile list per kernel.
-    {
-        std::vector<RowTile> tiles, tiles3;
-        for (int j = 0; j < CQ_BINS; ++j) {
-            const int L2 = pl.bands[j].L2, r0 = pl.bands[j].r0;
-            const int G = std::max(1, std::min(CQ_L1, r0 ? 16 / r0 : CQ_ROW_POINTS / L2));
-            for (int c0 = 0; c0 < CQ_L1; c0 += G) {
-                const int g = std::min(G, CQ_L1 - c0);
-                if (r0) {
-                    tiles3.push_back({j, c0, g});
-                } else {
-                    tiles.push_back({j, c0, g});
-                    pl.smem_rows = std::max(pl.smem_rows, czt_row_smem(L2, g));
-                }
+    std::vector<RowTile> tiles, tiles3, ftiles;
+    pl.smem_rows = 0;
+    for (int j = 0; j < CQ_BINS; ++j) {
+        const int L2 = bands[j].L2, r0 = bands[j].r0;
+        const int G = std::max(1, std::min(CQ_L1, r0 ? 16 / r0 : CQ_ROW_POINTS / L2));
+        for (int c0 = 0; c0 < CQ_L1; c0 += G) {
+            const int g = std::min(G, CQ_L1 - c0);
+            if (r0) {
+                tiles3.push_back({j, c0, g});
+            } else {
+                tiles.push_back({j, c0, g});
+                pl.smem_rows = std::max(pl.smem_rows, czt_row_smem(L2, g));
             }
         }
-        pl.n_tiles = (int)tiles.size();
-        pl.n_tiles3 = (int)tiles3.size();
-        HPFW_TRY(pl.d_tiles.reserve(sizeof(RowTile) * std::max<size_t>(1, tiles.size())));
-        HPFW_TRY(pl.d_tiles3.reserve(sizeof(RowTile) * std::max<size_t>(1, tiles3.size())));
-        if (!tiles.empty())
-            HPFW_CUDA_TRY(cudaMemcpy(pl.d_tiles.ptr, tiles.data(), sizeof(RowTile) * tiles.size(), cudaMemcpyHostToDevice));
-        if (!tiles3.empty())
-            HPFW_CUDA_TRY(cudaMemcpy(pl.d_tiles3.ptr, tiles3.data(), sizeof(RowTile) * tiles3.size(),
-                                     cudaMemcpyHostToDevice));
     }
+    pl.n_tiles = (int)tiles.size();
+    pl.n_tiles3 = (int)tiles3.size();
 
-    // per distinct L: row-FFT descriptor + twiddles, chirp-filter spectrum (computed below with the same kernels)
-    std::vector<FftDesc> descs(Ls.size());
-    std::vector<const float2 *> twp(Ls.size()), btp(Ls.size()), ttp(Ls.size());
-    for (size_t i = 0; i < Ls.size(); ++i) {
-        if (!factor_smooth(Ls[i] / CQ_L1, descs[i])) HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: too many FFT stages");
-        auto t = twiddle_table(descs[i]);
-        pl.rowtws.emplace_back(new DeviceBuffer());
-        HPFW_TRY(pl.rowtws.back()->reserve(sizeof(float2) * t.size()));
-        HPFW_CUDA_TRY(cudaMemcpy(pl.rowtws.back()->ptr, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice));
-        twp[i] = pl.rowtws.back()->as<float2>();
-        pl.btabs.emplace_back(new DeviceBuffer());
-        HPFW_TRY(pl.btabs.back()->reserve(sizeof(float2) * (size_t)Ls[i]));
-        btp[i] = pl.btabs.back()->as<float2>();
-        // T[m] = e^{-2 pi i m / L2}: the one twiddle table of czt_rows3_kernel
-        const int n2r = Ls[i] / CQ_L1;
-        std::vector<float2> tt((size_t)n2r);
-        for (int m = 0; m < n2r; ++m) {
-            const double a = -2.0 * M_PI * (double)m / (double)n2r;
-            tt[(size_t)m] = make_float2((float)std::cos(a), (float)std::sin(a));
-        }
-        pl.ttabs.emplace_back(new DeviceBuffer());
-        HPFW_TRY(pl.ttabs.back()->reserve(sizeof(float2) * tt.size()));
-        HPFW_CUDA_TRY(cudaMemcpy(pl.ttabs.back()->ptr, tt.data(), sizeof(float2) * tt.size(), cudaMemcpyHostToDevice));
-        ttp[i] = pl.ttabs.back()->as<float2>();
+    // ---- arena layout: tables (float2 units) first, then the metadata block (bytes, 16-byte aligned pieces)
+    const long long lenP = pl.bluestein ? pl.P : pl.H;
+    long long fo = 0;
+    auto take = [&](long long n) { const long long o = fo; fo += (n + 1) & ~1ll; return o; };   // keep 16-byte alignment
+    std::vector<TabJob> jobs;
+    const long long o_tw1 = take(n1), o_tw2 = take(n2);
+    jobs.push_back({TAB_UNIT, n1, o_tw1, n1});
+    jobs.push_back({TAB_UNIT, n2, o_tw2, n2});
+    const long long nhiP = lenP / CQ_TW_S + 2, o_hhi = take(nhiP), o_hlo = take(CQ_TW_S);
+    jobs.push_back({TAB_HI, (int)nhiP, o_hhi, lenP});
+    jobs.push_back({TAB_LO, CQ_TW_S, o_hlo, lenP});
+    long long o_nhi = 0, o_nlo = 0;
+    if (!pl.bluestein) {
+        const long long nhiN = N / CQ_TW_S + 2;
+        o_nhi = take(nhiN);
+        o_nlo = take(CQ_TW_S);
+        jobs.push_back({TAB_HI, (int)nhiN, o_nhi, (long long)N});
+        jobs.push_back({TAB_LO, CQ_TW_S, o_nlo, (long long)N});
     }
-    HPFW_TRY(pl.d_tt_ptrs.reserve(sizeof(void *) * ttp.size()));
-    HPFW_CUDA_TRY(cudaMemcpy(pl.d_tt_ptrs.ptr, ttp.data(), sizeof(void *) * ttp.size(), cudaMemcpyHostToDevice));
-    HPFW_TRY(pl.d_descs.reserve(sizeof(FftDesc) * descs.size()));
-    HPFW_TRY(pl.d_tw_ptrs.reserve(sizeof(void *) * twp.size()));
-    HPFW_TRY(pl.d_btab_ptrs.reserve(sizeof(void *) * btp.size()));
-    HPFW_CUDA_TRY(cudaMemcpy(pl.d_descs.ptr, descs.data(), sizeof(FftDesc) * descs.size(), cudaMemcpyHostToDevice));
-    HPFW_CUDA_TRY(cudaMemcpy(pl.d_tw_ptrs.ptr, twp.data(), sizeof(void *) * twp.size(), cudaMemcpyHostToDevice));
-    HPFW_CUDA_TRY(cudaMemcpy(pl.d_btab_ptrs.ptr, btp.data(), sizeof(void *) * btp.size(), cudaMemcpyHostToDevice));
-
-    HPFW_TRY(set_smem_limits(ctx));
-
-    // chirp-filter spectra: one pseudo-band per distinct L whose work area IS the table
-    {
-        std::vector<BandMeta> fb(Ls.size());
-        DeviceBuffer d_fb, d_ft;
-        std::vector<RowTile> ft(CQ_L1);
-        for (int c = 0; c < CQ_L1; ++c) ft[c] = RowTile{0, c, 1};
-        HPFW_TRY(d_ft.reserve(sizeof(RowTile) * ft.size()));
-        HPFW_CUDA_TRY(cudaMemcpy(d_ft.ptr, ft.data(), sizeof(RowTile) * ft.size(), cudaMemcpyHostToDevice));
-        // the kernels address work + work_off: express each table as an offset from table 0 is not possible (separate
-        // allocations), so run one launch per table with work = that table and work_off = 0
-        for (size_t i = 0; i < Ls.size(); ++i) {
-            fb[i] = BandMeta{0, 0, 0, Ls[i], Ls[i] / CQ_L1, (int)i, 0, 0};
-        }
-        HPFW_TRY(d_fb.reserve(sizeof(BandMeta) * fb.size()));
-        HPFW_CUDA_TRY(cudaMemcpy(d_fb.ptr, fb.data(), sizeof(BandMeta) * fb.size(), cudaMemcpyHostToDevice));
-        for (size_t i = 0; i < Ls.size(); ++i) {
-            const BandMeta *dbm = d_fb.as<BandMeta>() + i;
-            float2 *tab = pl.btabs[i]->as<float2>();
-            dim3 g1((fb[i].L2 + CQ_THREADS - 1) / CQ_THREADS, 1);
-            {
-                KernelScope ks(ctx, HPFW_K_CQT, stream);
-                czt_cols_kernel<1><<<g1, CQ_THREADS, 0, stream>>>(dbm, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr,
-                                                                   d.M, d.F, tab);
-            }
-            {
-                KernelScope ks(ctx, HPFW_K_CQT, stream);
-                czt_rows_kernel<1><<<CQ_L1, CQ_FFT_THREADS, czt_row_smem(fb[i].L2, 1), stream>>>(
-                    dbm, d_ft.as<RowTile>(), tab, pl.d_btab_ptrs.as<const float2 *>(), pl.d_descs.as<FftDesc>(),
-                    pl.d_tw_ptrs.as<const float2 *>());
-            }
-        }
-        HPFW_CUDA_TRY(cudaGetLastError());
-        HPFW_CUDA_TRY(cudaStreamSynchronize(stream));
-        d_fb.release();
-        d_ft.release();
+    const long long o_chirp = take(d.M);
+    jobs.push_back({TAB_CHIRP, d.M, o_chirp, d.M});
+    std::vector<FftDesc> descs((size_t)nL);
+    std::vector<long long> o_rowtw((size_t)nL), o_tt((size_t)nL), o_bt((size_t)nL);
+    std::vector<BandMeta> fb((size_t)nL);
+    int max_fL2 = 0;
+    for (int i = 0; i < nL; ++i) {
+        const int L2 = Ls[(size_t)i] / CQ_L1;
+        if (!factor_smooth(L2, descs[(size_t)i])) HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: too many FFT stages");
+        o_rowtw[(size_t)i] = take(L2);
+        o_tt[(size_t)i] = take(L2);
+        o_bt[(size_t)i] = take(Ls[(size_t)i]);
+        jobs.push_back({TAB_STAGE, L2, o_rowtw[(size_t)i], i});
+        jobs.push_back({TAB_UNIT, L2, o_tt[(size_t)i], L2});
+        // chirp-filter spectrum: a pseudo-band whose work area IS the table
+        fb[(size_t)i] = BandMeta{0, 0, 0, Ls[(size_t)i], L2, i, 0, o_bt[(size_t)i]};
+        for (int c = 0; c < CQ_L1; ++c) ftiles.push_back({i, c, 1});
+        max_fL2 = std::max(max_fL2, L2);
     }
+    const size_t table_bytes = sizeof(float2) * (size_t)fo;
+    size_t mo = 0;
+    auto mtake = [&](size_t bytes) { const size_t o = mo; mo += (bytes + 15) & ~size_t(15); return o; };
+    const size_t m_bands = mtake(sizeof(BandMeta) * CQ_BINS), m_fb = mtake(sizeof(BandMeta) * (size_t)nL),
+                 m_tiles = mtake(sizeof(RowTile) * std::max<size_t>(1, tiles.size())),
+                 m_tiles3 = mtake(sizeof(RowTile) * std::max<size_t>(1, tiles3.size())),
+                 m_ftiles = mtake(sizeof(RowTile) * ftiles.size()), m_descs = mtake(sizeof(FftDesc) * (size_t)nL),
+                 m_twp = mtake(sizeof(void *) * (size_t)nL), m_btp = mtake(sizeof(void *) * (size_t)nL),
+                 m_ttp = mtake(sizeof(void *) * (size_t)nL), m_jobs = mtake(sizeof(TabJob) * jobs.size());
+    const size_t meta_bytes = mo, arena_bytes = table_bytes + meta_bytes;
 
-    HPFW_TRY(pl.lane_reserve(0));
-    if (pl.bluestein) {     // FFT_P of the shifted chirp filter, through lane 0's scratch
-        CqtPlan::Scratch &sc = pl.lanes[0];
+    take_mem(cache->free_mem, arena_bytes, pl.mem);
+    HPFW_TRY(pl.mem.dev.reserve(arena_bytes));
+    HPFW_TRY(pl.mem.pin.reserve(meta_bytes));
+    char *arena = pl.mem.dev.as<char>();
+    float2 *tab = pl.mem.dev.as<float2>();
+    char *dmeta = arena + table_bytes, *hmeta = pl.mem.pin.as<char>();
+    std::vector<const float2 *> twp((size_t)nL), btp((size_t)nL), ttp((size_t)nL);
+    for (int i = 0; i < nL; ++i) {
+        twp[(size_t)i] = tab + o_rowtw[(size_t)i];
+        btp[(size_t)i] = tab + o_bt[(size_t)i];
+        ttp[(size_t)i] = tab + o_tt[(size_t)i];
+    }
+    memcpy(hmeta + m_bands, bands.data(), sizeof(BandMeta) * CQ_BINS);
+    memcpy(hmeta + m_fb, fb.data(), sizeof(BandMeta) * (size_t)nL);
+    if (!tiles.empty()) memcpy(hmeta + m_tiles, tiles.data(), sizeof(RowTile) * tiles.size());
+    if (!tiles3.empty()) memcpy(hmeta + m_tiles3, tiles3.data(), sizeof(RowTile) * tiles3.size());
+    memcpy(hmeta + m_ftiles, ftiles.data(), sizeof(RowTile) * ftiles.size());
+    memcpy(hmeta + m_descs, descs.data(), sizeof(FftDesc) * (size_t)nL);
+    memcpy(hmeta + m_twp, twp.data(), sizeof(void *) * (size_t)nL);
+    memcpy(hmeta + m_btp, btp.data(), sizeof(void *) * (size_t)nL);
+    memcpy(hmeta + m_ttp, ttp.data(), sizeof(void *) * (size_t)nL);
+    memcpy(hmeta + m_jobs, jobs.data(), sizeof(TabJob) * jobs.size());
+    HPFW_CUDA_TRY(cudaMemcpyAsync(dmeta, hmeta, meta_bytes, cudaMemcpyHostToDevice, stream));
+
+    pl.tw1 = tab + o_tw1;
+    pl.tw2 = tab + o_tw2;
+    pl.twH_hi = tab + o_hhi;
+    pl.twH_lo = tab + o_hlo;
+    pl.twN_hi = pl.bluestein ? nullptr : tab + o_nhi;
+    pl.twN_lo = pl.bluestein ? nullptr : tab + o_nlo;
+    pl.chirp = tab + o_chirp;
+    pl.d_bands = reinterpret_cast<const BandMeta *>(dmeta + m_bands);
+    pl.d_tiles = reinterpret_cast<const RowTile *>(dmeta + m_tiles);
+    pl.d_tiles3 = reinterpret_cast<const RowTile *>(dmeta + m_tiles3);
+    pl.d_descs = reinterpret_cast<const FftDesc *>(dmeta + m_descs);
+    pl.d_tw_ptrs = reinterpret_cast<const float2 *const *>(dmeta + m_twp);
+    pl.d_btab_ptrs = reinterpret_cast<const float2 *const *>(dmeta + m_btp);
+    pl.d_tt_ptrs = reinterpret_cast<const float2 *const *>(dmeta + m_ttp);
+
+    if (!cache->smem_set) {
+        HPFW_TRY(set_smem_limits(ctx));
+        cache->smem_set = true;
+    }
+    {   // every twiddle / chirp table in one launch
+        int maxc = 0;
+        for (const TabJob &j : jobs) maxc = std::max(maxc, j.count);
+        KernelScope ks(ctx, HPFW_K_CQT, stream);
+        table_fill_kernel<<<dim3((unsigned)std::min(64, (maxc + CQ_THREADS - 1) / CQ_THREADS), (unsigned)jobs.size()),
+                            CQ_THREADS, 0, stream>>>(reinterpret_cast<const TabJob *>(dmeta + m_jobs), pl.d_descs, tab);
+    }
+    {   // chirp-filter spectra of all distinct lengths: b -> radix-16 columns -> row FFTs, in place in the arena
+        const BandMeta *dfb = reinterpret_cast<const BandMeta *>(dmeta + m_fb);
+        {
+            KernelScope ks(ctx, HPFW_K_CQT, stream);
+            czt_cols_kernel<1><<<dim3((max_fL2 + CQ_THREADS - 1) / CQ_THREADS, nL), CQ_THREADS, 0, stream>>>(
+                dfb, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, d.M, d.F, tab);
+        }
+        {
+            KernelScope ks(ctx, HPFW_K_CQT, stream);
+            czt_rows_kernel<1><<<(unsigned)ftiles.size(), CQ_FFT_THREADS, czt_row_smem(max_fL2, 1), stream>>>(
+                dfb, reinterpret_cast<const RowTile *>(dmeta + m_ftiles), tab, pl.d_btab_ptrs, pl.d_descs, pl.d_tw_ptrs);
+        }
+    }
+    if (pl.bluestein) {     // FFT_P of the shifted chirp filter, through the calling lane's scratch (same stream)
+        HPFW_TRY(lane_reserve(cache, pl, lane));
+        CqtLane &sc = cache->lanes[lane];
         const int P = pl.P, K = pl.khi - pl.klo + 1, gb = (P + CQ_THREADS - 1) / CQ_THREADS;
+        take_big(cache->free_big, sizeof(float2) * (size_t)P, pl.bhat);
         HPFW_TRY(pl.bhat.reserve(sizeof(float2) * (size_t)P));
         {
             KernelScope ks(ctx, HPFW_K_CQT, stream);
@@ -1453,29 +1586,36 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
         }
         HPFW_TRY(fft_two_pass(ctx, pl, sc.bl_a.as<float2>(), sc.zbuf.as<float2>(), pl.bhat.as<float2>(), nullptr, 0, 0, 1,
                               -1, stream));
-        HPFW_CUDA_TRY(cudaGetLastError());
-        HPFW_CUDA_TRY(cudaStreamSynchronize(stream));
     }
+    HPFW_CUDA_TRY(cudaGetLastError());
+    // other streams wait on `ready` before they use this plan; eviction waits on the per-lane `last_done` events
+    HPFW_TRY(event_get(cache, &pl.ready));
+    HPFW_CUDA_TRY(cudaEventRecord(pl.ready, stream));
+    pl.created_on = stream;
     return HPFW_OK;
 }
 
-static int plan_get(hpfw_ctx *ctx, int64_t N, CqtPlan **out, cudaStream_t stream) {
+constexpr size_t CQ_PLAN_CACHE = 48;   // plans are a few MB of tables each
+
+static int plan_get(hpfw_ctx *ctx, int64_t N, CqtPlan **out, cudaStream_t stream, int lane) {
     if (!ctx->cqt) ctx->cqt = new CqtPlanCache();
     CqtPlanCache *c = ctx->cqt;
     auto it = c->plans.find(N);
     if (it == c->plans.end()) {
-        if (c->plans.size() >= 6) {   // evict the least recently used plan (each holds ~3x the track in scratch)
+        if (c->plans.size() >= CQ_PLAN_CACHE) {   // evict the least recently used plan; its memory goes to the free lists
             auto victim = c->plans.begin();
             for (auto k = c->plans.begin(); k != c->plans.end(); ++k)
                 if (k->second->last_use < victim->second->last_use) victim = k;
-            HPFW_CUDA_TRY(cudaDeviceSynchronize());
-            victim->second->release();
+            for (cudaEvent_t e : victim->second->last_done)
+                if (e) HPFW_CUDA_TRY(cudaEventSynchronize(e));
+            plan_release(c, *victim->second, true);
             c->plans.erase(victim);
         }
         std::unique_ptr<CqtPlan> p(new CqtPlan());
-        int st = plan_create(ctx, N, *p, stream);
+        int st = plan_create(ctx, N, *p, stream, lane);
         if (st != HPFW_OK) {
-            p->release();
+            cudaStreamSynchronize(stream);
+            plan_release(c, *p, false);
             return st;
         }
         it = c->plans.emplace(N, std::move(p)).first;
@@ -1489,9 +1629,11 @@ static int plan_get(hpfw_ctx *ctx, int64_t N, CqtPlan **out, cudaStream_t stream
 static int cqt_run(hpfw_ctx *ctx, const float *d_audio, int64_t N, float *d_out, int mode, cudaStream_t stream,
                    int lane = 0) {
     CqtPlan *pl = nullptr;
-    HPFW_TRY(plan_get(ctx, N, &pl, stream));
-    HPFW_TRY(pl->lane_reserve(lane));
-    CqtPlan::Scratch *sc = &pl->lanes[lane];
+    HPFW_TRY(plan_get(ctx, N, &pl, stream, lane));
+    CqtPlanCache *cache = ctx->cqt;
+    HPFW_TRY(lane_reserve(cache, *pl, lane));
+    CqtLane *sc = &cache->lanes[lane];
+    if (stream != pl->created_on) HPFW_CUDA_TRY(cudaStreamWaitEvent(stream, pl->ready, 0));
     const CqtDesign &d = pl->des;
     if (!pl->bluestein) {
         if ((reinterpret_cast<uintptr_t>(d_audio) & 7) != 0)
@@ -1523,30 +1665,30 @@ static int cqt_run(hpfw_ctx *ctx, const float *d_audio, int64_t N, float *d_out,
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
         if (pl->bluestein)
-            czt_cols_kernel<2><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands.as<BandMeta>(), sc->zlo.as<float2>(), nullptr,
+            czt_cols_kernel<2><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, sc->zlo.as<float2>(), nullptr,
                                                                  pl->klo, pl->khi, nullptr, nullptr,
-                                                                 pl->chirp.as<float2>(), d.M, d.F, sc->work.as<float2>());
+                                                                 pl->chirp, d.M, d.F, sc->work.as<float2>());
         else
-            czt_cols_kernel<0><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands.as<BandMeta>(), sc->zlo.as<float2>(),
+            czt_cols_kernel<0><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, sc->zlo.as<float2>(),
                                                                  sc->zhi.as<float2>(), pl->klo, pl->khi,
-                                                                 pl->twN.hi.as<float2>(), pl->twN.lo.as<float2>(),
-                                                                 pl->chirp.as<float2>(), d.M, d.F, sc->work.as<float2>());
+                                                                 pl->twN_hi, pl->twN_lo,
+                                                                 pl->chirp, d.M, d.F, sc->work.as<float2>());
     }
     if (pl->n_tiles3 > 0) {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
         czt_rows3_kernel<<<pl->n_tiles3, 256, rows3_smem(), stream>>>(
-            pl->d_bands.as<BandMeta>(), pl->d_tiles3.as<RowTile>(), sc->work.as<float2>(),
-            pl->d_btab_ptrs.as<const float2 *>(), pl->d_tt_ptrs.as<const float2 *>());
+            pl->d_bands, pl->d_tiles3, sc->work.as<float2>(),
+            pl->d_btab_ptrs, pl->d_tt_ptrs);
     }
     if (pl->n_tiles > 0) {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
         czt_rows_kernel<0><<<pl->n_tiles, CQ_FFT_THREADS, pl->smem_rows, stream>>>(
-            pl->d_bands.as<BandMeta>(), pl->d_tiles.as<RowTile>(), sc->work.as<float2>(),
-            pl->d_btab_ptrs.as<const float2 *>(), pl->d_descs.as<FftDesc>(), pl->d_tw_ptrs.as<const float2 *>());
+            pl->d_bands, pl->d_tiles, sc->work.as<float2>(),
+            pl->d_btab_ptrs, pl->d_descs, pl->d_tw_ptrs);
     }
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
-        czt_out_kernel<<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands.as<BandMeta>(), sc->work.as<float2>(), d.M, d.F,
+        czt_out_kernel<<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, sc->work.as<float2>(), d.M, d.F,
                                                          pl->fpitch, sc->power.as<float>(),
                                                          sc->pmax.as<unsigned int>());
     }
@@ -1561,6 +1703,8 @@ static int cqt_run(hpfw_ctx *ctx, const float *d_audio, int64_t N, float *d_out,
                                                          pl->fpitch, d_out);
     }
     HPFW_CUDA_TRY(cudaGetLastError());
+    if (!pl->last_done[lane]) HPFW_TRY(event_get(cache, &pl->last_done[lane]));
+    HPFW_CUDA_TRY(cudaEventRecord(pl->last_done[lane], stream));
     return HPFW_OK;
 }
 

@@ -33,7 +33,9 @@ constexpr int TC_NF = HPFW_NFILTERS;     // 64
 constexpr int TC_M = 128;                // frames per tile
 constexpr int TC_AROWS = 152;            // 128 + 19 rounded up to a multiple of 8
 constexpr int TC_KB = 4;                 // 32-band swizzle atoms per tap
-constexpr int TC_STAGES_1 = 3;          // B ring depth, impl 1
+constexpr int TC_STAGES_1 = 4;          // B ring depth, impl 1: one 8 KB swizzle atom (one tap x 32 bands) per stage, so that
+                                        // A (76 KB) + ring (32 KB) lets TWO CTAs share an SM: one tile's prologue and
+                                        // epilogue overlap the other's MMA stream
 constexpr int TC_STAGES_2 = 2;          // A+B ring depth, impl 2 (96 KB per stage)
 constexpr uint32_t TC_A_ATOM_BYTES = TC_AROWS * 128;        // 19,456
 constexpr uint32_t TC_A1_ATOM_BYTES = TC_M * 128;           // 16,384 (impl 2)
@@ -123,7 +125,7 @@ tc_delta_kernel(const float *__restrict__ spectro, const int64_t *__restrict__ c
 
 // ---- main kernel ------------------------------------------------------------------------------------------------------------
 template <int IMPL>   // 1: one A block + row-offset descriptors; 2: A window reloaded per tap
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, IMPL == 1 ? 2 : 1)
 project_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const TcTile *__restrict__ tiles, const TcTrack *__restrict__ tracks, uint64_t *__restrict__ hp_out) {
     extern __shared__ uint8_t tsm_raw[];
@@ -167,36 +169,59 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_expect_tx(&bar_a, TC_KB * TC_A_ATOM_BYTES);
             for (int kb = 0; kb < TC_KB; ++kb) tma_load_2d(&tmA, &bar_a, smA + kb * TC_A_ATOM_BYTES, kb * 32, row0);
         }
-        for (int c = 0; c < TC_CTX; ++c) {
-            const int s = c % TC_STAGES;
-            if (c >= TC_STAGES) mbar_wait(&bar_empty[s], ((c / TC_STAGES) - 1) & 1);
-            mbar_expect_tx(&bar_full[s], TC_B_STAGE_BYTES + (IMPL == 2 ? TC_KB * TC_A1_ATOM_BYTES : 0));
-            for (int kb = 0; kb < TC_KB; ++kb)
-                tma_load_2d(&tmB, &bar_full[s], smB + s * TC_B_STAGE_BYTES + kb * TC_B_ATOM_BYTES, kb * 32, c * TC_NF);
-            if (IMPL == 2)
+        if (IMPL == 1) {
+            for (int it = 0; it < TC_CTX * TC_KB; ++it) {        // stage = one (tap, 32-band atom) of B
+                const int s = it % TC_STAGES, c = it / TC_KB, kb = it % TC_KB;
+                if (it >= TC_STAGES) mbar_wait(&bar_empty[s], ((it / TC_STAGES) - 1) & 1);
+                mbar_expect_tx(&bar_full[s], TC_B_ATOM_BYTES);
+                tma_load_2d(&tmB, &bar_full[s], smB + s * TC_B_ATOM_BYTES, kb * 32, c * TC_NF);
+            }
+        } else {
+            for (int c = 0; c < TC_CTX; ++c) {
+                const int s = c % TC_STAGES;
+                if (c >= TC_STAGES) mbar_wait(&bar_empty[s], ((c / TC_STAGES) - 1) & 1);
+                mbar_expect_tx(&bar_full[s], TC_B_STAGE_BYTES + TC_KB * TC_A1_ATOM_BYTES);
+                for (int kb = 0; kb < TC_KB; ++kb)
+                    tma_load_2d(&tmB, &bar_full[s], smB + s * TC_B_STAGE_BYTES + kb * TC_B_ATOM_BYTES, kb * 32, c * TC_NF);
                 for (int kb = 0; kb < TC_KB; ++kb)
                     tma_load_2d(&tmA, &bar_full[s], smA + (s * TC_KB + kb) * TC_A1_ATOM_BYTES, kb * 32, row0 + c);
+            }
         }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
         if (IMPL == 1) mbar_wait(&bar_a, 0);
         uint32_t acc = 0;
-        for (int c = 0; c < TC_CTX; ++c) {
-            const int s = c % TC_STAGES;
-            mbar_wait(&bar_full[s], (c / TC_STAGES) & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int kb = 0; kb < TC_KB; ++kb) {
-                const uint32_t a_addr = (IMPL == 1) ? smem_u32(smA + kb * TC_A_ATOM_BYTES) + c * 128
-                                                    : smem_u32(smA + (s * TC_KB + kb) * TC_A1_ATOM_BYTES);
-                const uint32_t b_addr = smem_u32(smB + s * TC_B_STAGE_BYTES + kb * TC_B_ATOM_BYTES);
+        if (IMPL == 1) {
+            for (int it = 0; it < TC_CTX * TC_KB; ++it) {
+                const int s = it % TC_STAGES, c = it / TC_KB, kb = it % TC_KB;
+                mbar_wait(&bar_full[s], (it / TC_STAGES) & 1);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smA + kb * TC_A_ATOM_BYTES) + c * 128;
+                const uint32_t b_addr = smem_u32(smB + s * TC_B_ATOM_BYTES);
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {     // 8 tf32 = 32 bytes per MMA along K inside the 128-byte atom
                     tc_mma_tf32(tmem_base, smem_desc_sw128(a_addr + k4 * 32), smem_desc_sw128(b_addr + k4 * 32), TC_IDESC, acc);
                     acc = 1;
                 }
+                tc_commit(&bar_empty[s]);     // arrives when the MMAs above have finished reading this stage
             }
-            tc_commit(&bar_empty[s]);     // arrives when the MMAs above have finished reading this stage
+        } else {
+            for (int c = 0; c < TC_CTX; ++c) {
+                const int s = c % TC_STAGES;
+                mbar_wait(&bar_full[s], (c / TC_STAGES) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kb = 0; kb < TC_KB; ++kb) {
+                    const uint32_t a_addr = smem_u32(smA + (s * TC_KB + kb) * TC_A1_ATOM_BYTES);
+                    const uint32_t b_addr = smem_u32(smB + s * TC_B_STAGE_BYTES + kb * TC_B_ATOM_BYTES);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        tc_mma_tf32(tmem_base, smem_desc_sw128(a_addr + k4 * 32), smem_desc_sw128(b_addr + k4 * 32), TC_IDESC, acc);
+                        acc = 1;
+                    }
+                }
+                tc_commit(&bar_empty[s]);
+            }
         }
         tc_commit(&bar_acc);              // accumulator complete
     }
@@ -335,7 +360,7 @@ int project_tc_run(hpfw_ctx *ctx, int impl, const float *d_spectro, const int64_
     CUtensorMap tmA, tmB;
     HPFW_TRY(make_map_2d(&tmA, ctx->delta_tc.ptr, map_rows, impl == 1 ? TC_AROWS : TC_M));
     HPFW_TRY(make_map_2d(&tmB, ctx->filters_tc.ptr, (uint64_t)TC_CTX * TC_NF, TC_NF));
-    const size_t smem1 = TC_KB * TC_A_ATOM_BYTES + TC_STAGES_1 * TC_B_STAGE_BYTES + 1024;
+    const size_t smem1 = TC_KB * TC_A_ATOM_BYTES + TC_STAGES_1 * TC_B_ATOM_BYTES + 1024;
     const size_t smem2 = TC_STAGES_2 * TC_KB * TC_A1_ATOM_BYTES + TC_STAGES_2 * TC_B_STAGE_BYTES + 1024;
     {
         KernelScope ks(ctx, HPFW_K_PROJECT, stream);

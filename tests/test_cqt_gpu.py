@@ -147,6 +147,40 @@ def test_cqt_bluestein_matches_packed_path(ctx, monkeypatch):
     assert np.max(np.abs(a - b)) <= 2e-6 * np.abs(a).max()
 
 
+def test_batch_of_distinct_lengths_equals_single_calls(ctx, hashprint_golden):
+    """A library whose tracks all have different sample counts: every track plans (more lengths than the plan cache
+    holds; smooth, non-smooth and odd lengths mixed; four lanes). The batched device entry must give exactly the
+    per-track result of a fresh context."""
+    import torch
+    import hpfw_b200
+    ex = hpfw_b200.HashprintExtractor(ctx)
+    ex.set_filters(hashprint_golden["filters"])
+    base = synth.synth_track(77, 4.0, 44100)
+    # even lengths first (the packed path wants 8-byte aligned tracks), odd lengths (Bluestein) last
+    lens = [88200 + 882 * i for i in range(40)] + [90002 + 2 * i for i in range(8)] + [88201 + 2 * i for i in range(8)]
+    parts = [base[:n] * np.float32(0.5 + 0.01 * i) for i, n in enumerate(lens)]
+    so = np.zeros(len(lens) + 1, dtype=np.int64)
+    so[1:] = np.cumsum(lens)
+    words = [ex.words(n) for n in lens]
+    d_audio = torch.from_numpy(np.concatenate(parts)).cuda()
+    d_hp = torch.zeros(int(sum(words)), dtype=torch.int64, device="cuda")
+    ex.calc_hashprint_batch_device(d_audio.data_ptr(), so, d_hp.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = d_hp.cpu().numpy().view(np.uint64)
+    ctx2 = hpfw_b200.Context(0)
+    try:
+        ex2 = hpfw_b200.HashprintExtractor(ctx2)
+        ex2.set_filters(hashprint_golden["filters"])
+        w0 = 0
+        for n, part, w in zip(lens, parts, words):
+            ref = ex2.calc_hashprint(part)
+            assert len(ref) == w
+            assert np.array_equal(got[w0:w0 + w], ref), f"track of {n} samples differs"
+            w0 += w
+    finally:
+        ctx2.close()
+
+
 def test_cqt_limits(ctx):
     from hpfw_b200 import HpfwError
     from hpfw_b200._lib import ERR_SHORT
