@@ -996,47 +996,64 @@ static int env_int(const char *name, int dflt) {
 // Radix sequence of a {2,3,5,7}-smooth n: the fewest Stockham stages over the butterflies this file has (every stage is
 // one shared-memory round trip + barrier), ties broken towards the smaller radix sum; stages run in ascending radix order
 // (the first stage, Ns = 1, is twiddle-free and its strided stores conflict least for a small radix).
-static bool factor_smooth_uncached(int n, FftDesc &d, int maxrad);
-static bool factor_smooth(int n, FftDesc &d) {      // planning calls this thousands of times per new length: memoised
+// The best radix list depends only on the exponents of 2, 3, 5, 7: memoised on those (a few thousand states at most), so
+// that planning a new audio length costs map look-ups, not a search.
+struct RadixPlan {
+    int cost = 1 << 30;      // stages * 1000 + radix sum
+    int nrad = 0;
+    int rad[CQ_MAXRAD] = {};
+};
+static const RadixPlan &radix_plan(int e2, int e3, int e5, int e7, int maxrad) {
     static std::mutex mu;
-    static std::map<std::pair<int, int>, std::pair<bool, FftDesc>> cache;
-    const int maxrad = env_int("HPFW_CQT_MAXRADIX", 16);
+    static std::map<long long, RadixPlan> memo;
+    static const int all[13] = {16, 15, 14, 12, 10, 9, 8, 7, 6, 5, 4, 3, 2};
+    static const int ex[13][4] = {{4, 0, 0, 0}, {0, 1, 1, 0}, {1, 0, 0, 1}, {2, 1, 0, 0}, {1, 0, 1, 0}, {0, 2, 0, 0}, {3, 0, 0, 0},
+                                  {0, 0, 0, 1}, {1, 1, 0, 0}, {0, 0, 1, 0}, {2, 0, 0, 0}, {0, 1, 0, 0}, {1, 0, 0, 0}};
     std::lock_guard<std::mutex> lk(mu);
-    auto it = cache.find({n, maxrad});
-    if (it == cache.end()) {
-        FftDesc t{};
-        const bool ok = factor_smooth_uncached(n, t, maxrad);
-        it = cache.emplace(std::make_pair(n, maxrad), std::make_pair(ok, t)).first;
-    }
-    d = it->second.second;
-    return it->second.first;
+    std::function<const RadixPlan &(int, int, int, int)> go = [&](int a, int b, int c, int d) -> const RadixPlan & {
+        const long long key = ((((long long)maxrad * 64 + a) * 64 + b) * 64 + c) * 64 + d;
+        auto it = memo.find(key);
+        if (it != memo.end()) return it->second;
+        RadixPlan best;
+        if (a == 0 && b == 0 && c == 0 && d == 0) {
+            best.cost = 0;
+        } else {
+            for (int i = 0; i < 13; ++i) {
+                if (all[i] > maxrad || ex[i][0] > a || ex[i][1] > b || ex[i][2] > c || ex[i][3] > d) continue;
+                const RadixPlan &sub = go(a - ex[i][0], b - ex[i][1], c - ex[i][2], d - ex[i][3]);
+                if (sub.cost >= (1 << 29) || sub.nrad >= CQ_MAXRAD) continue;
+                const int cst = sub.cost + 1000 + all[i];
+                if (cst < best.cost) {
+                    best = sub;
+                    best.cost = cst;
+                    best.rad[best.nrad++] = all[i];
+                }
+            }
+        }
+        return memo.emplace(key, best).first->second;
+    };
+    return go(e2, e3, e5, e7);
 }
-static bool factor_smooth_uncached(int n, FftDesc &d, int maxrad) {
+static bool smooth_exponents(int n, int (&e)[4]) {
+    const int p[4] = {2, 3, 5, 7};
+    for (int i = 0; i < 4; ++i) {
+        e[i] = 0;
+        while (n > 1 && n % p[i] == 0) { n /= p[i]; e[i]++; }
+    }
+    return n == 1;
+}
+static bool factor_smooth(int n, FftDesc &d) {
     d.n = n;
     d.nrad = 0;
-    const int all[13] = {16, 15, 14, 12, 10, 9, 8, 7, 6, 5, 4, 3, 2};
-    std::map<int, std::pair<int, int>> memo;   // n -> (stages * 1000 + radix sum, first radix)
-    std::function<int(int)> best = [&](int m) -> int {
-        if (m == 1) return 0;
-        auto it = memo.find(m);
-        if (it != memo.end()) return it->second.first;
-        int bc = 1 << 30, br = 0;
-        for (int r : all) {
-            if (r > maxrad || m % r) continue;
-            const int sub = best(m / r);
-            if (sub >= (1 << 29)) continue;
-            const int c = sub + 1000 + r;
-            if (c < bc) { bc = c; br = r; }
-        }
-        memo[m] = {bc, br};
-        return bc;
-    };
-    if (best(n) >= (1 << 29)) return false;
-    std::vector<int> rads;
-    for (int m = n; m > 1; m /= memo[m].second) rads.push_back(memo[m].second);
-    std::sort(rads.begin(), rads.end());
-    if ((int)rads.size() > CQ_MAXRAD) return false;
-    for (int r : rads) d.rad[d.nrad++] = r;
+    int e[4];
+    if (n < 1 || !smooth_exponents(n, e)) return false;
+    const RadixPlan &rp = radix_plan(e[0], e[1], e[2], e[3], env_int("HPFW_CQT_MAXRADIX", 16));
+    if (rp.cost >= (1 << 29)) return false;
+    for (int i = 0; i < rp.nrad; ++i) {     // ascending radix order (insertion sort of <= 14 entries)
+        int j = d.nrad++;
+        for (; j > 0 && d.rad[j - 1] > rp.rad[i]; --j) d.rad[j] = d.rad[j - 1];
+        d.rad[j] = rp.rad[i];
+    }
     int off = 0, Ns = 1;
     auto magic = [](unsigned long long dv) { return ((1ull << 40) + dv - 1) / dv; };
     for (int s = 0; s < d.nrad; ++s) {
@@ -1184,15 +1201,18 @@ static void take_big(std::vector<DeviceBuffer> &pool, size_t bytes, DeviceBuffer
     pool.erase(pool.begin() + best);
 }
 
+// Grow-only; a buffer that has to grow takes 50 % headroom so that a library of mixed track lengths stops reallocating
+// after its first few tracks (cudaFree / cudaMalloc of tens of MB stall the device for milliseconds).
+static int reserve_roomy(DeviceBuffer &b, size_t bytes) { return bytes <= b.cap ? HPFW_OK : b.reserve(bytes + bytes / 2); }
 static int lane_reserve(CqtPlanCache *c, const CqtPlan &pl, int lane) {
     CqtLane &sc = c->lanes[lane];
     const size_t nkeep = (size_t)(pl.khi - pl.klo + 1);
-    HPFW_TRY(sc.zbuf.reserve(sizeof(float2) * (size_t)(pl.bluestein ? pl.P : pl.H)));
-    HPFW_TRY(sc.zlo.reserve(sizeof(float2) * nkeep));
-    if (pl.bluestein) HPFW_TRY(sc.bl_a.reserve(sizeof(float2) * (size_t)pl.P));
-    else HPFW_TRY(sc.zhi.reserve(sizeof(float2) * nkeep));
-    HPFW_TRY(sc.work.reserve(sizeof(float2) * (size_t)pl.work_elems));
-    HPFW_TRY(sc.power.reserve(sizeof(float) * (size_t)CQ_BINS * pl.fpitch));
+    HPFW_TRY(reserve_roomy(sc.zbuf, sizeof(float2) * (size_t)(pl.bluestein ? pl.P : pl.H)));
+    HPFW_TRY(reserve_roomy(sc.zlo, sizeof(float2) * nkeep));
+    if (pl.bluestein) HPFW_TRY(reserve_roomy(sc.bl_a, sizeof(float2) * (size_t)pl.P));
+    else HPFW_TRY(reserve_roomy(sc.zhi, sizeof(float2) * nkeep));
+    HPFW_TRY(reserve_roomy(sc.work, sizeof(float2) * (size_t)pl.work_elems));
+    HPFW_TRY(reserve_roomy(sc.power, sizeof(float) * (size_t)CQ_BINS * pl.fpitch));
     HPFW_TRY(sc.pmax.reserve(sizeof(unsigned int)));
     return HPFW_OK;
 }
@@ -1251,34 +1271,34 @@ static int pick_row_len(long long need2) {
 // split H = n1 * n2 (n1 <= n2 <= CQ_MAX_ROW), both {2,3,5,7}-smooth: the fewest Stockham stages in total, then a row pitch
 // that keeps pass A's column groups sector-aligned, then the most balanced; returns false if there is none
 static bool split_smooth_capped(int H, int n1max, int &n1, int &n2) {
-    int rest = H;
-    int e[4] = {0, 0, 0, 0};
-    const int p[4] = {2, 3, 5, 7};
-    for (int i = 0; i < 4; ++i)
-        while (rest % p[i] == 0) { rest /= p[i]; e[i]++; }
-    if (rest != 1) return false;
+    int e[4];
+    if (H < 4 || !smooth_exponents(H, e)) return false;
+    const int maxrad = env_int("HPFW_CQT_MAXRADIX", 16);
     long long best = -1;
     int best_stages = 1 << 30, best_al = -1;
-    for (int a = 0; a <= e[0]; ++a)
-        for (int b = 0; b <= e[1]; ++b)
-            for (int c = 0; c <= e[2]; ++c)
-                for (int d = 0; d <= e[3]; ++d) {
-                    long long v = 1;
-                    for (int i = 0; i < a; ++i) v *= 2;
-                    for (int i = 0; i < b; ++i) v *= 3;
-                    for (int i = 0; i < c; ++i) v *= 5;
-                    for (int i = 0; i < d; ++i) v *= 7;
+    long long va = 1;
+    for (int a = 0; a <= e[0]; ++a, va *= 2) {
+        long long vb = va;
+        for (int b = 0; b <= e[1]; ++b, vb *= 3) {
+            long long vc = vb;
+            for (int c = 0; c <= e[2]; ++c, vc *= 5) {
+                long long v = vc;
+                for (int d = 0; d <= e[3]; ++d, v *= 7) {
                     const long long w = H / v;
                     if (!(v <= w && w <= CQ_MAX_ROW && v >= 2 && v <= n1max)) continue;
-                    FftDesc da{}, db{};
-                    if (!factor_smooth((int)v, da) || !factor_smooth((int)w, db)) continue;
-                    const int st = da.nrad + db.nrad;
+                    const RadixPlan &pa = radix_plan(a, b, c, d, maxrad);
+                    const RadixPlan &pb = radix_plan(e[0] - a, e[1] - b, e[2] - c, e[3] - d, maxrad);
+                    if (pa.cost >= (1 << 29) || pb.cost >= (1 << 29)) continue;
+                    const int st = pa.nrad + pb.nrad;
                     // pass A touches 4 adjacent columns = one 32-byte sector only if the row pitch n2 is a multiple of 4
                     const int al = (w % 4 == 0) ? 1 : 0;
                     if (st < best_stages || (st == best_stages && (al > best_al || (al == best_al && v > best)))) {
                         best_stages = st; best_al = al; best = v;
                     }
                 }
+            }
+        }
+    }
     if (best < 2) return false;
     n1 = (int)best;
     n2 = (int)(H / best);
@@ -1512,7 +1532,7 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
     const size_t meta_bytes = mo, arena_bytes = table_bytes + meta_bytes;
 
     take_mem(cache->free_mem, arena_bytes, pl.mem);
-    HPFW_TRY(pl.mem.dev.reserve(arena_bytes));
+    HPFW_TRY(reserve_roomy(pl.mem.dev, arena_bytes));
     HPFW_TRY(pl.mem.pin.reserve(meta_bytes));
     char *arena = pl.mem.dev.as<char>();
     float2 *tab = pl.mem.dev.as<float2>();
@@ -1579,7 +1599,7 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
         CqtLane &sc = cache->lanes[lane];
         const int P = pl.P, K = pl.khi - pl.klo + 1, gb = (P + CQ_THREADS - 1) / CQ_THREADS;
         take_big(cache->free_big, sizeof(float2) * (size_t)P, pl.bhat);
-        HPFW_TRY(pl.bhat.reserve(sizeof(float2) * (size_t)P));
+        HPFW_TRY(reserve_roomy(pl.bhat, sizeof(float2) * (size_t)P));
         {
             KernelScope ks(ctx, HPFW_K_CQT, stream);
             bl_filter_kernel<<<gb, CQ_THREADS, 0, stream>>>((long long)N, P, pl.klo, K, sc.bl_a.as<float2>());
@@ -1595,17 +1615,27 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
     return HPFW_OK;
 }
 
-constexpr size_t CQ_PLAN_CACHE = 48;   // plans are a few MB of tables each
+constexpr size_t CQ_PLAN_CACHE = 48;        // plans are a few MB of tables each ...
+constexpr size_t CQ_PLAN_CACHE_BLUESTEIN = 6;   // ... except Bluestein plans, which also hold a P-point filter spectrum (70 MB at 3 min)
 
 static int plan_get(hpfw_ctx *ctx, int64_t N, CqtPlan **out, cudaStream_t stream, int lane) {
     if (!ctx->cqt) ctx->cqt = new CqtPlanCache();
     CqtPlanCache *c = ctx->cqt;
     auto it = c->plans.find(N);
     if (it == c->plans.end()) {
-        if (c->plans.size() >= CQ_PLAN_CACHE) {   // evict the least recently used plan; its memory goes to the free lists
-            auto victim = c->plans.begin();
-            for (auto k = c->plans.begin(); k != c->plans.end(); ++k)
-                if (k->second->last_use < victim->second->last_use) victim = k;
+        // evict the least recently used plan when the cache is full; its memory goes to the free lists. Whether the new length
+        // needs the Bluestein path is a property of N alone (odd, or N/2 not smooth).
+        int e4[4];
+        const bool will_bluestein = (N & 1) || !smooth_exponents((int)(N / 2), e4) || env_int("HPFW_CQT_BLUESTEIN", 0);
+        size_t n_bl = 0;
+        for (auto &kv : c->plans) n_bl += kv.second->bluestein ? 1 : 0;
+        const bool evict_bl = will_bluestein && n_bl >= CQ_PLAN_CACHE_BLUESTEIN;
+        if (c->plans.size() >= CQ_PLAN_CACHE || evict_bl) {
+            auto victim = c->plans.end();
+            for (auto k = c->plans.begin(); k != c->plans.end(); ++k) {
+                if (evict_bl && !k->second->bluestein) continue;
+                if (victim == c->plans.end() || k->second->last_use < victim->second->last_use) victim = k;
+            }
             for (cudaEvent_t e : victim->second->last_done)
                 if (e) HPFW_CUDA_TRY(cudaEventSynchronize(e));
             plan_release(c, *victim->second, true);
