@@ -369,6 +369,63 @@ def run_extraction(args, ctx, rank, world, dev, max_over_ranks, barrier):
                                "sample": f"{nt} synthetic 3-min tracks in {dt:.1f} s on {cores} threads: numpy/pocketfft "
                                          f"restatement of the essentia CQT (oracle/nsgcq.py; essentia itself is absent) + the "
                                          f"reference's frames/projection/fingerprint code (Eigen GEBP, no MKL)"}
+    # ---- index-time filter learning (row a10: calc_cov per track + calc_filters once), rank 0 only: the covariance is
+    # accumulated in HBM per GPU; a multi-GPU index would add one all-reduce of 2420 x 2420 floats (not part of this leg)
+    if rank == 0:
+        n_idx = min(per_rank, 32)
+        spec = torch.empty((n_idx, cols, 121), dtype=torch.float32, device=dev)
+        for i in range(n_idx):
+            check(ctx._lib.hpfw_cqt_spectrogram_device(ctx.handle, C.c_void_p(audio[i].data_ptr()), n,
+                                                       C.c_void_p(spec[i].data_ptr()), stream_arg(stream)))
+        torch.cuda.synchronize()
+
+        def cov_pass():
+            check(ctx._lib.hpfw_cov_reset(ctx.handle))
+            for i in range(n_idx):
+                check(ctx._lib.hpfw_cov_add_spectrogram_device(ctx.handle, C.c_void_p(spec[i].data_ptr()), cols,
+                                                               stream_arg(stream)))
+        cov_pass()
+        torch.cuda.synchronize()
+        e0.record()
+        cov_pass()
+        e1.record()
+        torch.cuda.synchronize()
+        cov_ms = e0.elapsed_time(e1) / n_idx
+        f_out = np.zeros((2420, 64), dtype=np.float32)
+        ev = np.zeros(64, dtype=np.float32)
+        t0 = time.perf_counter()
+        check(ctx._lib.hpfw_calc_filters(ctx.handle, None, f_out.ctypes.data_as(C.c_void_p), ev.ctypes.data_as(C.c_void_p)))
+        filt_ms = (time.perf_counter() - t0) * 1e3
+        ex.set_filters(filters)          # the timed legs above and the CPU sample below use the golden filters
+        syrk_flop = 2.0 * 2420 * 2420 * frames
+        out["index"] = {
+            "what": "index-time filter learning, rows a10: HashprintHandle::calc_cov per track (accumulated in HBM) and "
+                    "calc_filters once (top-64 eigenvectors of the 2420 x 2420 covariance)",
+            "cov_ms_per_track": cov_ms, "tracks": n_idx,
+            "cov_equivalent_tflops": syrk_flop / (cov_ms * 1e-3) / 1e12,
+            "cov_note": "the reference forms the 2420 x 2420 x frames SYRK (170 GFLOP per 3-min track); the context window "
+                        "makes it twenty 121 x 121 x frames correlations + edge corrections (4.2 GFLOP), learn.cu",
+            "calc_filters_ms": filt_ms,
+            "calc_filters_note": "block subspace iteration on the GPU + Rayleigh-Ritz on the host, wall clock",
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            import oracle
+            if oracle.ref_available():
+                R = oracle.ref()
+                sp = np.ascontiguousarray(spec[0].cpu().numpy())
+                cov = np.zeros((2420, 2420), dtype=np.float32)
+                t0 = time.perf_counter()
+                R.ref_calc_cov(sp.reshape(-1), cols, cov.reshape(-1))
+                cpu_cov_s = time.perf_counter() - t0
+                fl = np.zeros((2420, 64), dtype=np.float32)
+                t0 = time.perf_counter()
+                R.ref_calc_filters(cov.reshape(-1), fl.reshape(-1))
+                cpu_filt_s = time.perf_counter() - t0
+                out["index"]["cpu_baseline"] = {
+                    "kind": "reference", "cores": 1, "cov_ms_per_track": cpu_cov_s * 1e3, "calc_filters_ms": cpu_filt_s * 1e3,
+                    "sample": "one 3-min spectrogram through the reference's calc_cov and one calc_filters "
+                              "(hashprint_handle.h:96-112, Eigen 3.3.7 without MKL), single thread as in one taskflow worker"}
+        del spec
     del audio, base, hp
     torch.cuda.empty_cache()
     return out

@@ -12,8 +12,9 @@
 // in fp32. cov = (G - nf mu_i mu_j) / (nf - 1) is added to the device-resident accumulator of the context.
 //
 // calc_filters: only the top 64 eigenvectors are needed, so instead of a dense eigen-solve the GPU runs block subspace
-// iteration (Z = A V, one 2420 x 2420 x 128 GEMM per step) while the host orthonormalises the 2420 x 128 block
-// (modified Gram-Schmidt, double) and does the 128 x 128 Rayleigh-Ritz step (cyclic Jacobi, double). Eigenvector signs are
+// iteration V <- orth(A V) on a 2420 x 128 block, device-resident: the product and the CholQR2 orthonormalisation (Gram
+// matrix, Cholesky and triangular inverse in one CTA, block rotation) accumulate in double and store float; the host only
+// does the 128 x 128 Rayleigh-Ritz eigenproblem (cyclic Jacobi, double) at checkpoints 4, 8, 16, ... Eigenvector signs are
 // arbitrary in any solver (MKL ssyev vs Eigen's QL differ too); they are normalised so that the largest-magnitude component is
 // positive. Hamming distances do not depend on the sign as long as DB and queries use the same filters.
 #include "common.cuh"
@@ -140,16 +141,17 @@ cov_finish_kernel(const float *__restrict__ Sc, int nf, const float *__restrict_
     }
 }
 
-// ---- Z = A V for the subspace iteration: A symmetric n x n, V and Z column-major n x p ----------------------------------------
+// ---- subspace iteration on the GPU: every product accumulates in double, blocks are stored in float ----------------------------
+// Z = A V: A symmetric n x n, V and Z column-major n x p. 32 x 64 output tile per CTA (152 CTAs at n = 2420, p = 128).
 __global__ void __launch_bounds__(256)
 symm_block_mul_kernel(const float *__restrict__ A, const float *__restrict__ V, float *__restrict__ Z, int n, int p) {
-    __shared__ float As[16][64 + 4], Vs[16][64 + 4];
-    const int m0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    float acc[4][4] = {};
+    __shared__ float As[16][32 + 1], Vs[16][64 + 4];
+    const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // thread: rows ty*2 .. +1, columns tx*4 .. +3
+    double acc[2][4] = {};
     for (int k0 = 0; k0 < n; k0 += 16) {
-        for (int e = threadIdx.x; e < 16 * 64; e += 256) {
-            const int kk = e >> 6, col = e & 63;
+        for (int e = threadIdx.x; e < 16 * 32; e += 256) {
+            const int kk = e >> 5, col = e & 31;
             const int k = k0 + kk;
             // A(m, k) = A(k, m): read row k of the column-major matrix as a contiguous run over m
             As[kk][col] = (k < n && m0 + col < n) ? A[(size_t)k * n + m0 + col] : 0.f;
@@ -162,50 +164,139 @@ symm_block_mul_kernel(const float *__restrict__ A, const float *__restrict__ V, 
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < 16; ++kk) {
-            float a[4], b[4];
+            double a[2], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+            for (int i = 0; i < 2; ++i) a[i] = (double)As[kk][ty * 2 + i];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Vs[kk][tx * 4 + j];
+            for (int j = 0; j < 4; ++j) b[j] = (double)Vs[kk][tx * 4 + j];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int m = m0 + ty * 4 + i, c = c0 + tx * 4 + j;
-            if (m < n && c < p) Z[(size_t)c * n + m] = acc[i][j];
+            const int m = m0 + ty * 2 + i, c = c0 + tx * 4 + j;
+            if (m < n && c < p) Z[(size_t)c * n + m] = (float)acc[i][j];
         }
 }
 
-// ================================================================================================ host numerics (double)
-// modified Gram-Schmidt with one re-orthogonalisation pass; V is column-major n x p
-static void orthonormalise(std::vector<double> &V, int n, int p) {
-    for (int j = 0; j < p; ++j) {
-        double *vj = &V[(size_t)j * n];
-        for (int pass = 0; pass < 2; ++pass)
-            for (int i = 0; i < j; ++i) {
-                const double *vi = &V[(size_t)i * n];
-                double dot = 0.0;
-                for (int k = 0; k < n; ++k) dot += vi[k] * vj[k];
-                for (int k = 0; k < n; ++k) vj[k] -= dot * vi[k];
-            }
-        double nrm = 0.0;
-        for (int k = 0; k < n; ++k) nrm += vj[k] * vj[k];
-        nrm = std::sqrt(nrm);
-        if (nrm < 1e-300) {   // degenerate direction: replace by a unit vector not yet used
-            for (int k = 0; k < n; ++k) vj[k] = (k == j) ? 1.0 : 0.0;
-            nrm = 1.0;
+// C[i*p + j] += sum_k X[i*n + k] * Y[j*n + k] over this CTA's K-chunk (C double, zeroed by the caller). grid (p/32, p/32, KS).
+__global__ void __launch_bounds__(256)
+gram_tn_kernel(const float *__restrict__ X, const float *__restrict__ Y, double *__restrict__ C, int n, int p) {
+    __shared__ float Xs[32][32 + 1], Ys[32][32 + 1];
+    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    const int per = (n + gridDim.z - 1) / gridDim.z, kb = blockIdx.z * per, ke = min(n, kb + per);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // thread: rows ty*2 .. +1, columns tx*2 .. +1
+    double acc[2][2] = {};
+    for (int k0 = kb; k0 < ke; k0 += 32) {
+        for (int e = threadIdx.x; e < 32 * 32; e += 256) {
+            const int col = e >> 5, kk = e & 31;
+            const int k = k0 + kk;
+            Xs[kk][col] = (k < ke && i0 + col < p) ? X[(size_t)(i0 + col) * n + k] : 0.f;
+            Ys[kk][col] = (k < ke && j0 + col < p) ? Y[(size_t)(j0 + col) * n + k] : 0.f;
         }
-        for (int k = 0; k < n; ++k) vj[k] /= nrm;
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < 32; ++kk) {
+            const double a0 = Xs[kk][ty * 2], a1 = Xs[kk][ty * 2 + 1], b0 = Ys[kk][tx * 2], b1 = Ys[kk][tx * 2 + 1];
+            acc[0][0] = fma(a0, b0, acc[0][0]);
+            acc[0][1] = fma(a0, b1, acc[0][1]);
+            acc[1][0] = fma(a1, b0, acc[1][0]);
+            acc[1][1] = fma(a1, b1, acc[1][1]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int r = i0 + ty * 2 + i, c = j0 + tx * 2 + j;
+            if (r < p && c < p) atomicAdd(&C[(size_t)r * p + c], acc[i][j]);
+        }
+}
+
+// One CTA: G = Z^T Z (p x p, double, p <= 128) -> Cholesky G = L L^T in shared memory -> W = L^{-T}, so that Q = Z W has
+// orthonormal columns. W[k*p + j] = Linv[j][k] (zero for k > j). A pivot that has lost all its digits (dependent column)
+// is clamped; the second CholQR pass and the Rayleigh-Ritz step clean that direction up.
+__global__ void __launch_bounds__(256) chol_inv_kernel(const double *__restrict__ G, double *__restrict__ W, int p) {
+    extern __shared__ double Ls[];          // p x p, row-major
+    for (int e = threadIdx.x; e < p * p; e += blockDim.x) Ls[e] = G[e];
+    __syncthreads();
+    double trace = 0.0;
+    for (int i = 0; i < p; ++i) trace += Ls[(size_t)i * p + i];
+    const double tiny = trace * 1e-28 + 1e-300;
+    for (int j = 0; j < p; ++j) {
+        const double d = sqrt(fmax(Ls[(size_t)j * p + j], tiny));
+        __syncthreads();
+        if (threadIdx.x == 0) Ls[(size_t)j * p + j] = d;
+        for (int i = j + 1 + threadIdx.x; i < p; i += blockDim.x) Ls[(size_t)i * p + j] /= d;
+        __syncthreads();
+        const int m = p - j - 1;            // trailing (i, k), j < k <= i < p
+        for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+            const int i = j + 1 + e / m, k = j + 1 + e % m;
+            if (k <= i) Ls[(size_t)i * p + k] -= Ls[(size_t)i * p + j] * Ls[(size_t)k * p + j];
+        }
+        __syncthreads();
+    }
+    // column c of Linv by forward substitution (one thread per column); x lives in the unused upper triangle: Ls[c][i], i > c
+    for (int c = threadIdx.x; c < p; c += blockDim.x) {
+        const double xc = 1.0 / Ls[(size_t)c * p + c];
+        W[(size_t)c * p + c] = xc;                      // Linv[c][c]
+        for (int k = 0; k < c; ++k) W[(size_t)c * p + k] = 0.0;      // W[k'=c][j=k<c] = Linv[k][c] = 0
+        for (int i = c + 1; i < p; ++i) {
+            double sum = Ls[(size_t)i * p + c] * xc;
+            for (int k = c + 1; k < i; ++k) sum = fma(Ls[(size_t)i * p + k], Ls[(size_t)c * p + k], sum);   // x[k] stored at Ls[c][k]
+            const double xi = -sum / Ls[(size_t)i * p + i];
+            Ls[(size_t)c * p + i] = xi;                 // upper triangle, row c: never read by other threads
+            W[(size_t)c * p + i] = xi;                  // W[k=c][j=i] = Linv[i][c]
+        }
     }
 }
 
+// V = Z W: Z column-major n x p (float), W row-major p x p (double), V column-major n x p (float). One thread per (row, 4 columns).
+__global__ void __launch_bounds__(256)
+gemm_nn_kernel(const float *__restrict__ Z, const double *__restrict__ W, float *__restrict__ V, int n, int p) {
+    const int row = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int cg = blockIdx.y * 4 + (threadIdx.x >> 6);       // column group of 8
+    if (row >= n) return;
+    double acc[8] = {};
+    for (int k = 0; k < p; ++k) {
+        const double z = (double)Z[(size_t)k * n + row];
+        const double *w = W + (size_t)k * p + cg * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fma(z, w[j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (cg * 8 + j < p) V[(size_t)(cg * 8 + j) * n + row] = (float)acc[j];
+}
+
+// r[c] = || Zr[:, c] - theta[c] Vr[:, c] ||_2  (one CTA per column)
+__global__ void __launch_bounds__(256)
+resid_kernel(const float *__restrict__ Zr, const float *__restrict__ Vr, const double *__restrict__ theta, int n,
+             double *__restrict__ r) {
+    __shared__ double red[256];
+    const int c = blockIdx.x;
+    double acc = 0.0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const double d = (double)Zr[(size_t)c * n + k] - theta[c] * (double)Vr[(size_t)c * n + k];
+        acc = fma(d, d, acc);
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) r[c] = sqrt(red[0]);
+}
+
+// ================================================================================================ host numerics (double)
 // cyclic Jacobi eigen-decomposition of the symmetric p x p matrix H (row-major); eigenvectors in the columns of Q
 static void jacobi_eigh(std::vector<double> &H, int p, std::vector<double> &w, std::vector<double> &Q) {
     Q.assign((size_t)p * p, 0.0);
@@ -339,7 +430,8 @@ int hpfw_calc_filters(hpfw_ctx *ctx, const float *cov, float *filters_out, float
     if (!ctx || !filters_out) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_calc_filters: NULL argument");
     DeviceGuard g(ctx->device);
     const int n = LN_FS, p = LN_P, want = HPFW_NFILTERS;
-    DeviceBuffer dA, dV, dZ;
+    cudaStream_t s = ctx->stream;
+    DeviceBuffer dA, dV, dZ, dT, dG, dW, dR;
     const float *A = nullptr;
     if (cov) {
         HPFW_TRY(dA.reserve(sizeof(float) * (size_t)n * n));
@@ -349,84 +441,118 @@ int hpfw_calc_filters(hpfw_ctx *ctx, const float *cov, float *filters_out, float
         if (!ctx->cov_accum.ptr) HPFW_FAIL(HPFW_ERR_STATE, "hpfw_calc_filters: no covariance accumulated");
         A = ctx->cov_accum.as<float>();
     }
-    HPFW_TRY(dV.reserve(sizeof(float) * (size_t)n * p));
-    HPFW_TRY(dZ.reserve(sizeof(float) * (size_t)n * p));
-    std::vector<double> V((size_t)n * p), Z((size_t)n * p);
-    std::vector<float> Vf((size_t)n * p), Zf((size_t)n * p);
-    uint64_t lcg = 0x9E3779B97F4A7C15ull;
-    for (auto &v : V) {
-        lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
-        v = (double)((lcg >> 11) & 0xFFFFFF) / 16777216.0 - 0.5;
-    }
-    orthonormalise(V, n, p);
-    std::vector<double> H, w, Q, prev(want, 0.0);
-    const dim3 grid((n + 63) / 64, (p + 63) / 64);
+    const size_t blk = sizeof(float) * (size_t)n * p, pp = sizeof(double) * (size_t)p * p;
     int status = HPFW_OK;
-    for (int it = 0; it < 300; ++it) {
-        for (size_t i = 0; i < V.size(); ++i) Vf[i] = (float)V[i];
-        cudaError_t e = cudaMemcpyAsync(dV.ptr, Vf.data(), sizeof(float) * Vf.size(), cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess) {
-            KernelScope ks(ctx, HPFW_K_OTHER, ctx->stream);
-            symm_block_mul_kernel<<<grid, 256, 0, ctx->stream>>>(A, dV.as<float>(), dZ.as<float>(), n, p);
-            e = cudaGetLastError();
+    auto fail = [&](int st) { status = st; };
+    if (dV.reserve(blk) || dZ.reserve(blk) || dT.reserve(blk) || dG.reserve(pp) || dW.reserve(pp) ||
+        dR.reserve(sizeof(double) * 2 * p))
+        fail(HPFW_ERR_CUDA);
+    float *V = dV.as<float>(), *Z = dZ.as<float>(), *T = dT.as<float>();
+    double *G = dG.as<double>(), *W = dW.as<double>(), *R = dR.as<double>();
+    if (status == HPFW_OK &&
+        cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp) != cudaSuccess)
+        fail(HPFW_ERR_CUDA);
+
+    const dim3 g_mul((n + 31) / 32, (p + 63) / 64), g_gram((p + 31) / 32, (p + 31) / 32, 8), g_nn((n + 63) / 64, (p + 31) / 32);
+    auto gram = [&](const float *X, const float *Y) {
+        cudaMemsetAsync(G, 0, pp, s);
+        KernelScope ks(ctx, HPFW_K_OTHER, s);
+        gram_tn_kernel<<<g_gram, 256, 0, s>>>(X, Y, G, n, p);
+    };
+    auto rotate = [&](const float *X, const double *Wm, float *Y) {       // Y = X Wm
+        KernelScope ks(ctx, HPFW_K_OTHER, s);
+        gemm_nn_kernel<<<g_nn, 256, 0, s>>>(X, Wm, Y, n, p);
+    };
+    // dst = orthonormal basis of span(src) by CholQR2 (Gram matrices and triangular factors in double); src is overwritten
+    auto orth = [&](float *src, float *tmp, float *dst) {
+        gram(src, src);
+        { KernelScope ks(ctx, HPFW_K_OTHER, s); chol_inv_kernel<<<1, 256, pp, s>>>(G, W, p); }
+        rotate(src, W, tmp);
+        gram(tmp, tmp);
+        { KernelScope ks(ctx, HPFW_K_OTHER, s); chol_inv_kernel<<<1, 256, pp, s>>>(G, W, p); }
+        rotate(tmp, W, dst);
+    };
+
+    std::vector<float> Vf((size_t)n * p);
+    std::vector<double> H, w, Q, Wq((size_t)p * p), theta(p), prev(want, 0.0), res(p);
+    if (status == HPFW_OK) {
+        uint64_t lcg = 0x9E3779B97F4A7C15ull;
+        for (auto &v : Vf) {
+            lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+            v = (float)((double)((lcg >> 11) & 0xFFFFFF) / 16777216.0 - 0.5);
         }
-        if (e == cudaSuccess) e = cudaMemcpyAsync(Zf.data(), dZ.ptr, sizeof(float) * Zf.size(), cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) {
-            set_error("hpfw_calc_filters: %s", cudaGetErrorString(e));
-            status = HPFW_ERR_CUDA;
-            break;
+        if (cudaMemcpyAsync(Z, Vf.data(), blk, cudaMemcpyHostToDevice, s) != cudaSuccess) fail(HPFW_ERR_CUDA);
+        orth(Z, T, V);
+    }
+    // Block subspace iteration V <- orth(A V), entirely on the device; a Rayleigh-Ritz checkpoint (p x p eigenproblem on the
+    // host, cyclic Jacobi in double) at iterations 4, 8, 16, ... rotates the block to Ritz vectors and tests the residuals.
+    const int max_it = 4096;
+    int next_check = 4;
+    bool done = false;
+    for (int it = 1; status == HPFW_OK && !done; ++it) {
+        { KernelScope ks(ctx, HPFW_K_OTHER, s); symm_block_mul_kernel<<<g_mul, 256, 0, s>>>(A, V, Z, n, p); }
+        if (it < next_check && it < max_it) {
+            orth(Z, T, V);
+            continue;
         }
-        // Rayleigh-Ritz: H = V^T (A V), rotate, then the power step V <- orth(A V Q)
-        H.assign((size_t)p * p, 0.0);
+        gram(V, Z);                                            // H = V^T A V
+        H.resize((size_t)p * p);
+        cudaError_t e = cudaMemcpyAsync(H.data(), G, pp, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { set_error("hpfw_calc_filters: %s", cudaGetErrorString(e)); fail(HPFW_ERR_CUDA); break; }
         for (int i = 0; i < p; ++i)
-            for (int j = i; j < p; ++j) {
-                double dot = 0.0;
-                const double *vi = &V[(size_t)i * n];
-                const float *zj = &Zf[(size_t)j * n];
-                for (int k = 0; k < n; ++k) dot += vi[k] * (double)zj[k];
-                H[(size_t)i * p + j] = H[(size_t)j * p + i] = dot;
-            }
+            for (int j = i + 1; j < p; ++j) H[(size_t)i * p + j] = H[(size_t)j * p + i] = 0.5 * (H[(size_t)i * p + j] + H[(size_t)j * p + i]);
         jacobi_eigh(H, p, w, Q);
         std::vector<int> order(p);
         for (int i = 0; i < p; ++i) order[i] = i;
         std::sort(order.begin(), order.end(), [&](int a, int b) { return w[a] > w[b]; });
-        // Z' = (A V) Q_sorted ; these are A * (Ritz vectors): use them as the next block (one power step)
-        for (int c = 0; c < p; ++c) {
-            double *zc = &Z[(size_t)c * n];
-            std::fill(zc, zc + n, 0.0);
-            for (int j = 0; j < p; ++j) {
-                const double q = Q[(size_t)j * p + order[c]];
-                if (q == 0.0) continue;
-                const float *zj = &Zf[(size_t)j * n];
-                for (int k = 0; k < n; ++k) zc[k] += q * (double)zj[k];
-            }
-        }
-        double change = 0.0, top = std::fabs(w[order[0]]) + 1e-300;
+        for (int k = 0; k < p; ++k)
+            for (int j = 0; j < p; ++j) Wq[(size_t)k * p + j] = Q[(size_t)k * p + order[j]];
+        for (int j = 0; j < p; ++j) theta[j] = w[order[j]];
+        e = cudaMemcpyAsync(W, Wq.data(), pp, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(R, theta.data(), sizeof(double) * p, cudaMemcpyHostToDevice, s);
+        rotate(V, W, T);                                       // T = Ritz vectors
+        rotate(Z, W, V);                                       // V = A * Ritz vectors
+        { KernelScope ks(ctx, HPFW_K_OTHER, s); resid_kernel<<<p, 256, 0, s>>>(V, T, R, n, R + p); }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(res.data(), R + p, sizeof(double) * p, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { set_error("hpfw_calc_filters: %s", cudaGetErrorString(e)); fail(HPFW_ERR_CUDA); break; }
+        const double top = std::fabs(theta[0]) + 1e-300;
+        double rmax = 0.0, change = 0.0;
         for (int i = 0; i < want; ++i) {
-            change = std::max(change, std::fabs(w[order[i]] - prev[i]) / top);
-            prev[i] = w[order[i]];
+            rmax = std::max(rmax, res[i]);
+            change = std::max(change, std::fabs(theta[i] - prev[i]) / top);
+            prev[i] = theta[i];
         }
-        V.swap(Z);
-        orthonormalise(V, n, p);
-        if (it >= 3 && change < 1e-9) break;
+        // converged: residuals at the float noise floor of the block, or the Ritz values have stopped moving
+        if (rmax <= 2e-6 * top || (it > 4 && change < 1e-10) || it >= max_it) {
+            done = true;                                       // T holds the Ritz vectors
+        } else {
+            orth(V, Z, T);                                     // next block = orth(A * Ritz vectors) -> T
+            std::swap(V, T);
+            next_check = std::min(next_check * 2, it + 512);
+        }
     }
     if (status == HPFW_OK) {
-        // V now holds orth(A * Ritz vectors), converged to the eigenvectors in descending eigenvalue order.
+        // final polish of the wanted vectors' orthonormality (they are Ritz vectors of an orthonormal block already)
+        cudaError_t e = cudaMemcpyAsync(Vf.data(), T, blk, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { set_error("hpfw_calc_filters: %s", cudaGetErrorString(e)); fail(HPFW_ERR_CUDA); }
+    }
+    if (status == HPFW_OK) {
         // filters(f, i) = eigenvector_f[i], column-major 64 x 2420; sign: largest-|component| positive.
         for (int f = 0; f < want; ++f) {
-            const double *v = &V[(size_t)f * n];
+            const float *v = &Vf[(size_t)f * n];
             int arg = 0;
             for (int k = 1; k < n; ++k)
                 if (std::fabs(v[k]) > std::fabs(v[arg])) arg = k;
-            const double sgn = v[arg] < 0 ? -1.0 : 1.0;
-            for (int k = 0; k < n; ++k) filters_out[(size_t)f + (size_t)want * k] = (float)(sgn * v[k]);
+            const float sgn = v[arg] < 0 ? -1.f : 1.f;
+            for (int k = 0; k < n; ++k) filters_out[(size_t)f + (size_t)want * k] = sgn * v[k];
             if (eigenvalues_out) eigenvalues_out[f] = (float)prev[f];
         }
     }
-    dA.release();
-    dV.release();
-    dZ.release();
+    cudaStreamSynchronize(s);
+    dA.release(); dV.release(); dZ.release(); dT.release(); dG.release(); dW.release(); dR.release();
     return status;
 }
 
