@@ -21,37 +21,70 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace hpfw_b200 {
 
+int cov_tc_run(hpfw_ctx *ctx, const float *d_hi, const float *d_lo, int cols, int nf, int splits, float *d_part,
+               int *rows_done, cudaStream_t stream);
+
+
 constexpr int LN_BINS = HPFW_BINS;          // 121
 constexpr int LN_CTX = HPFW_CONTEXT;        // 20
 constexpr int LN_FS = HPFW_FRAME_SIZE;      // 2420
-constexpr int LN_KS = 16;                   // split-K factor of the T0 GEMMs
+constexpr int LN_KS = 29;                   // time splits of the T0 GEMMs: 29 x 5 lag groups = 145 CTAs of cov_tc_kernel
 constexpr int LN_P = 128;                   // subspace block size (64 wanted + 64 guard vectors)
 
-// ---- per-band mean over all columns; centred copy Sc[t][b] = S[t][b] - mean_b ------------------------------------------
-__global__ void __launch_bounds__(256) band_mean_kernel(const float *__restrict__ S, int cols, float *__restrict__ mean) {
-    // one CTA per band; double accumulation (cols up to ~3e4)
-    __shared__ double red[256];
-    const int b = blockIdx.x;
-    double acc = 0.0;
-    for (int t = threadIdx.x; t < cols; t += blockDim.x) acc += (double)S[(size_t)t * LN_BINS + b];
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) mean[b] = (float)(red[0] / (double)cols);
+// ---- per-band sums in one coalesced pass: partial[cta][0][b] = sum_{t < nf} S[t][b], partial[cta][1][b] = sum_{t >= nf} S[t][b] --
+constexpr int LN_SUM_CTAS = 148;
+__global__ void __launch_bounds__(128) band_sums_kernel(const float *__restrict__ S, int cols, int nf, double *__restrict__ partial) {
+    const int b = threadIdx.x;
+    double a0 = 0.0, a1 = 0.0;
+    if (b < LN_BINS)
+        for (int t = blockIdx.x; t < cols; t += gridDim.x) {
+            const double v = (double)S[(size_t)t * LN_BINS + b];
+            if (t < nf) a0 += v; else a1 += v;
+        }
+    partial[((size_t)blockIdx.x * 2 + 0) * 128 + b] = a0;
+    partial[((size_t)blockIdx.x * 2 + 1) * 128 + b] = a1;
 }
 
-__global__ void __launch_bounds__(256) center_kernel(const float *__restrict__ S, int cols, const float *__restrict__ mean,
-                                                     float *__restrict__ Sc) {
-    const size_t n = (size_t)cols * LN_BINS;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        Sc[i] = S[i] - mean[i % LN_BINS];
+// ---- centred copy Sc[t][b] = S[t][b] - mean_b (+ its tf32 hi / lo parts, bands padded to 128, for the tensor-core kernel) and
+// sum0[b] = sum_{t < nf} Sc[t][b]. The means are reduced from the partial sums in a fixed order by every CTA.
+__global__ void __launch_bounds__(256)
+center_kernel(const float *__restrict__ S, int cols, int nf, const double *__restrict__ partial, int nparts, float *__restrict__ Sc,
+              float *__restrict__ hi, float *__restrict__ lo, float *__restrict__ sum0) {
+    __shared__ float mean_s[128];
+    if (threadIdx.x < 128) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int p = 0; p < nparts; ++p) {
+            a0 += partial[((size_t)p * 2 + 0) * 128 + threadIdx.x];
+            a1 += partial[((size_t)p * 2 + 1) * 128 + threadIdx.x];
+        }
+        const double mean = (a0 + a1) / (double)cols;
+        mean_s[threadIdx.x] = threadIdx.x < LN_BINS ? (float)mean : 0.f;
+        if (blockIdx.x == 0 && threadIdx.x < LN_BINS) sum0[threadIdx.x] = (float)(a0 - (double)nf * (double)(float)mean);
+    }
+    __syncthreads();
+    const size_t total = (size_t)cols * 128;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t t = i >> 7;
+        const int b = (int)(i & 127);
+        float v = 0.f;
+        if (b < LN_BINS) {
+            v = S[t * LN_BINS + b] - mean_s[b];
+            Sc[t * LN_BINS + b] = v;
+        }
+        if (hi) {
+            uint32_t h, l;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+            const float r = v - __uint_as_float(h);
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
+            hi[i] = __uint_as_float(h);
+            lo[i] = __uint_as_float(l);
+        }
+    }
 }
 
 // ---- T0 partials: part[ks][d][b][b'] = sum_{u in chunk ks} Sc[u][b] * Sc[u+d][b'] ------------------------------------------
@@ -95,49 +128,76 @@ t0_gemm_kernel(const float *__restrict__ Sc, int nf, float *__restrict__ part) {
         for (int j = 0; j < 4; ++j) dst[(m0 + ty * 4 + i) * 128 + n0 + tx * 4 + j] = acc[i][j];
 }
 
-// ---- column sums over [0, nf) of the centred spectrogram, for the frame means ------------------------------------------
-__global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ Sc, int nf, float *__restrict__ sum0) {
-    __shared__ double red[256];
-    const int b = blockIdx.x;
-    double acc = 0.0;
-    for (int t = threadIdx.x; t < nf; t += blockDim.x) acc += (double)Sc[(size_t)t * LN_BINS + b];
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) sum0[b] = (float)red[0];
-}
-
-// ---- edge corrections, means, normalisation, accumulate --------------------------------------------------------------------
-// one thread per (d, b, b'): entries (i = b*20+c, j = b'*20+c+d), c = 0 .. 19-d, plus the mirrored entry when d > 0.
+// ---- T0[d][b][b'] = sum over the time splits (+ the rows the tensor-core kernel left out of its whole 8-row K steps) -----------
+// Lag 0 is symmetric: (b, b') and (b', b) both take the upper-triangle entry, so that the covariance stays exactly symmetric
+// whatever the order in which the GEMM kernel accumulated its split products.
 __global__ void __launch_bounds__(256)
-cov_finish_kernel(const float *__restrict__ Sc, int nf, const float *__restrict__ part, const float *__restrict__ sum0,
-                  float *__restrict__ accum) {
+t0_reduce_kernel(const float *__restrict__ part, const float *__restrict__ Sc, int nf, int tail_begin, float *__restrict__ T0) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= LN_CTX * LN_BINS * LN_BINS) return;
     const int bp = idx % LN_BINS, b = (idx / LN_BINS) % LN_BINS, d = idx / (LN_BINS * LN_BINS);
+    const int rb = (d == 0 && b > bp) ? bp : b, rbp = (d == 0 && b > bp) ? b : bp;
     float t0 = 0.f;
-    for (int ks = 0; ks < LN_KS; ++ks) t0 += part[((size_t)ks * LN_CTX + d) * (128 * 128) + b * 128 + bp];
-    // running sums for the means of rows (b,c) and (b',c+d): sum_{u=c}^{c+nf-1} Sc[u][b] = sum0[b] - head + tail
-    float g = t0;
-    float si = sum0[b];                 // row (b, c) with c = 0
-    float sj = sum0[bp];                // row (b', c') with c' = d: shift d times first
-    for (int c = 0; c < d; ++c) sj += Sc[(size_t)(nf + c) * LN_BINS + bp] - Sc[(size_t)c * LN_BINS + bp];
+    for (int ks = 0; ks < LN_KS; ++ks) t0 += part[((size_t)ks * LN_CTX + d) * (128 * 128) + rb * 128 + rbp];
+    for (int u = tail_begin; u < nf; ++u) t0 = fmaf(Sc[(size_t)u * LN_BINS + rb], Sc[(size_t)(u + d) * LN_BINS + rbp], t0);
+    T0[idx] = t0;
+}
+
+// ---- rs[b][c] = sum_{u=c}^{c+nf-1} Sc[u][b]: the frame-row sums behind the means, by the running update from sum0 ----------------
+__global__ void __launch_bounds__(128) rowsum_kernel(const float *__restrict__ Sc, int nf, const float *__restrict__ sum0,
+                                                     float *__restrict__ rs) {
+    const int b = threadIdx.x;
+    if (b >= LN_BINS) return;
+    float s = sum0[b];
+    for (int c = 0; c < LN_CTX; ++c) {
+        rs[b * LN_CTX + c] = s;
+        if (c + 1 < LN_CTX) s += Sc[(size_t)(nf + c) * LN_BINS + b] - Sc[(size_t)c * LN_BINS + b];      // nf + 18 = cols - 1
+    }
+}
+
+// ---- edge corrections, means, normalisation, accumulate: one warp per ordered band pair (b, b') ------------------------------
+// Lane d < 20 walks diagonal d of the 20 x 20 block: entries (i = b*20 + c, j = b'*20 + c + d), c = 0 .. 19 - d, with
+//   g_{c+1} = g_c + Sc[nf+c][b] Sc[nf+c+d][b'] - Sc[c][b] Sc[c+d][b']      (window slides by one frame),   g_0 = T0_d[b, b'].
+// The block is staged in shared memory and added to the accumulator in runs that are contiguous in memory: directly
+// (column j, rows i) and mirrored for d > 0 (column i, rows j) - the same value goes to both, so the matrix stays symmetric.
+__global__ void __launch_bounds__(128)
+cov_block_kernel(const float *__restrict__ Sc, int nf, const float *__restrict__ T0, const float *__restrict__ rs,
+                 float *__restrict__ accum) {
+    __shared__ float tile[4][LN_CTX][LN_CTX + 1];
+    __shared__ float edge[4][4][LN_CTX];              // [head b, head b', tail b, tail b'][row offset 0 .. 18]
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = blockIdx.x * 4 + w;
+    const bool live = pair < LN_BINS * LN_BINS;
+    const int b = live ? pair / LN_BINS : 0, bp = live ? pair % LN_BINS : 0;
+    if (lane < LN_CTX - 1) {       // the recurrence touches rows 0 .. 18 and nf .. nf + 18 (= cols - 1) of both bands
+        edge[w][0][lane] = Sc[(size_t)lane * LN_BINS + b];
+        edge[w][1][lane] = Sc[(size_t)lane * LN_BINS + bp];
+        edge[w][2][lane] = Sc[(size_t)(nf + lane) * LN_BINS + b];
+        edge[w][3][lane] = Sc[(size_t)(nf + lane) * LN_BINS + bp];
+    }
+    __syncwarp();
     const float inv_nf = 1.0f / (float)nf, inv_nm1 = 1.0f / (float)(nf - 1);
-    for (int c = 0; c + d < LN_CTX; ++c) {
-        const float mi = si * inv_nf, mj = sj * inv_nf;
-        const float cov = (g - (float)nf * (mi * mj)) * inv_nm1;   // (mi * mj) first: bit-identical for (i,j) and (j,i)
-        const int i = b * LN_CTX + c, j = bp * LN_CTX + c + d;
-        accum[(size_t)i + (size_t)LN_FS * j] += cov;
-        if (d > 0) accum[(size_t)j + (size_t)LN_FS * i] += cov;
-        if (c + d + 1 >= LN_CTX) break;   // last entry of this diagonal: the next window would read past the last column
-        // advance c -> c+1: drop u = c, add u = nf + c (both factors shifted by d in the second operand)
-        g += Sc[(size_t)(nf + c) * LN_BINS + b] * Sc[(size_t)(nf + c + d) * LN_BINS + bp] -
-             Sc[(size_t)c * LN_BINS + b] * Sc[(size_t)(c + d) * LN_BINS + bp];
-        si += Sc[(size_t)(nf + c) * LN_BINS + b] - Sc[(size_t)c * LN_BINS + b];
-        sj += Sc[(size_t)(nf + c + d) * LN_BINS + bp] - Sc[(size_t)(c + d) * LN_BINS + bp];
+    if (live && lane < LN_CTX) {
+        const int d = lane;
+        float g = T0[((size_t)d * LN_BINS + b) * LN_BINS + bp];
+        for (int c = 0; c + d < LN_CTX; ++c) {
+            const float mi = rs[b * LN_CTX + c] * inv_nf, mj = rs[bp * LN_CTX + c + d] * inv_nf;
+            tile[w][c][c + d] = (g - (float)nf * (mi * mj)) * inv_nm1;   // (mi * mj) first: bit-identical for (i,j) and (j,i)
+            if (c + d + 1 >= LN_CTX) break;
+            g += edge[w][2][c] * edge[w][3][c + d] - edge[w][0][c] * edge[w][1][c + d];
+        }
+    }
+    __syncwarp();
+    if (!live) return;
+    // direct: column j = b'*20 + cp, rows i = b*20 + c for c <= cp
+    for (int e = lane; e < LN_CTX * LN_CTX; e += 32) {
+        const int cp = e / LN_CTX, c = e % LN_CTX;
+        if (c <= cp) accum[(size_t)(b * LN_CTX + c) + (size_t)LN_FS * (bp * LN_CTX + cp)] += tile[w][c][cp];
+    }
+    // mirror (d > 0): column i = b*20 + c, rows j = b'*20 + cp for cp > c
+    for (int e = lane; e < LN_CTX * LN_CTX; e += 32) {
+        const int c = e / LN_CTX, cp = e % LN_CTX;
+        if (cp > c) accum[(size_t)(bp * LN_CTX + cp) + (size_t)LN_FS * (b * LN_CTX + c)] += tile[w][c][cp];
     }
 }
 
@@ -339,6 +399,12 @@ static void jacobi_eigh(std::vector<double> &H, int p, std::vector<double> &w, s
 
 using namespace hpfw_b200;
 
+// HPFW_COV_IMPL: 1 = tcgen05 correlation kernel (default), 0 = CUDA-core kernel (measurement baseline)
+static int cov_impl() {
+    const char *v = getenv("HPFW_COV_IMPL");
+    return (v && *v) ? atoi(v) : 1;
+}
+
 static int cov_add_device(hpfw_ctx *ctx, const float *d_spec, int cols, cudaStream_t s) {
     const int nf = cols - (LN_CTX - 1);
     if (nf < 2) HPFW_FAIL(HPFW_ERR_SHORT, "covariance needs at least 21 spectrogram columns (got %d)", cols);
@@ -346,31 +412,46 @@ static int cov_add_device(hpfw_ctx *ctx, const float *d_spec, int cols, cudaStre
         HPFW_TRY(ctx->cov_accum.reserve(sizeof(float) * (size_t)LN_FS * LN_FS));
         HPFW_CUDA_TRY(cudaMemsetAsync(ctx->cov_accum.ptr, 0, sizeof(float) * (size_t)LN_FS * LN_FS, s));
     }
-    HPFW_TRY(ctx->cov_scratch.reserve(sizeof(float) * ((size_t)cols * LN_BINS + 2 * 128 + (size_t)LN_KS * LN_CTX * 128 * 128)));
-    float *Sc = ctx->cov_scratch.as<float>();
-    float *mean = Sc + (size_t)cols * LN_BINS;
-    float *sum0 = mean + 128;
-    float *part = sum0 + 128;
+    // scratch: [part | hi | lo | Sc | T0 | rs | sum0 | partial sums (double)]; hi / lo start on 1 KB boundaries for the TMA maps
+    const size_t n_part = (size_t)LN_KS * LN_CTX * 128 * 128, n_pad = ((size_t)std::max(cols, 128) * 128 + 255) & ~size_t(255);
+    const size_t n_sc = ((size_t)cols * LN_BINS + 255) & ~size_t(255), n_t0 = ((size_t)LN_CTX * LN_BINS * LN_BINS + 255) & ~size_t(255);
+    const size_t n_rs = 128 * LN_CTX, n_floats = n_part + 2 * n_pad + n_sc + n_t0 + n_rs + 128;
+    HPFW_TRY(ctx->cov_scratch.reserve(sizeof(float) * n_floats + sizeof(double) * LN_SUM_CTAS * 2 * 128));
+    float *part = ctx->cov_scratch.as<float>();
+    float *hi = part + n_part, *lo = hi + n_pad;
+    float *Sc = lo + n_pad;
+    float *T0 = Sc + n_sc, *rs = T0 + n_t0, *sum0 = rs + n_rs;
+    double *partial = reinterpret_cast<double *>(sum0 + 128);
+    const int impl = cov_impl();
     {
         KernelScope ks(ctx, HPFW_K_OTHER, s);
-        band_mean_kernel<<<LN_BINS, 256, 0, s>>>(d_spec, cols, mean);
+        band_sums_kernel<<<LN_SUM_CTAS, 128, 0, s>>>(d_spec, cols, nf, partial);
     }
+    if (impl == 1 && cols < 128) HPFW_CUDA_TRY(cudaMemsetAsync(hi, 0, sizeof(float) * 2 * n_pad, s));   // rows a TMA box may touch
     {
         KernelScope ks(ctx, HPFW_K_OTHER, s);
-        center_kernel<<<ctx->sm_count * 4, 256, 0, s>>>(d_spec, cols, mean, Sc);
+        center_kernel<<<ctx->sm_count * 4, 256, 0, s>>>(d_spec, cols, nf, partial, LN_SUM_CTAS, Sc, impl == 1 ? hi : nullptr,
+                                                        impl == 1 ? lo : nullptr, sum0);
     }
-    {
-        KernelScope ks(ctx, HPFW_K_OTHER, s);
-        colsum_kernel<<<LN_BINS, 256, 0, s>>>(Sc, nf, sum0);
-    }
-    {
+    int tail_begin = nf;
+    if (impl == 1) {      // tcgen05: 3 x tf32 split products, cov_tc.cu
+        HPFW_TRY(cov_tc_run(ctx, hi, lo, std::max(cols, 128), nf, LN_KS, part, &tail_begin, s));
+    } else {
         KernelScope ks(ctx, HPFW_K_OTHER, s);
         t0_gemm_kernel<<<dim3(2, 2, LN_CTX * LN_KS), 256, 0, s>>>(Sc, nf, part);
     }
     {
         KernelScope ks(ctx, HPFW_K_OTHER, s);
         const int total = LN_CTX * LN_BINS * LN_BINS;
-        cov_finish_kernel<<<(total + 255) / 256, 256, 0, s>>>(Sc, nf, part, sum0, ctx->cov_accum.as<float>());
+        t0_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(part, Sc, nf, tail_begin, T0);
+    }
+    {
+        KernelScope ks(ctx, HPFW_K_OTHER, s);
+        rowsum_kernel<<<1, 128, 0, s>>>(Sc, nf, sum0, rs);
+    }
+    {
+        KernelScope ks(ctx, HPFW_K_OTHER, s);
+        cov_block_kernel<<<(LN_BINS * LN_BINS + 3) / 4, 128, 0, s>>>(Sc, nf, T0, rs, ctx->cov_accum.as<float>());
     }
     HPFW_CUDA_TRY(cudaGetLastError());
     ctx->cov_tracks++;

@@ -17,9 +17,7 @@
 // reloads the [128 x 128] window per tap; both are tested against the CUDA-core kernel and the oracle.)
 // B_c streams through a 3-stage TMA/mbarrier ring. The epilogue reads the TMEM accumulator with tcgen05.ld (one frame per
 // thread, 64 filters in registers), thresholds and packs the 64-bit word.
-#include "common.cuh"
-
-#include <cuda.h>
+#include "tc_ptx.cuh"
 
 #include <cstring>
 
@@ -55,53 +53,6 @@ struct TcTrack {
     int32_t n_out;       // hashprint words
     int32_t pad;
 };
-
-// ---- PTX wrappers --------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, P1;\n\t"
-        "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Bounded wait: a pipeline bug must surface as a launch failure (trap), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
-        if (spin > (1u << 24)) __trap();
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int x, int y) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
-}
-// shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30) = 1,
-// SBO>>4 [32,46) = 1024 B between 8-row groups, version 1 [46,48), layout type 2 [61,64)
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
-    return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
 
 // ---- pre-pass: Dd[row][b] = tf32(S[t][b] - S[t+80][b]), bands 121..127 = 0 ------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -230,23 +181,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_wait(&bar_acc, 0);
     tc_fence_after();
     uint32_t v[64];
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
-        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]),
-          "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]),
-          "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]),
-          "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]),
-          "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    tmem_ld_x64(tmem_base + ((uint32_t)(warp * 32) << 16), v);
     uint64_t word = 0;
 #pragma unroll
     for (int f = 0; f < 64; ++f) word |= (uint64_t)(__uint_as_float(v[f]) >= 0.f ? 1u : 0u) << (63 - f);
@@ -261,7 +196,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 }
 
-static int make_map_2d(CUtensorMap *map, const void *base, uint64_t rows, uint32_t box_rows) {
+int tc_make_map_2d(CUtensorMap *map, const void *base, uint64_t rows, uint32_t box_rows, bool atom32) {
     // row-major [rows][128] float: dim0 = 128 bands (contiguous), dim1 = rows, pitch 512 B; box = 32 bands x box_rows rows
     const cuuint64_t dims[2] = {TC_BPAD, rows};
     const cuuint64_t strides[1] = {TC_BPAD * sizeof(float)};
@@ -281,7 +216,8 @@ static int make_map_2d(CUtensorMap *map, const void *base, uint64_t rows, uint32
         encode = reinterpret_cast<EncodeTiled>(fn);
     }
     CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) HPFW_FAIL(HPFW_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return HPFW_OK;
@@ -358,8 +294,8 @@ int project_tc_run(hpfw_ctx *ctx, int impl, const float *d_spectro, const int64_
                                                          ctx->delta_tc.as<float>());
     }
     CUtensorMap tmA, tmB;
-    HPFW_TRY(make_map_2d(&tmA, ctx->delta_tc.ptr, map_rows, impl == 1 ? TC_AROWS : TC_M));
-    HPFW_TRY(make_map_2d(&tmB, ctx->filters_tc.ptr, (uint64_t)TC_CTX * TC_NF, TC_NF));
+    HPFW_TRY(tc_make_map_2d(&tmA, ctx->delta_tc.ptr, map_rows, impl == 1 ? TC_AROWS : TC_M, false));
+    HPFW_TRY(tc_make_map_2d(&tmB, ctx->filters_tc.ptr, (uint64_t)TC_CTX * TC_NF, TC_NF, false));
     const size_t smem1 = TC_KB * TC_A_ATOM_BYTES + TC_STAGES_1 * TC_B_ATOM_BYTES + 1024;
     const size_t smem2 = TC_STAGES_2 * TC_KB * TC_A1_ATOM_BYTES + TC_STAGES_2 * TC_B_STAGE_BYTES + 1024;
     {
