@@ -37,35 +37,58 @@ constexpr int LN_KS = 29;                   // time splits of the T0 GEMMs: 29 x
 constexpr int LN_P = 128;                   // subspace block size (64 wanted + 64 guard vectors)
 
 // ---- per-band sums in one coalesced pass: partial[cta][0][b] = sum_{t < nf} S[t][b], partial[cta][1][b] = sum_{t >= nf} S[t][b] --
-constexpr int LN_SUM_CTAS = 148;
+constexpr int LN_SUM_CTAS = 592;
 __global__ void __launch_bounds__(128) band_sums_kernel(const float *__restrict__ S, int cols, int nf, double *__restrict__ partial) {
     const int b = threadIdx.x;
     double a0 = 0.0, a1 = 0.0;
-    if (b < LN_BINS)
-        for (int t = blockIdx.x; t < cols; t += gridDim.x) {
+    if (b < LN_BINS) {
+        int t = blockIdx.x;
+        for (; t + 3 * (int)gridDim.x < cols; t += 4 * gridDim.x) {      // four independent loads in flight
+            const float v0 = S[(size_t)t * LN_BINS + b], v1 = S[(size_t)(t + gridDim.x) * LN_BINS + b];
+            const float v2 = S[(size_t)(t + 2 * gridDim.x) * LN_BINS + b], v3 = S[(size_t)(t + 3 * gridDim.x) * LN_BINS + b];
+            if (t < nf) a0 += (double)v0; else a1 += (double)v0;
+            if (t + (int)gridDim.x < nf) a0 += (double)v1; else a1 += (double)v1;
+            if (t + 2 * (int)gridDim.x < nf) a0 += (double)v2; else a1 += (double)v2;
+            if (t + 3 * (int)gridDim.x < nf) a0 += (double)v3; else a1 += (double)v3;
+        }
+        for (; t < cols; t += gridDim.x) {
             const double v = (double)S[(size_t)t * LN_BINS + b];
             if (t < nf) a0 += v; else a1 += v;
         }
+    }
     partial[((size_t)blockIdx.x * 2 + 0) * 128 + b] = a0;
     partial[((size_t)blockIdx.x * 2 + 1) * 128 + b] = a1;
 }
 
-// ---- centred copy Sc[t][b] = S[t][b] - mean_b (+ its tf32 hi / lo parts, bands padded to 128, for the tensor-core kernel) and
-// sum0[b] = sum_{t < nf} Sc[t][b]. The means are reduced from the partial sums in a fixed order by every CTA.
-__global__ void __launch_bounds__(256)
-center_kernel(const float *__restrict__ S, int cols, int nf, const double *__restrict__ partial, int nparts, float *__restrict__ Sc,
-              float *__restrict__ hi, float *__restrict__ lo, float *__restrict__ sum0) {
-    __shared__ float mean_s[128];
-    if (threadIdx.x < 128) {
-        double a0 = 0.0, a1 = 0.0;
-        for (int p = 0; p < nparts; ++p) {
-            a0 += partial[((size_t)p * 2 + 0) * 128 + threadIdx.x];
-            a1 += partial[((size_t)p * 2 + 1) * 128 + threadIdx.x];
-        }
-        const double mean = (a0 + a1) / (double)cols;
-        mean_s[threadIdx.x] = threadIdx.x < LN_BINS ? (float)mean : 0.f;
-        if (blockIdx.x == 0 && threadIdx.x < LN_BINS) sum0[threadIdx.x] = (float)(a0 - (double)nf * (double)(float)mean);
+// mean[b] over all columns and sum0[b] = sum_{t < nf} (S[t][b] - mean_b), from the partial sums in a fixed order
+__global__ void __launch_bounds__(128)
+band_mean_kernel(const double *__restrict__ partial, int nparts, int cols, int nf, float *__restrict__ mean, float *__restrict__ sum0) {
+    const int b = threadIdx.x;
+    double a0 = 0.0, a1 = 0.0, c0 = 0.0, c1 = 0.0;
+    int p = 0;
+    for (; p + 1 < nparts; p += 2) {
+        a0 += partial[((size_t)p * 2 + 0) * 128 + b];
+        a1 += partial[((size_t)p * 2 + 1) * 128 + b];
+        c0 += partial[((size_t)(p + 1) * 2 + 0) * 128 + b];
+        c1 += partial[((size_t)(p + 1) * 2 + 1) * 128 + b];
     }
+    for (; p < nparts; ++p) {
+        a0 += partial[((size_t)p * 2 + 0) * 128 + b];
+        a1 += partial[((size_t)p * 2 + 1) * 128 + b];
+    }
+    a0 += c0;
+    a1 += c1;
+    const float m = b < LN_BINS ? (float)((a0 + a1) / (double)cols) : 0.f;
+    mean[b] = m;
+    sum0[b] = b < LN_BINS ? (float)(a0 - (double)nf * (double)m) : 0.f;
+}
+
+// ---- centred copy Sc[t][b] = S[t][b] - mean_b (+ its tf32 hi / lo parts, bands padded to 128, for the tensor-core kernel) ------
+__global__ void __launch_bounds__(256)
+center_kernel(const float *__restrict__ S, int cols, const float *__restrict__ mean, float *__restrict__ Sc,
+              float *__restrict__ hi, float *__restrict__ lo) {
+    __shared__ float mean_s[128];
+    if (threadIdx.x < 128) mean_s[threadIdx.x] = mean[threadIdx.x];
     __syncthreads();
     const size_t total = (size_t)cols * 128;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -415,23 +438,27 @@ static int cov_add_device(hpfw_ctx *ctx, const float *d_spec, int cols, cudaStre
     // scratch: [part | hi | lo | Sc | T0 | rs | sum0 | partial sums (double)]; hi / lo start on 1 KB boundaries for the TMA maps
     const size_t n_part = (size_t)LN_KS * LN_CTX * 128 * 128, n_pad = ((size_t)std::max(cols, 128) * 128 + 255) & ~size_t(255);
     const size_t n_sc = ((size_t)cols * LN_BINS + 255) & ~size_t(255), n_t0 = ((size_t)LN_CTX * LN_BINS * LN_BINS + 255) & ~size_t(255);
-    const size_t n_rs = 128 * LN_CTX, n_floats = n_part + 2 * n_pad + n_sc + n_t0 + n_rs + 128;
+    const size_t n_rs = 128 * LN_CTX, n_floats = n_part + 2 * n_pad + n_sc + n_t0 + n_rs + 256;
     HPFW_TRY(ctx->cov_scratch.reserve(sizeof(float) * n_floats + sizeof(double) * LN_SUM_CTAS * 2 * 128));
     float *part = ctx->cov_scratch.as<float>();
     float *hi = part + n_part, *lo = hi + n_pad;
     float *Sc = lo + n_pad;
-    float *T0 = Sc + n_sc, *rs = T0 + n_t0, *sum0 = rs + n_rs;
-    double *partial = reinterpret_cast<double *>(sum0 + 128);
+    float *T0 = Sc + n_sc, *rs = T0 + n_t0, *sum0 = rs + n_rs, *mean = sum0 + 128;
+    double *partial = reinterpret_cast<double *>(mean + 128);
     const int impl = cov_impl();
     {
         KernelScope ks(ctx, HPFW_K_OTHER, s);
         band_sums_kernel<<<LN_SUM_CTAS, 128, 0, s>>>(d_spec, cols, nf, partial);
     }
+    {
+        KernelScope ks(ctx, HPFW_K_OTHER, s);
+        band_mean_kernel<<<1, 128, 0, s>>>(partial, LN_SUM_CTAS, cols, nf, mean, sum0);
+    }
     if (impl == 1 && cols < 128) HPFW_CUDA_TRY(cudaMemsetAsync(hi, 0, sizeof(float) * 2 * n_pad, s));   // rows a TMA box may touch
     {
         KernelScope ks(ctx, HPFW_K_OTHER, s);
-        center_kernel<<<ctx->sm_count * 4, 256, 0, s>>>(d_spec, cols, nf, partial, LN_SUM_CTAS, Sc, impl == 1 ? hi : nullptr,
-                                                        impl == 1 ? lo : nullptr, sum0);
+        center_kernel<<<ctx->sm_count * 4, 256, 0, s>>>(d_spec, cols, mean, Sc, impl == 1 ? hi : nullptr,
+                                                        impl == 1 ? lo : nullptr);
     }
     int tail_begin = nf;
     if (impl == 1) {      // tcgen05: 3 x tf32 split products, cov_tc.cu
