@@ -448,9 +448,12 @@ def run_cuda(args):
         args.gpus = world
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # stdout carries exactly one JSON line: everything any library writes to fd 1 meanwhile (NCCL prints its version banner
+    # there) is sent to stderr; the JSON line goes to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's banner / debug output goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     ctx = hpfw_b200.Context(local_rank)
 
@@ -663,7 +666,8 @@ def run_cuda(args):
                 "sample": f"{nqc} queries x {sample_tracks}-track subset ({dt:.1f} s on {cores} host threads), scaled "
                           f"x{sample_tracks}/{TRACKS} to the 10k-track DB; reference MemoryStorage::find, "
                           f"-Ofast -march=native"}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
