@@ -102,6 +102,9 @@ struct hpfw_ctx {
     hpfw_b200::DeviceBuffer qwords;    // staged query words (host entry points)
     hpfw_b200::DeviceBuffer keys;      // staged result keys (host entry points)
     hpfw_b200::PinnedBuffer pin_in, pin_out;
+    hpfw_b200::DeviceBuffer qexp;      // match_tc.cu: queries expanded to signed bytes
+    int match_impl = 2;                // 2 = tensor cores for (nearly) full groups of 128 queries, integer pipes for the rest
+                                       // (default); 1 = tensor cores always; 0 = integer pipes always
 
     // projection state
     hpfw_b200::DeviceBuffer filters_perm;  // filters permuted to [context][band(padded 128)][filter] etc. (project.cu)

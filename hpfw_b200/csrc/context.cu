@@ -1,6 +1,8 @@
 // hpfw_b200/csrc/context.cu — context lifetime, error reporting.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace hpfw_b200 {
 static thread_local char g_err[1024] = "";
 void set_error(const char *fmt, ...) {
@@ -41,6 +43,10 @@ int hpfw_ctx_create(int device, hpfw_ctx **out) {
         delete c;
         HPFW_FAIL(HPFW_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
     }
+    if (const char *env = getenv("HPFW_MATCH_IMPL")) {
+        const int v = atoi(env);
+        if (v >= 0 && v <= 2) c->match_impl = v;
+    }
     *out = c;
     return HPFW_OK;
 }
@@ -53,6 +59,7 @@ void hpfw_ctx_destroy(hpfw_ctx *c) {
     c->qmeta.release();
     c->qwords.release();
     c->keys.release();
+    c->qexp.release();
     c->pin_in.release();
     c->pin_out.release();
     c->filters_perm.release();

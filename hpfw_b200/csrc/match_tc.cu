@@ -1,0 +1,332 @@
+// hpfw_b200/csrc/match_tc.cu — stage 4 on the 5th-generation tensor cores: the Hamming cross-correlation of
+// db::MemoryStorage::find (/root/reference/include/hpfw/audioproblems/live-song-id/storage.h:27-64) as an EXACT int8 GEMM.
+//
+// For a query q[0..k) and a reference track r[0..n):  D[i] = sum_j popc(q[j] ^ r[i+j]). With every bit b of a word mapped to
+// the signed byte s(b) = +1 (set) / -1 (clear),  sum_bits s(q) * s(r) = 64 - 2 * popc(q ^ r),  so
+//     D[i] = (64 k - dot[i]) / 2,      dot[i] = sum_{j < k} sum_{b < 64} s(q[j])_b * s(r[i + j])_b
+// and dot[] is a GEMM whose "offset" operand is a HANKEL matrix: row i of it is the byte expansion of r[i .. i+k), i.e. row
+// i+1 is row i moved one word (64 bytes) along K. tcgen05.mma.kind::i8 multiplies s8 x s8 into s32 accumulators in TMEM:
+// integer arithmetic, no rounding, |dot| <= 64 * 4096 — the distances and the rankings stay bit-exact.
+//
+// Mapping (one CTA per SM, persistent over (query group, tile) items):
+//   * M = 128 queries of one group (TMEM lanes), N = 512 alignment offsets of one track (2 MMAs of N = 256 = all 512 TMEM
+//     columns), K = 64 k bytes, walked one 64-bit word (2 MMAs of K = 32) at a time.
+//   * offset operand: the tile's reference words are expanded ONCE per K chunk (<= 192 words) into shared memory as
+//     R[16-byte chunk c (4)][row w][16 B] — the no-swizzle K-major canonical layout with the 8-row core matrices of one chunk
+//     column contiguous (SBO = 128 B, LBO = rows * 16 B). Row w+1 is 16 bytes after row w, so the operand for query word j
+//     is the SAME buffer addressed through a descriptor whose start address is moved by j rows: no shifted copy is made,
+//     a tile reads (512 + k) words instead of 512 * k. Rows beyond the end of the track are 0 bytes and contribute
+//     nothing, which is exactly the reference's truncation of a query that is longer than the track (storage.h:34-38).
+//   * query operand: expanded once per call by xt_expand_queries_kernel to [word j][chunk c][query m][16 B] (bytes of the
+//     words beyond a shorter query's end are 0), streamed by 1-D bulk TMA copies through a 4-stage mbarrier ring
+//     (4 words = 32 KB per stage; the 3 MB of a group stay in L2 for all 148 CTAs).
+//   * warp roles: 0 = TMA producer, 1 = MMA issuer, 2-5 = reference expanders (double-buffered R), 6-9 = epilogue.
+//   * epilogue: tcgen05.ld 64 columns at a time; per query (lane) the maximum of (dot << 6 | 63 - column) inside the valid
+//     offset range, chunks visited in ascending order with a strict '>' = the lowest offset among equal distances; one
+//     64-bit atomicMin per (query, tile) into best[query][track], the array match_kernel and topk_kernel share.
+#include "matcher.cuh"
+#include "tc_ptx.cuh"
+
+#include <algorithm>
+
+namespace hpfw_b200 {
+
+constexpr int XT_HALF = 256;                                   // N of one MMA
+constexpr int XT_STAGES = 4;                                   // query ring depth
+constexpr int XT_JCMAX = 192;                                  // words per K chunk (multiple of XT_JS)
+constexpr int XT_NR = XT_NOFF + XT_JCMAX;                      // rows of an expanded reference buffer
+constexpr uint32_t XT_R_LBO = XT_NR * 16;                      // 11,264 B between the 16-byte K chunks of a row
+constexpr uint32_t XT_R_BYTES = 4 * XT_R_LBO;                  // 45,056
+constexpr uint32_t XT_Q_LBO = XT_NQ * 16;                      // 2,048
+constexpr uint32_t XT_QWORD_BYTES = 4 * XT_Q_LBO;              // 8,192: one query word of a group
+constexpr uint32_t XT_STAGE_BYTES = XT_JS * XT_QWORD_BYTES;    // 32,768
+constexpr int XT_THREADS = 320;
+constexpr int XT_BIAS = (1 << 18) + 1;                         // dot + bias >= 1 for every valid offset
+static_assert(XT_JCMAX % XT_JS == 0, "chunk boundaries must be stage boundaries");
+
+// 4 bits -> 4 bytes of +1 / -1
+__device__ __forceinline__ uint32_t xt_nib(uint32_t n) {
+    const uint32_t x = (n * 0x00204081u) & 0x01010101u;
+    return ~(x * 0xFEu);
+}
+__device__ __forceinline__ uint4 xt_expand16(uint32_t h) {
+    return make_uint4(xt_nib(h & 15u), xt_nib((h >> 4) & 15u), xt_nib((h >> 8) & 15u), xt_nib((h >> 12) & 15u));
+}
+
+// shared-memory matrix descriptor, K-major, no swizzle: start >> 4 [0,14), LBO >> 4 [16,30) (between the two 16-byte K
+// chunks of a K = 32 step), SBO >> 4 [32,46) (between 8-row core matrices), version 1 [46,48), layout type 0 [61,64)
+__device__ __forceinline__ uint64_t xt_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor: D = S32, A = B = signed 8-bit, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t xt_idesc(int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// qexp[group].exp_off + ((j * 4 + c) * 128 + m) * 16: bytes 16c .. 16c+15 of word j of the group's m-th query
+__global__ void __launch_bounds__(XT_NQ)
+xt_expand_queries_kernel(const uint64_t *__restrict__ qwords, const int64_t *__restrict__ qstart,
+                         const XtGroup *__restrict__ groups, const int32_t *__restrict__ row_q,
+                         const int32_t *__restrict__ row_k, uint8_t *__restrict__ qexp) {
+    const int g = blockIdx.y, j = blockIdx.x, m = threadIdx.x;
+    const XtGroup grp = groups[g];
+    const int kpad = ((grp.kmax < 1 ? 1 : grp.kmax) + XT_JS - 1) / XT_JS * XT_JS;
+    if (j >= kpad) return;
+    const int q = row_q[g * XT_NQ + m];
+    const bool valid = q >= 0 && j < row_k[g * XT_NQ + m];
+    const uint64_t w = valid ? qwords[qstart[q] + j] : 0ull;
+    uint4 *dst = reinterpret_cast<uint4 *>(qexp + grp.exp_off) + (size_t)j * 4 * XT_NQ + m;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        dst[c * XT_NQ] = valid ? xt_expand16((uint32_t)(w >> (16 * c)) & 0xFFFFu) : make_uint4(0u, 0u, 0u, 0u);
+}
+
+struct XtItem {
+    int g, track, tile_start, n_r;
+    int64_t tbeg;
+    int kmax;    // >= 1
+    int need;    // columns of this tile that hold a valid offset for at least one query of the group (<= 0: skip)
+    int nchunks, jc;
+};
+
+__device__ __forceinline__ XtItem xt_item(long long item, int n_tiles, const MatchTile *__restrict__ tiles,
+                                          const int64_t *__restrict__ track_start, const XtGroup *__restrict__ groups) {
+    XtItem it;
+    it.g = int(item / n_tiles);
+    const MatchTile t = tiles[item % n_tiles];
+    const XtGroup grp = groups[it.g];
+    it.track = t.track;
+    it.tile_start = t.start;
+    it.tbeg = track_start[t.track];
+    it.n_r = int(track_start[t.track + 1] - it.tbeg);
+    it.kmax = max(grp.kmax, 1);
+    const int last_valid = it.n_r - min(grp.kmin, it.n_r);    // the shortest query reaches the furthest offset
+    it.need = min(XT_NOFF, last_valid - t.start + 1);
+    it.nchunks = (it.kmax + XT_JCMAX - 1) / XT_JCMAX;
+    it.jc = ((it.kmax + it.nchunks - 1) / it.nchunks + XT_JS - 1) / XT_JS * XT_JS;
+    return it;
+}
+
+__global__ void __launch_bounds__(XT_THREADS, 1)
+match_tc_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ track_start,
+                const MatchTile *__restrict__ tiles, int n_tiles, const XtGroup *__restrict__ groups, int n_groups,
+                const int32_t *__restrict__ row_q, const int32_t *__restrict__ row_k, const uint8_t *__restrict__ qexp,
+                int n_tracks, unsigned long long *__restrict__ best) {
+    extern __shared__ uint8_t xsm_raw[];
+    uint8_t *xsm = xsm_raw + ((128u - (smem_u32(xsm_raw) & 127u)) & 127u);
+    uint8_t *r_s = xsm;                              // 2 x XT_R_BYTES
+    uint8_t *q_s = xsm + 2 * XT_R_BYTES;             // XT_STAGES x XT_STAGE_BYTES
+    __shared__ __align__(8) uint64_t q_full[XT_STAGES], q_empty[XT_STAGES], r_full[2], r_empty[2], acc_full, acc_empty;
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long total = (long long)n_groups * n_tiles;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x == 32) {
+        for (int s = 0; s < XT_STAGES; ++s) {
+            mbar_init(&q_full[s], 1);
+            mbar_init(&q_empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&r_full[b], 128);
+            mbar_init(&r_empty[b], 1);
+        }
+        mbar_init(&acc_full, 1);
+        mbar_init(&acc_empty, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer: the group's expanded query words, XT_JS words per stage =====
+            uint32_t sidx = 0;
+            for (long long item = blockIdx.x; item < total; item += gridDim.x) {
+                const XtItem it = xt_item(item, n_tiles, tiles, track_start, groups);
+                if (it.need <= 0) continue;
+                const uint8_t *src = qexp + groups[it.g].exp_off;
+                const int nst = (it.kmax + XT_JS - 1) / XT_JS;
+                for (int st = 0; st < nst; ++st, ++sidx) {
+                    const uint32_t s = sidx % XT_STAGES;
+                    if (sidx >= XT_STAGES) mbar_wait(&q_empty[s], ((sidx / XT_STAGES) - 1) & 1);
+                    mbar_expect_tx(&q_full[s], XT_STAGE_BYTES);
+                    bulk_load_1d(q_s + s * XT_STAGE_BYTES, src + (size_t)st * XT_STAGE_BYTES, XT_STAGE_BYTES, &q_full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            uint32_t sidx = 0, ridx = 0, tcount = 0;
+            const uint64_t a_hi = xt_desc(0, XT_Q_LBO, 128), b_hi = xt_desc(0, XT_R_LBO, 128);
+            for (long long item = blockIdx.x; item < total; item += gridDim.x) {
+                const XtItem it = xt_item(item, n_tiles, tiles, track_start, groups);
+                if (it.need <= 0) continue;
+                const int n1 = min(XT_HALF, (it.need + 15) & ~15);
+                const int n2 = it.need > XT_HALF ? (it.need - XT_HALF + 15) & ~15 : 0;
+                const uint32_t id1 = xt_idesc(n1), id2 = xt_idesc(n2 ? n2 : 16);
+                if (tcount > 0) mbar_wait(&acc_empty, (tcount - 1) & 1);     // epilogue has drained the accumulators
+                tc_fence_after();
+                uint32_t acc = 0;
+                for (int c = 0; c < it.nchunks; ++c, ++ridx) {
+                    const uint32_t rb = ridx & 1;
+                    mbar_wait(&r_full[rb], (ridx >> 1) & 1);
+                    tc_fence_after();
+                    const int j0 = c * it.jc, j1 = min(it.kmax, j0 + it.jc);
+                    const uint64_t b_base = b_hi + (uint64_t)(smem_u32(r_s + rb * XT_R_BYTES) >> 4);
+                    for (int j = j0; j < j1; j += XT_JS, ++sidx) {
+                        const uint32_t s = sidx % XT_STAGES;
+                        mbar_wait(&q_full[s], (sidx / XT_STAGES) & 1);
+                        tc_fence_after();
+                        const uint64_t a_base = a_hi + (uint64_t)(smem_u32(q_s + s * XT_STAGE_BYTES) >> 4);
+                        const int nj = min(XT_JS, j1 - j);
+                        for (int jj = 0; jj < nj; ++jj) {
+#pragma unroll
+                            for (int kk = 0; kk < 2; ++kk) {
+                                const uint64_t a_desc = a_base + (uint64_t)((jj * XT_QWORD_BYTES + kk * 2 * XT_Q_LBO) >> 4);
+                                const uint64_t b_desc = b_base + (uint64_t)(j - j0 + jj) + (uint64_t)((kk * 2 * XT_R_LBO) >> 4);
+                                tc_mma_i8(tmem_base, a_desc, b_desc, id1, acc);
+                                if (n2) tc_mma_i8(tmem_base + XT_HALF, a_desc, b_desc + XT_HALF, id2, acc);
+                                acc = 1;
+                            }
+                        }
+                        tc_commit(&q_empty[s]);
+                    }
+                    tc_commit(&r_empty[rb]);
+                }
+                tc_commit(&acc_full);
+                ++tcount;
+            }
+        }
+    } else if (warp < 6) {
+        // ===== reference expanders: rows [tile_start + j0, + 512 + (j1 - j0)) of the track -> s8, chunk-column layout =====
+        const int et = threadIdx.x - 64;
+        uint32_t ridx = 0;
+        for (long long item = blockIdx.x; item < total; item += gridDim.x) {
+            const XtItem it = xt_item(item, n_tiles, tiles, track_start, groups);
+            if (it.need <= 0) continue;
+            for (int c = 0; c < it.nchunks; ++c, ++ridx) {
+                const uint32_t rb = ridx & 1;
+                if (ridx >= 2) mbar_wait(&r_empty[rb], ((ridx >> 1) - 1) & 1);
+                const int j0 = c * it.jc, j1 = min(it.kmax, j0 + it.jc);
+                const int nrows = XT_NOFF + (j1 - j0);
+                uint4 *dst = reinterpret_cast<uint4 *>(r_s + rb * XT_R_BYTES);
+                const uint64_t *src = words + it.tbeg;
+                const int g0 = it.tile_start + j0;
+                for (int w = et; w < nrows; w += 128) {
+                    const int g = g0 + w;
+                    const bool valid = g < it.n_r;
+                    const uint64_t x = valid ? src[g] : 0ull;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc)
+                        dst[cc * XT_NR + w] = valid ? xt_expand16((uint32_t)(x >> (16 * cc)) & 0xFFFFu)
+                                                    : make_uint4(0u, 0u, 0u, 0u);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tcgen05 reads
+                mbar_arrive(&r_full[rb]);
+            }
+        }
+    } else {
+        // ===== epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 = queries; columns = offsets of the tile =====
+        const int m = (warp & 3) * 32 + lane;
+        const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t tcount = 0;
+        for (long long item = blockIdx.x; item < total; item += gridDim.x) {
+            const XtItem it = xt_item(item, n_tiles, tiles, track_start, groups);
+            if (it.need <= 0) continue;
+            const int q = row_q[it.g * XT_NQ + m];
+            const int k_eff = min(row_k[it.g * XT_NQ + m], it.n_r);      // storage.h:34-38
+            const int lim = q >= 0 ? (it.n_r - k_eff) - it.tile_start : -1;   // valid columns: n <= lim
+            mbar_wait(&acc_full, tcount & 1);
+            tc_fence_after();
+            int best_d = 0, best_n = 0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < it.need; c0 += 64) {
+                uint32_t v[64];
+                tmem_ld_x64(t_lane + (uint32_t)c0, v);
+                const int li = lim - c0;
+                uint32_t bk = 0;
+                if (__all_sync(0xFFFFFFFFu, li >= 63)) {
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) bk = max(bk, ((uint32_t)((int)v[i] + XT_BIAS) << 6) | (uint32_t)(63 - i));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) {
+                        const uint32_t key = ((uint32_t)((int)v[i] + XT_BIAS) << 6) | (uint32_t)(63 - i);
+                        bk = max(bk, i <= li ? key : 0u);
+                    }
+                }
+                const int d = int(bk >> 6);
+                if (d > best_d) {          // strict: an equal distance at a higher offset never replaces
+                    best_d = d;
+                    best_n = c0 + 63 - int(bk & 63u);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty);
+            if (best_d > 0) {
+                const long long dot = (long long)best_d - XT_BIAS;
+                const unsigned long long dist = (unsigned long long)((64ll * k_eff - dot) >> 1);
+                atomicMin(best + (size_t)q * (size_t)n_tracks + (size_t)it.track,
+                          (dist << HPFW_KEY_OFFSET_BITS) | (unsigned long long)(it.tile_start + best_n));
+            }
+            ++tcount;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+int match_tc_run(hpfw_ctx *ctx, const hpfw_db *db, const uint64_t *d_qwords, const int64_t *d_qstart,
+                 const XtGroup *d_groups, const int32_t *d_row_q, const int32_t *d_row_k, int n_groups, int kpad_max,
+                 uint8_t *d_qexp, unsigned long long *d_best, cudaStream_t stream) {
+    if (n_groups <= 0 || db->n_tiles_tc <= 0) return HPFW_OK;
+    {
+        KernelScope ks(ctx, HPFW_K_OTHER, stream);
+        xt_expand_queries_kernel<<<dim3(kpad_max, n_groups), XT_NQ, 0, stream>>>(d_qwords, d_qstart, d_groups, d_row_q,
+                                                                                 d_row_k, d_qexp);
+        HPFW_CUDA_TRY(cudaGetLastError());
+    }
+    const size_t smem = 2 * (size_t)XT_R_BYTES + (size_t)XT_STAGES * XT_STAGE_BYTES + 128;
+    if (smem > size_t(ctx->max_smem_optin))
+        HPFW_FAIL(HPFW_ERR_LIMIT, "match_tc: needs %zu B shared memory (> %d)", smem, ctx->max_smem_optin);
+    HPFW_CUDA_TRY(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const long long total = (long long)n_groups * db->n_tiles_tc;
+    const int grid = int(std::min<long long>(total, ctx->sm_count));
+    KernelScope ks(ctx, HPFW_K_MATCH_TC, stream);
+    match_tc_kernel<<<grid, XT_THREADS, smem, stream>>>(db->d_words, db->d_track_start, db->d_tiles_tc, db->n_tiles_tc,
+                                                        d_groups, n_groups, d_row_q, d_row_k, d_qexp, db->n_tracks, d_best);
+    HPFW_CUDA_TRY(cudaGetLastError());
+    return HPFW_OK;
+}
+
+}  // namespace hpfw_b200

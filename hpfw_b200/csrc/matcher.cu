@@ -15,9 +15,11 @@
 //   * per (tile, query) the minimum is a 32-bit key (dist << 11 | local offset): REDUX.MIN across the warp, a shared
 //     atomicMin across warps, then one global 64-bit atomicMin into best[query][track] (dist << 20 | offset);
 //   * a second kernel selects each query's top-k packed keys (dist << 40 | track << 20 | offset).
-#include "common.cuh"
+#include "matcher.cuh"
 
 #include <algorithm>
+#include <climits>
+#include <cstring>
 #include <numeric>
 
 namespace hpfw_b200 {
@@ -30,11 +32,6 @@ constexpr int MT_QB = 2;                      // queries per register block
 constexpr int MT_LOCAL_BITS = 11;             // log2(MT_TILE)
 constexpr int MT_BLOCKS_PER_CTA = 16;         // query register blocks a CTA runs against its staged tile
 static_assert((1 << MT_LOCAL_BITS) == MT_TILE, "tile / key mismatch");
-
-struct MatchTile {
-    int32_t track;
-    int32_t start;
-};
 
 __device__ __forceinline__ void lds_block8(const uint64_t *p, uint2 (&w)[8]) {
     const uint4 *v = reinterpret_cast<const uint4 *>(p);
@@ -287,25 +284,13 @@ __global__ void merge_kernel(const unsigned long long *__restrict__ in, int n_ra
 
 using namespace hpfw_b200;
 
-struct hpfw_db {
-    hpfw_ctx *ctx = nullptr;
-    int n_tracks = 0;
-    int64_t total_words = 0;
-    int64_t track_base = 0;
-    uint64_t *d_words = nullptr;
-    int64_t *d_track_start = nullptr;
-    MatchTile *d_tiles = nullptr;
-    int n_tiles = 0;
-    std::vector<int64_t> offsets;  // host copy
-};
-
 static int db_alloc_common(hpfw_ctx *ctx, const int64_t *offsets, int n_tracks, int64_t track_base, hpfw_db **out) {
     if (!ctx || !out || (n_tracks > 0 && !offsets)) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_build: NULL argument");
     if (n_tracks < 0) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_build: n_tracks < 0");
     if (track_base < 0 || track_base + n_tracks > HPFW_MAX_TRACKS)
         HPFW_FAIL(HPFW_ERR_LIMIT, "hpfw_db_build: track index %lld exceeds the %d-bit key field",
                   (long long)(track_base + n_tracks), HPFW_KEY_TRACK_BITS);
-    std::vector<MatchTile> tiles;
+    std::vector<MatchTile> tiles, tiles_tc;
     for (int r = 0; r < n_tracks; ++r) {
         const int64_t n = offsets[r + 1] - offsets[r];
         if (n < 0) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_build: offsets not monotone at track %d", r);
@@ -314,6 +299,8 @@ static int db_alloc_common(hpfw_ctx *ctx, const int64_t *offsets, int n_tracks, 
                       (long long)n, HPFW_MAX_TRACK_WORDS);
         const int nt = std::max<int64_t>(1, (n + MT_TILE - 1) / MT_TILE);  // >= 1: an empty track still matches at 0
         for (int t = 0; t < nt; ++t) tiles.push_back({r, t * MT_TILE});
+        const int nt_tc = std::max<int64_t>(1, (n + XT_NOFF - 1) / XT_NOFF);
+        for (int t = 0; t < nt_tc; ++t) tiles_tc.push_back({r, t * XT_NOFF});
     }
     hpfw_db *db = new hpfw_db();
     db->ctx = ctx;
@@ -323,14 +310,18 @@ static int db_alloc_common(hpfw_ctx *ctx, const int64_t *offsets, int n_tracks, 
     db->offsets.resize(size_t(n_tracks) + 1);
     for (int r = 0; r <= n_tracks; ++r) db->offsets[r] = (n_tracks ? offsets[r] - offsets[0] : 0);
     db->n_tiles = int(tiles.size());
+    db->n_tiles_tc = int(tiles_tc.size());
     cudaError_t e = cudaMalloc(&db->d_words, sizeof(uint64_t) * size_t(db->total_words + 16));
     if (e == cudaSuccess) e = cudaMalloc(&db->d_track_start, sizeof(int64_t) * (size_t(n_tracks) + 1));
     if (e == cudaSuccess) e = cudaMalloc(&db->d_tiles, sizeof(MatchTile) * std::max<size_t>(1, tiles.size()));
+    if (e == cudaSuccess) e = cudaMalloc(&db->d_tiles_tc, sizeof(MatchTile) * std::max<size_t>(1, tiles_tc.size()));
     if (e == cudaSuccess)
         e = cudaMemcpy(db->d_track_start, db->offsets.data(), sizeof(int64_t) * (size_t(n_tracks) + 1),
                        cudaMemcpyHostToDevice);
     if (e == cudaSuccess && !tiles.empty())
         e = cudaMemcpy(db->d_tiles, tiles.data(), sizeof(MatchTile) * tiles.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !tiles_tc.empty())
+        e = cudaMemcpy(db->d_tiles_tc, tiles_tc.data(), sizeof(MatchTile) * tiles_tc.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         hpfw_db_destroy(db);
         HPFW_FAIL(HPFW_ERR_CUDA, "hpfw_db_build: %s", cudaGetErrorString(e));
@@ -389,6 +380,7 @@ void hpfw_db_destroy(hpfw_db *db) {
     if (db->d_words) cudaFree(db->d_words);
     if (db->d_track_start) cudaFree(db->d_track_start);
     if (db->d_tiles) cudaFree(db->d_tiles);
+    if (db->d_tiles_tc) cudaFree(db->d_tiles_tc);
     delete db;
 }
 
@@ -446,38 +438,76 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
     }
     if (!d_qwords && qoffsets[n_queries] > qoffsets[0]) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_match_device: d_qwords is NULL");
 
-    // queries per chunk: bound the best[] scratch to ~1 GiB
+    // queries per chunk: bound the best[] scratch to ~1 GiB (and the tensor-core matcher's expanded queries to ~2 GiB)
+    const int impl = ctx->match_impl;
     const size_t row_bytes = sizeof(uint64_t) * std::max<size_t>(1, size_t(R));
     int qchunk = int(std::min<size_t>(size_t(n_queries), std::max<size_t>(1, (size_t(1) << 30) / row_bytes)));
     qchunk = std::min(qchunk, 1 << 20);  // keeps gridDim.y within 65535
+    if (impl != 0) {
+        const size_t per_query = size_t(xt_kpad(kmax)) * 64;
+        const size_t fit = std::max<size_t>(XT_NQ, ((size_t(2) << 30) / per_query) / XT_NQ * XT_NQ);
+        qchunk = int(std::min<size_t>(size_t(qchunk), fit));
+    }
     const int n_chunks = (n_queries + qchunk - 1) / qchunk;
 
-    // host metadata: [qstart int64 (n_queries+1)] then per chunk [qb_idx int32 (nb*QB)] [qb_k int32 (nb)]
-    struct ChunkMeta { size_t idx_off, k_off; int nb, q0, nq; };
+    // host metadata: [qstart int64 (n_queries+1)] then per chunk
+    //   integer-pipe kernel: [qb_idx int32 (nb*QB)] [qb_k int32 (nb)]
+    //   tensor-core kernel:  [XtGroup (ng)] [row_q int32 (ng*128)] [row_k int32 (ng*128)]
+    struct ChunkMeta { size_t idx_off, k_off, grp_off, rowq_off, rowk_off; int nb, q0, nq, ng, kpad_max; size_t exp_bytes; };
     std::vector<ChunkMeta> cm(n_chunks);
     size_t meta_bytes = sizeof(int64_t) * (size_t(n_queries) + 1);
     std::vector<int32_t> tables;
+    size_t exp_max = 0;
     for (int c = 0; c < n_chunks; ++c) {
         const int q0 = c * qchunk, nq = std::min(qchunk, n_queries - q0);
+        auto klen = [&](int i) { return qoffsets[q0 + i + 1] - qoffsets[q0 + i]; };
         std::vector<int> order(nq);
         std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-            return (qoffsets[q0 + a + 1] - qoffsets[q0 + a]) < (qoffsets[q0 + b + 1] - qoffsets[q0 + b]);
-        });
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return klen(a) < klen(b); });
+        // Which queries go to the tensor cores: whole groups of 128 always; a last partial group only when it is full enough
+        // to beat the integer-pipe kernel (a group costs the same with 1 or 128 queries), or when impl 1 forces it.
+        const int rem = nq % XT_NQ;
+        const int n_tc = impl == 0 ? 0 : (impl == 1 || rem >= XT_MIN_FILL) ? nq : nq - rem;
+        cm[c].q0 = q0;
+        cm[c].nq = nq;
+        cm[c].ng = (n_tc + XT_NQ - 1) / XT_NQ;
+        cm[c].kpad_max = 0;
+        cm[c].exp_bytes = 0;
+        if (tables.size() & 1) tables.push_back(0);          // XtGroup holds an int64
+        cm[c].grp_off = meta_bytes + tables.size() * sizeof(int32_t);
+        std::vector<int32_t> rq(size_t(cm[c].ng) * XT_NQ, -1), rk(size_t(cm[c].ng) * XT_NQ, 0);
+        for (int g = 0; g < cm[c].ng; ++g) {
+            XtGroup grp{int64_t(cm[c].exp_bytes), 0, INT32_MAX};
+            for (int m = 0; m < XT_NQ && g * XT_NQ + m < n_tc; ++m) {
+                const int qi = order[g * XT_NQ + m];
+                const int32_t k = int32_t(klen(qi));
+                rq[size_t(g) * XT_NQ + m] = qi;
+                rk[size_t(g) * XT_NQ + m] = k;
+                grp.kmax = std::max(grp.kmax, k);
+                grp.kmin = std::min(grp.kmin, k);
+            }
+            cm[c].kpad_max = std::max(cm[c].kpad_max, xt_kpad(grp.kmax));
+            cm[c].exp_bytes += size_t(xt_kpad(grp.kmax)) * XT_NQ * 64;
+            const int32_t *raw = reinterpret_cast<const int32_t *>(&grp);
+            tables.insert(tables.end(), raw, raw + sizeof(XtGroup) / sizeof(int32_t));
+        }
+        exp_max = std::max(exp_max, cm[c].exp_bytes);
+        cm[c].rowq_off = meta_bytes + tables.size() * sizeof(int32_t);
+        tables.insert(tables.end(), rq.begin(), rq.end());
+        cm[c].rowk_off = meta_bytes + tables.size() * sizeof(int32_t);
+        tables.insert(tables.end(), rk.begin(), rk.end());
+
         std::vector<int32_t> idx, ks;
-        for (int i = 0; i < nq;) {
-            const int64_t k = qoffsets[q0 + order[i] + 1] - qoffsets[q0 + order[i]];
+        for (int i = n_tc; i < nq;) {
+            const int64_t k = klen(order[i]);
             int32_t blk[MT_QB];
             int got = 0;
-            while (got < MT_QB && i < nq && qoffsets[q0 + order[i] + 1] - qoffsets[q0 + order[i]] == k)
-                blk[got++] = order[i++];
+            while (got < MT_QB && i < nq && klen(order[i]) == k) blk[got++] = order[i++];
             for (int f = got; f < MT_QB; ++f) blk[f] = blk[got - 1];  // pad a short block by repeating a query
             for (int f = 0; f < MT_QB; ++f) idx.push_back(blk[f]);
             ks.push_back(int32_t(k));
         }
         cm[c].nb = int(ks.size());
-        cm[c].q0 = q0;
-        cm[c].nq = nq;
         cm[c].idx_off = meta_bytes + tables.size() * sizeof(int32_t);
         tables.insert(tables.end(), idx.begin(), idx.end());
         cm[c].k_off = meta_bytes + tables.size() * sizeof(int32_t);
@@ -490,6 +520,7 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
     HPFW_TRY(ctx->pin_in.reserve(total_meta));
     HPFW_TRY(ctx->qmeta.reserve(total_meta));
     HPFW_TRY(ctx->best.reserve(row_bytes * size_t(qchunk)));
+    if (exp_max) HPFW_TRY(ctx->qexp.reserve(exp_max));
     {
         int64_t *qs = ctx->pin_in.as<int64_t>();
         for (int q = 0; q <= n_queries; ++q) qs[q] = qoffsets[q] - qoffsets[0];
@@ -502,10 +533,14 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
     const int kpad = (kmax + 7) & ~7;
     const int nload = MT_TILE + kpad + 8;
     const size_t smem = sizeof(uint64_t) * (size_t(nload / 8) * MT_PITCH + size_t(kpad) * MT_QB);
-    if (smem > size_t(ctx->max_smem_optin))
-        HPFW_FAIL(HPFW_ERR_LIMIT, "hpfw_db_match_device: query of %d words needs %zu B shared memory (> %d)", kmax, smem,
-                  ctx->max_smem_optin);
-    HPFW_CUDA_TRY(cudaFuncSetAttribute(match_kernel<MT_QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    bool any_blocks = false;
+    for (int c = 0; c < n_chunks; ++c) any_blocks |= cm[c].nb > 0;
+    if (any_blocks) {
+        if (smem > size_t(ctx->max_smem_optin))
+            HPFW_FAIL(HPFW_ERR_LIMIT, "hpfw_db_match_device: query of %d words needs %zu B shared memory (> %d)", kmax,
+                      smem, ctx->max_smem_optin);
+        HPFW_CUDA_TRY(cudaFuncSetAttribute(match_kernel<MT_QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    }
 
     const char *meta = ctx->qmeta.as<char>();
     const int64_t *d_qstart = reinterpret_cast<const int64_t *>(meta);
@@ -513,6 +548,11 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
     for (int c = 0; c < n_chunks; ++c) {
         unsigned long long *best = ctx->best.as<unsigned long long>();
         HPFW_CUDA_TRY(cudaMemsetAsync(best, 0xFF, row_bytes * size_t(cm[c].nq), stream));
+        if (cm[c].ng > 0)
+            HPFW_TRY(match_tc_run(ctx, db, d_q, d_qstart + cm[c].q0, reinterpret_cast<const XtGroup *>(meta + cm[c].grp_off),
+                                  reinterpret_cast<const int32_t *>(meta + cm[c].rowq_off),
+                                  reinterpret_cast<const int32_t *>(meta + cm[c].rowk_off), cm[c].ng, cm[c].kpad_max,
+                                  ctx->qexp.as<uint8_t>(), best, stream));
         if (db->n_tiles > 0 && cm[c].nb > 0) {
             // a CTA = one reference tile x up to MT_BLOCKS_PER_CTA register blocks of queries: the staged tile is reused
             // 16x, and a CTA stays a few ms of work so the last partial wave is a small tail
@@ -531,6 +571,12 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
                                                     reinterpret_cast<unsigned long long *>(d_keys_out) + size_t(cm[c].q0) * topk);
         HPFW_CUDA_TRY(cudaGetLastError());
     }
+    return HPFW_OK;
+}
+
+int hpfw_set_match_impl(hpfw_ctx *ctx, int impl) {
+    if (!ctx || impl < 0 || impl > 2) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_set_match_impl: impl must be 0, 1 or 2");
+    ctx->match_impl = impl;
     return HPFW_OK;
 }
 

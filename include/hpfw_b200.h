@@ -95,7 +95,8 @@ int hpfw_ctx_synchronize(hpfw_ctx *ctx);
 #define HPFW_K_PROJECT 2  /* project_kernel (stages 2-3) */
 #define HPFW_K_CQT 3      /* all CQT kernels (stage 1) */
 #define HPFW_K_OTHER 4
-#define HPFW_K_COUNT 5
+#define HPFW_K_MATCH_TC 5 /* match_tc_kernel (stage 4 on the tensor cores) */
+#define HPFW_K_COUNT 6
 int hpfw_ctx_timing_enable(hpfw_ctx *ctx, int on);
 int hpfw_ctx_timing_read(hpfw_ctx *ctx, int kernel, double *total_ms, uint64_t *launches, int reset);
 
@@ -119,6 +120,11 @@ int hpfw_db_find_topk(hpfw_db *db, const uint64_t *qwords, const int64_t *qoffse
 /* Device path: d_qwords on the device, qoffsets on the host (metadata); d_keys_out[n_queries * topk] packed keys. */
 int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *qoffsets, int n_queries, int topk,
                          uint64_t *d_keys_out, void *stream);
+/* which kernel runs the cross-correlation: 0 = XOR + POPC on the integer pipes (matcher.cu); 1 = exact int8 GEMM on the
+ * tensor cores, tcgen05.mma.kind::i8 over +1/-1 bytes with s32 accumulation (match_tc.cu); 2 (default) = tensor cores for
+ * groups of 128 queries that are at least 24 full, integer pipes for the remainder. All three give identical results.
+ * The environment variable HPFW_MATCH_IMPL sets the initial value of a new context. */
+int hpfw_set_match_impl(hpfw_ctx *ctx, int impl);
 /* Multi-GPU merge after an all-gather: d_keys_in[n_ranks][n_queries][topk] -> d_keys_out[n_queries][topk]. */
 int hpfw_topk_merge_device(hpfw_ctx *ctx, const uint64_t *d_keys_in, int n_ranks, int n_queries, int topk,
                            uint64_t *d_keys_out, void *stream);

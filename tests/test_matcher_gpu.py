@@ -10,6 +10,16 @@ from hpfw_b200.api import SIZE_MAX
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[0, 1, 2], ids=["popc", "tc", "auto"], autouse=True)
+def match_impl(ctx, request):
+    """Every test of this file runs three times: integer-pipe kernel (matcher.cu), tensor-core kernel for every query
+    (match_tc.cu), and the default routing (tensor cores for well-filled groups of 128, integer pipes for the rest)."""
+    from hpfw_b200._lib import check
+    check(ctx._lib.hpfw_set_match_impl(ctx.handle, request.param))
+    yield request.param
+    check(ctx._lib.hpfw_set_match_impl(ctx.handle, 2))
+
+
 def _triple(r):
     return (r.track, -1 if r.cnt >= (1 << 63) else r.cnt, r.offset)
 
@@ -142,6 +152,57 @@ def test_full_size_properties(ctx):
     assert np.array_equal(out["track"][:4], tr) and np.array_equal(out["cnt"][:4], d) and np.array_equal(out["offset"][:4], o)
     again = st.find_topk_packed(qw, qo, 10)
     assert np.array_equal(again, out)
+
+
+def _popcount_rows(x):
+    return np.unpackbits(np.ascontiguousarray(x).view(np.uint8)).reshape(len(x), -1).sum(axis=1)
+
+
+def test_extreme_distances(ctx):
+    """Accumulator range of the int8 GEMM: exact copies (distance 0, dot = +64 k), bitwise complements (distance 64 k,
+    dot = -64 k), all-zero / all-one words, at the longest query the ABI accepts (4096 words) and at odd lengths."""
+    rng = np.random.default_rng(41)
+    lens = np.array([4096, 5000, 4609, 700, 4097], dtype=np.int64)
+    words, offs = synth.synth_hashprint_db(41, len(lens), lens)
+    words = words.copy()
+    words[offs[3]:offs[3] + 300] = 0
+    words[offs[3] + 300:offs[3] + 600] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    queries = []
+    for k in (4096, 4095, 385, 193, 192, 5, 1):
+        a = int(offs[1]) + 17
+        queries.append(words[a:a + k].copy())                       # exact copy of track 1 at offset 17
+        queries.append(~words[a:a + k])                             # its complement
+    queries.append(np.zeros(300, dtype=np.uint64))
+    queries.append(np.full(300, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64))
+    queries.append(np.zeros(0, dtype=np.uint64))                    # empty query: distance 0 at offset 0 of track 0
+    qo = np.zeros(len(queries) + 1, dtype=np.int64)
+    np.cumsum([len(q) for q in queries], out=qo[1:])
+    qw = np.concatenate(queries)
+    st = MemoryStorage(ctx).build_packed(words, offs)
+    out = st.find_topk_packed(qw, qo, len(lens))
+    tr, d, o = oracle.find_topk_batch(words, offs, qw, qo, len(lens), 8)
+    assert np.array_equal(out["track"], tr) and np.array_equal(out["cnt"], d) and np.array_equal(out["offset"], o)
+    assert out["cnt"][0, 0] == 0 and out["track"][0, 0] == 1 and out["offset"][0, 0] == 17
+
+
+def test_many_queries_mixed_lengths(ctx):
+    """300 queries of 7 different lengths against ragged tracks: several groups of 128 with different k inside one group
+    (zero-padded query rows), a partial last group, queries longer than some tracks."""
+    rng = np.random.default_rng(51)
+    n_tracks = 24
+    lens = rng.integers(100, 1800, size=n_tracks)
+    lens[3] = 30
+    lens[7] = 513
+    lens[8] = 512
+    lens[9] = 511
+    words, offs = synth.synth_hashprint_db(51, n_tracks, lens)
+    ks = np.array([63, 64, 65, 143, 385, 386, 40], dtype=np.int64)
+    kk = ks[rng.integers(0, len(ks), size=300)]
+    qw, qo, _ = synth.synth_hashprint_queries(52, words, offs, len(kk), kk)
+    st = MemoryStorage(ctx).build_packed(words, offs)
+    out = st.find_topk_packed(qw, qo, 6)
+    tr, d, o = oracle.find_topk_batch(words, offs, qw, qo, 6, 8)
+    assert np.array_equal(out["track"], tr) and np.array_equal(out["cnt"], d) and np.array_equal(out["offset"], o)
 
 
 def test_limits_reported(ctx):
