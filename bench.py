@@ -14,7 +14,9 @@ in N ("weak").
   value   device-resident: query words already in HBM when the timed region starts
   e2e     through the host API (ShardedMemoryStorage.search_host): pinned host query words -> H2D -> match -> (allgather,
           merge) -> D2H of the top-k records, every step
-  roofline  the match kernel against the POPC-pipe roof; duration from CUDA events around every launch
+  roofline  the dominant kernel — match_tc_kernel (exact int8 GEMM on the tensor cores) against the int8 tensor-pipe
+          ceiling; roofline_popc: the integer-pipe match_kernel on the same step against the POPC/LOP3 pipe roof
+          (see DESIGN.md); durations from CUDA events around every launch
   cpu_baseline  the reference's own MemoryStorage::find (oracle/_ref, compiled from /root/reference headers) on all host
           cores over a bounded sample, on rank 0 at N=1 only
 """
@@ -44,6 +46,9 @@ METRIC = "live_id_queries_per_sec_vs_10k_track_db"
 UNIT = "queries/s"
 WORDOPS_PER_CLK_SM = 16     # carry-save matcher: min(64 LOP3 lanes / 4, 16 POPC lanes / 1) per clk per SM
 POPC32_PER_CLK_SM = 16      # CUDA programming guide arithmetic-throughput table (population count); checked by the microbenchmark
+I8_OPS_PER_CLK_SM = 16384   # tcgen05.mma kind::i8, M=128 N=256 K=32 in 128 clk (B300_MICROARCH.md pacing law): 8192 MAC/clk/SM
+F4_OPS_PER_CLK_SM = 32768   # tcgen05.mma kind::mxf4, M=128 N=256 K=64 in 128 clk: 16384 MAC/clk/SM (nominal 9 PFLOP/s fp4 dense)
+OPS_PER_WORDOP = 128        # tensor-core matcher: one 64-bit word-op = 64 s8 multiply-adds
 
 
 def host_cores() -> int:
@@ -71,7 +76,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                                          "200", "-i", str(self.device)], stdout=subprocess.PIPE,
+                                          "50", "-i", str(self.device)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -510,6 +515,28 @@ def run_cuda(args):
     # ---- pipe microbenchmark (rank 0, untimed): pins the POPC roof
     micro = ctx.microbench_pipes() if rank == 0 else None
 
+    # ---- the integer-pipe kernel (matcher.cu) on the same step, timed first: its roofline is reported beside the default's
+    from hpfw_b200._lib import check
+    popc_leg = None
+    if args.match_impl != 0 and not args.no_popc_leg:
+        check(ctx._lib.hpfw_set_match_impl(ctx.handle, 0))
+        keys = st.search_device(d_q, qoffs, TOPK)
+        barrier()
+        ctx.timing_read(_lib.K_MATCH, reset=True)
+        ctx.timing_enable(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(2):
+            keys = st.search_device(d_q, qoffs, TOPK)
+        e1.record()
+        barrier()
+        p_ms = max_over_ranks(e0.elapsed_time(e1)) / 2
+        pk_ms, pk_n = ctx.timing_read(_lib.K_MATCH, reset=True)
+        ctx.timing_enable(False)
+        popc_leg = {"ms_per_step": p_ms, "kernel_ms": pk_ms, "launches": pk_n, "steps": 2,
+                    "keys": keys.clone()}
+    check(ctx._lib.hpfw_set_match_impl(ctx.handle, args.match_impl))
+
     # ---- device-resident arm
     for _ in range(args.warmup):
         keys = st.search_device(d_q, qoffs, TOPK)
@@ -518,6 +545,7 @@ def run_cuda(args):
     if rank == 0:
         sampler.start()
     ctx.timing_read(_lib.K_MATCH, reset=True)
+    ctx.timing_read(_lib.K_MATCH_TC, reset=True)
     ctx.timing_read(_lib.K_TOPK, reset=True)
     ctx.timing_enable(True)
     launches0 = ctx.launch_count()
@@ -530,10 +558,15 @@ def run_cuda(args):
     ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     launches = ctx.launch_count() - launches0
     match_ms, match_n = ctx.timing_read(_lib.K_MATCH, reset=True)
+    tc_ms, tc_n = ctx.timing_read(_lib.K_MATCH_TC, reset=True)
     topk_ms, topk_n = ctx.timing_read(_lib.K_TOPK, reset=True)
     ctx.timing_enable(False)
     clocks = sampler.stop() if rank == 0 else None
     value = nq / (ms * 1e-3)
+    # the two kernels must agree bit for bit on the step that was timed
+    impls_equal = None
+    if popc_leg is not None:
+        impls_equal = bool(torch.equal(popc_leg.pop("keys"), keys))
 
     # correctness of what was just timed: planted queries must come back at their true (track, offset)
     got = hpfw_b200.api.decode_keys(keys.cpu().numpy().view(np.uint64))
@@ -620,9 +653,16 @@ def run_cuda(args):
         # The plain XOR+POPC formulation (2 POPC per word-op) is capped at 8 word-ops/clk/SM.
         peak = sms * WORDOPS_PER_CLK_SM * sm_max * 1e6 / 1e9                  # Gword-op/s
         plain_peak = sms * (POPC32_PER_CLK_SM / 2.0) * sm_max * 1e6 / 1e9
-        ops_per_launch = word_ops_per_query(hi - lo) * nq / max(1, match_n / args.steps)
-        avg_ms = match_ms / max(1, match_n)
-        achieved = ops_per_launch / (avg_ms * 1e-3) / 1e9
+        if args.match_impl == 0:
+            p_match_ms, p_match_n, p_steps, p_step_ms = match_ms, match_n, args.steps, ms
+        elif popc_leg is not None:
+            p_match_ms, p_match_n, p_steps, p_step_ms = (popc_leg["kernel_ms"], popc_leg["launches"], popc_leg["steps"],
+                                                         popc_leg["ms_per_step"])
+        else:
+            p_match_ms, p_match_n, p_steps, p_step_ms = 0.0, 0, 1, 1.0
+        ops_per_launch = word_ops_per_query(hi - lo) * nq / max(1, p_match_n / p_steps)
+        avg_ms = p_match_ms / max(1, p_match_n)
+        achieved = ops_per_launch / (avg_ms * 1e-3) / 1e9 if p_match_n else 0.0
         roof = {"bound": "int-pipe (alu lop3 + xu popc)", "achieved": achieved, "peak": peak, "unit": "Gwordop/s",
                 "frac": achieved / peak,
                 "traffic": 8.0 * (hi - lo) * TRACK_WORDS * ((nq // 2 + 15) // 16),
@@ -630,17 +670,59 @@ def run_cuda(args):
                                 "capture at 2000 tracks x 128 queries measured 0.949 GB against 0.922 GB modelled "
                                 "(profiles/r01b_*). HBM is <0.1 % utilised: the kernel is integer-pipe bound",
                 "vs_plain_popc_roof": achieved / plain_peak, "plain_popc_roof": plain_peak,
-                "kernel": "match_kernel", "avg_launch_ms": avg_ms, "launches": match_n,
-                "kernel_share_of_step": match_ms / args.steps / ms,
+                "kernel": "match_kernel", "avg_launch_ms": avg_ms, "launches": p_match_n,
+                "kernel_share_of_step": p_match_ms / p_steps / p_step_ms,
+                "queries_per_s": nq / (p_step_ms * 1e-3),
                 "peak_how": f"{sms} SMs x {WORDOPS_PER_CLK_SM} word-ops/clk/SM (4 LOP3 @64 lanes/clk + 1 POPC @16 "
                             f"lanes/clk per word-op, carry-save) x {sm_max:.0f} MHz ({peaks_src}); 1 word-op = XOR64 + "
                             f"popcount64; pipe rates measured by the in-run microbenchmark below",
                 "microbench": micro,
                 "hbm_view": {"algorithmic_bytes_per_launch": 8.0 * (hi - lo) * TRACK_WORDS + 8.0 * nq * QUERY_WORDS,
                              "note": "compute-bound: AI = k word-ops per 8 B of reference, HBM need is <1 % of peak"}}
+        roof_popc = None
+        dtype = "u64"
+        if args.match_impl != 0:
+            # default path: the cross-correlation as an exact int8 GEMM on the tensor cores (match_tc.cu); the integer-pipe
+            # kernel's roofline (the same step, timed above) goes beside it
+            roof_popc = roof if popc_leg is not None else None
+            f4 = args.match_impl == 3 or (args.match_impl == 2 and os.environ.get("HPFW_MATCH_TC_F4", "1") != "0")
+            dtype = ("e2m1 x e2m1 -> f32 (exact: +1.0/-1.0 per hashprint bit, unit block scales, sums < 2^24)" if f4 else
+                     "s8 x s8 -> s32 (exact; +1/-1 byte per hashprint bit)")
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                    bf16_burst = float(json.load(f)["bf16_tflops"])
+            except (OSError, KeyError, ValueError):
+                bf16_burst = 1590.0
+            ops_clk = F4_OPS_PER_CLK_SM if f4 else I8_OPS_PER_CLK_SM
+            tc_peak = sms * ops_clk * sm_max * 1e6 / 1e12                      # TOP/s
+            tc_ops_per_launch = OPS_PER_WORDOP * word_ops_per_query(hi - lo) * nq / max(1, tc_n / args.steps)
+            tc_avg_ms = tc_ms / max(1, tc_n)
+            tc_achieved = tc_ops_per_launch / (tc_avg_ms * 1e-3) / 1e12
+            kq = (QUERY_WORDS + 7) // 8 * 8 if f4 else (QUERY_WORDS + 3) // 4 * 4
+            lib_x = 4 if f4 else 2
+            roof = {"bound": "tensor", "achieved": tc_achieved, "peak": tc_peak, "unit": "TOP/s", "frac": tc_achieved / tc_peak,
+                    "traffic": None,
+                    "kernel": ("match_tc_kernel<1> (tcgen05.mma kind::mxf4.block_scale, M=128 queries x N=2x240 offsets, "
+                               "f32 in TMEM)" if f4 else
+                               "match_tc_kernel<0> (tcgen05.mma kind::i8, M=128 queries x N=2x256 offsets, s32 in TMEM)"),
+                    "avg_launch_ms": tc_avg_ms, "launches": tc_n, "kernel_share_of_step": tc_ms / args.steps / ms,
+                    "algorithmic_ops_per_launch": tc_ops_per_launch,
+                    "peak_how": f"{sms} SMs x {ops_clk} {'fp4' if f4 else 'int8'} ops/clk/SM ({ops_clk // 2} MAC/clk: one "
+                                f"M=128,N=256,K={64 if f4 else 32} tcgen05.mma per 128 clk) x {sm_max:.0f} MHz ({peaks_src}); "
+                                f"1 word-op (XOR64+popcount64) = 64 multiply-adds = {OPS_PER_WORDOP} ops. MEASURED_PEAKS.json "
+                                f"holds no {'fp4' if f4 else 'int8'} figure: {lib_x}x its bf16 cuBLAS burst rate would be "
+                                f"{lib_x * bf16_burst:.0f} TOP/s, which this kernel exceeds, so the pipe ceiling at the maximum "
+                                f"SM clock is the denominator (under sw_power_cap the clock is lower: see clocks)",
+                    "peak_bf16_cublas_scaled": lib_x * bf16_burst, "frac_of_bf16_cublas_scaled": tc_achieved / (lib_x * bf16_burst),
+                    "wordops_per_s_G": tc_achieved * 1e3 / OPS_PER_WORDOP,
+                    "vs_popc_pipe_roof": tc_achieved * 1e3 / OPS_PER_WORDOP / plain_peak,
+                    "hbm_view": {"algorithmic_bytes_per_launch": 8.0 * (hi - lo) * TRACK_WORDS + 64.0 * nq * kq,
+                                 "note": "tensor-bound: a tile reads (480 or 512) + k reference words (expanded in shared "
+                                         "memory) for that many x k word-ops per query; the expanded queries (1.6 or 3 MB "
+                                         "per group of 128) stream from L2"}}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
             "data": "synthetic", "config": workload_config(n) | {"tracks": tracks, "queries_per_step": nq},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_audio.numel() * 4 * n),
@@ -651,9 +733,16 @@ def run_cuda(args):
                                      "h2d_bytes_per_step": int(h_q.numel() * 8), "top1_ok": hp_ok}},
             "gpu_launches": launches,
             "roofline": roof,
+            "match_impl": {0: "integer pipes (matcher.cu)", 1: "tensor cores, int8 operands (match_tc.cu)",
+                           2: "tensor cores (fp4 operands unless HPFW_MATCH_TC_F4=0) for groups of 128 queries, integer "
+                              "pipes for a small remainder (default)",
+                           3: "tensor cores, fp4 operands (match_tc.cu)"}[args.match_impl],
             "top1_ok": top1_ok,
             "topk_ms_per_step": topk_ms / args.steps,
         }
+        if roof_popc is not None:
+            line["roofline_popc"] = roof_popc
+            line["impls_bit_identical"] = impls_equal
         if extraction is not None:
             line["extraction"] = extraction
         if n == 1 and not args.no_cpu_baseline:
@@ -683,6 +772,10 @@ def main():
     ap.add_argument("--tracks", type=int, default=TRACKS)
     ap.add_argument("--queries-per-gpu", type=int, default=QUERIES_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--match-impl", type=int, default=2, choices=[0, 1, 2, 3],
+                    help="0 = integer-pipe matcher, 1 = tensor-core matcher (int8), 3 = tensor-core matcher (fp4), "
+                         "2 = default routing (hpfw_set_match_impl)")
+    ap.add_argument("--no-popc-leg", action="store_true", help="skip timing the integer-pipe kernel beside the default")
     ap.add_argument("--no-extraction", action="store_true", help="skip the secondary hashprint-extraction leg")
     ap.add_argument("--extract-tracks", type=int, default=1000, help="3-min tracks of the extraction leg (all GPUs together)")
     args = ap.parse_args()

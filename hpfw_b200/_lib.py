@@ -20,7 +20,7 @@ class Match(C.Structure):
     _fields_ = [("track", C.c_int64), ("cnt", C.c_uint64), ("offset", C.c_int64)]
 
 
-K_MATCH, K_TOPK, K_PROJECT, K_CQT, K_OTHER = range(5)
+K_MATCH, K_TOPK, K_PROJECT, K_CQT, K_OTHER, K_MATCH_TC = range(6)
 OK, ERR_CUDA, ERR_ARG, ERR_LIMIT, ERR_STATE, ERR_SHORT = 0, -1, -2, -3, -4, -5
 
 _SIGS = {

@@ -104,7 +104,9 @@ struct hpfw_ctx {
     hpfw_b200::PinnedBuffer pin_in, pin_out;
     hpfw_b200::DeviceBuffer qexp;      // match_tc.cu: queries expanded to signed bytes
     int match_impl = 2;                // 2 = tensor cores for (nearly) full groups of 128 queries, integer pipes for the rest
-                                       // (default); 1 = tensor cores always; 0 = integer pipes always
+                                       // (default); 1 = tensor cores (int8) always; 3 = tensor cores (fp4) always;
+                                       // 0 = integer pipes always
+    int match_tc_f4 = 1;               // operand encoding the default routing (impl 2) uses: 1 = fp4 (default), 0 = int8
 
     // projection state
     hpfw_b200::DeviceBuffer filters_perm;  // filters permuted to [context][band(padded 128)][filter] etc. (project.cu)

@@ -45,8 +45,9 @@ int hpfw_ctx_create(int device, hpfw_ctx **out) {
     }
     if (const char *env = getenv("HPFW_MATCH_IMPL")) {
         const int v = atoi(env);
-        if (v >= 0 && v <= 2) c->match_impl = v;
+        if (v >= 0 && v <= 3) c->match_impl = v;
     }
+    if (const char *env = getenv("HPFW_MATCH_TC_F4")) c->match_tc_f4 = atoi(env) != 0;
     *out = c;
     return HPFW_OK;
 }

@@ -31,18 +31,33 @@
 
 namespace hpfw_b200 {
 
-constexpr int XT_HALF = 256;                                   // N of one MMA
+// Two operand encodings share the kernel (template parameter F4):
+//   F4 = 0: signed bytes +1 / -1, tcgen05.mma.kind::i8, s32 accumulators; a 64-bit word is 64 bytes = four 16-byte K chunks
+//           = 2 MMAs of K = 32; tile = 512 offsets = 2 x N(256) = all 512 TMEM columns.
+//   F4 = 1: e2m1 nibbles +1.0 / -1.0, tcgen05.mma.kind::mxf4.block_scale with every UE8M0 scale = 1.0, f32 accumulators
+//           (sums of +-1 below 2^24 are exact in f32); a word is 32 bytes = two K chunks = 1 MMA of K = 64, i.e. twice the
+//           word rate per clock; tile = 480 offsets = 2 x N(240), the last 32 TMEM columns hold the scale factors.
+template <int F4>
+struct Xt {
+    static constexpr int NOFF = F4 ? XT_NOFF_F4 : XT_NOFF;         // offsets per tile
+    static constexpr int HALF = NOFF / 2;                          // N of one MMA
+    static constexpr int CPW = F4 ? 2 : 4;                         // 16-byte K chunks per word
+    static constexpr int JS = F4 ? XT_JS_F4 : XT_JS;               // query words per TMA stage (32 KB either way)
+    static constexpr int JCMAX = F4 ? 448 : 192;                   // words per K chunk (multiple of JS)
+    static constexpr int NR = NOFF + JCMAX;                        // rows of an expanded reference buffer
+    static constexpr uint32_t R_LBO = NR * 16;                     // between the 16-byte K chunks of a row
+    static constexpr uint32_t R_BYTES = CPW * R_LBO;               // 45,056 / 29,696
+    static constexpr uint32_t Q_LBO = XT_NQ * 16;                  // 2,048
+    static constexpr uint32_t QWORD_BYTES = CPW * Q_LBO;           // one query word of a group: 8,192 / 4,096
+    static constexpr uint32_t STAGE_BYTES = JS * QWORD_BYTES;      // 32,768
+    static constexpr int KSTEPS = F4 ? 1 : 2;                      // MMAs (per N half) per word
+    static constexpr int ECH = F4 ? 32 : 64;                       // TMEM columns per epilogue load
+    static_assert(JCMAX % JS == 0, "chunk boundaries must be stage boundaries");
+};
 constexpr int XT_STAGES = 4;                                   // query ring depth
-constexpr int XT_JCMAX = 192;                                  // words per K chunk (multiple of XT_JS)
-constexpr int XT_NR = XT_NOFF + XT_JCMAX;                      // rows of an expanded reference buffer
-constexpr uint32_t XT_R_LBO = XT_NR * 16;                      // 11,264 B between the 16-byte K chunks of a row
-constexpr uint32_t XT_R_BYTES = 4 * XT_R_LBO;                  // 45,056
-constexpr uint32_t XT_Q_LBO = XT_NQ * 16;                      // 2,048
-constexpr uint32_t XT_QWORD_BYTES = 4 * XT_Q_LBO;              // 8,192: one query word of a group
-constexpr uint32_t XT_STAGE_BYTES = XT_JS * XT_QWORD_BYTES;    // 32,768
 constexpr int XT_THREADS = 320;
 constexpr int XT_BIAS = (1 << 18) + 1;                         // dot + bias >= 1 for every valid offset
-static_assert(XT_JCMAX % XT_JS == 0, "chunk boundaries must be stage boundaries");
+constexpr uint32_t XT_SF_COL = 480;                            // F4: TMEM columns 480..511 = scale factors, all 1.0
 
 // 4 bits -> 4 bytes of +1 / -1
 __device__ __forceinline__ uint32_t xt_nib(uint32_t n) {
@@ -51,6 +66,23 @@ __device__ __forceinline__ uint32_t xt_nib(uint32_t n) {
 }
 __device__ __forceinline__ uint4 xt_expand16(uint32_t h) {
     return make_uint4(xt_nib(h & 15u), xt_nib((h >> 4) & 15u), xt_nib((h >> 8) & 15u), xt_nib((h >> 12) & 15u));
+}
+
+// 8 bits -> 8 e2m1 nibbles: +1.0 = 0b0010, -1.0 = 0b1010
+__device__ __forceinline__ uint32_t xt_nib8(uint32_t b) {
+    uint32_t x = (b | (b << 12)) & 0x000F000Fu;
+    x = (x | (x << 6)) & 0x03030303u;
+    x = (x | (x << 3)) & 0x11111111u;       // bit i of b at position 4 i
+    return 0xAAAAAAAAu ^ (x << 3);          // clear the sign bit where the hashprint bit is set
+}
+__device__ __forceinline__ uint4 xt_expand32_f4(uint32_t h) {
+    return make_uint4(xt_nib8(h & 255u), xt_nib8((h >> 8) & 255u), xt_nib8((h >> 16) & 255u), xt_nib8(h >> 24));
+}
+// chunk c of a word in the operand encoding
+template <int F4>
+__device__ __forceinline__ uint4 xt_chunk(uint64_t w, int c) {
+    if (F4) return xt_expand32_f4((uint32_t)(w >> (32 * c)));
+    return xt_expand16((uint32_t)(w >> (16 * c)) & 0xFFFFu);
 }
 
 // shared-memory matrix descriptor, K-major, no swizzle: start >> 4 [0,14), LBO >> 4 [16,30) (between the two 16-byte K
@@ -71,6 +103,41 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
+// block-scaled instruction descriptor: A = B = e2m1 (MXF4 format 1), K-major, UE8M0 scales (bit 23), M = 128, N = n, K = 64
+__device__ __forceinline__ uint32_t xt_idesc_f4(int n) {
+    return (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | (1u << 23) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_mxf4(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t sfa,
+                                            uint32_t sfb, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%4], [%5], p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(sfa), "r"(sfb), "r"(acc) : "memory");
+}
+// tcgen05.ld.32x32b.x32: 32 consecutive TMEM columns of this thread's lane
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// the same value into 32 consecutive TMEM columns of this warp's 32 lanes
+__device__ __forceinline__ void tmem_fill_x32(uint32_t taddr, uint32_t x) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+        "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+        ::"r"(taddr), "r"(x) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -79,22 +146,23 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// qexp[group].exp_off + ((j * 4 + c) * 128 + m) * 16: bytes 16c .. 16c+15 of word j of the group's m-th query
+// qexp[group].exp_off + ((j * CPW + c) * 128 + m) * 16: chunk c of word j of the group's m-th query
+template <int F4>
 __global__ void __launch_bounds__(XT_NQ)
 xt_expand_queries_kernel(const uint64_t *__restrict__ qwords, const int64_t *__restrict__ qstart,
                          const XtGroup *__restrict__ groups, const int32_t *__restrict__ row_q,
                          const int32_t *__restrict__ row_k, uint8_t *__restrict__ qexp) {
+    using G = Xt<F4>;
     const int g = blockIdx.y, j = blockIdx.x, m = threadIdx.x;
     const XtGroup grp = groups[g];
-    const int kpad = ((grp.kmax < 1 ? 1 : grp.kmax) + XT_JS - 1) / XT_JS * XT_JS;
+    const int kpad = ((grp.kmax < 1 ? 1 : grp.kmax) + G::JS - 1) / G::JS * G::JS;
     if (j >= kpad) return;
     const int q = row_q[g * XT_NQ + m];
     const bool valid = q >= 0 && j < row_k[g * XT_NQ + m];
     const uint64_t w = valid ? qwords[qstart[q] + j] : 0ull;
-    uint4 *dst = reinterpret_cast<uint4 *>(qexp + grp.exp_off) + (size_t)j * 4 * XT_NQ + m;
+    uint4 *dst = reinterpret_cast<uint4 *>(qexp + grp.exp_off) + (size_t)j * G::CPW * XT_NQ + m;
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-        dst[c * XT_NQ] = valid ? xt_expand16((uint32_t)(w >> (16 * c)) & 0xFFFFu) : make_uint4(0u, 0u, 0u, 0u);
+    for (int c = 0; c < G::CPW; ++c) dst[c * XT_NQ] = valid ? xt_chunk<F4>(w, c) : make_uint4(0u, 0u, 0u, 0u);
 }
 
 struct XtItem {
@@ -105,8 +173,10 @@ struct XtItem {
     int nchunks, jc;
 };
 
+template <int F4>
 __device__ __forceinline__ XtItem xt_item(long long item, int n_tiles, const MatchTile *__restrict__ tiles,
                                           const int64_t *__restrict__ track_start, const XtGroup *__restrict__ groups) {
+    using G = Xt<F4>;
     XtItem it;
     it.g = int(item / n_tiles);
     const MatchTile t = tiles[item % n_tiles];
@@ -117,21 +187,23 @@ __device__ __forceinline__ XtItem xt_item(long long item, int n_tiles, const Mat
     it.n_r = int(track_start[t.track + 1] - it.tbeg);
     it.kmax = max(grp.kmax, 1);
     const int last_valid = it.n_r - min(grp.kmin, it.n_r);    // the shortest query reaches the furthest offset
-    it.need = min(XT_NOFF, last_valid - t.start + 1);
-    it.nchunks = (it.kmax + XT_JCMAX - 1) / XT_JCMAX;
-    it.jc = ((it.kmax + it.nchunks - 1) / it.nchunks + XT_JS - 1) / XT_JS * XT_JS;
+    it.need = min(G::NOFF, last_valid - t.start + 1);
+    it.nchunks = (it.kmax + G::JCMAX - 1) / G::JCMAX;
+    it.jc = ((it.kmax + it.nchunks - 1) / it.nchunks + G::JS - 1) / G::JS * G::JS;
     return it;
 }
 
+template <int F4>
 __global__ void __launch_bounds__(XT_THREADS, 1)
 match_tc_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ track_start,
                 const MatchTile *__restrict__ tiles, int n_tiles, const XtGroup *__restrict__ groups, int n_groups,
                 const int32_t *__restrict__ row_q, const int32_t *__restrict__ row_k, const uint8_t *__restrict__ qexp,
                 int n_tracks, unsigned long long *__restrict__ best) {
+    using G = Xt<F4>;
     extern __shared__ uint8_t xsm_raw[];
     uint8_t *xsm = xsm_raw + ((128u - (smem_u32(xsm_raw) & 127u)) & 127u);
-    uint8_t *r_s = xsm;                              // 2 x XT_R_BYTES
-    uint8_t *q_s = xsm + 2 * XT_R_BYTES;             // XT_STAGES x XT_STAGE_BYTES
+    uint8_t *r_s = xsm;                              // 2 x R_BYTES
+    uint8_t *q_s = xsm + 2 * G::R_BYTES;             // XT_STAGES x STAGE_BYTES
     __shared__ __align__(8) uint64_t q_full[XT_STAGES], q_empty[XT_STAGES], r_full[2], r_empty[2], acc_full, acc_empty;
     __shared__ uint32_t tmem_base_s;
 
@@ -160,21 +232,28 @@ match_tc_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    if (F4) {
+        // every block scale = 2^0: UE8M0 byte 0x7F in all four bytes of TMEM columns 480..511, whatever the layout
+        if (warp >= 6) tmem_fill_x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + XT_SF_COL, 0x7F7F7F7Fu);
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
 
     if (warp == 0) {
         if (lane == 0) {
-            // ===== TMA producer: the group's expanded query words, XT_JS words per stage =====
+            // ===== TMA producer: the group's expanded query words, JS words per stage =====
             uint32_t sidx = 0;
             for (long long item = blockIdx.x; item < total; item += gridDim.x) {
-                const XtItem it = xt_item(item, n_tiles, tiles, track_start, groups);
+                const XtItem it = xt_item<F4>(item, n_tiles, tiles, track_start, groups);
                 if (it.need <= 0) continue;
                 const uint8_t *src = qexp + groups[it.g].exp_off;
-                const int nst = (it.kmax + XT_JS - 1) / XT_JS;
+                const int nst = (it.kmax + G::JS - 1) / G::JS;
                 for (int st = 0; st < nst; ++st, ++sidx) {
                     const uint32_t s = sidx % XT_STAGES;
                     if (sidx >= XT_STAGES) mbar_wait(&q_empty[s], ((sidx / XT_STAGES) - 1) & 1);
-                    mbar_expect_tx(&q_full[s], XT_STAGE_BYTES);
-                    bulk_load_1d(q_s + s * XT_STAGE_BYTES, src + (size_t)st * XT_STAGE_BYTES, XT_STAGE_BYTES, &q_full[s]);
+                    mbar_expect_tx(&q_full[s], G::STAGE_BYTES);
+                    bulk_load_1d(q_s + s * G::STAGE_BYTES, src + (size_t)st * G::STAGE_BYTES, G::STAGE_BYTES, &q_full[s]);
                 }
             }
         }
@@ -182,13 +261,15 @@ match_tc_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ 
         if (lane == 0) {
             // ===== MMA issuer =====
             uint32_t sidx = 0, ridx = 0, tcount = 0;
-            const uint64_t a_hi = xt_desc(0, XT_Q_LBO, 128), b_hi = xt_desc(0, XT_R_LBO, 128);
+            const uint64_t a_hi = xt_desc(0, G::Q_LBO, 128), b_hi = xt_desc(0, G::R_LBO, 128);
+            const uint32_t sfa = tmem_base + XT_SF_COL, sfb = tmem_base + XT_SF_COL + 16;
             for (long long item = blockIdx.x; item < total; item += gridDim.x) {
-                const XtItem it = xt_item(item, n_tiles, tiles, track_start, groups);
+                const XtItem it = xt_item<F4>(item, n_tiles, tiles, track_start, groups);
                 if (it.need <= 0) continue;
-                const int n1 = min(XT_HALF, (it.need + 15) & ~15);
-                const int n2 = it.need > XT_HALF ? (it.need - XT_HALF + 15) & ~15 : 0;
-                const uint32_t id1 = xt_idesc(n1), id2 = xt_idesc(n2 ? n2 : 16);
+                const int n1 = min(G::HALF, (it.need + 15) & ~15);
+                const int n2 = it.need > G::HALF ? (it.need - G::HALF + 15) & ~15 : 0;
+                const uint32_t id1 = F4 ? xt_idesc_f4(n1) : xt_idesc(n1);
+                const uint32_t id2 = F4 ? xt_idesc_f4(n2 ? n2 : 16) : xt_idesc(n2 ? n2 : 16);
                 if (tcount > 0) mbar_wait(&acc_empty, (tcount - 1) & 1);     // epilogue has drained the accumulators
                 tc_fence_after();
                 uint32_t acc = 0;
@@ -197,20 +278,25 @@ match_tc_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ 
                     mbar_wait(&r_full[rb], (ridx >> 1) & 1);
                     tc_fence_after();
                     const int j0 = c * it.jc, j1 = min(it.kmax, j0 + it.jc);
-                    const uint64_t b_base = b_hi + (uint64_t)(smem_u32(r_s + rb * XT_R_BYTES) >> 4);
-                    for (int j = j0; j < j1; j += XT_JS, ++sidx) {
+                    const uint64_t b_base = b_hi + (uint64_t)(smem_u32(r_s + rb * G::R_BYTES) >> 4);
+                    for (int j = j0; j < j1; j += G::JS, ++sidx) {
                         const uint32_t s = sidx % XT_STAGES;
                         mbar_wait(&q_full[s], (sidx / XT_STAGES) & 1);
                         tc_fence_after();
-                        const uint64_t a_base = a_hi + (uint64_t)(smem_u32(q_s + s * XT_STAGE_BYTES) >> 4);
-                        const int nj = min(XT_JS, j1 - j);
+                        const uint64_t a_base = a_hi + (uint64_t)(smem_u32(q_s + s * G::STAGE_BYTES) >> 4);
+                        const int nj = min(G::JS, j1 - j);
                         for (int jj = 0; jj < nj; ++jj) {
 #pragma unroll
-                            for (int kk = 0; kk < 2; ++kk) {
-                                const uint64_t a_desc = a_base + (uint64_t)((jj * XT_QWORD_BYTES + kk * 2 * XT_Q_LBO) >> 4);
-                                const uint64_t b_desc = b_base + (uint64_t)(j - j0 + jj) + (uint64_t)((kk * 2 * XT_R_LBO) >> 4);
-                                tc_mma_i8(tmem_base, a_desc, b_desc, id1, acc);
-                                if (n2) tc_mma_i8(tmem_base + XT_HALF, a_desc, b_desc + XT_HALF, id2, acc);
+                            for (int kk = 0; kk < G::KSTEPS; ++kk) {
+                                const uint64_t a_desc = a_base + (uint64_t)((jj * G::QWORD_BYTES + kk * 2 * G::Q_LBO) >> 4);
+                                const uint64_t b_desc = b_base + (uint64_t)(j - j0 + jj) + (uint64_t)((kk * 2 * G::R_LBO) >> 4);
+                                if (F4) {
+                                    tc_mma_mxf4(tmem_base, a_desc, b_desc, id1, sfa, sfb, acc);
+                                    if (n2) tc_mma_mxf4(tmem_base + G::HALF, a_desc, b_desc + G::HALF, id2, sfa, sfb, acc);
+                                } else {
+                                    tc_mma_i8(tmem_base, a_desc, b_desc, id1, acc);
+                                    if (n2) tc_mma_i8(tmem_base + G::HALF, a_desc, b_desc + G::HALF, id2, acc);
+                                }
                                 acc = 1;
                             }
                         }
@@ -223,18 +309,18 @@ match_tc_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ 
             }
         }
     } else if (warp < 6) {
-        // ===== reference expanders: rows [tile_start + j0, + 512 + (j1 - j0)) of the track -> s8, chunk-column layout =====
+        // ===== reference expanders: rows [tile_start + j0, + NOFF + (j1 - j0)) of the track, chunk-column layout =====
         const int et = threadIdx.x - 64;
         uint32_t ridx = 0;
         for (long long item = blockIdx.x; item < total; item += gridDim.x) {
-            const XtItem it = xt_item(item, n_tiles, tiles, track_start, groups);
+            const XtItem it = xt_item<F4>(item, n_tiles, tiles, track_start, groups);
             if (it.need <= 0) continue;
             for (int c = 0; c < it.nchunks; ++c, ++ridx) {
                 const uint32_t rb = ridx & 1;
                 if (ridx >= 2) mbar_wait(&r_empty[rb], ((ridx >> 1) - 1) & 1);
                 const int j0 = c * it.jc, j1 = min(it.kmax, j0 + it.jc);
-                const int nrows = XT_NOFF + (j1 - j0);
-                uint4 *dst = reinterpret_cast<uint4 *>(r_s + rb * XT_R_BYTES);
+                const int nrows = G::NOFF + (j1 - j0);
+                uint4 *dst = reinterpret_cast<uint4 *>(r_s + rb * G::R_BYTES);
                 const uint64_t *src = words + it.tbeg;
                 const int g0 = it.tile_start + j0;
                 for (int w = et; w < nrows; w += 128) {
@@ -242,9 +328,8 @@ match_tc_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ 
                     const bool valid = g < it.n_r;
                     const uint64_t x = valid ? src[g] : 0ull;
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc)
-                        dst[cc * XT_NR + w] = valid ? xt_expand16((uint32_t)(x >> (16 * cc)) & 0xFFFFu)
-                                                    : make_uint4(0u, 0u, 0u, 0u);
+                    for (int cc = 0; cc < G::CPW; ++cc)
+                        dst[cc * G::NR + w] = valid ? xt_chunk<F4>(x, cc) : make_uint4(0u, 0u, 0u, 0u);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tcgen05 reads
                 mbar_arrive(&r_full[rb]);
@@ -256,34 +341,63 @@ match_tc_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ 
         const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t tcount = 0;
         for (long long item = blockIdx.x; item < total; item += gridDim.x) {
-            const XtItem it = xt_item(item, n_tiles, tiles, track_start, groups);
+            const XtItem it = xt_item<F4>(item, n_tiles, tiles, track_start, groups);
             if (it.need <= 0) continue;
             const int q = row_q[it.g * XT_NQ + m];
             const int k_eff = min(row_k[it.g * XT_NQ + m], it.n_r);      // storage.h:34-38
             const int lim = q >= 0 ? (it.n_r - k_eff) - it.tile_start : -1;   // valid columns: n <= lim
             mbar_wait(&acc_full, tcount & 1);
             tc_fence_after();
-            int best_d = 0, best_n = 0;
+            int best_d = 0, best_n = 0;      // best_d = dot + XT_BIAS of the best column so far (0: none)
 #pragma unroll 1
-            for (int c0 = 0; c0 < it.need; c0 += 64) {
-                uint32_t v[64];
-                tmem_ld_x64(t_lane + (uint32_t)c0, v);
+            for (int c0 = 0; c0 < it.need; c0 += G::ECH) {
                 const int li = lim - c0;
-                uint32_t bk = 0;
-                if (__all_sync(0xFFFFFFFFu, li >= 63)) {
+                const bool all = __all_sync(0xFFFFFFFFu, li >= G::ECH - 1);
+                int d, col;
+                if (F4) {
+                    // f32 accumulators holding exact integers: key = dot * 32 + (31 - i) stays below 2^24, exact in f32
+                    uint32_t v[32];
+                    tmem_ld_x32(t_lane + (uint32_t)c0, v);
+                    float bk = -3.0e38f;
+                    if (all) {
 #pragma unroll
-                    for (int i = 0; i < 64; ++i) bk = max(bk, ((uint32_t)((int)v[i] + XT_BIAS) << 6) | (uint32_t)(63 - i));
-                } else {
+                        for (int i = 0; i < 32; ++i) bk = fmaxf(bk, fmaf(__uint_as_float(v[i]), 32.0f, float(31 - i)));
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < 64; ++i) {
-                        const uint32_t key = ((uint32_t)((int)v[i] + XT_BIAS) << 6) | (uint32_t)(63 - i);
-                        bk = max(bk, i <= li ? key : 0u);
+                        for (int i = 0; i < 32; ++i) {
+                            const float key = fmaf(__uint_as_float(v[i]), 32.0f, float(31 - i));
+                            bk = fmaxf(bk, i <= li ? key : -3.0e38f);
+                        }
                     }
+                    if (bk > -1.0e38f) {
+                        const int ki = __float2int_rn(bk);
+                        d = (ki >> 5) + XT_BIAS;
+                        col = 31 - (ki & 31);
+                    } else {
+                        d = 0;
+                        col = 0;
+                    }
+                } else {
+                    uint32_t v[64];
+                    tmem_ld_x64(t_lane + (uint32_t)c0, v);
+                    uint32_t bk = 0;
+                    if (all) {
+#pragma unroll
+                        for (int i = 0; i < 64; ++i)
+                            bk = max(bk, ((uint32_t)((int)v[i] + XT_BIAS) << 6) | (uint32_t)(63 - i));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 64; ++i) {
+                            const uint32_t key = ((uint32_t)((int)v[i] + XT_BIAS) << 6) | (uint32_t)(63 - i);
+                            bk = max(bk, i <= li ? key : 0u);
+                        }
+                    }
+                    d = int(bk >> 6);
+                    col = 63 - int(bk & 63u);
                 }
-                const int d = int(bk >> 6);
                 if (d > best_d) {          // strict: an equal distance at a higher offset never replaces
                     best_d = d;
-                    best_n = c0 + 63 - int(bk & 63u);
+                    best_n = c0 + col;
                 }
             }
             tc_fence_before();
@@ -306,27 +420,40 @@ match_tc_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ 
     }
 }
 
-int match_tc_run(hpfw_ctx *ctx, const hpfw_db *db, const uint64_t *d_qwords, const int64_t *d_qstart,
-                 const XtGroup *d_groups, const int32_t *d_row_q, const int32_t *d_row_k, int n_groups, int kpad_max,
-                 uint8_t *d_qexp, unsigned long long *d_best, cudaStream_t stream) {
-    if (n_groups <= 0 || db->n_tiles_tc <= 0) return HPFW_OK;
+template <int F4>
+static int match_tc_launch(hpfw_ctx *ctx, const hpfw_db *db, const uint64_t *d_qwords, const int64_t *d_qstart,
+                           const XtGroup *d_groups, const int32_t *d_row_q, const int32_t *d_row_k, int n_groups,
+                           int kpad_max, uint8_t *d_qexp, unsigned long long *d_best, cudaStream_t stream) {
+    using G = Xt<F4>;
+    const MatchTile *tiles = F4 ? db->d_tiles_f4 : db->d_tiles_tc;
+    const int n_tiles = F4 ? db->n_tiles_f4 : db->n_tiles_tc;
+    if (n_groups <= 0 || n_tiles <= 0) return HPFW_OK;
     {
         KernelScope ks(ctx, HPFW_K_OTHER, stream);
-        xt_expand_queries_kernel<<<dim3(kpad_max, n_groups), XT_NQ, 0, stream>>>(d_qwords, d_qstart, d_groups, d_row_q,
-                                                                                 d_row_k, d_qexp);
+        xt_expand_queries_kernel<F4><<<dim3(kpad_max, n_groups), XT_NQ, 0, stream>>>(d_qwords, d_qstart, d_groups, d_row_q,
+                                                                                     d_row_k, d_qexp);
         HPFW_CUDA_TRY(cudaGetLastError());
     }
-    const size_t smem = 2 * (size_t)XT_R_BYTES + (size_t)XT_STAGES * XT_STAGE_BYTES + 128;
+    const size_t smem = 2 * (size_t)G::R_BYTES + (size_t)XT_STAGES * G::STAGE_BYTES + 128;
     if (smem > size_t(ctx->max_smem_optin))
         HPFW_FAIL(HPFW_ERR_LIMIT, "match_tc: needs %zu B shared memory (> %d)", smem, ctx->max_smem_optin);
-    HPFW_CUDA_TRY(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    const long long total = (long long)n_groups * db->n_tiles_tc;
+    HPFW_CUDA_TRY(cudaFuncSetAttribute(match_tc_kernel<F4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const long long total = (long long)n_groups * n_tiles;
     const int grid = int(std::min<long long>(total, ctx->sm_count));
     KernelScope ks(ctx, HPFW_K_MATCH_TC, stream);
-    match_tc_kernel<<<grid, XT_THREADS, smem, stream>>>(db->d_words, db->d_track_start, db->d_tiles_tc, db->n_tiles_tc,
-                                                        d_groups, n_groups, d_row_q, d_row_k, d_qexp, db->n_tracks, d_best);
+    match_tc_kernel<F4><<<grid, XT_THREADS, smem, stream>>>(db->d_words, db->d_track_start, tiles, n_tiles, d_groups, n_groups,
+                                                            d_row_q, d_row_k, d_qexp, db->n_tracks, d_best);
     HPFW_CUDA_TRY(cudaGetLastError());
     return HPFW_OK;
+}
+
+int match_tc_run(hpfw_ctx *ctx, const hpfw_db *db, int f4, const uint64_t *d_qwords, const int64_t *d_qstart,
+                 const XtGroup *d_groups, const int32_t *d_row_q, const int32_t *d_row_k, int n_groups, int kpad_max,
+                 uint8_t *d_qexp, unsigned long long *d_best, cudaStream_t stream) {
+    return f4 ? match_tc_launch<1>(ctx, db, d_qwords, d_qstart, d_groups, d_row_q, d_row_k, n_groups, kpad_max, d_qexp,
+                                   d_best, stream)
+              : match_tc_launch<0>(ctx, db, d_qwords, d_qstart, d_groups, d_row_q, d_row_k, n_groups, kpad_max, d_qexp,
+                                   d_best, stream);
 }
 
 }  // namespace hpfw_b200

@@ -290,7 +290,7 @@ static int db_alloc_common(hpfw_ctx *ctx, const int64_t *offsets, int n_tracks, 
     if (track_base < 0 || track_base + n_tracks > HPFW_MAX_TRACKS)
         HPFW_FAIL(HPFW_ERR_LIMIT, "hpfw_db_build: track index %lld exceeds the %d-bit key field",
                   (long long)(track_base + n_tracks), HPFW_KEY_TRACK_BITS);
-    std::vector<MatchTile> tiles, tiles_tc;
+    std::vector<MatchTile> tiles, tiles_tc, tiles_f4;
     for (int r = 0; r < n_tracks; ++r) {
         const int64_t n = offsets[r + 1] - offsets[r];
         if (n < 0) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_build: offsets not monotone at track %d", r);
@@ -301,6 +301,8 @@ static int db_alloc_common(hpfw_ctx *ctx, const int64_t *offsets, int n_tracks, 
         for (int t = 0; t < nt; ++t) tiles.push_back({r, t * MT_TILE});
         const int nt_tc = std::max<int64_t>(1, (n + XT_NOFF - 1) / XT_NOFF);
         for (int t = 0; t < nt_tc; ++t) tiles_tc.push_back({r, t * XT_NOFF});
+        const int nt_f4 = std::max<int64_t>(1, (n + XT_NOFF_F4 - 1) / XT_NOFF_F4);
+        for (int t = 0; t < nt_f4; ++t) tiles_f4.push_back({r, t * XT_NOFF_F4});
     }
     hpfw_db *db = new hpfw_db();
     db->ctx = ctx;
@@ -311,10 +313,12 @@ static int db_alloc_common(hpfw_ctx *ctx, const int64_t *offsets, int n_tracks, 
     for (int r = 0; r <= n_tracks; ++r) db->offsets[r] = (n_tracks ? offsets[r] - offsets[0] : 0);
     db->n_tiles = int(tiles.size());
     db->n_tiles_tc = int(tiles_tc.size());
+    db->n_tiles_f4 = int(tiles_f4.size());
     cudaError_t e = cudaMalloc(&db->d_words, sizeof(uint64_t) * size_t(db->total_words + 16));
     if (e == cudaSuccess) e = cudaMalloc(&db->d_track_start, sizeof(int64_t) * (size_t(n_tracks) + 1));
     if (e == cudaSuccess) e = cudaMalloc(&db->d_tiles, sizeof(MatchTile) * std::max<size_t>(1, tiles.size()));
     if (e == cudaSuccess) e = cudaMalloc(&db->d_tiles_tc, sizeof(MatchTile) * std::max<size_t>(1, tiles_tc.size()));
+    if (e == cudaSuccess) e = cudaMalloc(&db->d_tiles_f4, sizeof(MatchTile) * std::max<size_t>(1, tiles_f4.size()));
     if (e == cudaSuccess)
         e = cudaMemcpy(db->d_track_start, db->offsets.data(), sizeof(int64_t) * (size_t(n_tracks) + 1),
                        cudaMemcpyHostToDevice);
@@ -322,6 +326,8 @@ static int db_alloc_common(hpfw_ctx *ctx, const int64_t *offsets, int n_tracks, 
         e = cudaMemcpy(db->d_tiles, tiles.data(), sizeof(MatchTile) * tiles.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess && !tiles_tc.empty())
         e = cudaMemcpy(db->d_tiles_tc, tiles_tc.data(), sizeof(MatchTile) * tiles_tc.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !tiles_f4.empty())
+        e = cudaMemcpy(db->d_tiles_f4, tiles_f4.data(), sizeof(MatchTile) * tiles_f4.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         hpfw_db_destroy(db);
         HPFW_FAIL(HPFW_ERR_CUDA, "hpfw_db_build: %s", cudaGetErrorString(e));
@@ -381,6 +387,7 @@ void hpfw_db_destroy(hpfw_db *db) {
     if (db->d_track_start) cudaFree(db->d_track_start);
     if (db->d_tiles) cudaFree(db->d_tiles);
     if (db->d_tiles_tc) cudaFree(db->d_tiles_tc);
+    if (db->d_tiles_f4) cudaFree(db->d_tiles_f4);
     delete db;
 }
 
@@ -440,11 +447,12 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
 
     // queries per chunk: bound the best[] scratch to ~1 GiB (and the tensor-core matcher's expanded queries to ~2 GiB)
     const int impl = ctx->match_impl;
+    const int f4 = impl == 3 || (impl == 2 && ctx->match_tc_f4);   // operand encoding of the tensor-core kernel
     const size_t row_bytes = sizeof(uint64_t) * std::max<size_t>(1, size_t(R));
     int qchunk = int(std::min<size_t>(size_t(n_queries), std::max<size_t>(1, (size_t(1) << 30) / row_bytes)));
     qchunk = std::min(qchunk, 1 << 20);  // keeps gridDim.y within 65535
     if (impl != 0) {
-        const size_t per_query = size_t(xt_kpad(kmax)) * 64;
+        const size_t per_query = size_t(xt_kpad(kmax, f4)) * xt_word_bytes(f4);
         const size_t fit = std::max<size_t>(XT_NQ, ((size_t(2) << 30) / per_query) / XT_NQ * XT_NQ);
         qchunk = int(std::min<size_t>(size_t(qchunk), fit));
     }
@@ -467,7 +475,7 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
         // Which queries go to the tensor cores: whole groups of 128 always; a last partial group only when it is full enough
         // to beat the integer-pipe kernel (a group costs the same with 1 or 128 queries), or when impl 1 forces it.
         const int rem = nq % XT_NQ;
-        const int n_tc = impl == 0 ? 0 : (impl == 1 || rem >= XT_MIN_FILL) ? nq : nq - rem;
+        const int n_tc = impl == 0 ? 0 : (impl != 2 || rem >= xt_min_fill(f4)) ? nq : nq - rem;
         cm[c].q0 = q0;
         cm[c].nq = nq;
         cm[c].ng = (n_tc + XT_NQ - 1) / XT_NQ;
@@ -486,8 +494,8 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
                 grp.kmax = std::max(grp.kmax, k);
                 grp.kmin = std::min(grp.kmin, k);
             }
-            cm[c].kpad_max = std::max(cm[c].kpad_max, xt_kpad(grp.kmax));
-            cm[c].exp_bytes += size_t(xt_kpad(grp.kmax)) * XT_NQ * 64;
+            cm[c].kpad_max = std::max(cm[c].kpad_max, xt_kpad(grp.kmax, f4));
+            cm[c].exp_bytes += size_t(xt_kpad(grp.kmax, f4)) * XT_NQ * xt_word_bytes(f4);
             const int32_t *raw = reinterpret_cast<const int32_t *>(&grp);
             tables.insert(tables.end(), raw, raw + sizeof(XtGroup) / sizeof(int32_t));
         }
@@ -549,7 +557,7 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
         unsigned long long *best = ctx->best.as<unsigned long long>();
         HPFW_CUDA_TRY(cudaMemsetAsync(best, 0xFF, row_bytes * size_t(cm[c].nq), stream));
         if (cm[c].ng > 0)
-            HPFW_TRY(match_tc_run(ctx, db, d_q, d_qstart + cm[c].q0, reinterpret_cast<const XtGroup *>(meta + cm[c].grp_off),
+            HPFW_TRY(match_tc_run(ctx, db, f4, d_q, d_qstart + cm[c].q0, reinterpret_cast<const XtGroup *>(meta + cm[c].grp_off),
                                   reinterpret_cast<const int32_t *>(meta + cm[c].rowq_off),
                                   reinterpret_cast<const int32_t *>(meta + cm[c].rowk_off), cm[c].ng, cm[c].kpad_max,
                                   ctx->qexp.as<uint8_t>(), best, stream));
@@ -575,7 +583,7 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
 }
 
 int hpfw_set_match_impl(hpfw_ctx *ctx, int impl) {
-    if (!ctx || impl < 0 || impl > 2) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_set_match_impl: impl must be 0, 1 or 2");
+    if (!ctx || impl < 0 || impl > 3) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_set_match_impl: impl must be 0, 1, 2 or 3");
     ctx->match_impl = impl;
     return HPFW_OK;
 }

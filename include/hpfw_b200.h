@@ -120,10 +120,14 @@ int hpfw_db_find_topk(hpfw_db *db, const uint64_t *qwords, const int64_t *qoffse
 /* Device path: d_qwords on the device, qoffsets on the host (metadata); d_keys_out[n_queries * topk] packed keys. */
 int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *qoffsets, int n_queries, int topk,
                          uint64_t *d_keys_out, void *stream);
-/* which kernel runs the cross-correlation: 0 = XOR + POPC on the integer pipes (matcher.cu); 1 = exact int8 GEMM on the
- * tensor cores, tcgen05.mma.kind::i8 over +1/-1 bytes with s32 accumulation (match_tc.cu); 2 (default) = tensor cores for
- * groups of 128 queries that are at least 24 full, integer pipes for the remainder. All three give identical results.
- * The environment variable HPFW_MATCH_IMPL sets the initial value of a new context. */
+/* which kernel runs the cross-correlation:
+ *   0 = XOR + POPC on the integer pipes (matcher.cu);
+ *   1 = exact GEMM on the tensor cores over +1/-1 signed bytes, tcgen05.mma.kind::i8 with s32 accumulation (match_tc.cu);
+ *   3 = the same over +1.0/-1.0 e2m1 nibbles, tcgen05.mma.kind::mxf4.block_scale with unit scales and f32 accumulation
+ *       (sums of +-1 stay far below 2^24: exact), twice the word rate of 1;
+ *   2 (default) = tensor cores (fp4 operands; int8 if the environment variable HPFW_MATCH_TC_F4=0 was set when the context
+ *       was created) for groups of 128 queries that are at least 12 (int8: 24) full, integer pipes for the remainder.
+ * All four give bit-identical results. The environment variable HPFW_MATCH_IMPL sets the initial value of a new context. */
 int hpfw_set_match_impl(hpfw_ctx *ctx, int impl);
 /* Multi-GPU merge after an all-gather: d_keys_in[n_ranks][n_queries][topk] -> d_keys_out[n_queries][topk]. */
 int hpfw_topk_merge_device(hpfw_ctx *ctx, const uint64_t *d_keys_in, int n_ranks, int n_queries, int topk,

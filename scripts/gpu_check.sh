@@ -14,6 +14,8 @@ if [ "${NCU:-1}" = "1" ]; then
 CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --tracks 2000"
 echo "== ncu launch list"; timeout 600 $CMD > $OUT/ncu_plain.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv $CMD > $OUT/ncu_launches.log 2>&1; echo "ncu list exit $?"
-echo "== ncu full (match kernel)"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:match_kernel -s 3 -c 1 -o $OUT/match_full $CMD > $OUT/ncu_full.log 2>&1; echo "ncu full exit $?"
+CMD_TC="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --tracks 2000 --no-extraction --no-popc-leg"
+echo "== ncu full (tensor-core match kernel)"; timeout 600 $CMD_TC > $OUT/ncu_plain_tc.log 2>&1 && \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:match_tc_kernel -s 3 -c 1 -o $OUT/match_tc_full $CMD_TC > $OUT/ncu_full.log 2>&1; echo "ncu full exit $?"
 fi
 ls -la $OUT

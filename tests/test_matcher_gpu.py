@@ -10,10 +10,11 @@ from hpfw_b200.api import SIZE_MAX
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[0, 1, 2], ids=["popc", "tc", "auto"], autouse=True)
+@pytest.fixture(params=[0, 1, 2, 3], ids=["popc", "tc_i8", "auto", "tc_fp4"], autouse=True)
 def match_impl(ctx, request):
-    """Every test of this file runs three times: integer-pipe kernel (matcher.cu), tensor-core kernel for every query
-    (match_tc.cu), and the default routing (tensor cores for well-filled groups of 128, integer pipes for the rest)."""
+    """Every test of this file runs four times: integer-pipe kernel (matcher.cu), tensor-core kernel for every query
+    (match_tc.cu) with int8 and with fp4 operands, and the default routing (tensor cores for well-filled groups of 128,
+    integer pipes for the rest)."""
     from hpfw_b200._lib import check
     check(ctx._lib.hpfw_set_match_impl(ctx.handle, request.param))
     yield request.param
@@ -172,6 +173,12 @@ def test_extreme_distances(ctx):
         a = int(offs[1]) + 17
         queries.append(words[a:a + k].copy())                       # exact copy of track 1 at offset 17
         queries.append(~words[a:a + k])                             # its complement
+    # a long exact run followed (or preceded) by unrelated words: large partial sums, then many small increments
+    half = words[int(offs[1]) + 100:int(offs[1]) + 100 + 2048]
+    noise = rng.integers(0, 1 << 64, size=2048, dtype=np.uint64)
+    queries.append(np.concatenate([half, noise]))
+    queries.append(np.concatenate([noise, words[int(offs[1]) + 2148:int(offs[1]) + 4196]]))
+    queries.append(np.concatenate([~half, noise]))
     queries.append(np.zeros(300, dtype=np.uint64))
     queries.append(np.full(300, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64))
     queries.append(np.zeros(0, dtype=np.uint64))                    # empty query: distance 0 at offset 0 of track 0
