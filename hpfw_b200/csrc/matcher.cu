@@ -472,13 +472,43 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
         std::vector<int> order(nq);
         std::iota(order.begin(), order.end(), 0);
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return klen(a) < klen(b); });
-        // Which queries go to the tensor cores: whole groups of 128 always; a last partial group only when it is full enough
-        // to beat the integer-pipe kernel (a group costs the same with 1 or 128 queries), or when impl 1 forces it.
-        const int rem = nq % XT_NQ;
-        const int n_tc = impl == 0 ? 0 : (impl != 2 || rem >= xt_min_fill(f4)) ? nq : nq - rem;
+        // Which queries go to the tensor cores. A tensor-core group costs ~(kmax + fixed) per tile whether it holds 1 or
+        // 128 queries; a query on the integer-pipe kernel costs ~k / ratio. With the queries sorted by length the cheapest
+        // split is a one-dimensional dynamic programme: query i either runs on the integer pipes, or closes a group made of
+        // the (up to) 128 queries before it. impl 1 / 3 force the tensor cores, impl 0 the integer pipes.
+        std::vector<std::vector<int>> tc_groups;
+        std::vector<int> popc_list;
+        if (impl == 0) {
+            popc_list = order;
+        } else if (impl != 2) {
+            for (int i = 0; i < nq; i += XT_NQ)
+                tc_groups.emplace_back(order.begin() + i, order.begin() + std::min(nq, i + XT_NQ));
+        } else {
+            const double ratio = f4 ? 15.0 : 7.0, fixed = 24.0;
+            std::vector<double> dp(size_t(nq) + 1, 0.0);
+            std::vector<char> closes(size_t(nq) + 1, 0);
+            for (int i = 1; i <= nq; ++i) {
+                const double k = double(std::max<int64_t>(klen(order[i - 1]), 1));
+                const double on_pipes = dp[i - 1] + k / ratio + 0.5;
+                const double on_tc = dp[std::max(0, i - XT_NQ)] + k + fixed;
+                closes[i] = on_tc < on_pipes;
+                dp[i] = std::min(on_tc, on_pipes);
+            }
+            for (int i = nq; i > 0;) {
+                if (closes[i]) {
+                    const int lo = std::max(0, i - XT_NQ);
+                    tc_groups.emplace_back(order.begin() + lo, order.begin() + i);
+                    i = lo;
+                } else {
+                    popc_list.push_back(order[--i]);
+                }
+            }
+            std::reverse(tc_groups.begin(), tc_groups.end());
+            std::reverse(popc_list.begin(), popc_list.end());
+        }
         cm[c].q0 = q0;
         cm[c].nq = nq;
-        cm[c].ng = (n_tc + XT_NQ - 1) / XT_NQ;
+        cm[c].ng = int(tc_groups.size());
         cm[c].kpad_max = 0;
         cm[c].exp_bytes = 0;
         if (tables.size() & 1) tables.push_back(0);          // XtGroup holds an int64
@@ -486,8 +516,8 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
         std::vector<int32_t> rq(size_t(cm[c].ng) * XT_NQ, -1), rk(size_t(cm[c].ng) * XT_NQ, 0);
         for (int g = 0; g < cm[c].ng; ++g) {
             XtGroup grp{int64_t(cm[c].exp_bytes), 0, INT32_MAX};
-            for (int m = 0; m < XT_NQ && g * XT_NQ + m < n_tc; ++m) {
-                const int qi = order[g * XT_NQ + m];
+            for (size_t m = 0; m < tc_groups[g].size(); ++m) {
+                const int qi = tc_groups[g][m];
                 const int32_t k = int32_t(klen(qi));
                 rq[size_t(g) * XT_NQ + m] = qi;
                 rk[size_t(g) * XT_NQ + m] = k;
@@ -506,11 +536,12 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
         tables.insert(tables.end(), rk.begin(), rk.end());
 
         std::vector<int32_t> idx, ks;
-        for (int i = n_tc; i < nq;) {
-            const int64_t k = klen(order[i]);
+        const int np = int(popc_list.size());
+        for (int i = 0; i < np;) {
+            const int64_t k = klen(popc_list[i]);
             int32_t blk[MT_QB];
             int got = 0;
-            while (got < MT_QB && i < nq && klen(order[i]) == k) blk[got++] = order[i++];
+            while (got < MT_QB && i < np && klen(popc_list[i]) == k) blk[got++] = popc_list[i++];
             for (int f = got; f < MT_QB; ++f) blk[f] = blk[got - 1];  // pad a short block by repeating a query
             for (int f = 0; f < MT_QB; ++f) idx.push_back(blk[f]);
             ks.push_back(int32_t(k));

@@ -17,7 +17,6 @@ constexpr int XT_NOFF = 512;    // int8 kernel: alignment offsets per tile = 2 x
 constexpr int XT_NOFF_F4 = 480; // fp4 kernel: 2 x N(240); 32 TMEM columns are left for the block scale factors
 constexpr int XT_JS = 4;        // int8 kernel: query words per TMA stage (64 bytes per word and query)
 constexpr int XT_JS_F4 = 8;     // fp4 kernel (32 bytes per word and query)
-inline int xt_min_fill(int f4) { return f4 ? 12 : 24; }   // a partial group this full still beats the integer-pipe kernel
 
 // one group of up to XT_NQ queries of similar length: its expanded (s8) words start at exp_off bytes into the scratch
 struct XtGroup {

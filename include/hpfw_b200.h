@@ -125,8 +125,11 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
  *   1 = exact GEMM on the tensor cores over +1/-1 signed bytes, tcgen05.mma.kind::i8 with s32 accumulation (match_tc.cu);
  *   3 = the same over +1.0/-1.0 e2m1 nibbles, tcgen05.mma.kind::mxf4.block_scale with unit scales and f32 accumulation
  *       (sums of +-1 stay far below 2^24: exact), twice the word rate of 1;
- *   2 (default) = tensor cores (fp4 operands; int8 if the environment variable HPFW_MATCH_TC_F4=0 was set when the context
- *       was created) for groups of 128 queries that are at least 12 (int8: 24) full, integer pipes for the remainder.
+ *   2 (default) = per batch the cheapest mix: the queries, sorted by length, are split by a small dynamic programme into
+ *       tensor-core groups of up to 128 (fp4 operands; int8 if the environment variable HPFW_MATCH_TC_F4=0 was set when the
+ *       context was created; a group costs its longest query whether it holds 1 or 128) and queries that stay on the
+ *       integer pipes (about 1/15 of a group each): a batch of >= ~16 equal-length queries goes to the tensor cores, a
+ *       single find() stays on XOR + POPC.
  * All four give bit-identical results. The environment variable HPFW_MATCH_IMPL sets the initial value of a new context. */
 int hpfw_set_match_impl(hpfw_ctx *ctx, int impl);
 /* Multi-GPU merge after an all-gather: d_keys_in[n_ranks][n_queries][topk] -> d_keys_out[n_queries][topk]. */

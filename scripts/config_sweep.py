@@ -102,7 +102,7 @@ def main():
     # cfg2: 1k tracks x 1000 queries of 6 s
     run("cfg2: 1k-track DB, 1000 x 6 s queries", 1000, 14411, [385] * 1000, 10, ctx, dev, 40)
     # cfg4: 100k tracks, query length 2 .. 20 s
-    qlens = [63, 143, 385, 707, 1111, 1514] * 2
+    qlens = [63, 143, 385, 707, 1111, 1514] * int(os.environ.get("SWEEP_PER_LENGTH", "128"))
     run("cfg4: 100k-track DB, 2-20 s queries", 100000, 14411, qlens, 10, ctx, dev, 24)
     print(f"# total {time.time() - t0:.1f} s", file=sys.stderr)
     ctx.close()
