@@ -49,6 +49,8 @@ POPC32_PER_CLK_SM = 16      # CUDA programming guide arithmetic-throughput table
 I8_OPS_PER_CLK_SM = 16384   # tcgen05.mma kind::i8, M=128 N=256 K=32 in 128 clk (B300_MICROARCH.md pacing law): 8192 MAC/clk/SM
 F4_OPS_PER_CLK_SM = 32768   # tcgen05.mma kind::mxf4, M=128 N=256 K=64 in 128 clk: 16384 MAC/clk/SM (nominal 9 PFLOP/s fp4 dense)
 OPS_PER_WORDOP = 128        # tensor-core matcher: one 64-bit word-op = 64 s8 multiply-adds
+NCU_TC_TRAFFIC_RATIO = 243.07 / 233.8   # measured DRAM bytes / algorithmic bytes of match_tc_kernel<1> (profiles/r03d_*)
+NCU_CQT_TRAFFIC_PER_TRACK = 144.3e6     # measured DRAM bytes of the six CQT kernels on one 3-min track (profiles/r01y_*)
 
 
 def host_cores() -> int:
@@ -355,7 +357,11 @@ def run_extraction(args, ctx, rank, world, dev, max_over_ranks, barrier):
                 "h2d_bytes_per_track": 4 * n, "d2h_bytes_per_track": 8 * words,
                 "note": "pinned host audio, H2D on a copy stream double-buffered against compute, hashprint D2H per track"},
         "roofline": {"bound": "hbm", "kernel": "CQT (7 kernels per track, cqt.cu)", "achieved": cqt_bytes / (cq_per_track * 1e-3) / 1e9,
-                     "peak": hbm, "unit": "GB/s", "frac": cqt_bytes / (cq_per_track * 1e-3) / 1e9 / hbm, "traffic": None,
+                     "peak": hbm, "unit": "GB/s", "frac": cqt_bytes / (cq_per_track * 1e-3) / 1e9 / hbm,
+                     "traffic": NCU_CQT_TRAFFIC_PER_TRACK,
+                     "traffic_note": "per track: dram__bytes_read+write summed over the six CQT kernels of one 3-min track in the "
+                                     "ncu --set full capture profiles/r01y_cqt_kernels_ncu_full.md (two FFT passes + three "
+                                     "chirp-z passes re-read their predecessor's output)",
                      "ms_per_track": cq_per_track, "kernel_ms_sum_per_track_overlapped": cq_kernel_sum_per_track,
                      "peak_how": src,
                      "algorithmic_bytes_per_track": cqt_bytes},
@@ -700,8 +706,12 @@ def run_cuda(args):
             tc_achieved = tc_ops_per_launch / (tc_avg_ms * 1e-3) / 1e12
             kq = (QUERY_WORDS + 7) // 8 * 8 if f4 else (QUERY_WORDS + 3) // 4 * 4
             lib_x = 4 if f4 else 2
+            tc_alg_bytes = 8.0 * (hi - lo) * TRACK_WORDS + 64.0 * nq * kq
             roof = {"bound": "tensor", "achieved": tc_achieved, "peak": tc_peak, "unit": "TOP/s", "frac": tc_achieved / tc_peak,
-                    "traffic": None,
+                    "traffic": tc_alg_bytes * NCU_TC_TRAFFIC_RATIO,
+                    "traffic_note": "dram__bytes_read+write of one launch in the ncu --set full capture at 2000 tracks x 128 "
+                                    "queries (profiles/r03d_match_tc_fp4_ncu_full.md: 243.1 MB against 233.8 MB algorithmic), "
+                                    "scaled to this launch's algorithmic bytes; 0.14 % of HBM bandwidth",
                     "kernel": ("match_tc_kernel<1> (tcgen05.mma kind::mxf4.block_scale, M=128 queries x N=2x240 offsets, "
                                "f32 in TMEM)" if f4 else
                                "match_tc_kernel<0> (tcgen05.mma kind::i8, M=128 queries x N=2x256 offsets, s32 in TMEM)"),
