@@ -20,7 +20,7 @@
 //   * query operand: expanded once per call by xt_expand_queries_kernel to [word j][chunk c][query m][16 B] (bytes of the
 //     words beyond a shorter query's end are 0), streamed by 1-D bulk TMA copies through a 4-stage mbarrier ring
 //     (4 words = 32 KB per stage; the 3 MB of a group stay in L2 for all 148 CTAs).
-//   * warp roles: 0 = TMA producer, 1 = MMA issuer, 2-5 = reference expanders (double-buffered R), 6-9 = epilogue.
+//   * warp roles: 0 = TMA producer, 1 = MMA issuer, 2-5 = reference expanders (double-buffered R), 6-13 = epilogue.
 //   * epilogue: tcgen05.ld 64 columns at a time; per query (lane) the maximum of (dot << 6 | 63 - column) inside the valid
 //     offset range, chunks visited in ascending order with a strict '>' = the lowest offset among equal distances; one
 //     64-bit atomicMin per (query, tile) into best[query][track], the array match_kernel and topk_kernel share.
@@ -55,7 +55,7 @@ struct Xt {
     static_assert(JCMAX % JS == 0, "chunk boundaries must be stage boundaries");
 };
 constexpr int XT_STAGES = 4;                                   // query ring depth
-constexpr int XT_THREADS = 320;
+constexpr int XT_THREADS = 448;                                // TMA, MMA, 4 expander and 8 epilogue warps
 constexpr int XT_BIAS = (1 << 18) + 1;                         // dot + bias >= 1 for every valid offset
 constexpr uint32_t XT_SF_COL = 480;                            // F4: TMEM columns 480..511 = scale factors, all 1.0
 
@@ -225,7 +225,7 @@ match_tc_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ 
             mbar_init(&r_empty[b], 1);
         }
         mbar_init(&acc_full, 1);
-        mbar_init(&acc_empty, 128);
+        mbar_init(&acc_empty, 256);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
@@ -234,7 +234,7 @@ match_tc_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ 
     const uint32_t tmem_base = tmem_base_s;
     if (F4) {
         // every block scale = 2^0: UE8M0 byte 0x7F in all four bytes of TMEM columns 480..511, whatever the layout
-        if (warp >= 6) tmem_fill_x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + XT_SF_COL, 0x7F7F7F7Fu);
+        if (warp >= 6 && warp < 10) tmem_fill_x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + XT_SF_COL, 0x7F7F7F7Fu);
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
@@ -336,7 +336,11 @@ match_tc_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ 
             }
         }
     } else {
-        // ===== epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 = queries; columns = offsets of the tile =====
+        // ===== epilogue: 8 warps. Warp w reads TMEM lanes 32 (w % 4) .. +31 = queries; warps 6-9 take the columns (offsets)
+        // [0, 256) of the tile, warps 10-13 the columns from 256 on, 64 columns per tcgen05.ld. Each thread keeps the best
+        // (dot, column) of its columns; the two partial minima of a query meet in the 64-bit atomicMin, whose key carries the
+        // offset, so the lowest offset wins among equal distances. =====
+        const int half = (warp - 6) >> 2;
         const int m = (warp & 3) * 32 + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t tcount = 0;
@@ -345,43 +349,49 @@ match_tc_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ 
             if (it.need <= 0) continue;
             const int q = row_q[it.g * XT_NQ + m];
             const int k_eff = min(row_k[it.g * XT_NQ + m], it.n_r);      // storage.h:34-38
-            const int lim = q >= 0 ? (it.n_r - k_eff) - it.tile_start : -1;   // valid columns: n <= lim
+            // valid columns: n <= lim. Clamped to the tile: the last 64-column load of the fp4 kernel also covers the scale
+            // factor columns 480..511, which must never be taken for distances.
+            const int lim = q >= 0 ? min((it.n_r - k_eff) - it.tile_start, it.need - 1) : -1;
+            const int c_begin = half * 256, c_end = half ? it.need : min(it.need, 256);
             mbar_wait(&acc_full, tcount & 1);
             tc_fence_after();
             int best_d = 0, best_n = 0;      // best_d = dot + XT_BIAS of the best column so far (0: none)
 #pragma unroll 1
-            for (int c0 = 0; c0 < it.need; c0 += G::ECH) {
-                const int li = lim - c0;
-                const bool all = __all_sync(0xFFFFFFFFu, li >= G::ECH - 1);
-                int d, col;
+            for (int c0 = c_begin; c0 < c_end; c0 += 64) {
+                uint32_t v[64];
+                tmem_ld_x64(t_lane + (uint32_t)c0, v);
                 if (F4) {
-                    // f32 accumulators holding exact integers: key = dot * 32 + (31 - i) stays below 2^24, exact in f32
-                    uint32_t v[32];
-                    tmem_ld_x32(t_lane + (uint32_t)c0, v);
-                    float bk = -3.0e38f;
-                    if (all) {
+                    // f32 accumulators holding exact integers: key = dot * 32 + (31 - i) stays below 2^24, exact in f32.
+                    // Both warp votes come before any lane-dependent branch.
+                    const int li = lim - c0;
+                    const bool all0 = __all_sync(0xFFFFFFFFu, li >= 31), all1 = __all_sync(0xFFFFFFFFu, li >= 63);
+                    float bk[2] = {-3.0e38f, -3.0e38f};
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) bk = fmaxf(bk, fmaf(__uint_as_float(v[i]), 32.0f, float(31 - i)));
-                    } else {
+                    for (int h = 0; h < 2; ++h) {
+                        if (h ? all1 : all0) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float key = fmaf(__uint_as_float(v[i]), 32.0f, float(31 - i));
-                            bk = fmaxf(bk, i <= li ? key : -3.0e38f);
+                            for (int i = 0; i < 32; ++i)
+                                bk[h] = fmaxf(bk[h], fmaf(__uint_as_float(v[32 * h + i]), 32.0f, float(31 - i)));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const float key = fmaf(__uint_as_float(v[32 * h + i]), 32.0f, float(31 - i));
+                                bk[h] = fmaxf(bk[h], 32 * h + i <= li ? key : -3.0e38f);
+                            }
                         }
                     }
-                    if (bk > -1.0e38f) {
-                        const int ki = __float2int_rn(bk);
-                        d = (ki >> 5) + XT_BIAS;
-                        col = 31 - (ki & 31);
-                    } else {
-                        d = 0;
-                        col = 0;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int ki = __float2int_rn(fmaxf(bk[h], -1.0e9f));
+                        const int d = bk[h] > -1.0e38f ? (ki >> 5) + XT_BIAS : 0;
+                        const bool better = d > best_d;    // strict: an equal distance at a higher offset never replaces
+                        best_n = better ? c0 + 32 * h + 31 - (ki & 31) : best_n;
+                        best_d = better ? d : best_d;
                     }
                 } else {
-                    uint32_t v[64];
-                    tmem_ld_x64(t_lane + (uint32_t)c0, v);
+                    const int li = lim - c0;
                     uint32_t bk = 0;
-                    if (all) {
+                    if (__all_sync(0xFFFFFFFFu, li >= 63)) {
 #pragma unroll
                         for (int i = 0; i < 64; ++i)
                             bk = max(bk, ((uint32_t)((int)v[i] + XT_BIAS) << 6) | (uint32_t)(63 - i));
@@ -392,12 +402,11 @@ match_tc_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ 
                             bk = max(bk, i <= li ? key : 0u);
                         }
                     }
-                    d = int(bk >> 6);
-                    col = 63 - int(bk & 63u);
-                }
-                if (d > best_d) {          // strict: an equal distance at a higher offset never replaces
-                    best_d = d;
-                    best_n = c0 + col;
+                    const int d = int(bk >> 6);
+                    if (d > best_d) {
+                        best_d = d;
+                        best_n = c0 + 63 - int(bk & 63u);
+                    }
                 }
             }
             tc_fence_before();
