@@ -44,6 +44,7 @@ _SIGS = {
     "hpfw_db_find_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Match)]),
     "hpfw_db_match_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "hpfw_set_match_impl": (C.c_int, [C.c_void_p, C.c_int]),
+    "hpfw_match_route": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "hpfw_topk_merge_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "hpfw_keys_decode": (None, [C.c_void_p, C.c_int, C.POINTER(Match)]),
     "hpfw_db_word_ops": (C.c_double, [C.c_void_p, C.c_void_p, C.c_int]),

@@ -280,6 +280,48 @@ __global__ void merge_kernel(const unsigned long long *__restrict__ in, int n_ra
     }
 }
 
+// Which queries go to the tensor cores. A tensor-core group costs ~(kmax + fixed) per tile whether it holds 1 or 128
+// queries; a query on the integer-pipe kernel costs ~k / ratio. With the queries sorted by length the cheapest split is a
+// one-dimensional dynamic programme: query i either runs on the integer pipes, or closes a group made of the (up to) 128
+// queries before it. impl 1 / 3 force the tensor cores, impl 0 the integer pipes. Query indices are relative to qoffsets.
+void route_queries(const int64_t *qoffsets, int nq, int impl, int f4, std::vector<std::vector<int>> &tc_groups,
+                   std::vector<int> &popc_list) {
+    auto klen = [&](int i) { return qoffsets[i + 1] - qoffsets[i]; };
+    std::vector<int> order(nq);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return klen(a) < klen(b); });
+    tc_groups.clear();
+    popc_list.clear();
+    if (impl == 0) {
+        popc_list = order;
+    } else if (impl != 2) {
+        for (int i = 0; i < nq; i += XT_NQ)
+            tc_groups.emplace_back(order.begin() + i, order.begin() + std::min(nq, i + XT_NQ));
+    } else {
+        const double ratio = f4 ? 15.0 : 7.0, fixed = 24.0;
+        std::vector<double> dp(size_t(nq) + 1, 0.0);
+        std::vector<char> closes(size_t(nq) + 1, 0);
+        for (int i = 1; i <= nq; ++i) {
+            const double k = double(std::max<int64_t>(klen(order[i - 1]), 1));
+            const double on_pipes = dp[i - 1] + k / ratio + 0.5;
+            const double on_tc = dp[std::max(0, i - XT_NQ)] + k + fixed;
+            closes[i] = on_tc < on_pipes;
+            dp[i] = std::min(on_tc, on_pipes);
+        }
+        for (int i = nq; i > 0;) {
+            if (closes[i]) {
+                const int lo = std::max(0, i - XT_NQ);
+                tc_groups.emplace_back(order.begin() + lo, order.begin() + i);
+                i = lo;
+            } else {
+                popc_list.push_back(order[--i]);
+            }
+        }
+        std::reverse(tc_groups.begin(), tc_groups.end());
+        std::reverse(popc_list.begin(), popc_list.end());
+    }
+}
+
 }  // namespace hpfw_b200
 
 using namespace hpfw_b200;
@@ -469,43 +511,9 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
     for (int c = 0; c < n_chunks; ++c) {
         const int q0 = c * qchunk, nq = std::min(qchunk, n_queries - q0);
         auto klen = [&](int i) { return qoffsets[q0 + i + 1] - qoffsets[q0 + i]; };
-        std::vector<int> order(nq);
-        std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return klen(a) < klen(b); });
-        // Which queries go to the tensor cores. A tensor-core group costs ~(kmax + fixed) per tile whether it holds 1 or
-        // 128 queries; a query on the integer-pipe kernel costs ~k / ratio. With the queries sorted by length the cheapest
-        // split is a one-dimensional dynamic programme: query i either runs on the integer pipes, or closes a group made of
-        // the (up to) 128 queries before it. impl 1 / 3 force the tensor cores, impl 0 the integer pipes.
         std::vector<std::vector<int>> tc_groups;
         std::vector<int> popc_list;
-        if (impl == 0) {
-            popc_list = order;
-        } else if (impl != 2) {
-            for (int i = 0; i < nq; i += XT_NQ)
-                tc_groups.emplace_back(order.begin() + i, order.begin() + std::min(nq, i + XT_NQ));
-        } else {
-            const double ratio = f4 ? 15.0 : 7.0, fixed = 24.0;
-            std::vector<double> dp(size_t(nq) + 1, 0.0);
-            std::vector<char> closes(size_t(nq) + 1, 0);
-            for (int i = 1; i <= nq; ++i) {
-                const double k = double(std::max<int64_t>(klen(order[i - 1]), 1));
-                const double on_pipes = dp[i - 1] + k / ratio + 0.5;
-                const double on_tc = dp[std::max(0, i - XT_NQ)] + k + fixed;
-                closes[i] = on_tc < on_pipes;
-                dp[i] = std::min(on_tc, on_pipes);
-            }
-            for (int i = nq; i > 0;) {
-                if (closes[i]) {
-                    const int lo = std::max(0, i - XT_NQ);
-                    tc_groups.emplace_back(order.begin() + lo, order.begin() + i);
-                    i = lo;
-                } else {
-                    popc_list.push_back(order[--i]);
-                }
-            }
-            std::reverse(tc_groups.begin(), tc_groups.end());
-            std::reverse(popc_list.begin(), popc_list.end());
-        }
+        route_queries(qoffsets + q0, nq, impl, f4, tc_groups, popc_list);
         cm[c].q0 = q0;
         cm[c].nq = nq;
         cm[c].ng = int(tc_groups.size());
@@ -610,6 +618,18 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
                                                     reinterpret_cast<unsigned long long *>(d_keys_out) + size_t(cm[c].q0) * topk);
         HPFW_CUDA_TRY(cudaGetLastError());
     }
+    return HPFW_OK;
+}
+
+int hpfw_match_route(const int64_t *qoffsets, int n_queries, int impl, int fp4, int32_t *group_out) {
+    if (!qoffsets || !group_out || n_queries < 0 || impl < 0 || impl > 3)
+        HPFW_FAIL(HPFW_ERR_ARG, "hpfw_match_route: bad argument");
+    std::vector<std::vector<int>> groups;
+    std::vector<int> pipes;
+    route_queries(qoffsets, n_queries, impl, impl == 3 || (impl == 2 && fp4), groups, pipes);
+    for (int q : pipes) group_out[q] = -1;
+    for (size_t g = 0; g < groups.size(); ++g)
+        for (int q : groups[g]) group_out[q] = int32_t(g);
     return HPFW_OK;
 }
 

@@ -132,6 +132,9 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
  *       single find() stays on XOR + POPC.
  * All four give bit-identical results. The environment variable HPFW_MATCH_IMPL sets the initial value of a new context. */
 int hpfw_set_match_impl(hpfw_ctx *ctx, int impl);
+/* host-only (needs no device): the routing hpfw_db_match_device would apply to one batch under `impl` (fp4 != 0: fp4 operand
+ * encoding for impl 2). group_out[q] = index of the tensor-core group query q joins, or -1 for the integer-pipe kernel. */
+int hpfw_match_route(const int64_t *qoffsets, int n_queries, int impl, int fp4, int32_t *group_out);
 /* Multi-GPU merge after an all-gather: d_keys_in[n_ranks][n_queries][topk] -> d_keys_out[n_queries][topk]. */
 int hpfw_topk_merge_device(hpfw_ctx *ctx, const uint64_t *d_keys_in, int n_ranks, int n_queries, int topk,
                            uint64_t *d_keys_out, void *stream);

@@ -192,6 +192,22 @@ def test_extreme_distances(ctx):
     assert out["cnt"][0, 0] == 0 and out["track"][0, 0] == 1 and out["offset"][0, 0] == 17
 
 
+def test_planted_at_every_column_range(ctx):
+    """Exact copies planted around every boundary of the tensor-core tiles (480 / 512 offsets per tile, two N halves of
+    240 / 256, 64-column TMEM loads, the fp4 kernel's scale-factor columns 480..511) in a group that is mostly padding."""
+    rng = np.random.default_rng(61)
+    n, k = 2200, 50
+    words = rng.integers(0, 1 << 64, size=n, dtype=np.uint64)
+    offs = np.array([0, n], dtype=np.int64)
+    plant = [0, 5, 63, 64, 223, 224, 239, 240, 255, 256, 300, 447, 448, 470, 479, 480, 511, 512, 600, 959, 960, 1023, 1024,
+             1100, 1439, 1440, 1535, 1536, 2047, 2048, n - k]
+    qw = np.concatenate([words[p:p + k] for p in plant])
+    qo = np.arange(len(plant) + 1, dtype=np.int64) * k
+    out = MemoryStorage(ctx).build_packed(words, offs).find_topk_packed(qw, qo, 1)
+    assert np.array_equal(out["offset"][:, 0], np.array(plant))
+    assert not out["cnt"][:, 0].any()
+
+
 def test_many_queries_mixed_lengths(ctx):
     """300 queries of 7 different lengths against ragged tracks: several groups of 128 with different k inside one group
     (zero-padded query rows), a partial last group, queries longer than some tracks."""
