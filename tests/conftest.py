@@ -19,6 +19,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
 
 
+def pytest_sessionstart(session):
+    """A fresh checkout has no built library (the .so files are git-ignored): build them once, like
+    __graft_entry__.build() does. An existing library is used as it is."""
+    from hpfw_b200 import build as _build
+    if not os.path.exists(_build.LIB):
+        _build.build()
+
+
 def _load_cases(path):
     z = np.load(path)
     cases = {}
