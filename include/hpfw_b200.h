@@ -128,7 +128,7 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
  *   2 (default) = per batch the cheapest mix: the queries, sorted by length, are split by a small dynamic programme into
  *       tensor-core groups of up to 128 (fp4 operands; int8 if the environment variable HPFW_MATCH_TC_F4=0 was set when the
  *       context was created; a group costs its longest query whether it holds 1 or 128) and queries that stay on the
- *       integer pipes (about 1/15 of a group each): a batch of >= ~16 equal-length queries goes to the tensor cores, a
+ *       integer pipes (about 1/8 of a group each): a batch of >= ~9 equal-length queries goes to the tensor cores, a
  *       single find() stays on XOR + POPC.
  * All four give bit-identical results. The environment variable HPFW_MATCH_IMPL sets the initial value of a new context. */
 int hpfw_set_match_impl(hpfw_ctx *ctx, int impl);
