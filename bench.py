@@ -331,6 +331,32 @@ def run_extraction(args, ctx, rank, world, dev, max_over_ranks, barrier):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = e2e_tracks * world * frames / e2e_s
 
+    # the same with 16-bit PCM in pinned host memory (what a WAV file / decoder delivers; converted to float on the device)
+    pin16 = [torch.empty(n, dtype=torch.int16, pin_memory=True) for _ in range(npin)]
+    for k in range(npin):
+        pin16[k].copy_((audio[k % per_rank] * 16384.0).clamp_(-32768, 32767).to(torch.int16))
+    stage16 = [torch.empty(n, dtype=torch.int16, device=dev) for _ in range(2)]
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_tracks):
+        k = i & 1
+        with torch.cuda.stream(copy_s):
+            copy_s.wait_event(freed[k])
+            stage16[k].copy_(pin16[i % npin], non_blocking=True)
+            ready[k].record(copy_s)
+        with torch.cuda.stream(comp_s):
+            comp_s.wait_event(ready[k])
+            check(ctx._lib.hpfw_calc_hashprint_pcm16_device(ctx.handle, C.c_void_p(stage16[k].data_ptr()), n,
+                                                            C.c_void_p(hp_dev[k].data_ptr()), stream_arg(comp_s.cuda_stream)))
+            freed[k].record(comp_s)
+            hp_host[k].copy_(hp_dev[k], non_blocking=True)
+    torch.cuda.synchronize()
+    barrier()
+    e2e16_s = max_over_ranks(time.perf_counter() - t0)
+    e2e16_value = e2e_tracks * world * frames / e2e16_s
+    del pin16, stage16
+
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -355,7 +381,10 @@ def run_extraction(args, ctx, rank, world, dev, max_over_ranks, barrier):
         "ms_per_track": ms / per_rank, "frames_per_track": frames, "gpu_launches_per_step": launches,
         "e2e": {"value": e2e_value, "unit": "frames/s", "tracks": e2e_tracks * world,
                 "h2d_bytes_per_track": 4 * n, "d2h_bytes_per_track": 8 * words,
-                "note": "pinned host audio, H2D on a copy stream double-buffered against compute, hashprint D2H per track"},
+                "note": "pinned host audio, H2D on a copy stream double-buffered against compute, hashprint D2H per track",
+                "pcm16": {"value": e2e16_value, "unit": "frames/s", "h2d_bytes_per_track": 2 * n,
+                          "note": "the same from 16-bit PCM in pinned host memory (hpfw_calc_hashprint_pcm16_device: "
+                                  "sample / 32768 on the device)"}},
         "roofline": {"bound": "hbm", "kernel": "CQT (7 kernels per track, cqt.cu)", "achieved": cqt_bytes / (cq_per_track * 1e-3) / 1e9,
                      "peak": hbm, "unit": "GB/s", "frac": cqt_bytes / (cq_per_track * 1e-3) / 1e9 / hbm,
                      "traffic": NCU_CQT_TRAFFIC_PER_TRACK,
@@ -707,7 +736,8 @@ def run_cuda(args):
             kq = (QUERY_WORDS + 7) // 8 * 8 if f4 else (QUERY_WORDS + 3) // 4 * 4
             lib_x = 4 if f4 else 2
             tc_alg_bytes = 8.0 * (hi - lo) * TRACK_WORDS + 64.0 * nq * kq
-            roof = {"bound": "tensor", "achieved": tc_achieved, "peak": tc_peak, "unit": "TOP/s", "frac": tc_achieved / tc_peak,
+            roof = {"bound": "tensor", "achieved": tc_achieved, "peak": tc_peak, "unit": "TFLOP/s" if f4 else "TOP/s",
+                    "frac": tc_achieved / tc_peak,
                     "traffic": tc_alg_bytes * NCU_TC_TRAFFIC_RATIO,
                     "traffic_note": "dram__bytes_read+write of one launch in the ncu --set full capture at 2000 tracks x 128 "
                                     "queries (profiles/r03d_match_tc_fp4_ncu_full.md: 243.1 MB against 233.8 MB algorithmic), "

@@ -294,6 +294,22 @@ class HashprintExtractor:
             self.set_filters(f)
         return f, w
 
+    def calc_hashprint_pcm16(self, pcm: np.ndarray) -> np.ndarray:
+        """calc_hashprint on 16-bit PCM samples (host in, host out): half the PCIe bytes of the float call, same hashprint
+        as calc_hashprint(pcm / 32768)."""
+        a = np.ascontiguousarray(pcm, dtype=np.int16)
+        hp = np.zeros(max(self.words(len(a)), 1), dtype=np.uint64)
+        n = C.c_int()
+        check(self._lib.hpfw_calc_hashprint_pcm16(self.ctx.handle, _ptr(a), len(a), _ptr(hp), C.byref(n)))
+        return hp[:n.value]
+
+    def calc_hashprint_pcm16_batch_device(self, d_pcm_ptr: int, sample_offsets: np.ndarray, d_hp_out_ptr: int,
+                                          stream: int = 0) -> None:
+        """calc_hashprint_batch_device for int16 PCM already in HBM (converted to float on the device)."""
+        so = np.ascontiguousarray(sample_offsets, dtype=np.int64)
+        check(self._lib.hpfw_calc_hashprint_pcm16_batch_device(self.ctx.handle, C.c_void_p(d_pcm_ptr), _ptr(so),
+                                                               len(so) - 1, C.c_void_p(d_hp_out_ptr), stream_arg(stream)))
+
     def calc_hashprint_batch_device(self, d_audio_ptr: int, sample_offsets: np.ndarray, d_hp_out_ptr: int,
                                     stream: int = 0) -> None:
         """Many tracks already in HBM (concatenated, even offsets) -> concatenated hashprints in HBM; no host sync."""

@@ -126,6 +126,7 @@ struct hpfw_ctx {
     cudaEvent_t lane_join[HPFW_CTX_LANES] = {};
     cudaEvent_t lane_fork = nullptr;
     hpfw_b200::DeviceBuffer audio;
+    hpfw_b200::DeviceBuffer audio_f;   // pcm.cu: float copy of 16-bit PCM input
 
     // optional per-kernel device timing (CUDA events on the launching stream); see hpfw_ctx_timing_*
     bool timing = false;

@@ -71,6 +71,7 @@ void hpfw_ctx_destroy(hpfw_ctx *c) {
     c->filters_tc.release();
     c->delta_tc.release();
     c->audio.release();
+    c->audio_f.release();
     c->cov_accum.release();
     c->cov_scratch.release();
     hpfw_b200::cqt_cache_destroy(c->cqt);

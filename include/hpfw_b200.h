@@ -206,6 +206,16 @@ int hpfw_calc_hashprint_audio_device(hpfw_ctx *ctx, const float *d_audio, int64_
 int hpfw_calc_hashprint_audio_batch_device(hpfw_ctx *ctx, const float *d_audio, const int64_t *sample_offsets, int n,
                                            uint64_t *d_hp_out, void *stream);
 
+/* 16-bit PCM input (pcm.cu): the samples a WAV file or a decoder delivers before MonoLoader's conversion to float
+ * (cqt.h:45-52). Half the bytes of the float buffer across PCIe; `sample / 32768` is done on the device and is exact, so the
+ * hashprints equal those of the float entry points on the converted samples bit for bit. Same conventions as above. */
+int hpfw_pcm16_to_float_device(hpfw_ctx *ctx, const int16_t *d_pcm, int64_t n_samples, float *d_audio_out, void *stream);
+int hpfw_calc_hashprint_pcm16(hpfw_ctx *ctx, const int16_t *pcm, int64_t n_samples, uint64_t *hp_out, int *n_out);
+int hpfw_calc_hashprint_pcm16_device(hpfw_ctx *ctx, const int16_t *d_pcm, int64_t n_samples, uint64_t *d_hp_out,
+                                     void *stream);
+int hpfw_calc_hashprint_pcm16_batch_device(hpfw_ctx *ctx, const int16_t *d_pcm, const int64_t *sample_offsets, int n,
+                                           uint64_t *d_hp_out, void *stream);
+
 /* ------------------------------------------------------------------------------------------------ measurement aids */
 /* Pipe microbenchmark used to pin the matcher's roofline denominator: runs register-only loops and reports
  * lane-instructions per clock per SM for (0) POPC alone, (1) LOP3 alone, (2) the matcher's XOR/POPC/IADD3 mix,

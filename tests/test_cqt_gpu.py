@@ -187,3 +187,30 @@ def test_cqt_limits(ctx):
     with pytest.raises(HpfwError) as e:
         _cqt(ctx, np.zeros(4000, dtype=np.float32))          # too short for the 121-band design
     assert e.value.code == ERR_SHORT
+
+
+def test_pcm16_entry_points_equal_the_float_path(ctx, hashprint_golden):
+    """16-bit PCM in (host, device, batch): the device does MonoLoader's sample / 32768 (exact in float), so the hashprints
+    are those of the float entry points on the converted samples, bit for bit; odd lengths and unaligned batch offsets too."""
+    import torch
+    import hpfw_b200
+    ex = hpfw_b200.HashprintExtractor(ctx)
+    ex.set_filters(np.ascontiguousarray(hashprint_golden["filters"]))
+    lens = [88200, 132300, 100001, 264600]
+    pcm = [np.clip(np.round(synth.synth_track(70 + i, n / 44100.0 + 0.01, 44100)[:n] * 30000.0), -32768, 32767).astype(np.int16)
+           for i, n in enumerate(lens)]
+    ref = [ex.calc_hashprint(p.astype(np.float32) / np.float32(32768.0)) for p in pcm]
+    for p, r in zip(pcm, ref):
+        assert np.array_equal(ex.calc_hashprint_pcm16(p), r)
+    # batch on the device: even offsets (8-byte aligned floats), as the float batch call requires
+    padded = [np.concatenate([p, np.zeros(len(p) & 1, dtype=np.int16)]) for p in pcm]
+    so = np.zeros(len(pcm) + 1, dtype=np.int64)
+    np.cumsum([len(p) for p in padded], out=so[1:])
+    d_pcm = torch.from_numpy(np.concatenate(padded)).cuda()
+    # each track is taken with its padded length: compare against the float path on the same padded buffers
+    refp = [ex.calc_hashprint(p.astype(np.float32) / np.float32(32768.0)) for p in padded]
+    d_hp = torch.zeros(sum(len(r) for r in refp), dtype=torch.int64, device="cuda")
+    ex.calc_hashprint_pcm16_batch_device(d_pcm.data_ptr(), so, d_hp.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = d_hp.cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, np.concatenate(refp))
