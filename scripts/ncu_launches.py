@@ -10,7 +10,7 @@ for r in rows:
         d = dict(zip(hdr, r))
         if d.get("Metric Name") == "gpu__time_duration.sum":
             name = d["Kernel Name"]
-            if "hpfw" not in name:
+            if any(t in name for t in ("at::", "elementwise", "reduce_kernel", "distribution_")):   # torch's own kernels
                 continue
             k = name.split("(")[0][-48:] + " grid=" + d["Grid Size"] + " blk=" + d["Block Size"]
             a = agg.setdefault(k, [0, 0.0])
