@@ -367,10 +367,12 @@ def run_extraction(args, ctx, rank, world, dev, max_over_ranks, barrier):
     # tracks of a batch run concurrently on 4 streams, so the summed kernel durations overlap: the CQT stage time per track is
     # the step time minus the (serial) projection launches
     try:
-        tf32_peak = float(pk["bf16_tflops_sustained"]) / 2.0
-        tf32_src = "half of the measured sustained bf16 cuBLAS rate (MEASURED_PEAKS.json): tf32 dense = bf16 / 2"
+        f16_peak = float(pk["bf16_tflops_sustained"])
+        f16_src = ("the measured sustained bf16 cuBLAS rate (MEASURED_PEAKS.json; fp16 and bf16 share the tensor rate). The kernel "
+                   "itself is bound by shared-memory operand reads: N = 64 filters means 6 KB of operands per 32-clk MMA, 192 "
+                   "B/clk against the 128 B/clk an SM delivers")
     except (NameError, KeyError, ValueError):
-        tf32_peak, tf32_src = 1590.0 / 2.0, "half of the fallback bf16 rate (B200_PROFILING.md)"
+        f16_peak, f16_src = 1590.0, "the fallback bf16 rate (B200_PROFILING.md)"
     cq_per_track = max(1e-6, (ms * reps - pj_ms) / max(1, per_rank * reps))
     cq_kernel_sum_per_track = cq_ms / max(1, per_rank * reps)
     cqt_bytes = 4.0 * n + 4.0 * 121 * cols
@@ -394,11 +396,11 @@ def run_extraction(args, ctx, rank, world, dev, max_over_ranks, barrier):
                      "ms_per_track": cq_per_track, "kernel_ms_sum_per_track_overlapped": cq_kernel_sum_per_track,
                      "peak_how": src,
                      "algorithmic_bytes_per_track": cqt_bytes},
-        "roofline_projection": {"bound": "tensor", "kernel": "project_tc_kernel<1> (tcgen05 kind::tf32, + tc_delta_kernel pre-pass)",
+        "roofline_projection": {"bound": "tensor", "kernel": "project_tc_kernel<3> (tcgen05 kind::f16, fp16 operands, + tc_delta_kernel pre-pass)",
                                 "achieved": 2.0 * 64 * 2420 * frames * per_rank * reps / (pj_ms * 1e-3) / 1e12,
-                                "peak": tf32_peak, "unit": "TFLOP/s",
+                                "peak": f16_peak, "unit": "TFLOP/s",
                                 "ms_per_track": pj_ms / max(1, per_rank * reps), "launches": pj_n,
-                                "peak_how": tf32_src},
+                                "peak_how": f16_src},
     }
     out["roofline_projection"]["frac"] = out["roofline_projection"]["achieved"] / out["roofline_projection"]["peak"]
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -113,8 +113,10 @@ struct hpfw_ctx {
     std::vector<float> filters_host;       // column-major 64 x 2420 as given
     bool have_filters = false;
     hpfw_b200::DeviceBuffer spectro, hp, yproj, colmeta;
+    hpfw_b200::DeviceBuffer filters_tc16;           // project_tc.cu impl 3: fp16 filters [tap][filter][band]
     hpfw_b200::DeviceBuffer filters_tc, delta_tc;   // project_tc.cu: tf32 filters [tap][filter][band], differenced spectrogram
-    int project_impl = 1;                           // 1 = tcgen05 (one A block, default), 2 = tcgen05 (A per tap), 0 = CUDA-core kernel
+    int project_impl = 3;                           // 3 = tcgen05, fp16 operands (default); 1 = tcgen05, tf32 operands;
+                                                    // 2 = tcgen05, tf32, A window reloaded per tap; 0 = CUDA-core kernel
 
     // filter learning (learn.cu): device-resident covariance accumulator (2420 x 2420) and scratch
     hpfw_b200::DeviceBuffer cov_accum, cov_scratch;

@@ -69,6 +69,7 @@ void hpfw_ctx_destroy(hpfw_ctx *c) {
     c->yproj.release();
     c->colmeta.release();
     c->filters_tc.release();
+    c->filters_tc16.release();
     c->delta_tc.release();
     c->audio.release();
     c->audio_f.release();

@@ -15,9 +15,15 @@
 // address by c rows (c * 128 B): TMA and the MMA both derive the 128-byte swizzle phase from the shared-memory address
 // bits, so a row-offset start stays consistent with how the block was written. (impl 2 = conservative variant that
 // reloads the [128 x 128] window per tap; both are tested against the CUDA-core kernel and the oracle.)
+// impl 3 (default) = impl 1 with fp16 operands (kind::f16): fp16 has the 10 mantissa bits of tf32, the dB differences
+// (|x| <= 80) and the filter coefficients (|x| <= 1) are far inside its range, and a 128-byte swizzle atom then holds 64
+// bands instead of 32: half the MMAs (160 per tile, K = 16 each), half the shared-memory operand bytes per frame — the
+// kernel is bound by shared-memory operand reads (N = 64: 6 KB per 32-clk MMA) — and half the pre-pass bytes.
 // B_c streams through a 3-stage TMA/mbarrier ring. The epilogue reads the TMEM accumulator with tcgen05.ld (one frame per
 // thread, 64 filters in registers), thresholds and packs the 64-bit word.
 #include "tc_ptx.cuh"
+
+#include <cuda_fp16.h>
 
 #include <cstring>
 
@@ -55,36 +61,56 @@ struct TcTrack {
 };
 
 // ---- pre-pass: Dd[row][b] = tf32(S[t][b] - S[t+80][b]), bands 121..127 = 0 ------------------------------------------------
+template <int HALF>   // 0: tf32 values in float storage; 1: fp16
 __global__ void __launch_bounds__(256)
 tc_delta_kernel(const float *__restrict__ spectro, const int64_t *__restrict__ col_start, const int64_t *__restrict__ row_base,
-                const int32_t *__restrict__ rows, int n_tracks, float *__restrict__ dd) {
+                const int32_t *__restrict__ rows, int n_tracks, void *__restrict__ dd_) {
     const int trk = blockIdx.y;
     const int nr = rows[trk];
     const float *S = spectro + col_start[trk] * TC_BINS;
-    float *D = dd + row_base[trk] * TC_BPAD;
+    float *D = static_cast<float *>(dd_) + row_base[trk] * TC_BPAD;
+    __half *Dh = static_cast<__half *>(dd_) + row_base[trk] * TC_BPAD;
     const int64_t total = (int64_t)nr * TC_BPAD;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t t = i >> 7;
         const int b = (int)(i & 127);
         float v = 0.f;
         if (b < TC_BINS) v = S[t * TC_BINS + b] - S[(t + TC_LAG) * TC_BINS + b];
-        uint32_t r;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-        D[i] = __uint_as_float(r);
+        if (HALF) {
+            Dh[i] = __float2half_rn(v);
+        } else {
+            uint32_t r;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+            D[i] = __uint_as_float(r);
+        }
     }
 }
 
 // ---- main kernel ------------------------------------------------------------------------------------------------------------
-template <int IMPL>   // 1: one A block + row-offset descriptors; 2: A window reloaded per tap
-__global__ void __launch_bounds__(128, IMPL == 1 ? 2 : 1)
+// instruction descriptor for fp16 operands: c=F32, a=b=F16 (0), K-major both
+constexpr uint32_t TC_IDESC_H = (1u << 4) | ((TC_NF >> 3) << 17) | ((TC_M >> 4) << 24);
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+
+template <int IMPL>   // 1: one A block + row-offset descriptors; 2: A window reloaded per tap; 3: as 1 with fp16 operands
+__global__ void __launch_bounds__(128, IMPL == 1 ? 2 : (IMPL == 3 ? 3 : 1))
 project_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const TcTile *__restrict__ tiles, const TcTrack *__restrict__ tracks, uint64_t *__restrict__ hp_out) {
     extern __shared__ uint8_t tsm_raw[];
     // SWIZZLE_128B atoms must sit on 1024-byte boundaries: align the dynamic region by hand (1 KB of slack is allocated)
     uint8_t *tsm = tsm_raw + ((1024u - (smem_u32(tsm_raw) & 1023u)) & 1023u);
     // carve: [A region][B stages], every atom a multiple of 1024 bytes
-    constexpr int TC_STAGES = (IMPL == 1) ? TC_STAGES_1 : TC_STAGES_2;
-    constexpr uint32_t A_BYTES = (IMPL == 1) ? TC_KB * TC_A_ATOM_BYTES : TC_STAGES * TC_KB * TC_A1_ATOM_BYTES;
+    constexpr bool ONE = IMPL != 2;                 // one A block per tile
+    constexpr int KB = (IMPL == 3) ? 2 : TC_KB;     // 128-byte swizzle atoms per tap: 64 fp16 or 32 tf32 bands each
+    constexpr int XS = (IMPL == 3) ? 64 : 32;       // bands per atom (tensor-map x step)
+    constexpr int TC_STAGES = ONE ? TC_STAGES_1 : TC_STAGES_2;
+    constexpr uint32_t A_BYTES = ONE ? KB * TC_A_ATOM_BYTES : TC_STAGES * TC_KB * TC_A1_ATOM_BYTES;
     uint8_t *smA = tsm;
     uint8_t *smB = tsm + A_BYTES;
     __shared__ __align__(8) uint64_t bar_a, bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_acc;
@@ -116,16 +142,16 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
-        if (IMPL == 1) {
-            mbar_expect_tx(&bar_a, TC_KB * TC_A_ATOM_BYTES);
-            for (int kb = 0; kb < TC_KB; ++kb) tma_load_2d(&tmA, &bar_a, smA + kb * TC_A_ATOM_BYTES, kb * 32, row0);
+        if (ONE) {
+            mbar_expect_tx(&bar_a, KB * TC_A_ATOM_BYTES);
+            for (int kb = 0; kb < KB; ++kb) tma_load_2d(&tmA, &bar_a, smA + kb * TC_A_ATOM_BYTES, kb * XS, row0);
         }
-        if (IMPL == 1) {
-            for (int it = 0; it < TC_CTX * TC_KB; ++it) {        // stage = one (tap, 32-band atom) of B
-                const int s = it % TC_STAGES, c = it / TC_KB, kb = it % TC_KB;
+        if (ONE) {
+            for (int it = 0; it < TC_CTX * KB; ++it) {        // stage = one (tap, band atom) of B
+                const int s = it % TC_STAGES, c = it / KB, kb = it % KB;
                 if (it >= TC_STAGES) mbar_wait(&bar_empty[s], ((it / TC_STAGES) - 1) & 1);
                 mbar_expect_tx(&bar_full[s], TC_B_ATOM_BYTES);
-                tma_load_2d(&tmB, &bar_full[s], smB + s * TC_B_ATOM_BYTES, kb * 32, c * TC_NF);
+                tma_load_2d(&tmB, &bar_full[s], smB + s * TC_B_ATOM_BYTES, kb * XS, c * TC_NF);
             }
         } else {
             for (int c = 0; c < TC_CTX; ++c) {
@@ -140,18 +166,21 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
-        if (IMPL == 1) mbar_wait(&bar_a, 0);
+        if (ONE) mbar_wait(&bar_a, 0);
         uint32_t acc = 0;
-        if (IMPL == 1) {
-            for (int it = 0; it < TC_CTX * TC_KB; ++it) {
-                const int s = it % TC_STAGES, c = it / TC_KB, kb = it % TC_KB;
+        if (ONE) {
+            for (int it = 0; it < TC_CTX * KB; ++it) {
+                const int s = it % TC_STAGES, c = it / KB, kb = it % KB;
                 mbar_wait(&bar_full[s], (it / TC_STAGES) & 1);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smA + kb * TC_A_ATOM_BYTES) + c * 128;
                 const uint32_t b_addr = smem_u32(smB + s * TC_B_ATOM_BYTES);
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {     // 8 tf32 = 32 bytes per MMA along K inside the 128-byte atom
-                    tc_mma_tf32(tmem_base, smem_desc_sw128(a_addr + k4 * 32), smem_desc_sw128(b_addr + k4 * 32), TC_IDESC, acc);
+                for (int k4 = 0; k4 < 4; ++k4) {     // 8 tf32 or 16 fp16 = 32 bytes per MMA along K inside the 128-byte atom
+                    if (IMPL == 3)
+                        tc_mma_f16(tmem_base, smem_desc_sw128(a_addr + k4 * 32), smem_desc_sw128(b_addr + k4 * 32), TC_IDESC_H, acc);
+                    else
+                        tc_mma_tf32(tmem_base, smem_desc_sw128(a_addr + k4 * 32), smem_desc_sw128(b_addr + k4 * 32), TC_IDESC, acc);
                     acc = 1;
                 }
                 tc_commit(&bar_empty[s]);     // arrives when the MMAs above have finished reading this stage
@@ -196,11 +225,16 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 }
 
+static int tc_make_map_2d_t(CUtensorMap *map, const void *base, uint64_t rows, uint32_t box_rows, bool atom32, bool half);
 int tc_make_map_2d(CUtensorMap *map, const void *base, uint64_t rows, uint32_t box_rows, bool atom32) {
-    // row-major [rows][128] float: dim0 = 128 bands (contiguous), dim1 = rows, pitch 512 B; box = 32 bands x box_rows rows
+    return tc_make_map_2d_t(map, base, rows, box_rows, atom32, false);
+}
+static int tc_make_map_2d_t(CUtensorMap *map, const void *base, uint64_t rows, uint32_t box_rows, bool atom32, bool half) {
+    // row-major [rows][128] float (pitch 512 B, box = 32 bands x box_rows rows) or fp16 (pitch 256 B, box = 64 bands):
+    // dim0 = 128 bands (contiguous), dim1 = rows; a box row is one 128-byte swizzle row either way
     const cuuint64_t dims[2] = {TC_BPAD, rows};
-    const cuuint64_t strides[1] = {TC_BPAD * sizeof(float)};
-    const cuuint32_t box[2] = {32, box_rows};
+    const cuuint64_t strides[1] = {TC_BPAD * (half ? sizeof(__half) : sizeof(float))};
+    const cuuint32_t box[2] = {half ? 64u : 32u, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     // the driver entry point is resolved through the runtime so that the library does not link libcuda.so (it must load,
     // and fail loudly, on machines without a driver)
@@ -215,7 +249,7 @@ int tc_make_map_2d(CUtensorMap *map, const void *base, uint64_t rows, uint32_t b
         if (!fn || q != cudaDriverEntryPointSuccess) HPFW_FAIL(HPFW_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
         encode = reinterpret_cast<EncodeTiled>(fn);
     }
-    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
+    CUresult r = encode(map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -239,6 +273,15 @@ int project_tc_set_filters(hpfw_ctx *ctx, const float *f) {
             }
     HPFW_TRY(ctx->filters_tc.reserve(sizeof(float) * perm.size()));
     HPFW_CUDA_TRY(cudaMemcpy(ctx->filters_tc.ptr, perm.data(), sizeof(float) * perm.size(), cudaMemcpyHostToDevice));
+    // fp16 copy for impl 3, same [c][f][b] order (round to nearest even from the original floats)
+    std::vector<__half> permh(perm.size());
+    for (int c = 0; c < TC_CTX; ++c)
+        for (int fi = 0; fi < TC_NF; ++fi)
+            for (int b = 0; b < TC_BPAD; ++b)
+                permh[((size_t)c * TC_NF + fi) * TC_BPAD + b] =
+                    __float2half_rn(b < TC_BINS ? f[fi + (size_t)TC_NF * (b * TC_CTX + c)] : 0.f);
+    HPFW_TRY(ctx->filters_tc16.reserve(sizeof(__half) * permh.size()));
+    HPFW_CUDA_TRY(cudaMemcpy(ctx->filters_tc16.ptr, permh.data(), sizeof(__half) * permh.size(), cudaMemcpyHostToDevice));
     return HPFW_OK;
 }
 
@@ -285,22 +328,35 @@ int project_tc_run(hpfw_ctx *ctx, int impl, const float *d_spectro, const int64_
     // at least one TMA box of rows (rows past the last track are never part of a stored frame)
     const uint64_t map_rows = std::max<uint64_t>((uint64_t)rb, 256);
     HPFW_TRY(ctx->delta_tc.reserve(sizeof(float) * (size_t)map_rows * TC_BPAD));
+    const bool half = impl == 3;
     {
         KernelScope ks(ctx, HPFW_K_PROJECT, stream);
         const int gx = std::max(1, std::min(64, (max_rows * TC_BPAD + 256 * 8 - 1) / (256 * 8)));
-        tc_delta_kernel<<<dim3(gx, n), 256, 0, stream>>>(d_spectro, reinterpret_cast<const int64_t *>(dm + o_cs),
-                                                         reinterpret_cast<const int64_t *>(dm + o_rb),
-                                                         reinterpret_cast<const int32_t *>(dm + o_rows), n,
-                                                         ctx->delta_tc.as<float>());
+        if (half)
+            tc_delta_kernel<1><<<dim3(gx, n), 256, 0, stream>>>(d_spectro, reinterpret_cast<const int64_t *>(dm + o_cs),
+                                                                reinterpret_cast<const int64_t *>(dm + o_rb),
+                                                                reinterpret_cast<const int32_t *>(dm + o_rows), n,
+                                                                ctx->delta_tc.ptr);
+        else
+            tc_delta_kernel<0><<<dim3(gx, n), 256, 0, stream>>>(d_spectro, reinterpret_cast<const int64_t *>(dm + o_cs),
+                                                                reinterpret_cast<const int64_t *>(dm + o_rb),
+                                                                reinterpret_cast<const int32_t *>(dm + o_rows), n,
+                                                                ctx->delta_tc.ptr);
     }
     CUtensorMap tmA, tmB;
-    HPFW_TRY(tc_make_map_2d(&tmA, ctx->delta_tc.ptr, map_rows, impl == 1 ? TC_AROWS : TC_M, false));
-    HPFW_TRY(tc_make_map_2d(&tmB, ctx->filters_tc.ptr, (uint64_t)TC_CTX * TC_NF, TC_NF, false));
+    HPFW_TRY(tc_make_map_2d_t(&tmA, ctx->delta_tc.ptr, map_rows, impl != 2 ? TC_AROWS : TC_M, false, half));
+    HPFW_TRY(tc_make_map_2d_t(&tmB, half ? ctx->filters_tc16.ptr : ctx->filters_tc.ptr, (uint64_t)TC_CTX * TC_NF, TC_NF, false,
+                              half));
     const size_t smem1 = TC_KB * TC_A_ATOM_BYTES + TC_STAGES_1 * TC_B_ATOM_BYTES + 1024;
     const size_t smem2 = TC_STAGES_2 * TC_KB * TC_A1_ATOM_BYTES + TC_STAGES_2 * TC_B_STAGE_BYTES + 1024;
+    const size_t smem3 = 2 * TC_A_ATOM_BYTES + TC_STAGES_1 * TC_B_ATOM_BYTES + 1024;
     {
         KernelScope ks(ctx, HPFW_K_PROJECT, stream);
-        if (impl == 1) {
+        if (impl == 3) {
+            HPFW_CUDA_TRY(cudaFuncSetAttribute(project_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            project_tc_kernel<3><<<(unsigned)tiles.size(), 128, smem3, stream>>>(
+                tmA, tmB, reinterpret_cast<const TcTile *>(dm + o_tiles), reinterpret_cast<const TcTrack *>(dm), d_hp);
+        } else if (impl == 1) {
             HPFW_CUDA_TRY(cudaFuncSetAttribute(project_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
             project_tc_kernel<1><<<(unsigned)tiles.size(), 128, smem1, stream>>>(
                 tmA, tmB, reinterpret_cast<const TcTile *>(dm + o_tiles), reinterpret_cast<const TcTrack *>(dm), d_hp);

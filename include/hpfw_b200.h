@@ -155,9 +155,10 @@ int hpfw_hashprint_from_spectrogram(hpfw_ctx *ctx, const float *spectrogram, int
  * d_hp_out receives track i's words at hp_offsets[i] = sum_{j<i} max(cols_j - 99, 0). */
 int hpfw_hashprint_from_spectrogram_device(hpfw_ctx *ctx, const float *d_spectrograms, const int64_t *col_offsets,
                                            int n, uint64_t *d_hp_out, void *stream);
-/* which kernel runs stages 2-3: 1 (default) = tcgen05/TMEM/TMA implicit GEMM, tf32 inputs, fp32 accumulate, one context
- * block per tile addressed with row-offset descriptors (project_tc.cu); 2 = the same reloading the window per tap;
- * 0 = fp32 CUDA-core FFMA kernel (project.cu), kept as the measurement baseline and for bit-level comparisons. */
+/* which kernel runs stages 2-3: 1 = tcgen05/TMEM/TMA implicit GEMM, tf32 inputs, fp32 accumulate, one context
+ * block per tile addressed with row-offset descriptors (project_tc.cu); 3 = the same with fp16 inputs (the 10 mantissa bits of
+ * tf32; half the MMAs and operand bytes); 2 = as 1 but reloading the window per tap; 0 = fp32 CUDA-core FFMA kernel
+ * (project.cu), kept as the measurement baseline and for bit-level comparisons. */
 int hpfw_set_projection_impl(hpfw_ctx *ctx, int impl);
 /* diagnostic: the projection y = filters * frames itself (column-major float[64 x (cols-19)]), host buffers */
 int hpfw_project(hpfw_ctx *ctx, const float *spectrogram, int cols, float *y_out);

@@ -18,7 +18,7 @@ def _cuda_core_kernel(ctx):
     """This file pins the fp32 CUDA-core kernel (impl 0); the default tcgen05 kernel is covered by test_project_tc_gpu.py."""
     check(ctx._lib.hpfw_set_projection_impl(ctx.handle, 0))
     yield
-    check(ctx._lib.hpfw_set_projection_impl(ctx.handle, 1))
+    check(ctx._lib.hpfw_set_projection_impl(ctx.handle, 3))
 
 
 def _set_filters(ctx, filt):
