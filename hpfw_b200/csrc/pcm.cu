@@ -56,6 +56,26 @@ int hpfw_pcm16_to_float_device(hpfw_ctx *ctx, const int16_t *d_pcm, int64_t n_sa
     return pcm16_convert(ctx, d_pcm, d_audio_out, n_samples, ctx->pick(stream));
 }
 
+int hpfw_cqt_spectrogram_pcm16(hpfw_ctx *ctx, const int16_t *pcm, int64_t n_samples, float *spectrogram_out, int *cols_out) {
+    if (!ctx || !pcm || !spectrogram_out || !cols_out) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_cqt_spectrogram_pcm16: NULL argument");
+    *cols_out = 0;
+    DeviceGuard g(ctx->device);
+    const int cols = hpfw_cqt_cols(n_samples);
+    if (cols <= 0) HPFW_FAIL(HPFW_ERR_SHORT, "audio of %lld samples is too short for the CQT design", (long long)n_samples);
+    HPFW_TRY(ctx->audio.reserve(sizeof(int16_t) * size_t(n_samples + 8)));
+    HPFW_TRY(ctx->audio_f.reserve(sizeof(float) * size_t(n_samples + 8)));
+    HPFW_TRY(ctx->spectro.reserve(sizeof(float) * size_t(cols) * HPFW_BINS));
+    HPFW_CUDA_TRY(cudaMemcpyAsync(ctx->audio.ptr, pcm, sizeof(int16_t) * size_t(n_samples), cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    HPFW_TRY(pcm16_convert(ctx, ctx->audio.as<int16_t>(), ctx->audio_f.as<float>(), n_samples, ctx->stream));
+    HPFW_TRY(hpfw_cqt_spectrogram_device(ctx, ctx->audio_f.as<float>(), n_samples, ctx->spectro.as<float>(), ctx->stream));
+    HPFW_CUDA_TRY(cudaMemcpyAsync(spectrogram_out, ctx->spectro.ptr, sizeof(float) * size_t(cols) * HPFW_BINS,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    HPFW_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *cols_out = cols;
+    return HPFW_OK;
+}
+
 int hpfw_calc_hashprint_pcm16_batch_device(hpfw_ctx *ctx, const int16_t *d_pcm, const int64_t *sample_offsets, int n,
                                            uint64_t *d_hp_out, void *stream) {
     if (!ctx || !sample_offsets || n < 0) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_calc_hashprint_pcm16_batch_device: bad argument");

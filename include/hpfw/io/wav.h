@@ -16,9 +16,12 @@ namespace hpfw::io {
 struct WavData {
     int sample_rate = 0;
     std::vector<float> mono;
+    std::vector<int16_t> pcm16;   // filled INSTEAD of `mono` when keep_pcm16 was asked for and the file is mono 16-bit PCM
 };
 
-inline WavData read_wav(const std::string &filename) {
+/// keep_pcm16: a mono 16-bit PCM file is returned as its raw samples (`pcm16`; one bulk read, no per-sample work), for the
+/// hpfw_*_pcm16 entry points that convert on the device. Everything else is converted to float here.
+inline WavData read_wav(const std::string &filename, bool keep_pcm16 = false) {
     std::ifstream is(filename, std::ios::binary);
     if (!is) throw std::runtime_error("cannot open '" + filename + "'");
     auto rd = [&](void *p, size_t n) {
@@ -57,7 +60,25 @@ inline WavData read_wav(const std::string &filename) {
             const size_t bps = bits / 8, frame = bps * channels;
             if (bps == 0) throw std::runtime_error("'" + filename + "': bad bit depth");
             const size_t n = raw.size() / frame;
+            out.sample_rate = static_cast<int>(rate);
+            if (channels == 1 && fmt == 1 && bits == 16 && keep_pcm16) {
+                out.pcm16.resize(n);
+                std::memcpy(out.pcm16.data(), raw.data(), n * 2);
+                return out;
+            }
             out.mono.resize(n);
+            if (channels == 1 && fmt == 3 && bits == 32) {        // mono float32: the samples as they are
+                std::memcpy(out.mono.data(), raw.data(), n * 4);
+                return out;
+            }
+            if (channels == 1 && fmt == 1 && bits == 16) {        // mono 16-bit PCM: MonoLoader's sample / 32768, exact in float
+                for (size_t i = 0; i < n; ++i) {
+                    int16_t v;
+                    std::memcpy(&v, &raw[2 * i], 2);
+                    out.mono[i] = static_cast<float>(v) * (1.0f / 32768.0f);
+                }
+                return out;
+            }
             for (size_t i = 0; i < n; ++i) {
                 double acc = 0.0;
                 for (unsigned c = 0; c < channels; ++c) {

@@ -29,11 +29,23 @@ public:
 
     /// Reference signature (cqt.h:36). Decodes a WAV file whose rate must equal SampleRate (no resampler here).
     static Spectrogram spectrogram(const std::string &filename) {
-        const io::WavData wav = io::read_wav(filename);
+        const io::WavData wav = io::read_wav(filename, /*keep_pcm16=*/true);
         if (wav.sample_rate != static_cast<int>(SampleRate))
             throw Error(HPFW_ERR_ARG, "'" + filename + "' is sampled at " + std::to_string(wav.sample_rate) +
                                           " Hz; CQT<" + std::to_string(SampleRate) + "> needs that rate (no resampler)");
+        if (!wav.pcm16.empty()) return spectrogram(wav.pcm16.data(), static_cast<int64_t>(wav.pcm16.size()));
         return spectrogram(wav.mono.data(), static_cast<int64_t>(wav.mono.size()));
+    }
+
+    /// Mono 16-bit PCM samples: copied as they are (half the bytes), MonoLoader's sample / 32768 is done on the device.
+    static Spectrogram spectrogram(const int16_t *pcm, int64_t n_samples, int device = 0) {
+        auto ctx = device::Context::shared(device);
+        std::scoped_lock l(ctx->mutex());
+        const int cols = hpfw_cqt_cols(n_samples);
+        Spectrogram s(NumberBins, cols > 0 ? cols : 0);
+        int got = 0;
+        device::check(hpfw_cqt_spectrogram_pcm16(ctx->get(), pcm, n_samples, s.data(), &got));
+        return s;
     }
 
     /// Same on an already decoded mono buffer.

@@ -211,6 +211,7 @@ int hpfw_calc_hashprint_audio_batch_device(hpfw_ctx *ctx, const float *d_audio, 
  * (cqt.h:45-52). Half the bytes of the float buffer across PCIe; `sample / 32768` is done on the device and is exact, so the
  * hashprints equal those of the float entry points on the converted samples bit for bit. Same conventions as above. */
 int hpfw_pcm16_to_float_device(hpfw_ctx *ctx, const int16_t *d_pcm, int64_t n_samples, float *d_audio_out, void *stream);
+int hpfw_cqt_spectrogram_pcm16(hpfw_ctx *ctx, const int16_t *pcm, int64_t n_samples, float *spectrogram_out, int *cols_out);
 int hpfw_calc_hashprint_pcm16(hpfw_ctx *ctx, const int16_t *pcm, int64_t n_samples, uint64_t *hp_out, int *n_out);
 int hpfw_calc_hashprint_pcm16_device(hpfw_ctx *ctx, const int16_t *d_pcm, int64_t n_samples, uint64_t *d_hp_out,
                                      void *stream);

@@ -175,3 +175,38 @@ def test_pyhpfw_wrapper_matches_cpp_path(tmp_path, hashprint_golden):
     ref2 = oracle.hashprint_from_spectrogram(nsgcq.spectrogram(a), learned)
     diff2 = int(np.unpackbits((got[0][1] ^ ref2).view(np.uint8)).sum())
     assert diff2 <= 1e-3 * 64 * len(ref2)
+
+
+def _write_wav16(path, pcm, sr, channels=1):
+    x = np.ascontiguousarray(pcm, dtype=np.int16)
+    hdr = b"RIFF" + np.uint32(36 + x.nbytes).tobytes() + b"WAVEfmt " + np.uint32(16).tobytes() + \
+        np.uint16(1).tobytes() + np.uint16(channels).tobytes() + np.uint32(sr).tobytes() + \
+        np.uint32(sr * 2 * channels).tobytes() + np.uint16(2 * channels).tobytes() + np.uint16(16).tobytes() + \
+        b"data" + np.uint32(x.nbytes).tobytes()
+    with open(path, "wb") as f:
+        f.write(hdr)
+        f.write(x.tobytes())
+
+
+@pytest.mark.gpu
+def test_pcm16_wav_takes_the_device_conversion_and_matches_float(tmp_path, hashprint_golden):
+    """A mono 16-bit PCM WAV is shipped to the GPU as it is (hpfw_cqt_spectrogram_pcm16, sample / 32768 on the device); the
+    same samples as a float32 WAV, and as a stereo file with two equal channels (host down-mix path), give the same
+    hashprint bit for bit."""
+    from hpfw_b200.pyhpfw import ParallelCollector
+    from hpfw_b200 import synth
+    sr = 44100
+    cache = str(tmp_path / "cache") + "/"
+    os.makedirs(cache + "spectros")
+    _save_filters_cereal(cache + "filters.cereal", hashprint_golden["filters"])
+    pcm = np.clip(np.round(synth.synth_track(78, 6.0, sr) * 30000.0), -32768, 32767).astype(np.int16)
+    _write_wav16(tmp_path / "a16.wav", pcm, sr)
+    _write_wav(tmp_path / "af.wav", pcm.astype(np.float32) / np.float32(32768.0), sr)
+    _write_wav16(tmp_path / "a16s.wav", np.stack([pcm, pcm], axis=1), sr, channels=2)
+    pc = ParallelCollector()
+    pc.load(cache)
+    h16 = pc.calc_hashprint(str(tmp_path / "a16.wav"))
+    hf = pc.calc_hashprint(str(tmp_path / "af.wav"))
+    hs = pc.calc_hashprint(str(tmp_path / "a16s.wav"))
+    assert len(h16) == 385
+    assert np.array_equal(h16, hf) and np.array_equal(h16, hs)
