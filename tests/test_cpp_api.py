@@ -89,6 +89,60 @@ int main(int argc, char** argv) {
     assert raw == exp
 
 
+def test_wav_reader_formats_cpu(tmp_path):
+    """include/hpfw/io/wav.h on every sample format it accepts: the bulk paths (mono float32, mono 16-bit PCM, raw int16
+    hand-over) and the general per-sample path (8/24/32-bit PCM, float64, stereo down-mix) decode the same audio to the
+    same floats. Host-only."""
+    src = tmp_path / "w.cpp"
+    src.write_text(r'''
+#include <hpfw/io/wav.h>
+#include <cstdio>
+int main(int argc, char** argv) {
+    for (int i = 1; i < argc; ++i) {
+        auto w = hpfw::io::read_wav(argv[i]);
+        auto k = hpfw::io::read_wav(argv[i], true);
+        double s = 0, s2 = 0;
+        for (float v : w.mono) { s += v; s2 += double(v) * v; }
+        long long p = 0;
+        for (auto v : k.pcm16) p += v;
+        std::printf("%d %zu %.9g %.9g %zu %zu %lld\n", w.sample_rate, w.mono.size(), s, s2, k.mono.size(), k.pcm16.size(), p);
+    }
+    return 0;
+}''')
+    exe = tmp_path / "w"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    rng = np.random.default_rng(0)
+    pcm = rng.integers(-32768, 32768, size=1001).astype(np.int16)
+    f32 = pcm.astype(np.float32) / np.float32(32768.0)
+
+    def wav(path, fmt, bits, payload, channels=1, sr=44100):
+        hdr = b"RIFF" + np.uint32(36 + len(payload)).tobytes() + b"WAVEfmt " + np.uint32(16).tobytes() + \
+            np.uint16(fmt).tobytes() + np.uint16(channels).tobytes() + np.uint32(sr).tobytes() + \
+            np.uint32(sr * channels * bits // 8).tobytes() + np.uint16(channels * bits // 8).tobytes() + \
+            np.uint16(bits).tobytes() + b"data" + np.uint32(len(payload)).tobytes()
+        open(path, "wb").write(hdr + payload)
+        return str(path)
+
+    p24 = b"".join(int(v << 8).to_bytes(3, "little", signed=True) for v in pcm.tolist())
+    files = [
+        wav(tmp_path / "p16.wav", 1, 16, pcm.tobytes()),
+        wav(tmp_path / "f32.wav", 3, 32, f32.tobytes()),
+        wav(tmp_path / "f64.wav", 3, 64, f32.astype(np.float64).tobytes()),
+        wav(tmp_path / "p24.wav", 1, 24, p24),
+        wav(tmp_path / "p32.wav", 1, 32, (pcm.astype(np.int32) << 16).tobytes()),
+        wav(tmp_path / "p16s.wav", 1, 16, np.stack([pcm, pcm], axis=1).tobytes(), channels=2),
+    ]
+    rows = [ln.split() for ln in subprocess.check_output([str(exe)] + files, text=True).strip().splitlines()]
+    exp_s, exp_s2 = float(f32.astype(np.float64).sum()), float((f32.astype(np.float64) ** 2).sum())
+    for r in rows:
+        assert int(r[0]) == 44100 and int(r[1]) == len(pcm)
+        assert abs(float(r[2]) - exp_s) <= 1e-6 * max(1.0, abs(exp_s)) and abs(float(r[3]) - exp_s2) <= 1e-6 * exp_s2
+    # keep_pcm16: only the mono 16-bit file is handed over raw (and then not converted on the host)
+    assert [int(r[5]) for r in rows] == [len(pcm), 0, 0, 0, 0, 0]
+    assert int(rows[0][4]) == 0 and int(rows[0][6]) == int(pcm.astype(np.int64).sum())
+    assert all(int(r[4]) == len(pcm) for r in rows[1:])
+
+
 @pytest.mark.gpu
 def test_live_id_example_config0(tmp_path, hashprint_golden):
     import oracle
