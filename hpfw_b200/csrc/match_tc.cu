@@ -1,29 +1,31 @@
 // hpfw_b200/csrc/match_tc.cu — stage 4 on the 5th-generation tensor cores: the Hamming cross-correlation of
-// db::MemoryStorage::find (/root/reference/include/hpfw/audioproblems/live-song-id/storage.h:27-64) as an EXACT int8 GEMM.
+// db::MemoryStorage::find (/root/reference/include/hpfw/audioproblems/live-song-id/storage.h:27-64) as an EXACT GEMM.
 //
 // For a query q[0..k) and a reference track r[0..n):  D[i] = sum_j popc(q[j] ^ r[i+j]). With every bit b of a word mapped to
-// the signed byte s(b) = +1 (set) / -1 (clear),  sum_bits s(q) * s(r) = 64 - 2 * popc(q ^ r),  so
+// s(b) = +1 (set) / -1 (clear),  sum_bits s(q) * s(r) = 64 - 2 * popc(q ^ r),  so
 //     D[i] = (64 k - dot[i]) / 2,      dot[i] = sum_{j < k} sum_{b < 64} s(q[j])_b * s(r[i + j])_b
-// and dot[] is a GEMM whose "offset" operand is a HANKEL matrix: row i of it is the byte expansion of r[i .. i+k), i.e. row
-// i+1 is row i moved one word (64 bytes) along K. tcgen05.mma.kind::i8 multiplies s8 x s8 into s32 accumulators in TMEM:
-// integer arithmetic, no rounding, |dot| <= 64 * 4096 — the distances and the rankings stay bit-exact.
+// and dot[] is a GEMM whose "offset" operand is a HANKEL matrix: row i of it is the expansion of r[i .. i+k), i.e. row i+1
+// is row i moved one word along K. Every product is +-1 and |dot| <= 64 * 4096 = 2^18, so the sums are exact in the s32
+// accumulators of tcgen05.mma.kind::i8 (signed bytes) and in the f32 accumulators of kind::mxf4.block_scale (e2m1 nibbles,
+// unit scales; integers below 2^24): distances and rankings stay bit-exact. The two encodings are the template parameter.
 //
 // Mapping (one CTA per SM, persistent over (query group, tile) items):
-//   * M = 128 queries of one group (TMEM lanes), N = 512 alignment offsets of one track (2 MMAs of N = 256 = all 512 TMEM
-//     columns), K = 64 k bytes, walked one 64-bit word (2 MMAs of K = 32) at a time.
-//   * offset operand: the tile's reference words are expanded ONCE per K chunk (<= 192 words) into shared memory as
-//     R[16-byte chunk c (4)][row w][16 B] — the no-swizzle K-major canonical layout with the 8-row core matrices of one chunk
+//   * M = 128 queries of one group (TMEM lanes), N = the alignment offsets of one tile of one track (2 MMAs of N = 256 or
+//     240 = the TMEM columns), K = 64 k, walked one 64-bit word at a time (2 MMAs of K = 32 bytes, or 1 of K = 64 nibbles).
+//   * offset operand: the tile's reference words are expanded ONCE per K chunk into shared memory as
+//     R[16-byte chunk c][row w][16 B] — the no-swizzle K-major canonical layout with the 8-row core matrices of one chunk
 //     column contiguous (SBO = 128 B, LBO = rows * 16 B). Row w+1 is 16 bytes after row w, so the operand for query word j
 //     is the SAME buffer addressed through a descriptor whose start address is moved by j rows: no shifted copy is made,
-//     a tile reads (512 + k) words instead of 512 * k. Rows beyond the end of the track are 0 bytes and contribute
+//     a tile reads (tile + k) words instead of tile * k. Rows beyond the end of the track are zeros and contribute
 //     nothing, which is exactly the reference's truncation of a query that is longer than the track (storage.h:34-38).
-//   * query operand: expanded once per call by xt_expand_queries_kernel to [word j][chunk c][query m][16 B] (bytes of the
-//     words beyond a shorter query's end are 0), streamed by 1-D bulk TMA copies through a 4-stage mbarrier ring
-//     (4 words = 32 KB per stage; the 3 MB of a group stay in L2 for all 148 CTAs).
+//   * query operand: expanded once per call by xt_expand_queries_kernel to [word j][chunk c][query m][16 B] (the words
+//     beyond a shorter query's end are zeros), streamed by 1-D bulk TMA copies through a 4-stage mbarrier ring
+//     (32 KB per stage; the 1.6 / 3 MB of a group stay in L2 for all 148 CTAs).
 //   * warp roles: 0 = TMA producer, 1 = MMA issuer, 2-5 = reference expanders (double-buffered R), 6-13 = epilogue.
-//   * epilogue: tcgen05.ld 64 columns at a time; per query (lane) the maximum of (dot << 6 | 63 - column) inside the valid
-//     offset range, chunks visited in ascending order with a strict '>' = the lowest offset among equal distances; one
-//     64-bit atomicMin per (query, tile) into best[query][track], the array match_kernel and topk_kernel share.
+//   * epilogue: tcgen05.ld 64 columns at a time (warps 6-9: columns below 256, warps 10-13: the rest); per query (lane)
+//     the maximum of (dot, lowest column) over the valid offsets; one 64-bit atomicMin per (query, tile, column half) into
+//     best[query][track], the array match_kernel and topk_kernel share — its key carries the offset, so ties resolve to the
+//     lowest offset as the reference's strict '<' does.
 #include "matcher.cuh"
 #include "tc_ptx.cuh"
 
