@@ -468,6 +468,21 @@ def run_extraction(args, ctx, rank, world, dev, max_over_ranks, barrier):
                     "sample": "one 3-min spectrogram through the reference's calc_cov and one calc_filters "
                               "(hashprint_handle.h:96-112, Eigen 3.3.7 without MKL), single thread as in one taskflow worker"}
         del spec
+    if world > 1:
+        # multi-GPU index: every rank accumulates the covariance of its own tracks; ONE all-reduce of the 2420 x 2420
+        # accumulator (NCCL over NVLink, 23 MB) gives every rank the collection's covariance (sharded.allreduce_covariance)
+        from hpfw_b200.sharded import allreduce_covariance
+        allreduce_covariance(ctx)
+        barrier()
+        e0.record()
+        allreduce_covariance(ctx)
+        e1.record()
+        barrier()
+        ar_ms = max_over_ranks(e0.elapsed_time(e1))
+        if rank == 0 and "index" in out:
+            out["index"]["cov_allreduce_ms"] = ar_ms
+            out["index"]["cov_allreduce_note"] = (f"one all-reduce (sum) of the covariance accumulator over {world} ranks + "
+                                                  "the two device copies around it, once per index() call")
     del audio, base, hp
     torch.cuda.empty_cache()
     return out

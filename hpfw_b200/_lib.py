@@ -59,6 +59,8 @@ _SIGS = {
     "hpfw_cov_reset": (C.c_int, [C.c_void_p]),
     "hpfw_cov_set": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hpfw_cov_get": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hpfw_cov_get_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hpfw_cov_set_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hpfw_cov_add_spectrogram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "hpfw_cov_add_spectrogram_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "hpfw_calc_filters": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -516,6 +516,30 @@ int hpfw_cov_get(hpfw_ctx *ctx, float *accum_2420x2420) {
     return HPFW_OK;
 }
 
+// Device-side access to the accumulator for the multi-GPU index: every rank accumulates its own tracks, the accumulators are
+// summed by ONE all-reduce over NVLink (torch.distributed / NCCL on the caller's tensor) and written back, and
+// hpfw_calc_filters then sees the covariance of all tracks (hpfw_b200/sharded.py: allreduce_covariance).
+int hpfw_cov_get_device(hpfw_ctx *ctx, float *d_accum_out, void *stream) {
+    if (!ctx || !d_accum_out) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_cov_get_device: NULL argument");
+    DeviceGuard g(ctx->device);
+    if (!ctx->cov_accum.ptr) HPFW_TRY(hpfw_cov_reset(ctx));
+    HPFW_CUDA_TRY(cudaStreamSynchronize(ctx->stream));     // a reset / set on the context's stream comes first
+    HPFW_CUDA_TRY(cudaMemcpyAsync(d_accum_out, ctx->cov_accum.ptr, sizeof(float) * (size_t)LN_FS * LN_FS,
+                                  cudaMemcpyDeviceToDevice, ctx->pick(stream)));
+    return HPFW_OK;
+}
+
+int hpfw_cov_set_device(hpfw_ctx *ctx, const float *d_accum, void *stream) {
+    if (!ctx || !d_accum) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_cov_set_device: NULL argument");
+    DeviceGuard g(ctx->device);
+    HPFW_TRY(ctx->cov_accum.reserve(sizeof(float) * (size_t)LN_FS * LN_FS));
+    HPFW_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    HPFW_CUDA_TRY(cudaMemcpyAsync(ctx->cov_accum.ptr, d_accum, sizeof(float) * (size_t)LN_FS * LN_FS,
+                                  cudaMemcpyDeviceToDevice, ctx->pick(stream)));
+    HPFW_CUDA_TRY(cudaStreamSynchronize(ctx->pick(stream)));   // hpfw_calc_filters reads it on the context's stream
+    return HPFW_OK;
+}
+
 int hpfw_cov_add_spectrogram_device(hpfw_ctx *ctx, const float *d_spectrogram, int cols, void *stream) {
     if (!ctx || !d_spectrogram) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_cov_add_spectrogram_device: NULL argument");
     DeviceGuard g(ctx->device);

@@ -62,6 +62,30 @@ def allgather_keys(local, group=None):
     return out
 
 
+def allreduce_sum(t, group=None):
+    """In-place sum of a tensor over the ranks (NCCL over NVLink on GPUs, gloo in the CPU tests); a no-op for one rank."""
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def allreduce_covariance(ctx: Context, group=None, stream: int = 0):
+    """Index-time filter learning over tracks that are split across the ranks: every rank has added the
+    sample covariances of ITS tracks to its context's accumulator (HashprintExtractor.cov_add_spectrogram*, i.e.
+    HashprintHandle::calc_cov + the accumulate of ParallelCollector::preprocess, parallel_collector.h:92-97); this sums the
+    2420 x 2420 accumulators with ONE all-reduce and writes the sum back, so that calc_filters() on any rank returns the
+    filters of the whole collection (the reference's later division by the track count does not change eigenvectors)."""
+    import torch
+    dev = torch.device("cuda", ctx.device)
+    acc = torch.empty(2420 * 2420, dtype=torch.float32, device=dev)
+    s = stream or torch.cuda.current_stream(dev).cuda_stream
+    check(ctx._lib.hpfw_cov_get_device(ctx.handle, C.c_void_p(acc.data_ptr()), stream_arg(s)))
+    allreduce_sum(acc, group)
+    check(ctx._lib.hpfw_cov_set_device(ctx.handle, C.c_void_p(acc.data_ptr()), stream_arg(s)))
+    return acc
+
+
 class ShardedMemoryStorage:
     """MemoryStorage semantics over a DB sharded across the ranks of a torch.distributed group (1 rank = 1 GPU)."""
 

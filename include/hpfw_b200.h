@@ -170,6 +170,10 @@ int hpfw_project(hpfw_ctx *ctx, const float *spectrogram, int cols, float *y_out
 int hpfw_cov_reset(hpfw_ctx *ctx);
 int hpfw_cov_set(hpfw_ctx *ctx, const float *accum_2420x2420);     /* e.g. cache/accum_cov.cereal payload */
 int hpfw_cov_get(hpfw_ctx *ctx, float *accum_2420x2420);
+/* the same with device buffers (d_accum: 2420 x 2420 floats in HBM), for the multi-GPU index: the per-GPU accumulators are
+ * summed by one all-reduce between these two calls (hpfw_b200/sharded.py) */
+int hpfw_cov_get_device(hpfw_ctx *ctx, float *d_accum_out, void *stream);
+int hpfw_cov_set_device(hpfw_ctx *ctx, const float *d_accum, void *stream);
 int hpfw_cov_add_spectrogram(hpfw_ctx *ctx, const float *spectrogram, int cols);                       /* host buffer */
 int hpfw_cov_add_spectrogram_device(hpfw_ctx *ctx, const float *d_spectrogram, int cols, void *stream);
 /* HashprintHandle::calc_filters (hashprint_handle.h:105-112): the 64 eigenvectors of the largest eigenvalues as rows of

@@ -129,3 +129,37 @@ def test_index_learns_filters_from_scratch_cpp(tmp_path):
     assert tuple(f) == (64, 2420) and tuple(c) == (2420, 2420)
     F = np.fromfile(tmp_path / "cache" / "filters.cereal", dtype=np.float32, offset=8).reshape(2420, 64).T
     assert np.allclose(F @ F.T, np.eye(64), atol=1e-4)
+
+
+def test_partial_accumulators_sum_to_the_whole(ctx, hashprint_golden):
+    """Multi-GPU index (sharded.allreduce_covariance): per-shard accumulators, summed on the device and written back through
+    hpfw_cov_get_device / hpfw_cov_set_device, equal the accumulator of all tracks; the filters learned from the sum equal
+    the filters learned in one pass (same subspace: projector difference ~ 0)."""
+    import ctypes as C
+    import torch
+    from hpfw_b200._lib import check
+    from hpfw_b200.sharded import allreduce_covariance
+    ex = HashprintExtractor(ctx)
+    g = hashprint_golden
+    specs = [g["spec0"][:400], g["q_spec"], g["spec0"][300:900], g["spec0"][150:500]]
+    ex.cov_reset()
+    for s in specs:
+        ex.cov_add_spectrogram(s)
+    whole = ex.cov_get()
+    parts = []
+    for shard in (specs[:2], specs[2:]):
+        ex.cov_reset()
+        for s in shard:
+            ex.cov_add_spectrogram(s)
+        t = torch.empty(2420 * 2420, dtype=torch.float32, device="cuda")
+        check(ctx._lib.hpfw_cov_get_device(ctx.handle, C.c_void_p(t.data_ptr()), None))
+        torch.cuda.synchronize()
+        parts.append(t)
+    total = parts[0] + parts[1]
+    check(ctx._lib.hpfw_cov_set_device(ctx.handle, C.c_void_p(total.data_ptr()), None))
+    got = ex.cov_get()
+    assert np.max(np.abs(got - whole)) <= 1e-5 * np.abs(whole).max()
+    # world = 1: the all-reduce is the identity and leaves the accumulator as it is
+    allreduce_covariance(ctx)
+    torch.cuda.synchronize()
+    assert np.array_equal(ex.cov_get(), got)

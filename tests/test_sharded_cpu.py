@@ -9,7 +9,7 @@ import pytest
 
 import oracle
 from hpfw_b200 import synth
-from hpfw_b200.sharded import KEY_NONE, allgather_keys, pack_key, plan_shards
+from hpfw_b200.sharded import KEY_NONE, allgather_keys, allreduce_sum, pack_key, plan_shards
 
 
 def test_plan_shards_contiguous_and_balanced():
@@ -90,3 +90,54 @@ def test_sharded_allgather_merge_equals_unsharded_gloo(world):
         p.join(timeout=120)
         assert p.exitcode == 0
     assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+def _np_cov(spec):
+    """calc_cov(calc_frames(S)^T) in float64 (hashprint_handle.h:79-102), as in tests/test_learn_gpu.py."""
+    nf = spec.shape[0] - 19
+    X = np.empty((nf, 2420), dtype=np.float64)
+    for b in range(121):
+        for c in range(20):
+            X[:, b * 20 + c] = spec[c:c + nf, b]
+    X -= X.mean(axis=0)
+    return X.T @ X / (nf - 1)
+
+
+def _cov_worker(rank, world, port, ret):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # every rank accumulates the covariance of ITS tracks (the reference's calc_cov restated in numpy); the all-reduced
+        # sum must be the accumulator one process would have built over all tracks (index-time filter learning, §8(e))
+        rng = np.random.default_rng(3)
+        specs = [rng.standard_normal((40 + 7 * i, 121)).astype(np.float32) for i in range(5)]
+        mine = [s for i, s in enumerate(specs) if i % world == rank]
+        acc = np.zeros((2420, 2420), dtype=np.float64)
+        for s in mine:
+            acc += _np_cov(s)
+        t = torch.from_numpy(acc.astype(np.float32))
+        allreduce_sum(t)
+        full = np.zeros((2420, 2420), dtype=np.float64)
+        for s in specs:
+            full += _np_cov(s)
+        err = np.abs(t.numpy().astype(np.float64) - full).max() / np.abs(full).max()
+        ret[rank] = bool(err < 1e-5)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_covariance_allreduce_equals_single_process_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_cov_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    assert all(ret.get(r) for r in range(2)), dict(ret)
