@@ -138,3 +138,68 @@ class ShardedMemoryStorage:
         out_pinned.copy_(keys, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return decode_keys(out_pinned.numpy().view(np.uint64))
+
+
+class ShardedLiveSongIdentification:
+    """hpfw::LiveSongIdentification::index()/search() (live_song_id.h:31-54) over several GPUs, one process per GPU.
+
+    index(): the tracks are split into contiguous ranges (DB order = track order, as the tie rule needs); every rank runs
+    the CQT of ITS tracks, adds their covariances to its accumulator, ONE all-reduce gives every rank the collection's
+    covariance, rank 0's filters (calc_filters) are broadcast, and every rank hashes its own tracks into its shard of the
+    database — the hashprints never leave the GPU that computed them. search(): every rank extracts the (short) queries,
+    matches them against its shard, one all-gather of the top-k keys, merge. Results equal the single-GPU path's.
+
+    Decoded mono float32 buffers in, like ParallelCollector::calc_hashprint's decoded side; file decoding is the caller's.
+    """
+
+    def __init__(self, ctx: Context, rank: int = 0, world: int = 1, group=None):
+        from .api import HashprintExtractor
+        self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
+        self.extractor = HashprintExtractor(ctx)
+        self.storage = ShardedMemoryStorage(ctx, rank, world, group)
+        self.names: List[str] = []
+        self.filters = None
+
+    def index(self, tracks: Sequence[np.ndarray], names: Sequence[str] | None = None, filters: np.ndarray | None = None):
+        """tracks: ALL tracks of the collection on every rank (only this rank's range is touched). filters: skip the
+        learning step and use these (e.g. cache/filters.cereal) — the reference's search-only mode."""
+        import torch
+        import torch.distributed as dist
+        ex = self.extractor
+        n = len(tracks)
+        self.names = [str(x) for x in (names if names is not None else range(n))]
+        words = [max(ex.words(len(t)), 0) for t in tracks]
+        a, b = plan_shards(words, self.world)[self.rank]
+        dev = torch.device("cuda", self.ctx.device)
+        specs = [ex.spectrogram(np.ascontiguousarray(tracks[i], dtype=np.float32)) for i in range(a, b)]
+        if filters is None:
+            ex.cov_reset()
+            for sp in specs:
+                ex.cov_add_spectrogram(sp)
+            allreduce_covariance(self.ctx, self.group)
+            f = torch.zeros((2420, 64), dtype=torch.float32, device=dev)
+            if self.rank == 0:
+                f.copy_(torch.from_numpy(ex.calc_filters(install=False)[0]))
+            if self.world > 1:
+                dist.broadcast(f, src=0, group=self.group)
+            filters = f.cpu().numpy()
+        self.filters = np.ascontiguousarray(filters, dtype=np.float32)
+        ex.set_filters(self.filters)
+        hps = [ex.hashprint_from_spectrogram(sp) for sp in specs]
+        offs = np.zeros(len(hps) + 1, dtype=np.int64)
+        np.cumsum([len(h) for h in hps], out=offs[1:])
+        flat = np.concatenate(hps) if hps else np.zeros(0, dtype=np.uint64)
+        self.storage.build_local(flat, offs, track_base=a)
+        return self
+
+    def search(self, queries: Sequence[np.ndarray], topk: int = 1):
+        """queries: decoded query buffers (the same list on every rank). Returns a structured array [Q, topk] of
+        (track, cnt, offset) with GLOBAL track indices; self.names[track] is the reference's SearchResult::filename."""
+        import torch
+        ex = self.extractor
+        hps = [ex.calc_hashprint(np.ascontiguousarray(q, dtype=np.float32)) for q in queries]
+        qoffs = np.zeros(len(hps) + 1, dtype=np.int64)
+        np.cumsum([len(h) for h in hps], out=qoffs[1:])
+        flat = np.concatenate(hps) if hps else np.zeros(0, dtype=np.uint64)
+        pinned = torch.from_numpy(flat.view(np.int64).copy()).pin_memory()
+        return self.storage.search_host(pinned, qoffs, topk)
