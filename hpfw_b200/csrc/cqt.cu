@@ -22,6 +22,8 @@
 //       Hann window and the chirp), czt_rows3_kernel doing FFT_L2 -> multiply -> IFFT_L2 per row with the data in
 //       registers between stages, and a radix-16 register IFFT fused with |.|^2, the 1/(L M) scale and the per-track
 //       maximum. Rows shorter than 512 or longer than 4096 points use the generic shared-memory kernel (czt_rows_kernel).
+//       Tracks longer than 6.7 minutes need L > 16 * 8192: their plans use 32-point columns (dft32 in registers,
+//       L = 32 * L2 <= 262,144: up to ~13.5 minutes); everything else is unchanged.
 //   (3) dB conversion + transpose to the reference's column-major [121 x cols] layout.
 // Twiddles: one table W_n^m per transform length; a butterfly loads one entry and forms its powers by a depth-4 product
 // tree on the FMA pipe (error <= 5 ulp of a unit phasor) instead of R-1 table loads.
@@ -221,6 +223,36 @@ __device__ __forceinline__ void dft16(float2 (&v)[16], int sign) {
         v[c0] = t0; v[c0 + 4] = t1; v[c0 + 8] = t2; v[c0 + 12] = t3;
     }
 }
+
+// 32-point DFT in registers (natural order in and out): two 16-point DFTs of the even / odd inputs and one radix-2 stage.
+// Used by the chirp-z column passes of tracks longer than 6.7 minutes (column length 32 instead of 16).
+__device__ __forceinline__ void dft32(float2 (&v)[32], int sign) {
+    constexpr float C[16] = {1.f, 0.9807852804032304f, 0.9238795325112867f, 0.8314696123025452f, 0.7071067811865476f,
+                             0.5555702330196022f, 0.3826834323650898f, 0.19509032201612825f, 0.f, -0.19509032201612825f,
+                             -0.3826834323650898f, -0.5555702330196022f, -0.7071067811865476f, -0.8314696123025452f,
+                             -0.9238795325112867f, -0.9807852804032304f};                       // cos(2 pi k / 32)
+    constexpr float S[16] = {0.f, 0.19509032201612825f, 0.3826834323650898f, 0.5555702330196022f, 0.7071067811865476f,
+                             0.8314696123025452f, 0.9238795325112867f, 0.9807852804032304f, 1.f, 0.9807852804032304f,
+                             0.9238795325112867f, 0.8314696123025452f, 0.7071067811865476f, 0.5555702330196022f,
+                             0.3826834323650898f, 0.19509032201612825f};                        // sin(2 pi k / 32)
+    float2 e[16], o[16];
+#pragma unroll
+    for (int a = 0; a < 16; ++a) {
+        e[a] = v[2 * a];
+        o[a] = v[2 * a + 1];
+    }
+    dft16(e, sign);
+    dft16(o, sign);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const float2 t = cmul(o[k], make_float2(C[k], sign < 0 ? -S[k] : S[k]));
+        v[k] = cadd(e[k], t);
+        v[k + 16] = csub(e[k], t);
+    }
+}
+template <int L1> __device__ __forceinline__ void dft_col(float2 (&v)[L1], int sign);
+template <> __device__ __forceinline__ void dft_col<16>(float2 (&v)[16], int sign) { dft16(v, sign); }
+template <> __device__ __forceinline__ void dft_col<32>(float2 (&v)[32], int sign) { dft32(v, sign); }
 
 template <int R> __device__ __forceinline__ void dft_r(float2 (&v)[R], int sign);
 template <> __device__ __forceinline__ void dft_r<2>(float2 (&v)[2], int) { dft2(v); }
@@ -627,7 +659,7 @@ bl_post_kernel(float2 *__restrict__ x, long long N, int P, int klo, int K) {
 // MODE 1: chirp filter b[n] = e^{-i pi 3 n^2 / M}, n = k' (k' < F) or k' - L (k' >= F), for plan creation.
 // MODE 2: as MODE 0 but X[k] is read as is (the Bluestein path already produced the full-spectrum bins).
 // Then 16-point FFT down the columns (k' = L2*a + b), twiddle W_L^{b c}, store work[c*L2 + b].
-template <int MODE>
+template <int MODE, int L1>
 __global__ void __launch_bounds__(CQ_THREADS)
 czt_cols_kernel(const BandMeta *__restrict__ bands, const float2 *__restrict__ z_lo, const float2 *__restrict__ z_hi,
                 int klo, int khi, const float2 *__restrict__ twN_hi, const float2 *__restrict__ twN_lo,
@@ -636,9 +668,9 @@ czt_cols_kernel(const BandMeta *__restrict__ bands, const float2 *__restrict__ z
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= bm.L2) return;
     const unsigned long long twoM = 2ull * (unsigned long long)M;
-    float2 v[16];
+    float2 v[L1];
 #pragma unroll
-    for (int a = 0; a < 16; ++a) {
+    for (int a = 0; a < L1; ++a) {
         const int kp = bm.L2 * a + b;
         float2 val = make_float2(0.f, 0.f);
         if (MODE == 2) {          // Bluestein plans: z_lo holds X[klo ..] itself
@@ -668,15 +700,15 @@ czt_cols_kernel(const BandMeta *__restrict__ bands, const float2 *__restrict__ z
         }
         v[a] = val;
     }
-    dft16(v, -1);
+    dft_col<L1>(v, -1);
     float2 *dst = work + bm.work_off;
-    {   // inter-pass twiddle W_L^{b c}, c = 0..15: one sincospif, powers by product tree
+    {   // inter-pass twiddle W_L^{b c}, c = 0..L1-1: one sincospif, powers by product tree
         float s, co;
         sincospif(-2.0f * (float)b / (float)bm.L, &s, &co);
-        apply_powers<16>(v, make_float2(co, s));
+        apply_powers<L1>(v, make_float2(co, s));
     }
 #pragma unroll
-    for (int c = 0; c < 16; ++c) dst[c * bm.L2 + b] = v[c];
+    for (int c = 0; c < L1; ++c) dst[c * bm.L2 + b] = v[c];
 }
 
 // ------------------------------------------------------------------------------------------------ CZT row pass
@@ -836,7 +868,7 @@ czt_rows3_kernel(const BandMeta *__restrict__ bands, const RowTile *__restrict__
         for (int u = 0; u < 16; ++u) S1[cr_pad(base + blk * 256 + k + 16 * u)] = v[u];
     }
     __syncthreads();
-    const float invL = 1.0f / (float)bm.L, inv16r = 1.0f / (float)m16;
+    const float invL = 1.0f / (float)bm.L, inv16r = 256.0f / (float)bm.L;    // 256 / L = 1 / (L1 r0), L1 = column length
     switch (r0) {
         case 2: rows3_last<2>(rows, S1, T, G, N, tl.c0, invL, inv16r); break;
         case 3: rows3_last<3>(rows, S1, T, G, N, tl.c0, invL, inv16r); break;
@@ -857,6 +889,7 @@ czt_rows3_kernel(const BandMeta *__restrict__ bands, const RowTile *__restrict__
 // ------------------------------------------------------------------------------------------------ CZT output pass
 // 16-point inverse FFT up the columns (-> a'), output index i = L2*a' + b'; power[band][i] = |c|^2 / (L M)^2 for i < F,
 // plus the per-track maximum (atomicMax on the bit pattern of a non-negative float).
+template <int L1>
 __global__ void __launch_bounds__(CQ_THREADS)
 czt_out_kernel(const BandMeta *__restrict__ bands, const float2 *__restrict__ work, int M, int F, int fpitch,
                float *__restrict__ power, unsigned int *__restrict__ pmax) {
@@ -865,14 +898,14 @@ czt_out_kernel(const BandMeta *__restrict__ bands, const float2 *__restrict__ wo
     float best = 0.f;
     if (b < bm.L2 && b < F) {
         const float2 *src = work + bm.work_off;
-        float2 v[16];
+        float2 v[L1];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] = src[c * bm.L2 + b];
-        dft16(v, +1);
+        for (int c = 0; c < L1; ++c) v[c] = src[c * bm.L2 + b];
+        dft_col<L1>(v, +1);
         const float scale = 1.0f / ((float)bm.L * (float)M);
         float *dst = power + (long long)blockIdx.y * fpitch;
 #pragma unroll
-        for (int a = 0; a < 16; ++a) {
+        for (int a = 0; a < L1; ++a) {
             const int i = bm.L2 * a + b;
             if (i < F) {
                 const float re = v[a].x * scale, im = v[a].y * scale;
@@ -1120,6 +1153,7 @@ struct CqtPlan {
     int n_tiles = 0, n_tiles3 = 0;
     size_t smem_rows = 0;
     int max_L2 = 0;
+    int L1 = 16;             // chirp-z column length: 16, or 32 for tracks longer than 6.7 minutes (L = L1 * L2)
     long long work_elems = 0;
     int fpitch = 0;
     cudaEvent_t ready = nullptr;     // recorded on the creating stream after the tables are filled
@@ -1434,14 +1468,18 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
     std::vector<BandMeta> bands(CQ_BINS);
     std::vector<int> Ls;
     long long off = 0;
+    long long need_max = 0;
+    for (int j = 0; j < CQ_BINS; ++j) need_max = std::max(need_max, (long long)d.lg[j] + d.F - 1);
+    pl.L1 = need_max <= (long long)CQ_L1 * CQ_MAX_ROW ? CQ_L1 : 2 * CQ_L1;
+    const int L1 = pl.L1;
     for (int j = 0; j < CQ_BINS; ++j) {
         BandMeta &b = bands[j];
         b.lg = d.lg[j];
         b.half = d.lg[j] / 2;
         b.first_bin = d.pos[j] - b.half;
         const long long need = (long long)d.lg[j] + d.F - 1;
-        b.L2 = pick_row_len((need + CQ_L1 - 1) / CQ_L1);
-        b.L = b.L2 * CQ_L1;
+        b.L2 = pick_row_len((need + L1 - 1) / L1);
+        b.L = b.L2 * L1;
         b.r0 = 0;
         if (b.L2 > 256 && b.L2 <= 4096 && b.L2 % 256 == 0 && !env_int("HPFW_CQT_ROWS_GENERIC", 0)) {
             const int r0 = b.L2 / 256;
@@ -1449,7 +1487,7 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
         }
         if (b.L2 <= 0)
             HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: audio of %lld samples needs a %lld-point chirp-z transform; limit %d "
-                      "(about 6.7 minutes at 44.1 kHz)", (long long)N, need, CQ_L1 * CQ_MAX_ROW);
+                      "(about 13.5 minutes at 44.1 kHz)", (long long)N, need, 2 * CQ_L1 * CQ_MAX_ROW);
         auto it = std::find(Ls.begin(), Ls.end(), b.L);
         if (it == Ls.end()) { Ls.push_back(b.L); b.btab = (int)Ls.size() - 1; }
         else b.btab = (int)(it - Ls.begin());
@@ -1468,9 +1506,9 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
     pl.smem_rows = 0;
     for (int j = 0; j < CQ_BINS; ++j) {
         const int L2 = bands[j].L2, r0 = bands[j].r0;
-        const int G = std::max(1, std::min(CQ_L1, r0 ? 16 / r0 : CQ_ROW_POINTS / L2));
-        for (int c0 = 0; c0 < CQ_L1; c0 += G) {
-            const int g = std::min(G, CQ_L1 - c0);
+        const int G = std::max(1, std::min(L1, r0 ? 16 / r0 : CQ_ROW_POINTS / L2));
+        for (int c0 = 0; c0 < L1; c0 += G) {
+            const int g = std::min(G, L1 - c0);
             if (r0) {
                 tiles3.push_back({j, c0, g});
             } else {
@@ -1508,7 +1546,7 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
     std::vector<BandMeta> fb((size_t)nL);
     int max_fL2 = 0;
     for (int i = 0; i < nL; ++i) {
-        const int L2 = Ls[(size_t)i] / CQ_L1;
+        const int L2 = Ls[(size_t)i] / L1;
         if (!factor_smooth(L2, descs[(size_t)i])) HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: too many FFT stages");
         o_rowtw[(size_t)i] = take(L2);
         o_tt[(size_t)i] = take(L2);
@@ -1517,7 +1555,7 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
         jobs.push_back({TAB_UNIT, L2, o_tt[(size_t)i], L2});
         // chirp-filter spectrum: a pseudo-band whose work area IS the table
         fb[(size_t)i] = BandMeta{0, 0, 0, Ls[(size_t)i], L2, i, 0, o_bt[(size_t)i]};
-        for (int c = 0; c < CQ_L1; ++c) ftiles.push_back({i, c, 1});
+        for (int c = 0; c < L1; ++c) ftiles.push_back({i, c, 1});
         max_fL2 = std::max(max_fL2, L2);
     }
     const size_t table_bytes = sizeof(float2) * (size_t)fo;
@@ -1585,8 +1623,13 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
         const BandMeta *dfb = reinterpret_cast<const BandMeta *>(dmeta + m_fb);
         {
             KernelScope ks(ctx, HPFW_K_CQT, stream);
-            czt_cols_kernel<1><<<dim3((max_fL2 + CQ_THREADS - 1) / CQ_THREADS, nL), CQ_THREADS, 0, stream>>>(
-                dfb, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, d.M, d.F, tab);
+            const dim3 gf((max_fL2 + CQ_THREADS - 1) / CQ_THREADS, nL);
+            if (L1 == 16)
+                czt_cols_kernel<1, 16><<<gf, CQ_THREADS, 0, stream>>>(dfb, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr,
+                                                                      d.M, d.F, tab);
+            else
+                czt_cols_kernel<1, 32><<<gf, CQ_THREADS, 0, stream>>>(dfb, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr,
+                                                                      d.M, d.F, tab);
         }
         {
             KernelScope ks(ctx, HPFW_K_CQT, stream);
@@ -1694,15 +1737,22 @@ static int cqt_run(hpfw_ctx *ctx, const float *d_audio, int64_t N, float *d_out,
     const dim3 gcol((pl->max_L2 + CQ_THREADS - 1) / CQ_THREADS, CQ_BINS);
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
-        if (pl->bluestein)
-            czt_cols_kernel<2><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, sc->zlo.as<float2>(), nullptr,
-                                                                 pl->klo, pl->khi, nullptr, nullptr,
-                                                                 pl->chirp, d.M, d.F, sc->work.as<float2>());
-        else
-            czt_cols_kernel<0><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, sc->zlo.as<float2>(),
-                                                                 sc->zhi.as<float2>(), pl->klo, pl->khi,
-                                                                 pl->twN_hi, pl->twN_lo,
-                                                                 pl->chirp, d.M, d.F, sc->work.as<float2>());
+        float2 *zlo = sc->zlo.as<float2>(), *zhi = sc->zhi.as<float2>(), *wk = sc->work.as<float2>();
+        if (pl->bluestein) {
+            if (pl->L1 == 16)
+                czt_cols_kernel<2, 16><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, zlo, nullptr, pl->klo, pl->khi, nullptr,
+                                                                        nullptr, pl->chirp, d.M, d.F, wk);
+            else
+                czt_cols_kernel<2, 32><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, zlo, nullptr, pl->klo, pl->khi, nullptr,
+                                                                        nullptr, pl->chirp, d.M, d.F, wk);
+        } else {
+            if (pl->L1 == 16)
+                czt_cols_kernel<0, 16><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, zlo, zhi, pl->klo, pl->khi, pl->twN_hi,
+                                                                        pl->twN_lo, pl->chirp, d.M, d.F, wk);
+            else
+                czt_cols_kernel<0, 32><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, zlo, zhi, pl->klo, pl->khi, pl->twN_hi,
+                                                                        pl->twN_lo, pl->chirp, d.M, d.F, wk);
+        }
     }
     if (pl->n_tiles3 > 0) {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
@@ -1718,9 +1768,12 @@ static int cqt_run(hpfw_ctx *ctx, const float *d_audio, int64_t N, float *d_out,
     }
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
-        czt_out_kernel<<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, sc->work.as<float2>(), d.M, d.F,
-                                                         pl->fpitch, sc->power.as<float>(),
-                                                         sc->pmax.as<unsigned int>());
+        if (pl->L1 == 16)
+            czt_out_kernel<16><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, sc->work.as<float2>(), d.M, d.F, pl->fpitch,
+                                                                sc->power.as<float>(), sc->pmax.as<unsigned int>());
+        else
+            czt_out_kernel<32><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, sc->work.as<float2>(), d.M, d.F, pl->fpitch,
+                                                                sc->power.as<float>(), sc->pmax.as<unsigned int>());
     }
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);

@@ -4,8 +4,8 @@ unpinned" versus essentia, see its header), and the audio -> hashprint path agai
 Tolerances (north_star: "within a stated fp32 relative tolerance"):
   FFT:        max |err| <= 2e-6 * max |X|      (fp32 Stockham, up to 4M points)
   magnitude:  max |err| <= 1e-5 * max |mag|    per track
-  dB:         <= 0.01 dB wherever the oracle is above -79 dB (Bluestein path for non-smooth lengths: 0.01 dB above
-              -70 dB, 0.05 dB above -79 dB)
+  dB:         <= 0.01 dB wherever the oracle is above -79 dB (Bluestein path for non-smooth lengths and tracks longer
+              than 6.7 minutes: 0.01 dB above -70 dB, 0.05 dB above -79 dB)
 """
 import ctypes as C
 
@@ -60,7 +60,8 @@ def _cqt(ctx, audio, magnitude=False):
 
 
 @pytest.mark.parametrize("seconds,sr", [(6.0, 22050), (6.0, 44100), (30.0, 22050), (20.0, 44100), (2.0, 44100),
-                                        (180.0, 44100)])
+                                        (180.0, 44100),
+                                        (450.0, 44100), (780.0, 44100)])    # > 6.7 min: chirp-z column length 32
 def test_cqt_vs_oracle(ctx, seconds, sr):
     audio = synth.synth_track(int(seconds * 10) + sr, seconds, sr)
     ref_mag = nsgcq.nsgcq_magnitude(audio)
@@ -72,7 +73,13 @@ def test_cqt_vs_oracle(ctx, seconds, sr):
     db = _cqt(ctx, audio)
     above = ref_db > -79.0
     assert above.mean() > 0.5
-    assert np.max(np.abs(db[above] - ref_db[above])) <= 0.01
+    if seconds <= 400.0:
+        assert np.max(np.abs(db[above] - ref_db[above])) <= 0.01
+    else:
+        # 20-35 M-point transforms: the fp32 rounding noise (~3e-7 of the track maximum) is 0.2 % of an amplitude that sits
+        # 79 dB below it; same bar as the Bluestein path
+        assert np.max(np.abs(db[ref_db > -70.0] - ref_db[ref_db > -70.0])) <= 0.01
+        assert np.max(np.abs(db[above] - ref_db[above])) <= 0.05
     assert db.max() == 0.0 and db.min() >= -80.0
     m = nsgcq.nsg_design(len(audio))[2]
     if m % 3 == 0:      # the column the reference leaves unwritten (cqt.h:73-81): defined as amplitude 0 -> the floor
@@ -187,6 +194,10 @@ def test_cqt_limits(ctx):
     with pytest.raises(HpfwError) as e:
         _cqt(ctx, np.zeros(4000, dtype=np.float32))          # too short for the 121-band design
     assert e.value.code == ERR_SHORT
+    from hpfw_b200._lib import ERR_LIMIT
+    with pytest.raises(HpfwError) as e:
+        _cqt(ctx, np.zeros(44100 * 900, dtype=np.float32))   # 15 min: beyond the 32 x 8192-point chirp-z transform
+    assert e.value.code == ERR_LIMIT and "13.5 minutes" in str(e.value)
 
 
 def test_pcm16_entry_points_equal_the_float_path(ctx, hashprint_golden):
