@@ -23,7 +23,7 @@
 //       registers between stages, and a radix-16 register IFFT fused with |.|^2, the 1/(L M) scale and the per-track
 //       maximum. Rows shorter than 512 or longer than 4096 points use the generic shared-memory kernel (czt_rows_kernel).
 //       Tracks longer than 6.7 minutes need L > 16 * 8192: their plans use 32-point columns (dft32 in registers,
-//       L = 32 * L2 <= 262,144: up to ~13.5 minutes); everything else is unchanged.
+//       up to ~13.5 minutes) or 64-point columns (dft64, up to ~27 minutes); everything else is unchanged.
 //   (3) dB conversion + transpose to the reference's column-major [121 x cols] layout.
 // Twiddles: one table W_n^m per transform length; a butterfly loads one entry and forms its powers by a depth-4 product
 // tree on the FMA pipe (error <= 5 ulp of a unit phasor) instead of R-1 table loads.
@@ -250,9 +250,48 @@ __device__ __forceinline__ void dft32(float2 (&v)[32], int sign) {
         v[k + 16] = csub(e[k], t);
     }
 }
+// 64-point DFT in registers (natural order in and out): a = 4 a1 + a0 -> four 16-point DFTs over a1, twiddle W_64^(a0 c0),
+// radix-4 over a0: X[c0 + 16 c1]. Column pass of tracks between 13.5 and 27 minutes.
+__device__ __forceinline__ void dft64(float2 (&v)[64], int sign) {
+    constexpr float C[46] = {1.0000000000f, 0.9951847267f, 0.9807852804f, 0.9569403357f, 0.9238795325f,
+        0.8819212643f, 0.8314696123f, 0.7730104534f, 0.7071067812f, 0.6343932842f, 0.5555702330f, 0.4713967368f,
+        0.3826834324f, 0.2902846773f, 0.1950903220f, 0.0980171403f, 0.0000000000f, -0.0980171403f, -0.1950903220f,
+        -0.2902846773f, -0.3826834324f, -0.4713967368f, -0.5555702330f, -0.6343932842f, -0.7071067812f,
+        -0.7730104534f, -0.8314696123f, -0.8819212643f, -0.9238795325f, -0.9569403357f, -0.9807852804f,
+        -0.9951847267f, -1.0000000000f, -0.9951847267f, -0.9807852804f, -0.9569403357f, -0.9238795325f,
+        -0.8819212643f, -0.8314696123f, -0.7730104534f, -0.7071067812f, -0.6343932842f, -0.5555702330f,
+        -0.4713967368f, -0.3826834324f, -0.2902846773f};   // cos(2 pi m / 64), m = a0 c0 <= 45
+    constexpr float S[46] = {0.0000000000f, 0.0980171403f, 0.1950903220f, 0.2902846773f, 0.3826834324f,
+        0.4713967368f, 0.5555702330f, 0.6343932842f, 0.7071067812f, 0.7730104534f, 0.8314696123f, 0.8819212643f,
+        0.9238795325f, 0.9569403357f, 0.9807852804f, 0.9951847267f, 1.0000000000f, 0.9951847267f, 0.9807852804f,
+        0.9569403357f, 0.9238795325f, 0.8819212643f, 0.8314696123f, 0.7730104534f, 0.7071067812f, 0.6343932842f,
+        0.5555702330f, 0.4713967368f, 0.3826834324f, 0.2902846773f, 0.1950903220f, 0.0980171403f, 0.0000000000f,
+        -0.0980171403f, -0.1950903220f, -0.2902846773f, -0.3826834324f, -0.4713967368f, -0.5555702330f,
+        -0.6343932842f, -0.7071067812f, -0.7730104534f, -0.8314696123f, -0.8819212643f, -0.9238795325f,
+        -0.9569403357f};   // sin(2 pi m / 64)
+    float2 y[4][16];
+#pragma unroll
+    for (int a0 = 0; a0 < 4; ++a0) {
+#pragma unroll
+        for (int a1 = 0; a1 < 16; ++a1) y[a0][a1] = v[4 * a1 + a0];
+        dft16(y[a0], sign);
+    }
+#pragma unroll
+    for (int c0 = 0; c0 < 16; ++c0) {
+        float2 t0 = y[0][c0], t1 = y[1][c0], t2 = y[2][c0], t3 = y[3][c0];
+        if (c0 > 0) {
+            t1 = cmul(t1, make_float2(C[c0], sign < 0 ? -S[c0] : S[c0]));
+            t2 = cmul(t2, make_float2(C[2 * c0], sign < 0 ? -S[2 * c0] : S[2 * c0]));
+            t3 = cmul(t3, make_float2(C[3 * c0], sign < 0 ? -S[3 * c0] : S[3 * c0]));
+        }
+        dft4(t0, t1, t2, t3, sign);
+        v[c0] = t0; v[c0 + 16] = t1; v[c0 + 32] = t2; v[c0 + 48] = t3;
+    }
+}
 template <int L1> __device__ __forceinline__ void dft_col(float2 (&v)[L1], int sign);
 template <> __device__ __forceinline__ void dft_col<16>(float2 (&v)[16], int sign) { dft16(v, sign); }
 template <> __device__ __forceinline__ void dft_col<32>(float2 (&v)[32], int sign) { dft32(v, sign); }
+template <> __device__ __forceinline__ void dft_col<64>(float2 (&v)[64], int sign) { dft64(v, sign); }
 
 template <int R> __device__ __forceinline__ void dft_r(float2 (&v)[R], int sign);
 template <> __device__ __forceinline__ void dft_r<2>(float2 (&v)[2], int) { dft2(v); }
@@ -1153,7 +1192,7 @@ struct CqtPlan {
     int n_tiles = 0, n_tiles3 = 0;
     size_t smem_rows = 0;
     int max_L2 = 0;
-    int L1 = 16;             // chirp-z column length: 16, or 32 for tracks longer than 6.7 minutes (L = L1 * L2)
+    int L1 = 16;             // chirp-z column length: 16, 32 beyond 6.7 minutes, 64 beyond 13.5 minutes (L = L1 * L2)
     long long work_elems = 0;
     int fpitch = 0;
     cudaEvent_t ready = nullptr;     // recorded on the creating stream after the tables are filled
@@ -1470,7 +1509,7 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
     long long off = 0;
     long long need_max = 0;
     for (int j = 0; j < CQ_BINS; ++j) need_max = std::max(need_max, (long long)d.lg[j] + d.F - 1);
-    pl.L1 = need_max <= (long long)CQ_L1 * CQ_MAX_ROW ? CQ_L1 : 2 * CQ_L1;
+    pl.L1 = need_max <= (long long)CQ_L1 * CQ_MAX_ROW ? CQ_L1 : (need_max <= 2ll * CQ_L1 * CQ_MAX_ROW ? 2 * CQ_L1 : 4 * CQ_L1);
     const int L1 = pl.L1;
     for (int j = 0; j < CQ_BINS; ++j) {
         BandMeta &b = bands[j];
@@ -1487,7 +1526,7 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
         }
         if (b.L2 <= 0)
             HPFW_FAIL(HPFW_ERR_LIMIT, "CQT: audio of %lld samples needs a %lld-point chirp-z transform; limit %d "
-                      "(about 13.5 minutes at 44.1 kHz)", (long long)N, need, 2 * CQ_L1 * CQ_MAX_ROW);
+                      "(about 27 minutes at 44.1 kHz)", (long long)N, need, 4 * CQ_L1 * CQ_MAX_ROW);
         auto it = std::find(Ls.begin(), Ls.end(), b.L);
         if (it == Ls.end()) { Ls.push_back(b.L); b.btab = (int)Ls.size() - 1; }
         else b.btab = (int)(it - Ls.begin());
@@ -1627,8 +1666,11 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
             if (L1 == 16)
                 czt_cols_kernel<1, 16><<<gf, CQ_THREADS, 0, stream>>>(dfb, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr,
                                                                       d.M, d.F, tab);
-            else
+            else if (L1 == 32)
                 czt_cols_kernel<1, 32><<<gf, CQ_THREADS, 0, stream>>>(dfb, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr,
+                                                                      d.M, d.F, tab);
+            else
+                czt_cols_kernel<1, 64><<<gf, CQ_THREADS, 0, stream>>>(dfb, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr,
                                                                       d.M, d.F, tab);
         }
         {
@@ -1742,15 +1784,21 @@ static int cqt_run(hpfw_ctx *ctx, const float *d_audio, int64_t N, float *d_out,
             if (pl->L1 == 16)
                 czt_cols_kernel<2, 16><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, zlo, nullptr, pl->klo, pl->khi, nullptr,
                                                                         nullptr, pl->chirp, d.M, d.F, wk);
-            else
+            else if (pl->L1 == 32)
                 czt_cols_kernel<2, 32><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, zlo, nullptr, pl->klo, pl->khi, nullptr,
+                                                                        nullptr, pl->chirp, d.M, d.F, wk);
+            else
+                czt_cols_kernel<2, 64><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, zlo, nullptr, pl->klo, pl->khi, nullptr,
                                                                         nullptr, pl->chirp, d.M, d.F, wk);
         } else {
             if (pl->L1 == 16)
                 czt_cols_kernel<0, 16><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, zlo, zhi, pl->klo, pl->khi, pl->twN_hi,
                                                                         pl->twN_lo, pl->chirp, d.M, d.F, wk);
-            else
+            else if (pl->L1 == 32)
                 czt_cols_kernel<0, 32><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, zlo, zhi, pl->klo, pl->khi, pl->twN_hi,
+                                                                        pl->twN_lo, pl->chirp, d.M, d.F, wk);
+            else
+                czt_cols_kernel<0, 64><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, zlo, zhi, pl->klo, pl->khi, pl->twN_hi,
                                                                         pl->twN_lo, pl->chirp, d.M, d.F, wk);
         }
     }
@@ -1771,8 +1819,11 @@ static int cqt_run(hpfw_ctx *ctx, const float *d_audio, int64_t N, float *d_out,
         if (pl->L1 == 16)
             czt_out_kernel<16><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, sc->work.as<float2>(), d.M, d.F, pl->fpitch,
                                                                 sc->power.as<float>(), sc->pmax.as<unsigned int>());
-        else
+        else if (pl->L1 == 32)
             czt_out_kernel<32><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, sc->work.as<float2>(), d.M, d.F, pl->fpitch,
+                                                                sc->power.as<float>(), sc->pmax.as<unsigned int>());
+        else
+            czt_out_kernel<64><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, sc->work.as<float2>(), d.M, d.F, pl->fpitch,
                                                                 sc->power.as<float>(), sc->pmax.as<unsigned int>());
     }
     {

@@ -61,7 +61,8 @@ def _cqt(ctx, audio, magnitude=False):
 
 @pytest.mark.parametrize("seconds,sr", [(6.0, 22050), (6.0, 44100), (30.0, 22050), (20.0, 44100), (2.0, 44100),
                                         (180.0, 44100),
-                                        (450.0, 44100), (780.0, 44100)])    # > 6.7 min: chirp-z column length 32
+                                        (450.0, 44100), (780.0, 44100),     # > 6.7 min: chirp-z column length 32
+                                        (1500.0, 44100)])                   # > 13.5 min: column length 64
 def test_cqt_vs_oracle(ctx, seconds, sr):
     audio = synth.synth_track(int(seconds * 10) + sr, seconds, sr)
     ref_mag = nsgcq.nsgcq_magnitude(audio)
@@ -196,8 +197,8 @@ def test_cqt_limits(ctx):
     assert e.value.code == ERR_SHORT
     from hpfw_b200._lib import ERR_LIMIT
     with pytest.raises(HpfwError) as e:
-        _cqt(ctx, np.zeros(44100 * 900, dtype=np.float32))   # 15 min: beyond the 32 x 8192-point chirp-z transform
-    assert e.value.code == ERR_LIMIT and "13.5 minutes" in str(e.value)
+        _cqt(ctx, np.zeros(44100 * 1800, dtype=np.float32))   # 30 min: beyond the 64 x 8192-point chirp-z transform
+    assert e.value.code == ERR_LIMIT and "27 minutes" in str(e.value)
 
 
 def test_pcm16_entry_points_equal_the_float_path(ctx, hashprint_golden):
