@@ -1,5 +1,5 @@
 // hpfw_b200/csrc/matcher.cuh — the hashprint database object shared by the two matcher kernels (matcher.cu: XOR + POPC on
-// the integer pipes; match_tc.cu: the same cross-correlation as an exact int8 GEMM on the tensor cores).
+// the integer pipes; match_tc.cu: the same cross-correlation as an exact +-1 GEMM on the tensor cores, fp4 or int8 operands).
 #pragma once
 
 #include "common.cuh"
@@ -18,7 +18,7 @@ constexpr int XT_NOFF_F4 = 480; // fp4 kernel: 2 x N(240); 32 TMEM columns are l
 constexpr int XT_JS = 4;        // int8 kernel: query words per TMA stage (64 bytes per word and query)
 constexpr int XT_JS_F4 = 8;     // fp4 kernel (32 bytes per word and query)
 
-// one group of up to XT_NQ queries of similar length: its expanded (s8) words start at exp_off bytes into the scratch
+// one group of up to XT_NQ queries of similar length: its expanded words start at exp_off bytes into the scratch
 struct XtGroup {
     int64_t exp_off;
     int32_t kmax;   // longest query of the group (words)
@@ -48,8 +48,9 @@ struct hpfw_db {
 };
 
 namespace hpfw_b200 {
-// Expands the grouped queries to s8 (f4 = 0) or e2m1 (f4 = 1) and runs the tensor-core matcher for n_groups groups; best[q * n_tracks + track] receives
-// (dist << 20 | offset) minima exactly as match_kernel writes them. All table pointers are device pointers.
+// Expands the grouped queries to s8 (f4 = 0) or e2m1 (f4 = 1) and runs the tensor-core matcher for n_groups groups;
+// best[q * n_tracks + track] receives (dist << 20 | offset) minima exactly as match_kernel writes them. All table pointers
+// are device pointers. route_queries (matcher.cu) decides which queries come here.
 int match_tc_run(hpfw_ctx *ctx, const hpfw_db *db, int f4, const uint64_t *d_qwords, const int64_t *d_qstart,
                  const XtGroup *d_groups, const int32_t *d_row_q, const int32_t *d_row_k, int n_groups, int kpad_max,
                  uint8_t *d_qexp, unsigned long long *d_best, cudaStream_t stream);
