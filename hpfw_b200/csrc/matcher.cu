@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -489,11 +490,14 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
     }
     if (!d_qwords && qoffsets[n_queries] > qoffsets[0]) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_match_device: d_qwords is NULL");
 
-    // queries per chunk: bound the best[] scratch to ~1 GiB (and the tensor-core matcher's expanded queries to ~2 GiB)
+    // queries per chunk: bound the best[] scratch to ~1 GiB (HPFW_MATCH_SCRATCH_BYTES overrides the bound; the tests use it to
+    // exercise the multi-chunk path on small inputs) and the tensor-core matcher's expanded queries to ~2 GiB
     const int impl = ctx->match_impl;
     const int f4 = impl == 3 || (impl == 2 && ctx->match_tc_f4);   // operand encoding of the tensor-core kernel
     const size_t row_bytes = sizeof(uint64_t) * std::max<size_t>(1, size_t(R));
-    int qchunk = int(std::min<size_t>(size_t(n_queries), std::max<size_t>(1, (size_t(1) << 30) / row_bytes)));
+    size_t best_cap = size_t(1) << 30;
+    if (const char *env = getenv("HPFW_MATCH_SCRATCH_BYTES")) best_cap = std::max<size_t>(row_bytes, strtoull(env, nullptr, 10));
+    int qchunk = int(std::min<size_t>(size_t(n_queries), std::max<size_t>(1, best_cap / row_bytes)));
     qchunk = std::min(qchunk, 1 << 20);  // keeps gridDim.y within 65535
     if (impl != 0) {
         const size_t per_query = size_t(xt_kpad(kmax, f4)) * xt_word_bytes(f4);

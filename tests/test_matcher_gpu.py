@@ -228,6 +228,20 @@ def test_many_queries_mixed_lengths(ctx):
     assert np.array_equal(out["track"], tr) and np.array_equal(out["cnt"], d) and np.array_equal(out["offset"], o)
 
 
+def test_query_chunks(ctx, monkeypatch):
+    """More queries than the best[] scratch holds at once (forced here with a 64 KB bound instead of the 1 GiB default):
+    the batch is processed in chunks, each with its own routing, group tables and key slice."""
+    monkeypatch.setenv("HPFW_MATCH_SCRATCH_BYTES", str(64 * 1024))
+    rng = np.random.default_rng(71)
+    n_tracks = 37
+    words, offs = synth.synth_hashprint_db(71, n_tracks, rng.integers(60, 900, size=n_tracks))
+    kk = np.array([50, 51, 143, 40])[rng.integers(0, 4, size=700)]          # 64 KB / (37 * 8 B) = 221 queries per chunk
+    qw, qo, truth = synth.synth_hashprint_queries(72, words, offs, len(kk), kk)
+    out = MemoryStorage(ctx).build_packed(words, offs).find_topk_packed(qw, qo, 4)
+    tr, d, o = oracle.find_topk_batch(words, offs, qw, qo, 4, 8)
+    assert np.array_equal(out["track"], tr) and np.array_equal(out["cnt"], d) and np.array_equal(out["offset"], o)
+
+
 def test_limits_reported(ctx):
     from hpfw_b200 import HpfwError
     words, offs = synth.synth_hashprint_db(31, 2, 100)
