@@ -193,13 +193,39 @@ class ShardedLiveSongIdentification:
         return self
 
     def search(self, queries: Sequence[np.ndarray], topk: int = 1):
-        """queries: decoded query buffers (the same list on every rank). Returns a structured array [Q, topk] of
-        (track, cnt, offset) with GLOBAL track indices; self.names[track] is the reference's SearchResult::filename."""
+        """queries: decoded query buffers (the same list on every rank). Rank r extracts the hashprints of queries r, r+W,
+        r+2W, ...; one all-gather hands every rank all of them (their word counts follow from the sample counts, so every
+        rank knows the layout); then the sharded search. Returns a structured array [Q, topk] of (track, cnt, offset) with
+        GLOBAL track indices; self.names[track] is the reference's SearchResult::filename."""
         import torch
+        import torch.distributed as dist
         ex = self.extractor
-        hps = [ex.calc_hashprint(np.ascontiguousarray(q, dtype=np.float32)) for q in queries]
-        qoffs = np.zeros(len(hps) + 1, dtype=np.int64)
-        np.cumsum([len(h) for h in hps], out=qoffs[1:])
-        flat = np.concatenate(hps) if hps else np.zeros(0, dtype=np.uint64)
+        nq = len(queries)
+        words = [max(ex.words(len(q)), 0) for q in queries]
+        qoffs = np.zeros(nq + 1, dtype=np.int64)
+        np.cumsum(words, out=qoffs[1:])
+        mine = list(range(self.rank, nq, self.world))
+        local = [ex.calc_hashprint(np.ascontiguousarray(queries[i], dtype=np.float32)) for i in mine]
+        flat = np.zeros(int(qoffs[-1]), dtype=np.uint64)
+        if self.world == 1:
+            for i, h in zip(mine, local):
+                flat[qoffs[i]:qoffs[i + 1]] = h
+        else:
+            per_rank = [sum(words[i] for i in range(r, nq, self.world)) for r in range(self.world)]
+            pad = max(max(per_rank), 1)
+            dev = torch.device("cuda", self.ctx.device)
+            buf = np.zeros(pad, dtype=np.uint64)
+            if local:
+                cat = np.concatenate(local)
+                buf[:len(cat)] = cat
+            t_local = torch.from_numpy(buf.view(np.int64)).to(dev)
+            t_all = torch.empty((self.world, pad), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(t_all.view(-1), t_local, group=self.group)
+            allw = t_all.cpu().numpy().view(np.uint64)
+            for r in range(self.world):
+                pos = 0
+                for i in range(r, nq, self.world):
+                    flat[qoffs[i]:qoffs[i + 1]] = allw[r, pos:pos + words[i]]
+                    pos += words[i]
         pinned = torch.from_numpy(flat.view(np.int64).copy()).pin_memory()
         return self.storage.search_host(pinned, qoffs, topk)
