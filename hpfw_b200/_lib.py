@@ -44,6 +44,7 @@ _SIGS = {
     "hpfw_db_find_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Match)]),
     "hpfw_db_match_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "hpfw_set_match_impl": (C.c_int, [C.c_void_p, C.c_int]),
+    "hpfw_match_tc_selftest": (C.c_int, [C.c_void_p, C.c_int]),
     "hpfw_match_route": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "hpfw_topk_merge_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "hpfw_keys_decode": (None, [C.c_void_p, C.c_int, C.POINTER(Match)]),
@@ -64,6 +65,7 @@ _SIGS = {
     "hpfw_cov_add_spectrogram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "hpfw_cov_add_spectrogram_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "hpfw_calc_filters": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hpfw_set_cqt_window": (C.c_int, [C.c_void_p, C.c_int]),
     "hpfw_cqt_cols": (C.c_int, [C.c_int64]),
     "hpfw_cqt_spectrogram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int)]),
     "hpfw_cqt_spectrogram_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

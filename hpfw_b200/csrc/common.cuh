@@ -107,6 +107,8 @@ struct hpfw_ctx {
                                        // (default); 1 = tensor cores (int8) always; 3 = tensor cores (fp4) always;
                                        // 0 = integer pipes always
     int match_tc_f4 = 1;               // operand encoding the default routing (impl 2) uses: 1 = fp4 (default), 0 = int8
+    int tc_selftest[2] = {0, 0};       // known-answer self-test of the tensor-core matcher per encoding [int8, fp4]:
+                                       // 0 = not run yet, 1 = passed, -1 = failed (route disabled), 2 = running
 
     // projection state
     hpfw_b200::DeviceBuffer filters_perm;  // filters permuted to [context][band(padded 128)][filter] etc. (project.cu)
@@ -123,6 +125,7 @@ struct hpfw_ctx {
     uint64_t cov_tracks = 0;
 
     // cqt state
+    int cqt_window = 0;                // band window: 0 = periodic centred Hann (default), 1 = symmetric Hann (cqt.cu)
     hpfw_b200::CqtPlanCache *cqt = nullptr;
     cudaStream_t lane_stream[HPFW_CTX_LANES] = {};   // batched extraction: concurrent tracks
     cudaEvent_t lane_join[HPFW_CTX_LANES] = {};
@@ -138,7 +141,29 @@ struct hpfw_ctx {
     double timing_ms[HPFW_K_COUNT] = {};
     uint64_t timing_n[HPFW_K_COUNT] = {};
 
-    cudaStream_t pick(void *s) const { return s ? static_cast<cudaStream_t>(s) : stream; }
+    // Cross-stream ordering. All entry points of a context share its scratch buffers (best/qmeta/qexp, spectro, delta_tc,
+    // cov_accum, the CQT lanes ...), so work enqueued on one stream must not overtake work an earlier call enqueued on
+    // another. Every entry point announces the stream it is about to use: when that differs from the stream of the previous
+    // call, the new stream first waits (on the device, no host synchronisation) for everything enqueued so far on the old one.
+    // A caller that keeps to one stream per context pays nothing.
+    cudaStream_t last_stream = nullptr;
+    bool last_stream_valid = false;
+    cudaEvent_t order_ev = nullptr;
+    void order_on(cudaStream_t s) {
+        if (last_stream_valid && last_stream != s) {
+            if (!order_ev) cudaEventCreateWithFlags(&order_ev, cudaEventDisableTiming);
+            // a caller may have destroyed the previous stream (its work is then complete or abandoned): ignore that error
+            if (order_ev && cudaEventRecord(order_ev, last_stream) == cudaSuccess) cudaStreamWaitEvent(s, order_ev, 0);
+            else cudaGetLastError();
+        }
+        last_stream = s;
+        last_stream_valid = true;
+    }
+    cudaStream_t pick(void *s) {
+        cudaStream_t st = s ? static_cast<cudaStream_t>(s) : stream;
+        order_on(st);
+        return st;
+    }
 };
 
 namespace hpfw_b200 {

@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <cstdlib>
+#include <cstring>
 
 namespace hpfw_b200 {
 static thread_local char g_err[1024] = "";
@@ -48,6 +49,14 @@ int hpfw_ctx_create(int device, hpfw_ctx **out) {
         if (v >= 0 && v <= 3) c->match_impl = v;
     }
     if (const char *env = getenv("HPFW_MATCH_TC_F4")) c->match_tc_f4 = atoi(env) != 0;
+    if (const char *env = getenv("HPFW_CQT_WINDOW")) {
+        if (!strcmp(env, "symmetric") || !strcmp(env, "1")) c->cqt_window = 1;
+        else if (!strcmp(env, "periodic") || !strcmp(env, "0")) c->cqt_window = 0;
+        else {
+            delete c;
+            HPFW_FAIL(HPFW_ERR_ARG, "HPFW_CQT_WINDOW must be 'periodic' or 'symmetric' (got '%s')", env);
+        }
+    }
     *out = c;
     return HPFW_OK;
 }
@@ -87,6 +96,7 @@ void hpfw_ctx_destroy(hpfw_ctx *c) {
     }
     if (c->lane_fork) cudaEventDestroy(c->lane_fork);
     if (c->pin_in_free) cudaEventDestroy(c->pin_in_free);
+    if (c->order_ev) cudaEventDestroy(c->order_ev);
     cudaStreamDestroy(c->stream);
     delete c;
 }

@@ -693,6 +693,17 @@ bl_post_kernel(float2 *__restrict__ x, long long N, int P, int klo, int K) {
     x[i] = make_float2(v.x * inv, v.y * inv);
 }
 
+// The band window at index kp = k + floor(Lg/2), k = -floor(Lg/2) .. ceil(Lg/2)-1 (the reference passes "window","hann" to
+// NSGConstantQ, /root/reference/include/hpfw/spectrum/cqt.h:58; what essentia builds from that name cannot be checked here):
+//   0 (default) periodic Hann centred on k = 0:  0.5 + 0.5 cos(2 pi k / Lg)          (the NSG toolbox's winfuns('hann'))
+//   1           symmetric Hann over the Lg taps: 0.5 - 0.5 cos(2 pi kp / (Lg - 1))    (a generic "hann" window of size Lg,
+//               rotated so that tap floor(Lg/2) sits on the band centre)
+// Selected per context: HPFW_CQT_WINDOW={periodic,symmetric} or hpfw_set_cqt_window(); oracle/nsgcq.py has the same switch.
+__device__ __forceinline__ float band_window(int window, int kp, int half, int lg) {
+    if (window == 1) return 0.5f - 0.5f * cospif(2.0f * (float)kp / (float)(lg - 1));
+    return 0.5f + 0.5f * cospif(2.0f * (float)(kp - half) / (float)lg);
+}
+
 // ------------------------------------------------------------------------------------------------ CZT column pass
 // MODE 0: band input a[k'] = X[first_bin + k'] * hann * chirp from the packed half spectrum (untangled on the fly).
 // MODE 1: chirp filter b[n] = e^{-i pi 3 n^2 / M}, n = k' (k' < F) or k' - L (k' >= F), for plan creation.
@@ -702,7 +713,7 @@ template <int MODE, int L1>
 __global__ void __launch_bounds__(CQ_THREADS)
 czt_cols_kernel(const BandMeta *__restrict__ bands, const float2 *__restrict__ z_lo, const float2 *__restrict__ z_hi,
                 int klo, int khi, const float2 *__restrict__ twN_hi, const float2 *__restrict__ twN_lo,
-                const float2 *__restrict__ chirp, int M, int F, float2 *__restrict__ work) {
+                const float2 *__restrict__ chirp, int M, int F, float2 *__restrict__ work, int window) {
     const BandMeta bm = bands[blockIdx.y];
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= bm.L2) return;
@@ -715,7 +726,7 @@ czt_cols_kernel(const BandMeta *__restrict__ bands, const float2 *__restrict__ z
         if (MODE == 2) {          // Bluestein plans: z_lo holds X[klo ..] itself
             if (kp < bm.lg) {
                 const float2 X = z_lo[bm.first_bin + kp - klo];
-                const float hann = 0.5f + 0.5f * cospif(2.0f * (float)(kp - bm.half) / (float)bm.lg);
+                const float hann = band_window(window, kp, bm.half, bm.lg);
                 val = cmul(make_float2(X.x * hann, X.y * hann), chirp[kp]);
             }
         } else if (MODE == 0) {
@@ -727,7 +738,7 @@ czt_cols_kernel(const BandMeta *__restrict__ bands, const float2 *__restrict__ z
                 const float2 se = cadd(zk, zm), so = cmul(w, csub(zk, zm));
                 // X[k] = (Zk + conj Zm)/2 - (i/2) W (Zk - conj Zm)
                 const float2 X = make_float2(0.5f * (se.x + so.y), 0.5f * (se.y - so.x));
-                const float hann = 0.5f + 0.5f * cospif(2.0f * (float)(kp - bm.half) / (float)bm.lg);
+                const float hann = band_window(window, kp, bm.half, bm.lg);
                 val = cmul(make_float2(X.x * hann, X.y * hann), chirp[kp]);     // chirp[kp] = e^{+i pi 3 kp^2 / M}
             }
         } else {
@@ -1665,13 +1676,13 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
             const dim3 gf((max_fL2 + CQ_THREADS - 1) / CQ_THREADS, nL);
             if (L1 == 16)
                 czt_cols_kernel<1, 16><<<gf, CQ_THREADS, 0, stream>>>(dfb, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr,
-                                                                      d.M, d.F, tab);
+                                                                      d.M, d.F, tab, 0);
             else if (L1 == 32)
                 czt_cols_kernel<1, 32><<<gf, CQ_THREADS, 0, stream>>>(dfb, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr,
-                                                                      d.M, d.F, tab);
+                                                                      d.M, d.F, tab, 0);
             else
                 czt_cols_kernel<1, 64><<<gf, CQ_THREADS, 0, stream>>>(dfb, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr,
-                                                                      d.M, d.F, tab);
+                                                                      d.M, d.F, tab, 0);
         }
         {
             KernelScope ks(ctx, HPFW_K_CQT, stream);
@@ -1783,23 +1794,23 @@ static int cqt_run(hpfw_ctx *ctx, const float *d_audio, int64_t N, float *d_out,
         if (pl->bluestein) {
             if (pl->L1 == 16)
                 czt_cols_kernel<2, 16><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, zlo, nullptr, pl->klo, pl->khi, nullptr,
-                                                                        nullptr, pl->chirp, d.M, d.F, wk);
+                                                                        nullptr, pl->chirp, d.M, d.F, wk, ctx->cqt_window);
             else if (pl->L1 == 32)
                 czt_cols_kernel<2, 32><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, zlo, nullptr, pl->klo, pl->khi, nullptr,
-                                                                        nullptr, pl->chirp, d.M, d.F, wk);
+                                                                        nullptr, pl->chirp, d.M, d.F, wk, ctx->cqt_window);
             else
                 czt_cols_kernel<2, 64><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, zlo, nullptr, pl->klo, pl->khi, nullptr,
-                                                                        nullptr, pl->chirp, d.M, d.F, wk);
+                                                                        nullptr, pl->chirp, d.M, d.F, wk, ctx->cqt_window);
         } else {
             if (pl->L1 == 16)
                 czt_cols_kernel<0, 16><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, zlo, zhi, pl->klo, pl->khi, pl->twN_hi,
-                                                                        pl->twN_lo, pl->chirp, d.M, d.F, wk);
+                                                                        pl->twN_lo, pl->chirp, d.M, d.F, wk, ctx->cqt_window);
             else if (pl->L1 == 32)
                 czt_cols_kernel<0, 32><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, zlo, zhi, pl->klo, pl->khi, pl->twN_hi,
-                                                                        pl->twN_lo, pl->chirp, d.M, d.F, wk);
+                                                                        pl->twN_lo, pl->chirp, d.M, d.F, wk, ctx->cqt_window);
             else
                 czt_cols_kernel<0, 64><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, zlo, zhi, pl->klo, pl->khi, pl->twN_hi,
-                                                                        pl->twN_lo, pl->chirp, d.M, d.F, wk);
+                                                                        pl->twN_lo, pl->chirp, d.M, d.F, wk, ctx->cqt_window);
         }
     }
     if (pl->n_tiles3 > 0) {
@@ -1908,6 +1919,12 @@ int hpfw_cqt_design(int64_t n_samples, int *pos_out, int *lg_out, int *m_out) {
     return HPFW_OK;
 }
 
+int hpfw_set_cqt_window(hpfw_ctx *ctx, int window) {
+    if (!ctx || window < 0 || window > 1) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_set_cqt_window: window must be 0 (periodic) or 1 (symmetric)");
+    ctx->cqt_window = window;
+    return HPFW_OK;
+}
+
 int hpfw_cqt_cols(int64_t n_samples) {
     CqtDesign d;
     if (!cqt_design(n_samples, d)) return 0;
@@ -1928,6 +1945,7 @@ int hpfw_cqt_spectrogram_device(hpfw_ctx *ctx, const float *d_audio, int64_t n_s
 static int cqt_host(hpfw_ctx *ctx, const float *audio, int64_t n_samples, float *out, int *cols_out, int mode) {
     if (!ctx || !audio || !out) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_cqt: NULL argument");
     DeviceGuard g(ctx->device);
+    ctx->order_on(ctx->stream);
     const int cols = hpfw_cqt_cols(n_samples);
     if (cols <= 0) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_cqt: bad length");
     HPFW_TRY(ctx->audio.reserve(sizeof(float) * (size_t)n_samples));
@@ -1969,6 +1987,7 @@ int hpfw_calc_hashprint_audio(hpfw_ctx *ctx, const float *audio, int64_t n_sampl
     if (!ctx || !audio || !hp_out || !n_out) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_calc_hashprint_audio: NULL argument");
     *n_out = 0;
     DeviceGuard g(ctx->device);
+    ctx->order_on(ctx->stream);
     const int n = hpfw_hashprint_words_for_samples(n_samples);
     if (n <= 0)
         HPFW_FAIL(HPFW_ERR_SHORT, "audio of %lld samples is too short for one hashprint word", (long long)n_samples);
@@ -2033,6 +2052,7 @@ int hpfw_calc_hashprint_audio_batch_device(hpfw_ctx *ctx, const float *d_audio, 
 int hpfw_fft_c2c(hpfw_ctx *ctx, const float *in_interleaved, float *out_interleaved, int n, int inverse) {
     if (!ctx || !in_interleaved || !out_interleaved || n < 4) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_fft_c2c: bad argument");
     DeviceGuard g(ctx->device);
+    ctx->order_on(ctx->stream);
     DeviceBuffer a, b;
     HPFW_TRY(a.reserve(sizeof(float2) * (size_t)n));
     HPFW_TRY(b.reserve(sizeof(float2) * (size_t)n));

@@ -490,6 +490,7 @@ extern "C" {
 int hpfw_cov_reset(hpfw_ctx *ctx) {
     if (!ctx) HPFW_FAIL(HPFW_ERR_ARG, "ctx is NULL");
     DeviceGuard g(ctx->device);
+    ctx->order_on(ctx->stream);
     HPFW_TRY(ctx->cov_accum.reserve(sizeof(float) * (size_t)LN_FS * LN_FS));
     HPFW_CUDA_TRY(cudaMemsetAsync(ctx->cov_accum.ptr, 0, sizeof(float) * (size_t)LN_FS * LN_FS, ctx->stream));
     ctx->cov_tracks = 0;
@@ -499,6 +500,7 @@ int hpfw_cov_reset(hpfw_ctx *ctx) {
 int hpfw_cov_set(hpfw_ctx *ctx, const float *accum_2420x2420) {
     if (!ctx || !accum_2420x2420) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_cov_set: NULL argument");
     DeviceGuard g(ctx->device);
+    ctx->order_on(ctx->stream);
     HPFW_TRY(ctx->cov_accum.reserve(sizeof(float) * (size_t)LN_FS * LN_FS));
     HPFW_CUDA_TRY(cudaMemcpyAsync(ctx->cov_accum.ptr, accum_2420x2420, sizeof(float) * (size_t)LN_FS * LN_FS,
                                   cudaMemcpyHostToDevice, ctx->stream));
@@ -509,6 +511,7 @@ int hpfw_cov_set(hpfw_ctx *ctx, const float *accum_2420x2420) {
 int hpfw_cov_get(hpfw_ctx *ctx, float *accum_2420x2420) {
     if (!ctx || !accum_2420x2420) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_cov_get: NULL argument");
     DeviceGuard g(ctx->device);
+    ctx->order_on(ctx->stream);
     if (!ctx->cov_accum.ptr) HPFW_TRY(hpfw_cov_reset(ctx));
     HPFW_CUDA_TRY(cudaMemcpyAsync(accum_2420x2420, ctx->cov_accum.ptr, sizeof(float) * (size_t)LN_FS * LN_FS,
                                   cudaMemcpyDeviceToHost, ctx->stream));
@@ -550,6 +553,7 @@ int hpfw_cov_add_spectrogram(hpfw_ctx *ctx, const float *spectrogram, int cols) 
     if (!ctx || !spectrogram) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_cov_add_spectrogram: NULL argument");
     if (cols < LN_CTX + 1) HPFW_FAIL(HPFW_ERR_SHORT, "covariance needs at least 21 spectrogram columns (got %d)", cols);
     DeviceGuard g(ctx->device);
+    ctx->order_on(ctx->stream);
     const size_t sb = sizeof(float) * (size_t)cols * LN_BINS;
     HPFW_TRY(ctx->spectro.reserve(sb));
     HPFW_CUDA_TRY(cudaMemcpyAsync(ctx->spectro.ptr, spectrogram, sb, cudaMemcpyHostToDevice, ctx->stream));
@@ -561,6 +565,7 @@ int hpfw_cov_add_spectrogram(hpfw_ctx *ctx, const float *spectrogram, int cols) 
 int hpfw_calc_filters(hpfw_ctx *ctx, const float *cov, float *filters_out, float *eigenvalues_out) {
     if (!ctx || !filters_out) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_calc_filters: NULL argument");
     DeviceGuard g(ctx->device);
+    ctx->order_on(ctx->stream);
     const int n = LN_FS, p = LN_P, want = HPFW_NFILTERS;
     cudaStream_t s = ctx->stream;
     DeviceBuffer dA, dV, dZ, dT, dG, dW, dR;

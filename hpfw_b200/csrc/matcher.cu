@@ -329,6 +329,8 @@ void route_queries(const int64_t *qoffsets, int nq, int impl, int f4, std::vecto
 
 using namespace hpfw_b200;
 
+static int match_tc_selftest(hpfw_ctx *ctx, int f4);
+
 static int db_alloc_common(hpfw_ctx *ctx, const int64_t *offsets, int n_tracks, int64_t track_base, hpfw_db **out) {
     if (!ctx || !out || (n_tracks > 0 && !offsets)) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_build: NULL argument");
     if (n_tracks < 0) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_build: n_tracks < 0");
@@ -378,6 +380,112 @@ static int db_alloc_common(hpfw_ctx *ctx, const int64_t *offsets, int n_tracks, 
         HPFW_FAIL(HPFW_ERR_CUDA, "hpfw_db_build: %s", cudaGetErrorString(e));
     }
     *out = db;
+    return HPFW_OK;
+}
+
+// Known-answer self-test of the tensor-core matcher (match_tc.cu), run once per context and operand encoding before its first
+// use. The exactness of that kernel rests on the accumulate width of tcgen05.mma (s32 for kind::i8; for kind::mxf4.block_scale
+// the PTX ISA does not state the width of the internal f32 accumulation), so nothing is taken on trust: a small database is
+// matched with queries that drive the dot product to +2^18 and -2^18 at 4,096 words, through a long exact run followed by
+// noise, and with noisy slices of 7 lengths, once on the integer-pipe kernel (XOR + POPC, exact by construction) and once on
+// the tensor-core kernel, and the two top-k key arrays must be identical. On a mismatch the tensor-core route of this
+// context is disabled: hpfw_set_match_impl(ctx, 1 | 3) and matches under those settings return HPFW_ERR_STATE, the default
+// routing (2) runs everything on the integer-pipe kernel and says so once on stderr. There is no CPU fallback either way.
+// HPFW_MATCH_TC_SELFTEST_FAIL=1 injects a failure (tests/test_matcher_gpu.py exercises the loud path with it).
+static int match_tc_selftest(hpfw_ctx *ctx, int f4) {
+    int &state = ctx->tc_selftest[f4 ? 1 : 0];      // 0 = not run, 1 = passed, -1 = failed, 2 = running
+    if (state == 1 || state == 2) return HPFW_OK;
+    if (state == -1)
+        HPFW_FAIL(HPFW_ERR_STATE, "tensor-core matcher (%s operands) failed its known-answer self-test on this device; "
+                  "only the integer-pipe kernel (hpfw_set_match_impl 0 / default routing) is available",
+                  f4 ? "fp4" : "int8");
+    state = 2;
+    const int saved_impl = ctx->match_impl;
+    uint64_t rng = 0x9E3779B97F4A7C15ull;
+    auto next = [&]() {
+        rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+        return rng;
+    };
+    const int K = HPFW_MAX_QUERY_WORDS;
+    const int track_len[4] = {K + 700, K, 90, 1531};
+    std::vector<uint64_t> words;
+    std::vector<int64_t> offs{0};
+    for (int n : track_len) {
+        for (int i = 0; i < n; ++i) words.push_back(next());
+        offs.push_back(int64_t(words.size()));
+    }
+    std::vector<uint64_t> qw;
+    std::vector<int64_t> qo{0};
+    auto add_query = [&](int track, int off, int k, int exact_words, double flip) {
+        for (int j = 0; j < k; ++j) {
+            uint64_t w = words[size_t(offs[track]) + off + j];
+            if (j >= exact_words) {
+                uint64_t noise = 0;
+                for (int b = 0; b < 64; ++b) noise |= uint64_t((next() >> 11) * (1.0 / 9007199254740992.0) < flip) << b;
+                w ^= noise;
+            }
+            qw.push_back(w);
+        }
+        qo.push_back(int64_t(qw.size()));
+    };
+    add_query(0, 0, K, K, 0.0);                                   // dot = +2^18: distance 0 at offset 0
+    add_query(1, 0, K, K, 0.0);
+    for (size_t i = size_t(qo[1]); i < qw.size(); ++i) qw[i] = ~qw[i];   // dot = -2^18: track 1 has ONE offset, distance 64 * 4096
+    add_query(0, 311, K, 3000, 0.5);                              // a long exact run, then noise
+    add_query(0, 5, K - 1, 0, 0.25);
+    const int lens[7] = {1, 63, 143, 385, 777, 1514, 2048};
+    for (int i = 0; i < 7; ++i) {
+        add_query(i & 1, 17 * i, lens[i], 0, 0.25);
+        add_query(3, 1531 - std::min(lens[i], 1531), std::min(lens[i], 1531), 0, 0.3);   // the last offset of a track
+    }
+    add_query(1, 0, 200, 0, 0.25);                                // longer than track 2 (90 words): truncated there
+    const int nq = int(qo.size()) - 1, topk = 4;
+    hpfw_db *db = nullptr;
+    uint64_t *d_q = nullptr, *d_keys = nullptr;
+    std::vector<uint64_t> keys[2];
+    int status = hpfw_db_build(ctx, words.data(), offs.data(), 4, 0, &db);
+    cudaError_t e = cudaSuccess;
+    if (status == HPFW_OK) {
+        e = cudaMalloc(&d_q, sizeof(uint64_t) * qw.size());
+        if (e == cudaSuccess) e = cudaMalloc(&d_keys, sizeof(uint64_t) * size_t(nq) * topk);
+        if (e == cudaSuccess) e = cudaMemcpy(d_q, qw.data(), sizeof(uint64_t) * qw.size(), cudaMemcpyHostToDevice);
+        for (int pass = 0; pass < 2 && status == HPFW_OK && e == cudaSuccess; ++pass) {
+            ctx->match_impl = pass == 0 ? 0 : (f4 ? 3 : 1);
+            status = hpfw_db_match_device(db, d_q, qo.data(), nq, topk, d_keys, ctx->stream);
+            keys[pass].resize(size_t(nq) * topk);
+            if (status == HPFW_OK) e = cudaStreamSynchronize(ctx->stream);
+            if (status == HPFW_OK && e == cudaSuccess)
+                e = cudaMemcpy(keys[pass].data(), d_keys, sizeof(uint64_t) * keys[pass].size(), cudaMemcpyDeviceToHost);
+        }
+    }
+    ctx->match_impl = saved_impl;
+    if (d_q) cudaFree(d_q);
+    if (d_keys) cudaFree(d_keys);
+    if (db) hpfw_db_destroy(db);
+    if (status != HPFW_OK || e != cudaSuccess) {
+        state = 0;
+        if (status == HPFW_OK) HPFW_FAIL(HPFW_ERR_CUDA, "match_tc_selftest: %s", cudaGetErrorString(e));
+        return status;
+    }
+    bool same = keys[0] == keys[1];
+    // the two planted extremes must also be what the arithmetic says, independently of either kernel
+    same = same && keys[0][0] == 0ull;
+    bool saw_max = false;
+    for (int r = 0; r < topk; ++r) {
+        const uint64_t key = keys[0][size_t(topk) + r];
+        if (((key >> HPFW_KEY_OFFSET_BITS) & ((1ull << HPFW_KEY_TRACK_BITS) - 1)) == 1ull)
+            saw_max = (key >> HPFW_KEY_DIST_SHIFT) == uint64_t(64) * K;
+    }
+    same = same && saw_max;
+    if (const char *env = getenv("HPFW_MATCH_TC_SELFTEST_FAIL")) same = same && atoi(env) == 0;
+    state = same ? 1 : -1;
+    if (!same) {
+        fprintf(stderr, "[hpfw_b200] tensor-core matcher (%s operands) FAILED its known-answer self-test on device %d: its "
+                "results differ from the integer-pipe kernel's. The tensor-core route is disabled for this context; batches "
+                "run on the XOR+POPC kernel (exact, ~15x slower).\n", f4 ? "fp4" : "int8", ctx->device);
+        HPFW_FAIL(HPFW_ERR_STATE, "tensor-core matcher (%s operands) failed its known-answer self-test on this device",
+                  f4 ? "fp4" : "int8");
+    }
     return HPFW_OK;
 }
 
@@ -492,8 +600,16 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
 
     // queries per chunk: bound the best[] scratch to ~1 GiB (HPFW_MATCH_SCRATCH_BYTES overrides the bound; the tests use it to
     // exercise the multi-chunk path on small inputs) and the tensor-core matcher's expanded queries to ~2 GiB
-    const int impl = ctx->match_impl;
+    int impl = ctx->match_impl;
     const int f4 = impl == 3 || (impl == 2 && ctx->match_tc_f4);   // operand encoding of the tensor-core kernel
+    if (impl != 0) {
+        // the first batch that would use the tensor-core kernel in this encoding runs its known-answer self-test first
+        const int st = match_tc_selftest(ctx, f4);
+        if (st != HPFW_OK) {
+            if (impl != 2) return st;     // the caller asked for the tensor cores: fail loudly
+            impl = 0;                     // default routing: everything on the (exact) integer-pipe kernel, reported once
+        }
+    }
     const size_t row_bytes = sizeof(uint64_t) * std::max<size_t>(1, size_t(R));
     size_t best_cap = size_t(1) << 30;
     if (const char *env = getenv("HPFW_MATCH_SCRATCH_BYTES")) best_cap = std::max<size_t>(row_bytes, strtoull(env, nullptr, 10));
@@ -641,8 +757,14 @@ int hpfw_match_route(const int64_t *qoffsets, int n_queries, int impl, int fp4, 
 
 int hpfw_set_match_impl(hpfw_ctx *ctx, int impl) {
     if (!ctx || impl < 0 || impl > 3) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_set_match_impl: impl must be 0, 1, 2 or 3");
+    if (impl == 1 || impl == 3) HPFW_TRY(match_tc_selftest(ctx, impl == 3));
     ctx->match_impl = impl;
     return HPFW_OK;
+}
+
+int hpfw_match_tc_selftest(hpfw_ctx *ctx, int fp4) {
+    if (!ctx) HPFW_FAIL(HPFW_ERR_ARG, "ctx is NULL");
+    return match_tc_selftest(ctx, fp4 != 0);
 }
 
 int hpfw_topk_merge_device(hpfw_ctx *ctx, const uint64_t *d_keys_in, int n_ranks, int n_queries, int topk,
@@ -666,6 +788,7 @@ int hpfw_db_find_topk(hpfw_db *db, const uint64_t *qwords, const int64_t *qoffse
     if (topk < 1) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_find_topk: topk < 1");
     hpfw_ctx *ctx = db->ctx;
     DeviceGuard g(ctx->device);
+    ctx->order_on(ctx->stream);
     const size_t nw = size_t(qoffsets[n_queries] - qoffsets[0]);
     const size_t nkeys = size_t(n_queries) * size_t(topk);
     HPFW_TRY(ctx->qwords.reserve(sizeof(uint64_t) * std::max<size_t>(1, nw)));

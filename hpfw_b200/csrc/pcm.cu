@@ -60,6 +60,7 @@ int hpfw_cqt_spectrogram_pcm16(hpfw_ctx *ctx, const int16_t *pcm, int64_t n_samp
     if (!ctx || !pcm || !spectrogram_out || !cols_out) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_cqt_spectrogram_pcm16: NULL argument");
     *cols_out = 0;
     DeviceGuard g(ctx->device);
+    ctx->order_on(ctx->stream);
     const int cols = hpfw_cqt_cols(n_samples);
     if (cols <= 0) HPFW_FAIL(HPFW_ERR_SHORT, "audio of %lld samples is too short for the CQT design", (long long)n_samples);
     HPFW_TRY(ctx->audio.reserve(sizeof(int16_t) * size_t(n_samples + 8)));
@@ -119,6 +120,7 @@ int hpfw_calc_hashprint_pcm16(hpfw_ctx *ctx, const int16_t *pcm, int64_t n_sampl
     if (!ctx || !pcm || !hp_out || !n_out) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_calc_hashprint_pcm16: NULL argument");
     *n_out = 0;
     DeviceGuard g(ctx->device);
+    ctx->order_on(ctx->stream);
     const int n = hpfw_hashprint_words_for_samples(n_samples);
     if (n <= 0)
         HPFW_FAIL(HPFW_ERR_SHORT, "audio of %lld samples is too short for one hashprint word", (long long)n_samples);

@@ -262,6 +262,7 @@ int hpfw_hashprint_from_spectrogram(hpfw_ctx *ctx, const float *spectrogram, int
     // the reference underflows size_t here (hashprint_handle.h:84,119) and dies with bad_alloc; we report it
     if (n <= 0) HPFW_FAIL(HPFW_ERR_SHORT, "spectrogram has %d columns; at least 100 are needed for one hashprint word", cols);
     DeviceGuard g(ctx->device);
+    ctx->order_on(ctx->stream);
     const size_t sb = sizeof(float) * size_t(cols) * PJ_BINS;
     HPFW_TRY(ctx->spectro.reserve(sb));
     HPFW_TRY(ctx->hp.reserve(sizeof(uint64_t) * size_t(n)));
@@ -279,6 +280,7 @@ int hpfw_project(hpfw_ctx *ctx, const float *spectrogram, int cols, float *y_out
     const int nfr = cols - (PJ_CTX - 1);
     if (nfr <= 0) HPFW_FAIL(HPFW_ERR_SHORT, "spectrogram has %d columns; at least 20 are needed for one frame", cols);
     DeviceGuard g(ctx->device);
+    ctx->order_on(ctx->stream);
     const size_t sb = sizeof(float) * size_t(cols) * PJ_BINS, yb = sizeof(float) * size_t(nfr) * PJ_NF;
     HPFW_TRY(ctx->spectro.reserve(sb));
     HPFW_TRY(ctx->yproj.reserve(yb));

@@ -130,8 +130,14 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
  *       context was created; a group costs its longest query whether it holds 1 or 128) and queries that stay on the
  *       integer pipes (about 1/8 of a group each): a batch of >= ~9 equal-length queries goes to the tensor cores, a
  *       single find() stays on XOR + POPC.
- * All four give bit-identical results. The environment variable HPFW_MATCH_IMPL sets the initial value of a new context. */
+ * All four give bit-identical results. The environment variable HPFW_MATCH_IMPL sets the initial value of a new context.
+ * The tensor-core kernels are only used after a known-answer self-test against the integer-pipe kernel has passed on this
+ * context (dot products of +-2^18 at 4,096 words, a long exact run followed by noise, 7 query lengths); when it fails,
+ * impl 1 / 3 return HPFW_ERR_STATE here and from the match calls, and impl 2 runs every query on the integer pipes. */
 int hpfw_set_match_impl(hpfw_ctx *ctx, int impl);
+/* runs (once per context and encoding; later calls return the recorded verdict) the self-test described above:
+ * HPFW_OK, or HPFW_ERR_STATE when the tensor-core kernel's keys differ from the integer-pipe kernel's. */
+int hpfw_match_tc_selftest(hpfw_ctx *ctx, int fp4);
 /* host-only (needs no device): the routing hpfw_db_match_device would apply to one batch under `impl` (fp4 != 0: fp4 operand
  * encoding for impl 2). group_out[q] = index of the tensor-core group query q joins, or -1 for the integer-pipe kernel. */
 int hpfw_match_route(const int64_t *qoffsets, int n_queries, int impl, int fp4, int32_t *group_out);
@@ -183,6 +189,12 @@ int hpfw_cov_add_spectrogram_device(hpfw_ctx *ctx, const float *d_spectrogram, i
 int hpfw_calc_filters(hpfw_ctx *ctx, const float *cov, float *filters_out, float *eigenvalues_out);
 
 /* ------------------------------------------------------------------------------------------------- CQT (stage 1) */
+/* The band window NSGConstantQ is asked for is "hann" (cqt.h:58). essentia is not available to check which formula that
+ * name selects, so the convention is a switch (default 0; environment variable HPFW_CQT_WINDOW=periodic|symmetric):
+ *   0 = periodic Hann centred on the band, 0.5 + 0.5 cos(2 pi k / Lg), k = -floor(Lg/2) .. ceil(Lg/2)-1 (NSG toolbox);
+ *   1 = symmetric Hann over the Lg taps, 0.5 - 0.5 cos(2 pi n / (Lg - 1)), n = k + floor(Lg/2).
+ * Both are tested against oracle/nsgcq.py; which one equals essentia's is a to-be-verified item. */
+int hpfw_set_cqt_window(hpfw_ctx *ctx, int window);
 /* spectrogram columns for an n_samples-long buffer: M/3 + 1 (cqt.h:73); 0 if the design is degenerate */
 int hpfw_cqt_cols(int64_t n_samples);
 /* host: mono float audio (already at the analysis rate) -> dB spectrogram[121 x cols] col-major */

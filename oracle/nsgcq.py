@@ -18,7 +18,8 @@ the parameters of the reference's call site (cqt.h:54-61):
 
 Conventions we had to choose (cannot be verified against essentia here):
   * window  w_j[k] = 0.5 + 0.5 cos(2 pi k / Lg_j) for k = -floor(Lg/2) .. ceil(Lg/2)-1 (periodic Hann centred on k = 0,
-    the NSG toolbox's `winfuns('hann')` form);
+    the NSG toolbox's `winfuns('hann')` form) by default; `window="symmetric"` selects the generic symmetric Hann of
+    size Lg instead (see band_window) — the convention is a switch here and in the product, not a constant;
   * inverse FFT normalised by 1/M (a global scale: cancels in power_to_db except at the 1e-10 floor);
   * the global-phase rotation is omitted (only |c| is used by hpfw);
   * round() is C's half-away-from-zero;
@@ -66,7 +67,21 @@ def spectrogram_cols(n_samples: int) -> int:
     return m // DOWNSAMPLE + 1
 
 
-def nsgcq_magnitude(audio: np.ndarray) -> np.ndarray:
+def band_window(L: int, window: str = "periodic"):
+    """(k, w): tap offsets k = -floor(L/2) .. ceil(L/2)-1 relative to the band centre and the window on them.
+    "periodic": 0.5 + 0.5 cos(2 pi k / L) (NSG toolbox winfuns('hann'), the default here);
+    "symmetric": 0.5 - 0.5 cos(2 pi n / (L - 1)), n = k + floor(L/2) (a generic size-L "hann" window rotated onto the
+    band centre). Which of the two essentia builds for "window","hann" (cqt.h:58) is unverified; the product has the same
+    switch (HPFW_CQT_WINDOW / hpfw_set_cqt_window)."""
+    k = np.arange(-(L // 2), -(L // 2) + L, dtype=np.int64)
+    if window == "periodic":
+        return k, 0.5 + 0.5 * np.cos(2.0 * np.pi * k / L)
+    if window == "symmetric":
+        return k, 0.5 - 0.5 * np.cos(2.0 * np.pi * (k + L // 2) / (L - 1))
+    raise ValueError(f"window must be 'periodic' or 'symmetric', not {window!r}")
+
+
+def nsgcq_magnitude(audio: np.ndarray, window: str = "periodic") -> np.ndarray:
     """|c_j[3 i]| as float64 [cols, 121] (time-major, i.e. the memory order of the reference's column-major
     Eigen::Matrix<float,121,Dynamic>). Column M/3 is zero when M % 3 == 0 (see header)."""
     x = np.asarray(audio, dtype=np.float64)
@@ -78,8 +93,7 @@ def nsgcq_magnitude(audio: np.ndarray) -> np.ndarray:
     out = np.zeros((cols, N_BINS), dtype=np.float64)
     for j in range(N_BINS):
         L = int(lg[j])
-        k = np.arange(-(L // 2), -(L // 2) + L, dtype=np.int64)
-        w = 0.5 + 0.5 * np.cos(2.0 * np.pi * k / L)
+        k, w = band_window(L, window)
         buf = np.zeros(m, dtype=np.complex128)
         buf[k % m] = spec[(int(pos[j]) + k) % n] * w
         c = sfft.ifft(buf)
@@ -96,6 +110,6 @@ def amplitude_to_db(mag: np.ndarray) -> np.ndarray:
     return np.maximum(l, top - 80.0)
 
 
-def spectrogram(audio: np.ndarray) -> np.ndarray:
+def spectrogram(audio: np.ndarray, window: str = "periodic") -> np.ndarray:
     """Restated `CQT::spectrogram` on an already-decoded mono buffer: float32 [cols, 121] dB."""
-    return amplitude_to_db(nsgcq_magnitude(audio)).astype(np.float32)
+    return amplitude_to_db(nsgcq_magnitude(audio, window)).astype(np.float32)

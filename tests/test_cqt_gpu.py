@@ -226,3 +226,33 @@ def test_pcm16_entry_points_equal_the_float_path(ctx, hashprint_golden):
     torch.cuda.synchronize()
     got = d_hp.cpu().numpy().view(np.uint64)
     assert np.array_equal(got, np.concatenate(refp))
+
+
+@pytest.mark.parametrize("seconds,sr", [(6.0, 44100), (30.0, 22050), (20.0, 44100)])
+def test_cqt_window_switch_vs_oracle(ctx, seconds, sr):
+    """the band window convention ("window","hann" at /root/reference/include/hpfw/spectrum/cqt.h:58)
+    is a switch, not a constant. Both settings must match the oracle's same-named switch to the usual tolerance, and they
+    must differ from each other (otherwise the switch does nothing)."""
+    audio = synth.synth_track(int(seconds) + sr + 5, seconds, sr)
+    mags = {}
+    try:
+        for wid, name in ((1, "symmetric"), (0, "periodic")):
+            check(ctx._lib.hpfw_set_cqt_window(ctx.handle, wid))
+            ref = nsgcq.nsgcq_magnitude(audio, window=name)
+            mag = _cqt(ctx, audio, magnitude=True)
+            assert np.max(np.abs(mag - ref)) <= 1e-5 * np.abs(ref).max(), name
+            ref_db = nsgcq.amplitude_to_db(ref)
+            db = _cqt(ctx, audio)
+            above = ref_db > -79.0
+            assert np.max(np.abs(db[above] - ref_db[above])) <= 0.01, name
+            mags[name] = mag
+    finally:
+        check(ctx._lib.hpfw_set_cqt_window(ctx.handle, 0))
+    # the two conventions differ by O(1 / Lg) per tap: far above the 1e-5 comparison tolerance at these lengths
+    assert np.max(np.abs(mags["symmetric"] - mags["periodic"])) > 1e-4 * np.abs(mags["periodic"]).max()
+
+
+def test_cqt_window_rejects_unknown(ctx):
+    from hpfw_b200 import HpfwError
+    with pytest.raises(HpfwError):
+        check(ctx._lib.hpfw_set_cqt_window(ctx.handle, 2))

@@ -155,3 +155,21 @@ def test_live_reference_agrees_on_random_cases():
         for k in (1, 17, 64, 150, 450):
             q = rng.integers(0, 1 << 64, size=k, dtype=np.uint64)
             assert _res(oracle.find(w, o, q)) == _res(oracle.ref_find(w, o, q))
+
+
+def test_nsgcq_window_variants():
+    """The "hann" convention is a switch (oracle/nsgcq.py: band_window): the periodic form peaks at exactly 1 on the band
+    centre; the symmetric form is 0 on both end taps and mirror-symmetric over them. They differ by O(1/L) per tap."""
+    from oracle import nsgcq
+    for L in (96, 97, 725, 4836):
+        k, wp = nsgcq.band_window(L, "periodic")
+        k2, ws = nsgcq.band_window(L, "symmetric")
+        assert np.array_equal(k, k2) and len(k) == L and k[0] == -(L // 2)
+        assert wp[L // 2] == 1.0 and np.all(wp <= 1.0)
+        assert abs(ws[0]) < 1e-12 and abs(ws[-1]) < 1e-12 and np.allclose(ws, ws[::-1], atol=1e-12)
+        assert np.max(np.abs(wp - ws)) > 0.5 / L
+    with pytest.raises(ValueError):
+        nsgcq.band_window(96, "hamming")
+    x = np.random.default_rng(0).standard_normal(88200).astype(np.float32)
+    a, b = nsgcq.nsgcq_magnitude(x, "periodic"), nsgcq.nsgcq_magnitude(x, "symmetric")
+    assert a.shape == b.shape and np.max(np.abs(a - b)) > 1e-4 * a.max()
