@@ -1,0 +1,145 @@
+// examples/cpp/bench-liveid.cpp — times the reference's own C++ API (hpfw::LiveSongIdentification::index()/search(),
+// /root/reference/include/hpfw/audioproblems/live-song-id/live_song_id.h:31-54) on the B200 path, from WAV files.
+// bench.py runs it (rank 0, N = 1) and reports the numbers as `e2e_cpp`.
+//
+//   bench-liveid index  <wav_dir> [reps]
+//       one LiveSongIdentification per rep in the current directory (cache/ is created there, as in the reference);
+//       times index(files): decode threads -> pinned ring -> H2D -> CQT -> covariance -> filters -> batched projection -> DB
+//       built device-to-device. Prints frames/s (spectrogram columns - 19 per track).
+//   bench-liveid search <db_dump.cereal> <query_wav_dir> [reps] [expect.txt]
+//       filters from cache/filters.cereal (current directory), DB from a MemoryStorage dump (storage.h:67-86 format), then
+//       times search(files) over all query WAVs as one batch. expect.txt: one "<query file name> <track name>" pair per line;
+//       the bench fails when a query is not matched to its track.
+//
+// Build:  g++ -std=c++17 -O2 -Iinclude examples/cpp/bench-liveid.cpp -o bench-liveid -Lhpfw_b200 -lhpfw_b200 -lpthread
+//              -Wl,-rpath,$PWD/hpfw_b200
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include <hpfw/audioproblems/live-song-id/live_song_id.h>
+
+namespace {
+
+double now() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// stdout of search() (the reference prints every result) goes to a string while timing
+struct CoutCapture {
+    std::ostringstream sink;
+    std::streambuf *old;
+    CoutCapture() : old(std::cout.rdbuf(sink.rdbuf())) {}
+    ~CoutCapture() { std::cout.rdbuf(old); }
+};
+
+int run_index(int argc, char **argv) {
+    const std::string dir = argv[2];
+    const int reps = argc > 3 ? std::max(1, std::atoi(argv[3])) : 1;
+    auto files = hpfw::utils::get_dir_files(dir);
+    double frames = 0, bytes = 0;
+    for (const auto &f : files) {
+        const auto sz = std::filesystem::file_size(f);
+        bytes += double(sz);
+        const int64_t n = (int64_t(sz) - 44) / 2;            // the bench writes canonical 44-byte-header mono PCM16
+        frames += std::max(0, hpfw_cqt_cols(n) - (HPFW_CONTEXT - 1));
+    }
+    double best = 1e30, best_flush = 1e30, first = 0, last_db = 0;
+    std::filesystem::remove_all("cache");
+    {
+        // ONE application object, index() called reps + 1 times: call 0 pays the one-off costs (pinned staging ring, CQT plans,
+        // arena chunks, first-touch of the scratch buffers) and is reported separately as index_first_s
+        hpfw::LiveSongIdentification<> liveid;
+        for (int r = 0; r <= reps; ++r) {
+            const double t0 = now();
+            liveid.index(files);
+            const double t1 = now();
+            last_db = double(liveid.get_storage().size());
+            liveid.get_collector().flush_cache_writes();
+            const double t2 = now();
+            if (r == 0) first = t1 - t0;
+            else {
+                best = std::min(best, t1 - t0);
+                best_flush = std::min(best_flush, t2 - t0);
+            }
+        }
+    }
+    std::printf("{\"leg\": \"index\", \"files\": %zu, \"db_tracks\": %.0f, \"frames\": %.0f, \"wav_bytes\": %.0f, "
+                "\"index_s\": %.6f, \"frames_per_s\": %.1f, \"index_with_cache_flush_s\": %.6f, "
+                "\"frames_per_s_with_cache_flush\": %.1f, \"wav_gb_per_s\": %.3f, \"index_first_s\": %.6f, \"reps\": %d}\n",
+                files.size(), last_db, frames, bytes, best, frames / best, best_flush, frames / best_flush,
+                bytes / best / 1e9, first, reps);
+    return last_db == double(files.size()) ? 0 : 1;
+}
+
+int run_search(int argc, char **argv) {
+    const std::string dump = argv[2], qdir = argv[3];
+    const int reps = argc > 4 ? std::max(1, std::atoi(argv[4])) : 3;
+    std::map<std::string, std::string> expect;
+    if (argc > 5) {
+        std::ifstream is(argv[5]);
+        std::string q, t;
+        while (is >> q >> t) expect[q] = t;
+    }
+    auto files = hpfw::utils::get_dir_files(qdir);
+    hpfw::LiveSongIdentification<> liveid;                   // loads cache/filters.cereal (live_song_id.h:23-25)
+    const double tl0 = now();
+    liveid.get_storage().load(dump);
+    const double load_s = now() - tl0;
+    double best = 1e30;
+    size_t wrong = 0, failed = 0;
+    std::string text;
+    for (int r = 0; r <= reps; ++r) {                        // rep 0 = warm-up
+        CoutCapture cap;
+        const double t0 = now();
+        const auto s = liveid.search(files);
+        const double dt = now() - t0;
+        if (r > 0) best = std::min(best, dt);
+        failed = s.failed;
+        text = cap.sink.str();
+    }
+    // what search() printed: "=> Finding <file>" then "=> <track> <cnt> <offset>"
+    if (!expect.empty()) {
+        std::istringstream is(text);
+        std::string line, current;
+        while (std::getline(is, line)) {
+            if (line.rfind("=> Finding ", 0) == 0) {
+                current = std::filesystem::path(line.substr(11)).filename().string();
+            } else if (line.rfind("=> ", 0) == 0 && !current.empty()) {
+                std::istringstream ls(line.substr(3));
+                std::string track;
+                ls >> track;
+                auto it = expect.find(current);
+                if (it != expect.end() && it->second != track) ++wrong;
+                current.clear();
+            }
+        }
+    }
+    std::printf("{\"leg\": \"search\", \"queries\": %zu, \"db_tracks\": %zu, \"search_s\": %.6f, \"queries_per_s\": %.2f, "
+                "\"failed\": %zu, \"wrong\": %zu, \"checked\": %zu, \"db_load_s\": %.3f, \"reps\": %d}\n",
+                files.size(), liveid.get_storage().size(), best, double(files.size()) / best, failed, wrong, expect.size(),
+                load_s, reps);
+    return (failed == 0 && wrong == 0) ? 0 : 1;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    std::ios_base::sync_with_stdio(false);
+    try {
+        if (argc >= 3 && std::string(argv[1]) == "index") return run_index(argc, argv);
+        if (argc >= 4 && std::string(argv[1]) == "search") return run_search(argc, argv);
+        std::cerr << "usage: " << argv[0] << " index <wav_dir> [reps] | search <db_dump> <query_wav_dir> [reps] [expect.txt]"
+                  << std::endl;
+        return 2;
+    } catch (const std::exception &e) {
+        std::cerr << "bench-liveid: " << e.what() << std::endl;
+        return 1;
+    }
+}

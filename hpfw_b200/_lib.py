@@ -37,12 +37,15 @@ _SIGS = {
     "hpfw_db_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
     "hpfw_db_build_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
                                        C.POINTER(C.c_void_p)]),
+    "hpfw_db_build_gather_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
+                                              C.POINTER(C.c_void_p)]),
     "hpfw_db_destroy": (None, [C.c_void_p]),
     "hpfw_db_tracks": (C.c_int, [C.c_void_p]),
     "hpfw_db_words": (C.c_int64, [C.c_void_p]),
     "hpfw_db_find": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Match)]),
     "hpfw_db_find_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Match)]),
     "hpfw_db_match_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "hpfw_db_find_topk_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Match), C.c_void_p]),
     "hpfw_set_match_impl": (C.c_int, [C.c_void_p, C.c_int]),
     "hpfw_match_tc_selftest": (C.c_int, [C.c_void_p, C.c_int]),
     "hpfw_match_route": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -83,6 +86,26 @@ _SIGS = {
     "hpfw_calc_hashprint_pcm16_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "hpfw_calc_hashprint_pcm16_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                                          C.c_void_p]),
+    "hpfw_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "hpfw_host_free": (None, [C.c_void_p]),
+    "hpfw_xs_create": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "hpfw_xs_destroy": (None, [C.c_void_p]),
+    "hpfw_xs_acquire": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
+    "hpfw_xs_release": (C.c_int, [C.c_void_p, C.c_int]),
+    "hpfw_xs_submit": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_int)]),
+    "hpfw_xs_submit_spectrogram": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "hpfw_xs_tracks": (C.c_int, [C.c_void_p]),
+    "hpfw_xs_track_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "hpfw_xs_fetch_spectrogram": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "hpfw_xs_wait": (C.c_int, [C.c_void_p]),
+    "hpfw_xs_hash_kept": (C.c_int, [C.c_void_p]),
+    "hpfw_xs_drop_kept": (C.c_int, [C.c_void_p]),
+    "hpfw_xs_reset": (C.c_int, [C.c_void_p]),
+    "hpfw_xs_hashprints_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
+    "hpfw_xs_hashprint_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "hpfw_xs_hashprints_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "hpfw_xs_build_db": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
+    "hpfw_xs_match": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Match)]),
     "hpfw_microbench_pipes": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

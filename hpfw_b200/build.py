@@ -35,7 +35,8 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
+    deps = (sources() + glob.glob(os.path.join(CSRC, "*.cuh")) +
+            glob.glob(os.path.join(HERE, "..", "include", "**", "*.h"), recursive=True))   # pyhpfw_abi.cu includes include/hpfw/**
     return any(os.path.getmtime(d) > t for d in deps)
 
 

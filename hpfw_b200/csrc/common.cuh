@@ -180,6 +180,11 @@ struct DeviceGuard {
     }
 };
 void cqt_cache_destroy(CqtPlanCache *);
+// internal (no stream-ordering hook; xstream.cu forks and joins its own streams around these)
+int ctx_lanes_init(hpfw_ctx *ctx);                 // creates ctx->lane_stream[] / lane_join[] / lane_fork on first use
+int cqt_run_lane(hpfw_ctx *ctx, const float *d_audio, int64_t n_samples, float *d_out, cudaStream_t stream, int lane);
+int pcm16_convert(hpfw_ctx *ctx, const int16_t *d_pcm, float *d_out, int64_t n, cudaStream_t s);
+int cov_add_device(hpfw_ctx *ctx, const float *d_spec, int cols, cudaStream_t s);
 int project_tc_set_filters(hpfw_ctx *ctx, const float *filters_colmajor);
 int project_tc_run(hpfw_ctx *ctx, int impl, const float *d_spectro, const int64_t *col_offsets, int n, uint64_t *d_hp,
                    cudaStream_t stream);

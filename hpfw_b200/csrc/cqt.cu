@@ -1898,7 +1898,14 @@ static int fft_c2c_device(hpfw_ctx *ctx, const float2 *d_in, float2 *d_out, int 
 
 using namespace hpfw_b200;
 
-static int lanes_init(hpfw_ctx *ctx) {
+namespace hpfw_b200 {
+// internal entry points for the extraction stream (xstream.cu): no stream-ordering hooks, the caller forks / joins the lanes
+int cqt_run_lane(hpfw_ctx *ctx, const float *d_audio, int64_t n_samples, float *d_out, cudaStream_t stream, int lane) {
+    return cqt_run(ctx, d_audio, n_samples, d_out, 0, stream, lane);
+}
+}  // namespace hpfw_b200
+
+int hpfw_b200::ctx_lanes_init(hpfw_ctx *ctx) {
     if (ctx->lane_fork) return HPFW_OK;
     for (int l = 0; l < HPFW_CTX_LANES; ++l) {
         HPFW_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking));
@@ -2029,7 +2036,7 @@ int hpfw_calc_hashprint_audio_batch_device(hpfw_ctx *ctx, const float *d_audio, 
         HPFW_TRY(ctx->spectro.reserve(sizeof(float) * size_t(co.back()) * CQ_BINS));
         // fork: the tracks of the chunk run round-robin on CQ_LANES streams (own scratch each) so that the small tail waves
         // of one track's kernels overlap another track's; join before the chunk's single projection launch
-        HPFW_TRY(lanes_init(ctx));
+        HPFW_TRY(ctx_lanes_init(ctx));
         const int nl = std::max(1, std::min(std::min(CQ_LANES, env_int("HPFW_CQT_LANES", 4)), j - i));
         HPFW_CUDA_TRY(cudaEventRecord(ctx->lane_fork, s));
         for (int l = 0; l < nl; ++l) HPFW_CUDA_TRY(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->lane_fork, 0));

@@ -428,7 +428,7 @@ static int cov_impl() {
     return (v && *v) ? atoi(v) : 1;
 }
 
-static int cov_add_device(hpfw_ctx *ctx, const float *d_spec, int cols, cudaStream_t s) {
+int hpfw_b200::cov_add_device(hpfw_ctx *ctx, const float *d_spec, int cols, cudaStream_t s) {
     const int nf = cols - (LN_CTX - 1);
     if (nf < 2) HPFW_FAIL(HPFW_ERR_SHORT, "covariance needs at least 21 spectrogram columns (got %d)", cols);
     if (!ctx->cov_accum.ptr) {

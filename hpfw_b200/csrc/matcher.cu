@@ -285,6 +285,18 @@ __global__ void merge_kernel(const unsigned long long *__restrict__ in, int n_ra
 // queries; a query on the integer-pipe kernel costs ~k / ratio. With the queries sorted by length the cheapest split is a
 // one-dimensional dynamic programme: query i either runs on the integer pipes, or closes a group made of the (up to) 128
 // queries before it. impl 1 / 3 force the tensor cores, impl 0 the integer pipes. Query indices are relative to qoffsets.
+// DB build from hashprints that already sit in HBM in another order (xstream.cu: store order -> DB order): track r of the
+// DB is src[src_off[r] .. + len) -> dst[dst_off[r] ..). One CTA per (track, 4096-word slice), 16-byte accesses where aligned.
+__global__ void __launch_bounds__(256)
+gather_tracks_kernel(const uint64_t *__restrict__ src, const int64_t *__restrict__ src_off,
+                     const int64_t *__restrict__ dst_off, uint64_t *__restrict__ dst) {
+    const int r = blockIdx.y;
+    const int64_t len = dst_off[r + 1] - dst_off[r];
+    const uint64_t *s = src + src_off[r];
+    uint64_t *d = dst + dst_off[r];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) d[i] = s[i];
+}
+
 void route_queries(const int64_t *qoffsets, int nq, int impl, int f4, std::vector<std::vector<int>> &tc_groups,
                    std::vector<int> &popc_list) {
     auto klen = [&](int i) { return qoffsets[i + 1] - qoffsets[i]; };
@@ -526,6 +538,50 @@ int hpfw_db_build_device(hpfw_ctx *ctx, const uint64_t *d_words, const int64_t *
         if (e != cudaSuccess) {
             hpfw_db_destroy(db);
             HPFW_FAIL(HPFW_ERR_CUDA, "hpfw_db_build_device: D2D copy failed: %s", cudaGetErrorString(e));
+        }
+    }
+    *out = db;
+    return HPFW_OK;
+}
+
+int hpfw_db_build_gather_device(hpfw_ctx *ctx, const uint64_t *d_words, const int64_t *src_offsets, const int64_t *lengths,
+                                int n_tracks, int64_t track_base, void *stream, hpfw_db **out) {
+    if (!ctx || !out || (n_tracks > 0 && (!src_offsets || !lengths)))
+        HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_build_gather_device: NULL argument");
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = ctx->pick(stream);
+    std::vector<int64_t> offs(size_t(std::max(n_tracks, 0)) + 1, 0);
+    for (int r = 0; r < n_tracks; ++r) {
+        if (lengths[r] < 0 || src_offsets[r] < 0) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_build_gather_device: negative length/offset");
+        offs[size_t(r) + 1] = offs[size_t(r)] + lengths[r];
+    }
+    hpfw_db *db = nullptr;
+    HPFW_TRY(db_alloc_common(ctx, offs.data(), n_tracks, track_base, &db));
+    if (db->total_words > 0) {
+        if (!d_words) {
+            hpfw_db_destroy(db);
+            HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_build_gather_device: d_words is NULL");
+        }
+        int64_t *d_src = nullptr;
+        cudaError_t e = cudaMalloc(&d_src, sizeof(int64_t) * size_t(n_tracks));
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(d_src, src_offsets, sizeof(int64_t) * size_t(n_tracks), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) {
+            KernelScope ks(ctx, HPFW_K_OTHER, s);
+            int64_t longest = 0;
+            for (int r = 0; r < n_tracks; ++r) longest = std::max(longest, lengths[r]);
+            const int gx = int(std::min<int64_t>(64, std::max<int64_t>(1, (longest + 4095) / 4096)));
+            for (int r0 = 0; r0 < n_tracks && e == cudaSuccess; r0 += 65535) {    // gridDim.y limit
+                const int nr = std::min(65535, n_tracks - r0);
+                gather_tracks_kernel<<<dim3(gx, nr), 256, 0, s>>>(d_words, d_src + r0, db->d_track_start + r0, db->d_words);
+                e = cudaGetLastError();
+            }
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (d_src) cudaFree(d_src);
+        if (e != cudaSuccess) {
+            hpfw_db_destroy(db);
+            HPFW_FAIL(HPFW_ERR_CUDA, "hpfw_db_build_gather_device: %s", cudaGetErrorString(e));
         }
     }
     *out = db;
@@ -806,6 +862,24 @@ int hpfw_db_find_topk(hpfw_db *db, const uint64_t *qwords, const int64_t *qoffse
     HPFW_CUDA_TRY(cudaMemcpyAsync(ctx->pin_out.ptr, ctx->keys.ptr, sizeof(uint64_t) * nkeys, cudaMemcpyDeviceToHost,
                                   ctx->stream));
     HPFW_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    hpfw_keys_decode(ctx->pin_out.as<uint64_t>(), int(nkeys), out);
+    return HPFW_OK;
+}
+
+int hpfw_db_find_topk_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *qoffsets, int n_queries, int topk,
+                             hpfw_match *out, void *stream) {
+    if (!db || !qoffsets || !out) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_find_topk_device: NULL argument");
+    if (n_queries <= 0) return n_queries == 0 ? HPFW_OK : HPFW_ERR_ARG;
+    if (topk < 1) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_db_find_topk_device: topk < 1");
+    hpfw_ctx *ctx = db->ctx;
+    DeviceGuard g(ctx->device);
+    cudaStream_t s = ctx->pick(stream);
+    const size_t nkeys = size_t(n_queries) * size_t(topk);
+    HPFW_TRY(ctx->keys.reserve(sizeof(uint64_t) * nkeys));
+    HPFW_TRY(ctx->pin_out.reserve(sizeof(uint64_t) * nkeys));
+    HPFW_TRY(hpfw_db_match_device(db, d_qwords, qoffsets, n_queries, topk, ctx->keys.as<uint64_t>(), s));
+    HPFW_CUDA_TRY(cudaMemcpyAsync(ctx->pin_out.ptr, ctx->keys.ptr, sizeof(uint64_t) * nkeys, cudaMemcpyDeviceToHost, s));
+    HPFW_CUDA_TRY(cudaStreamSynchronize(s));
     hpfw_keys_decode(ctx->pin_out.as<uint64_t>(), int(nkeys), out);
     return HPFW_OK;
 }

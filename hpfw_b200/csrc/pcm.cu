@@ -34,7 +34,7 @@ pcm16_to_float_kernel(const int16_t *__restrict__ in, float *__restrict__ out, i
     }
 }
 
-static int pcm16_convert(hpfw_ctx *ctx, const int16_t *d_pcm, float *d_out, int64_t n, cudaStream_t s) {
+int pcm16_convert(hpfw_ctx *ctx, const int16_t *d_pcm, float *d_out, int64_t n, cudaStream_t s) {
     if (n <= 0) return HPFW_OK;
     KernelScope ks(ctx, HPFW_K_OTHER, s);
     const int64_t threads = (n + 7) / 8;

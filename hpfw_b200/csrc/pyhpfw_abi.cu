@@ -18,15 +18,17 @@ struct LiveIdCollector {
         if (!impl) impl.reset(new Collector(cache_dir));
         return *impl;
     }
+    // The reference's wrapper ignores the `cache` argument of save/load and always uses the live collector
+    // (modules/python/parallel_collector_wrapper.cpp:56-62). Here the directory is honoured, and the SAME collector keeps its
+    // learned state (filters, accum_cov): prepare() -> save(dir) -> load(dir) -> calc_hashprint works.
     void retarget(const char *cache) {
-        if (cache && cache[0]) {
-            std::string d(cache);
-            if (d.back() != '/') d.push_back('/');
-            if (d != cache_dir || !impl) {
-                cache_dir = d;
-                impl.reset(new Collector(cache_dir));
-            }
-        }
+        if (!cache || !cache[0]) return;
+        std::string d(cache);
+        if (d.back() != '/') d.push_back('/');
+        if (d == cache_dir && impl) return;
+        cache_dir = d;
+        if (impl) impl->set_cache_dir(cache_dir);
+        else impl.reset(new Collector(cache_dir));
     }
 };
 

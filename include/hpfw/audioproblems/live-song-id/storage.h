@@ -7,6 +7,7 @@
 #pragma once
 
 #include <cstdint>
+#include <functional>
 #include <limits>
 #include <memory>
 #include <optional>
@@ -48,8 +49,58 @@ public:
             offs.push_back(static_cast<int64_t>(words.size()));
         }
         upload(words, offs);
+        pending_words = nullptr;
         host_words = std::move(words);
         host_offs = std::move(offs);
+    }
+
+    /// build() from hashprints that are still in HBM (Collector::prepare_device): device-to-device, the words never visit
+    /// the host. DB order = order of d.names. The host copy save() needs is fetched lazily.
+    template <typename DeviceHashprints>
+    void build_device(const DeviceHashprints &d) {
+        names = d.names;
+        host_words.clear();
+        host_offs.assign(1, 0);
+        for (int w : d.words) host_offs.push_back(host_offs.back() + w);
+        std::scoped_lock l(ctx->mutex());
+        hpfw_db_destroy(db);
+        db = nullptr;
+        device::check(hpfw_xs_build_db(d.xs->get(), d.order.data(), static_cast<int>(d.order.size()), 0, &db));
+        // the dump written by save() needs the words on the host: one contiguous copy per track, only when asked for
+        pending_words = [xs = d.xs, gen = d.generation, order = d.order, words = d.words, ctx = ctx]() {
+            if (xs->generation != gen)
+                throw Error(HPFW_ERR_STATE, "MemoryStorage::save: the collector has started another batch since build_device(); "
+                                            "the hashprints are no longer resident in its stream (save() right after index())");
+            std::vector<uint64_t> out;
+            size_t total = 0;
+            for (int w : words) total += static_cast<size_t>(w);
+            out.resize(total);
+            size_t pos = 0;
+            std::scoped_lock l2(ctx->mutex());
+            for (size_t i = 0; i < order.size(); ++i) {
+                device::check(hpfw_xs_hashprint_host(xs->get(), order[i], out.data() + pos));
+                pos += static_cast<size_t>(words[i]);
+            }
+            return out;
+        };
+    }
+
+    /// Batched top-k of queries whose hashprints are still in HBM (Collector::calc_hashprints_device), one result list per
+    /// query in d.names order.
+    template <typename DeviceHashprints>
+    std::vector<std::vector<SearchResult>> find_topk_device(const DeviceHashprints &d, int topk) const {
+        const size_t nq = d.order.size();
+        std::vector<std::vector<SearchResult>> out(nq);
+        if (nq == 0) return out;
+        std::vector<hpfw_match> m(nq * static_cast<size_t>(topk));
+        {
+            std::scoped_lock l(ctx->mutex());
+            device::check(hpfw_xs_match(d.xs->get(), require(), topk, m.data()));
+        }
+        // the stream holds exactly the tracks of d.order, ascending (calc_hashprints_device sorts by stream track)
+        for (size_t q = 0; q < nq; ++q)
+            for (int r = 0; r < topk; ++r) out[q].push_back(to_result(m[q * topk + r]));
+        return out;
     }
 
     /// MemoryStorage::find (storage.h:27-64): best track by strict '<' over (distance, then DB order), lowest offset.
@@ -83,6 +134,10 @@ public:
     /// cereal-compatible dump of the DB (storage.h:67-76).
     std::string save(const std::optional<std::string> &filename) const {
         const std::string dump_name = filename.value_or("db/dump.cereal");
+        if (pending_words) {
+            host_words = pending_words();
+            pending_words = nullptr;
+        }
         std::vector<io::NamedHashprint> v;
         for (size_t r = 0; r < names.size(); ++r)
             v.emplace_back(names[r], std::vector<uint64_t>(host_words.begin() + host_offs[r],
@@ -104,8 +159,9 @@ private:
     std::shared_ptr<device::Context> ctx;
     hpfw_db *db = nullptr;
     std::vector<std::string> names;
-    std::vector<uint64_t> host_words;     // kept for save(); the matcher only reads the HBM copy
+    mutable std::vector<uint64_t> host_words;     // kept for save(); the matcher only reads the HBM copy
     std::vector<int64_t> host_offs;
+    mutable std::function<std::vector<uint64_t>()> pending_words;   // build_device: host copy fetched on the first save()
 
     hpfw_db *require() const {
         if (!db) throw Error(HPFW_ERR_STATE, "MemoryStorage: build() or load() has not been called");

@@ -23,6 +23,14 @@ public:
     void set_spectro(const std::string &filename, const typename Algo::Spectrogram &f) const {
         io::save_matrix(cache_dir + "spectros/" + std::filesystem::path(filename).stem().string(), f);
     }
+    /// The same file from a raw column-major float[121 x cols] buffer (the cache-writer threads of ParallelCollector hand over
+    /// the pinned buffer the spectrogram was copied into; no Matrix copy in between).
+    void set_spectro_raw(const std::string &filename, const float *data, int rows, int cols) const {
+        io::save_matrix_raw(cache_dir + "spectros/" + std::filesystem::path(filename).stem().string(), data, rows, cols);
+    }
+    std::string spectro_path(const std::string &filename) const {
+        return cache_dir + "spectros/" + std::filesystem::path(filename).stem().string();
+    }
     void set_cov(const typename Algo::CovarianceMatrix &accum_cov) const {
         io::save_matrix(cache_dir + "accum_cov.cereal", accum_cov);
     }

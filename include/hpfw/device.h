@@ -54,9 +54,52 @@ public:
         return sp;
     }
 
+    /// Whose filters the device context currently holds (a collector's id and the generation of its filter set): collectors
+    /// that share a context re-upload only when the tag differs. Read and written under mutex().
+    uint64_t filters_tag = 0;
+
 private:
     hpfw_ctx *ctx_ = nullptr;
     std::mutex mtx_;
+};
+
+/// RAII handle of an extraction stream (include/hpfw_b200.h, xstream.cu): the pinned staging ring the decode threads fill and
+/// the device-side store of resident spectrograms and hashprints.
+class ExtractionStream {
+public:
+    ExtractionStream(Context &ctx, int slots, size_t slot_bytes) { check(hpfw_xs_create(ctx.get(), slots, slot_bytes, &xs_)); }
+    ~ExtractionStream() { hpfw_xs_destroy(xs_); }
+    ExtractionStream(const ExtractionStream &) = delete;
+    ExtractionStream &operator=(const ExtractionStream &) = delete;
+    hpfw_xs *get() const { return xs_; }
+    /// bumped by the owner whenever it resets the stream: handles to earlier contents (DeviceHashprints) compare it
+    uint64_t generation = 0;
+
+private:
+    hpfw_xs *xs_ = nullptr;
+};
+
+/// Pinned host buffer (destination of hpfw_xs_fetch_spectrogram in the cache-writer threads).
+class PinnedBuffer {
+public:
+    PinnedBuffer() = default;
+    ~PinnedBuffer() { hpfw_host_free(p_); }
+    PinnedBuffer(const PinnedBuffer &) = delete;
+    PinnedBuffer &operator=(const PinnedBuffer &) = delete;
+    void *reserve(size_t bytes) {
+        if (bytes > cap_) {
+            hpfw_host_free(p_);
+            p_ = nullptr;
+            cap_ = 0;
+            check(hpfw_host_alloc(bytes + bytes / 4, &p_));
+            cap_ = bytes + bytes / 4;
+        }
+        return p_;
+    }
+
+private:
+    void *p_ = nullptr;
+    size_t cap_ = 0;
 };
 
 }  // namespace device

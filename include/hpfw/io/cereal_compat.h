@@ -30,6 +30,39 @@ inline void save_matrix(const std::string &filename, const Matrix<T, RM> &m) {
     os.write(reinterpret_cast<const char *>(m.data()), static_cast<std::streamsize>(sizeof(T)) * rows * cols);
 }
 
+/// save_matrix for a raw buffer (float, column-major rows x cols); written to a temporary name and renamed, so that a reader
+/// never sees a half-written cache file.
+inline void save_matrix_raw(const std::string &filename, const float *data, int32_t rows, int32_t cols) {
+    const std::string tmp = filename + ".tmp~";
+    {
+        std::ofstream os(tmp, std::ios::binary);
+        if (!os) throw std::runtime_error("cannot write '" + tmp + "'");
+        os.write(reinterpret_cast<const char *>(&rows), 4);
+        os.write(reinterpret_cast<const char *>(&cols), 4);
+        os.write(reinterpret_cast<const char *>(data), static_cast<std::streamsize>(sizeof(float)) * rows * cols);
+        if (!os) throw std::runtime_error("cannot write '" + tmp + "'");
+    }
+    std::filesystem::rename(tmp, filename);
+}
+
+/// Header of a matrix file: (rows, cols); the payload follows at byte 8.
+inline bool matrix_header(const std::string &filename, int32_t &rows, int32_t &cols) {
+    std::ifstream is(filename, std::ios::binary);
+    if (!is) return false;
+    is.read(reinterpret_cast<char *>(&rows), 4);
+    is.read(reinterpret_cast<char *>(&cols), 4);
+    return bool(is) && rows >= 0 && cols >= 0;
+}
+
+/// Payload of a matrix file straight into `dst` (rows * cols scalars of sizeof(T)).
+template <typename T>
+inline void load_matrix_payload(const std::string &filename, T *dst, size_t count) {
+    std::ifstream is(filename, std::ios::binary);
+    is.seekg(8);
+    is.read(reinterpret_cast<char *>(dst), static_cast<std::streamsize>(sizeof(T) * count));
+    if (!is) throw std::runtime_error("'" + filename + "': truncated matrix file");
+}
+
 /// Like DriveCache::load (cache.h:73-82): a missing file leaves `m` untouched and returns false.
 template <typename T, bool RM>
 inline bool load_matrix(const std::string &filename, Matrix<T, RM> &m) {

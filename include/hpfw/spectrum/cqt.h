@@ -6,6 +6,7 @@
 
 #include <cstdint>
 #include <string>
+#include <utility>
 
 #include "../device.h"
 #include "../io/wav.h"
@@ -28,13 +29,24 @@ public:
     CQT() = default;
 
     /// Reference signature (cqt.h:36). Decodes a WAV file whose rate must equal SampleRate (no resampler here).
-    static Spectrogram spectrogram(const std::string &filename) {
+    static Spectrogram spectrogram(const std::string &filename, int device = 0) {
         const io::WavData wav = io::read_wav(filename, /*keep_pcm16=*/true);
         if (wav.sample_rate != static_cast<int>(SampleRate))
             throw Error(HPFW_ERR_ARG, "'" + filename + "' is sampled at " + std::to_string(wav.sample_rate) +
                                           " Hz; CQT<" + std::to_string(SampleRate) + "> needs that rate (no resampler)");
-        if (!wav.pcm16.empty()) return spectrogram(wav.pcm16.data(), static_cast<int64_t>(wav.pcm16.size()));
-        return spectrogram(wav.mono.data(), static_cast<int64_t>(wav.mono.size()));
+        if (!wav.pcm16.empty()) return spectrogram(wav.pcm16.data(), static_cast<int64_t>(wav.pcm16.size()), device);
+        return spectrogram(wav.mono.data(), static_cast<int64_t>(wav.mono.size()), device);
+    }
+
+    /// Decode hook of the batched path (ParallelCollector::prepare / LiveSongIdentification::search): the samples go straight
+    /// into memory provided by `alloc(bytes)` — a pinned staging slot of the extraction stream — as mono int16 or float32.
+    template <typename Alloc>
+    static io::WavInfo decode(const std::string &filename, Alloc &&alloc) {
+        const io::WavInfo info = io::read_wav_into(filename, std::forward<Alloc>(alloc));
+        if (info.sample_rate != static_cast<int>(SampleRate))
+            throw Error(HPFW_ERR_ARG, "'" + filename + "' is sampled at " + std::to_string(info.sample_rate) +
+                                          " Hz; CQT<" + std::to_string(SampleRate) + "> needs that rate (no resampler)");
+        return info;
     }
 
     /// Mono 16-bit PCM samples: copied as they are (half the bytes), MonoLoader's sample / 32768 is done on the device.

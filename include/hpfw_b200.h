@@ -108,6 +108,9 @@ int hpfw_db_build(hpfw_ctx *ctx, const uint64_t *words, const int64_t *offsets, 
 /* same, words already on the device (copied device-to-device into the DB's own layout); offsets on the host */
 int hpfw_db_build_device(hpfw_ctx *ctx, const uint64_t *d_words, const int64_t *offsets, int n_tracks,
                          int64_t track_base, void *stream, hpfw_db **out);
+/* same from scattered device segments: DB track r = d_words[src_offsets[r] .. + lengths[r]) (host metadata) */
+int hpfw_db_build_gather_device(hpfw_ctx *ctx, const uint64_t *d_words, const int64_t *src_offsets, const int64_t *lengths,
+                                int n_tracks, int64_t track_base, void *stream, hpfw_db **out);
 void hpfw_db_destroy(hpfw_db *db);
 int hpfw_db_tracks(const hpfw_db *db);
 int64_t hpfw_db_words(const hpfw_db *db);
@@ -120,6 +123,10 @@ int hpfw_db_find_topk(hpfw_db *db, const uint64_t *qwords, const int64_t *qoffse
 /* Device path: d_qwords on the device, qoffsets on the host (metadata); d_keys_out[n_queries * topk] packed keys. */
 int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *qoffsets, int n_queries, int topk,
                          uint64_t *d_keys_out, void *stream);
+/* Query words already on the device, records on the host (synchronises `stream`): MemoryStorage::find for a batch whose
+ * hashprints were extracted on this GPU. */
+int hpfw_db_find_topk_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *qoffsets, int n_queries, int topk,
+                             hpfw_match *out, void *stream);
 /* which kernel runs the cross-correlation:
  *   0 = XOR + POPC on the integer pipes (matcher.cu);
  *   1 = exact GEMM on the tensor cores over +1/-1 signed bytes, tcgen05.mma.kind::i8 with s32 accumulation (match_tc.cu);
@@ -233,6 +240,59 @@ int hpfw_calc_hashprint_pcm16_device(hpfw_ctx *ctx, const int16_t *d_pcm, int64_
                                      void *stream);
 int hpfw_calc_hashprint_pcm16_batch_device(hpfw_ctx *ctx, const int16_t *d_pcm, const int64_t *sample_offsets, int n,
                                            uint64_t *d_hp_out, void *stream);
+
+/* ------------------------------------------------------------------ extraction stream (index / search runtime, xstream.cu) */
+/* The device-resident pipeline behind ParallelCollector::prepare (parallel_collector.h:48-52, 82-137: preprocess fan-out over
+ * files, covariance accumulate, collect_fingerprints over the cached spectrograms) and LiveSongIdentification::search
+ * (live_song_id.h:35-54). Decode threads write samples straight into pinned staging slots; a submit enqueues
+ * H2D -> [int16 -> float] -> CQT on one of 4 lane streams (-> covariance accumulate on a serial side stream) and KEEPS the dB
+ * spectrogram in HBM; after the filters are known hpfw_xs_hash_kept runs the projection/threshold/pack over all resident
+ * spectrograms in batched launches; the hashprints stay in HBM and become a database (hpfw_xs_build_db) or a query batch
+ * (hpfw_xs_match) without visiting the host.
+ * Threading: hpfw_xs_acquire, hpfw_xs_release and hpfw_xs_fetch_spectrogram may be called from any thread; all other calls
+ * follow the context's rule (one call at a time per context). */
+typedef struct hpfw_xs hpfw_xs;
+#define HPFW_XS_PCM16 1        /* the slot holds int16 samples (else float32) */
+#define HPFW_XS_COV 2          /* also add the track's frame covariance to the context's accumulator (hpfw_cov_*) */
+#define HPFW_XS_SPECTROGRAM 4  /* (set by hpfw_xs_submit_spectrogram) the slot holds a dB spectrogram, not audio */
+/* pinned host memory for the cache-writer side (hpfw_xs_fetch_spectrogram destinations) */
+int hpfw_host_alloc(size_t bytes, void **out);
+void hpfw_host_free(void *p);
+/* slots: pinned staging slots (>= 2 per decode thread is plenty); slot_bytes: initial size of each (slots grow on demand).
+ * HBM budget for resident spectrograms: HPFW_XS_ARENA_BYTES (default 70 % of the free device memory), in chunks of
+ * HPFW_XS_CHUNK_BYTES (default 1 GiB). */
+int hpfw_xs_create(hpfw_ctx *ctx, int slots, size_t slot_bytes, hpfw_xs **out);
+void hpfw_xs_destroy(hpfw_xs *xs);
+/* blocks until a staging slot is free; *host_ptr_out = its pinned buffer of at least `bytes` bytes (any thread) */
+int hpfw_xs_acquire(hpfw_xs *xs, size_t bytes, int *slot_out, void **host_ptr_out);
+/* give an acquired slot back without submitting it (decode failed; any thread) */
+int hpfw_xs_release(hpfw_xs *xs, int slot);
+/* Enqueue the slot's n_samples (flags: HPFW_XS_PCM16, HPFW_XS_COV); *track_out = index of the track in the stream (submission
+ * order). Returns without synchronising; the slot goes back to the ring when its upload has completed (also on failure).
+ * HPFW_ERR_SHORT: fewer than 100 spectrogram columns; HPFW_ERR_LIMIT: HBM budget for resident spectrograms exhausted. */
+int hpfw_xs_submit(hpfw_xs *xs, int slot, int64_t n_samples, int flags, int *track_out);
+/* the same for an already computed dB spectrogram (a cache/spectros/<stem> file, cache.h:30-33): slot = float[121 x cols] */
+int hpfw_xs_submit_spectrogram(hpfw_xs *xs, int slot, int cols, int flags, int *track_out);
+int hpfw_xs_tracks(hpfw_xs *xs);
+int hpfw_xs_track_info(hpfw_xs *xs, int track, int *cols_out, int *words_out, int *resident_out);
+/* copy a resident spectrogram to the host (waits for that track only; any thread; host_out best pinned: hpfw_host_alloc) */
+int hpfw_xs_fetch_spectrogram(hpfw_xs *xs, int track, float *host_out);
+/* wait for everything submitted so far (lanes, covariance) */
+int hpfw_xs_wait(hpfw_xs *xs);
+/* hash every resident spectrogram that has not been hashed yet with the context's current filters (batched launches) */
+int hpfw_xs_hash_kept(hpfw_xs *xs);
+/* free the resident spectrograms (their hashprints, if hashed, stay); the caller has joined its hpfw_xs_fetch_spectrogram threads */
+int hpfw_xs_drop_kept(hpfw_xs *xs);
+/* forget all tracks and hashprints, keep the buffers */
+int hpfw_xs_reset(hpfw_xs *xs);
+/* the hashprint store: device pointer, and per track its word offset (-1: not hashed) and length */
+int hpfw_xs_hashprints_device(hpfw_xs *xs, const uint64_t **d_words_out, int64_t *offsets_out, int64_t *lengths_out);
+int hpfw_xs_hashprint_host(hpfw_xs *xs, int track, uint64_t *out);
+int hpfw_xs_hashprints_host(hpfw_xs *xs, uint64_t *out, int64_t n_words);   /* the first n_words of the store */
+/* database from hashed tracks, DB index i = stream track order[i]; device-to-device */
+int hpfw_xs_build_db(hpfw_xs *xs, const int *order, int n, int64_t track_base, hpfw_db **out);
+/* all tracks of the stream as queries (store order) against db: out[tracks * topk] */
+int hpfw_xs_match(hpfw_xs *xs, hpfw_db *db, int topk, hpfw_match *out);
 
 /* ------------------------------------------------------------------------------------------------ measurement aids */
 /* Pipe microbenchmark used to pin the matcher's roofline denominator: runs register-only loops and reports
