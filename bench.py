@@ -8,15 +8,18 @@
 Workload (config.workload): DB = 10,000 tracks x 14,411 hashprint words (3-min tracks, SURVEY.md §8), synthetic iid words;
 one STEP = one batch of 128*N queries of 385 words (6 s), each a DB slice with 25 % of its bits flipped, matched at every
 alignment offset of every track (Hamming cross-correlation), top-10 per query. The DB is sharded by track over the N
-GPUs, queries are replicated, per-rank top-k keys are all-gathered (NCCL) and merged. Per-GPU work per step is constant
-in N ("weak").
+GPUs, queries are replicated, per-rank top-k keys are all-gathered and merged inside the library (hpfw_shard_match_device:
+ncclAllGather in place + merge kernel; torch.distributed only bootstraps the NCCL id and the barriers). Per-GPU work per step
+is constant in N ("weak"); a fixed-size batch and single-query latency are reported in `strong`.
 
   value   device-resident: query words already in HBM when the timed region starts
   e2e     through the host API (ShardedMemoryStorage.search_host): pinned host query words -> H2D -> match -> (allgather,
           merge) -> D2H of the top-k records, every step
-  roofline  the dominant kernel — match_tc_kernel (exact int8 GEMM on the tensor cores) against the int8 tensor-pipe
-          ceiling; roofline_popc: the integer-pipe match_kernel on the same step against the POPC/LOP3 pipe roof
-          (see DESIGN.md); durations from CUDA events around every launch
+  roofline  the dominant kernel — match_tc_kernel<1> (exact +-1 GEMM on the tensor cores, fp4 operands, f32 accumulators)
+          against the fp4 tensor-pipe ceiling; roofline_popc: the integer-pipe match_kernel on the same step against the
+          POPC/LOP3 pipe roof; durations from CUDA events around every launch
+  e2e_cpp   the reference's own C++ API timed from WAV files by examples/cpp/bench-liveid.cpp (rank 0): queries/s of
+          LiveSongIdentification::search() against the same 10k-track DB and frames/s of index()
   cpu_baseline  the reference's own MemoryStorage::find (oracle/_ref, compiled from /root/reference headers) on all host
           cores over a bounded sample, on rank 0 at N=1 only
 """
@@ -152,16 +155,22 @@ def cpu_find_batch(words, offs, q, qoffs, cores):
     return "port", tr[:, 0], d[:, 0], o[:, 0]
 
 
-def cpu_sample(cores: int, sample_tracks: int, nq: int, seed: int = 7):
-    """Time one bounded sample: nq queries x sample_tracks tracks; returns (kind, seconds, queries/s scaled to 10k tracks)."""
+def cpu_sample(cores: int, sample_tracks: int, nq: int, seed: int = 7, tracks: int = TRACKS):
+    """Time one bounded sample: nq queries x sample_tracks tracks; returns (kind, seconds, queries/s scaled to `tracks`)."""
     words, offs = host_db(seed, sample_tracks)
     q, qoffs, truth = host_queries(seed + 1, words, offs, nq)
     t0 = time.perf_counter()
     kind, tr, d, o = cpu_find_batch(words, offs, q, qoffs, cores)
     dt = time.perf_counter() - t0
     assert np.array_equal(tr, truth[:, 0]) and np.array_equal(o, truth[:, 1]), "CPU baseline returned wrong matches"
-    qps = nq / dt * (sample_tracks / TRACKS)       # find() is linear in the number of reference tracks
+    qps = nq / dt * (sample_tracks / tracks)       # find() is linear in the number of reference tracks
     return kind, dt, qps
+
+
+def cpu_wordops_per_core(qps: float, cores: int, tracks: int = TRACKS) -> float:
+    """word-ops (XOR64 + popcount64) per second per host core behind a queries/s figure quoted on a `tracks`-track DB:
+    comparable across boxes with different core counts."""
+    return qps * word_ops_per_query(tracks) / max(1, cores)
 
 
 def run_reference(args):
@@ -174,20 +183,21 @@ def run_reference(args):
     times = []
     kind = "reference"
     for i in range(args.warmup + args.steps):
-        kind, dt, qps = cpu_sample(cores, sample_tracks, nq, seed=11 + i)
+        kind, dt, qps = cpu_sample(cores, sample_tracks, nq, seed=11 + i, tracks=args.tracks)
         if i >= args.warmup:
             times.append((dt, qps))
     dt = float(np.mean([t[0] for t in times]))
     qps = float(np.mean([t[1] for t in times]))
     sample = (f"each step: {nq} queries x {sample_tracks}-track subset of the DB on {cores} host threads, "
-              f"scaled x{sample_tracks}/{TRACKS} (find is linear in tracks); MemoryStorage::find compiled from the "
+              f"scaled x{sample_tracks}/{args.tracks} (find is linear in tracks); MemoryStorage::find compiled from the "
               f"reference headers with -Ofast -march=native (no MKL involved in this path)")
     line = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "config": workload_config(args.gpus, args.tracks, args.queries_per_gpu),
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                         "wordops_per_s_per_core": cpu_wordops_per_core(qps, cores, args.tracks)},
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -195,13 +205,13 @@ def run_reference(args):
     return 0
 
 
-def workload_config(n_gpus: int):
-    return {"workload": f"live-id search: {TRACKS}-track DB x {TRACK_WORDS} words (3-min tracks), "
-                        f"{QUERIES_PER_GPU}*N x {QUERY_WORDS}-word (6 s) queries per step, full-offset Hamming "
+def workload_config(n_gpus: int, tracks: int = TRACKS, qpg: int = QUERIES_PER_GPU):
+    return {"workload": f"live-id search: {tracks}-track DB x {TRACK_WORDS} words (3-min tracks), "
+                        f"{qpg}*N x {QUERY_WORDS}-word (6 s) queries per step, full-offset Hamming "
                         f"cross-correlation, top-{TOPK}",
-            "tracks": TRACKS, "track_words": TRACK_WORDS, "query_words": QUERY_WORDS,
-            "queries_per_step": QUERIES_PER_GPU * n_gpus, "topk": TOPK,
-            "parallelism": f"db-shard x{n_gpus} (tracks), queries replicated, NCCL allgather of top-k keys",
+            "tracks": tracks, "track_words": TRACK_WORDS, "query_words": QUERY_WORDS,
+            "queries_per_step": qpg * n_gpus, "topk": TOPK,
+            "parallelism": f"db-shard x{n_gpus} (tracks), queries replicated, in-library ncclAllGather of top-k keys + merge kernel",
             "l2": "DB shard per GPU (>=144 MB) exceeds the 126 MB L2; no flush needed"}
 
 
@@ -238,7 +248,7 @@ def cpu_extraction_sample(cores: int, n_tracks: int, filters):
     return kind, dt, frames / dt
 
 
-def run_extraction(args, ctx, rank, world, dev, max_over_ranks, barrier):
+def run_extraction(args, ctx, rank, world, dev, max_over_ranks, barrier, st):
     """BASELINE.json configs[1]: hashprint extraction only, 1000 synthetic 3-min tracks (split over the ranks), CQT + 64-filter
     projection, frames/s. Audio resident in HBM for `value`; `e2e` streams every track from pinned host memory."""
     import torch
@@ -357,6 +367,19 @@ def run_extraction(args, ctx, rank, world, dev, max_over_ranks, barrier):
     e2e16_value = e2e_tracks * world * frames / e2e16_s
     del pin16, stage16
 
+    # host -> device copy rate of this box (the bound of the e2e extraction legs above)
+    pin_big = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
+    dev_big = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    best_copy = None
+    for _ in range(5):
+        e0.record()
+        dev_big.copy_(pin_big, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1)
+        best_copy = t if best_copy is None else min(best_copy, t)
+    pcie_gbs = (256 << 20) / (best_copy * 1e-3) / 1e9 if best_copy else None
+    del pin_big, dev_big
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -396,6 +419,12 @@ def run_extraction(args, ctx, rank, world, dev, max_over_ranks, barrier):
                      "ms_per_track": cq_per_track, "kernel_ms_sum_per_track_overlapped": cq_kernel_sum_per_track,
                      "peak_how": src,
                      "algorithmic_bytes_per_track": cqt_bytes},
+        "roofline_e2e": {"bound": "pcie", "what": "extraction.e2e.pcm16: every track crosses PCIe once as 16-bit PCM",
+                         "achieved": 2.0 * n * e2e_tracks / e2e16_s / 1e9, "peak": pcie_gbs, "unit": "GB/s",
+                         "frac": 2.0 * n * e2e_tracks / e2e16_s / 1e9 / pcie_gbs if pcie_gbs else None,
+                         "peak_how": "pinned host -> device copy of 256 MiB measured in this run (cudaMemcpyAsync, best of 5)",
+                         "float32": {"achieved": 4.0 * n * e2e_tracks / e2e_s / 1e9,
+                                     "frac": 4.0 * n * e2e_tracks / e2e_s / 1e9 / pcie_gbs if pcie_gbs else None}},
         "roofline_projection": {"bound": "tensor", "kernel": "project_tc_kernel<3> (tcgen05 kind::f16, fp16 operands, + tc_delta_kernel pre-pass)",
                                 "achieved": 2.0 * 64 * 2420 * frames * per_rank * reps / (pj_ms * 1e-3) / 1e12,
                                 "peak": f16_peak, "unit": "TFLOP/s",
@@ -471,20 +500,126 @@ def run_extraction(args, ctx, rank, world, dev, max_over_ranks, barrier):
     if world > 1:
         # multi-GPU index: every rank accumulates the covariance of its own tracks; ONE all-reduce of the 2420 x 2420
         # accumulator (NCCL over NVLink, 23 MB) gives every rank the collection's covariance (sharded.allreduce_covariance)
-        from hpfw_b200.sharded import allreduce_covariance
-        allreduce_covariance(ctx)
+        st.allreduce_covariance(stream)
         barrier()
         e0.record()
-        allreduce_covariance(ctx)
+        st.allreduce_covariance(stream)
         e1.record()
         barrier()
         ar_ms = max_over_ranks(e0.elapsed_time(e1))
         if rank == 0 and "index" in out:
             out["index"]["cov_allreduce_ms"] = ar_ms
-            out["index"]["cov_allreduce_note"] = (f"one all-reduce (sum) of the covariance accumulator over {world} ranks + "
-                                                  "the two device copies around it, once per index() call")
+            out["index"]["cov_allreduce_note"] = (f"one in-place ncclAllReduce (sum) of the covariance accumulator over {world} "
+                                                  "ranks inside the library (hpfw_shard_allreduce_cov), once per index() call")
     del audio, base, hp
     torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------ C++ API leg
+def build_cpp_bench():
+    exe = os.path.join(ROOT, "examples", "cpp", "bench-liveid")
+    src = os.path.join(ROOT, "examples", "cpp", "bench-liveid.cpp")
+    libdir = os.path.join(ROOT, "hpfw_b200")
+    deps = [src, os.path.join(libdir, "libhpfw_b200.so")]
+    for dp, _, fns in os.walk(os.path.join(ROOT, "include")):
+        deps += [os.path.join(dp, fn) for fn in fns]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), src, "-o", exe,
+                               "-L" + libdir, "-lhpfw_b200", "-lpthread", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def run_cpp_leg(args, ctx, ex, dev, world, tracks, audio_tracks, audio_hps, h_audio, src_track, filters, e2e_value):
+    """The reference's own C++ API from WAV files (rank 0): hpfw::LiveSongIdentification::search() over the 128 query WAVs
+    against the same database the Python arm uses (loaded from a MemoryStorage dump), and ::index() over 3-minute PCM16 WAVs.
+    Files live on tmpfs; the ranks of an N > 1 run idle at a barrier meanwhile and the binary uses db::ShardedMemoryStorage
+    over the N GPUs from ONE process."""
+    import shutil
+    import tempfile
+    import torch
+    from hpfw_b200 import bench_data
+    exe = build_cpp_bench()
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    work = tempfile.mkdtemp(prefix="hpfw_cpp_", dir=base)
+    out = {"binary": "examples/cpp/bench-liveid (g++ -O2, include/hpfw/*.h over libhpfw_b200.so)", "work_dir": work}
+    env = dict(os.environ, HPFW_NUM_GPUS=str(world))
+    try:
+        # ---- search leg: same DB content as the Python arm (synthetic words; the first tracks carry the audio hashprints)
+        os.makedirs(os.path.join(work, "cache", "spectros"))
+        os.makedirs(os.path.join(work, "queries"))
+        bench_data.write_matrix_cereal(os.path.join(work, "cache", "filters.cereal"), 64, 2420, filters)
+        rng = np.random.default_rng(4321)
+        names = [f"track{i:05d}" for i in range(tracks)]
+        with open(os.path.join(work, "db.cereal"), "wb") as f:
+            f.write(np.uint64(tracks).tobytes())
+            for i in range(tracks):
+                hp = rng.integers(0, 1 << 63, size=TRACK_WORDS, dtype=np.int64).view(np.uint64)
+                if i < len(audio_hps):
+                    hp[:len(audio_hps[i])] = audio_hps[i]
+                b = names[i].encode()
+                f.write(np.uint64(len(b)).tobytes() + b + np.uint64(TRACK_WORDS).tobytes())
+                f.write(hp.tobytes())
+        nqf = h_audio.shape[0]
+        expect = []
+        for q in range(nqf):
+            pcm = (h_audio[q].numpy() * 32768.0 * 0.9).round().clip(-32768, 32767).astype(np.int16)
+            fn = f"q{q:04d}_{names[int(src_track[q])]}.wav"
+            bench_data.write_wav_pcm16(os.path.join(work, "queries", fn), pcm, 44100)
+            expect.append(f"{fn} {names[int(src_track[q])]}")
+        with open(os.path.join(work, "expect.txt"), "w") as f:
+            f.write("\n".join(expect) + "\n")
+        cmd = "search-sharded" if world > 1 else "search"
+        p = subprocess.run([exe, cmd, "db.cereal", "queries", str(max(2, args.steps)), "expect.txt"], cwd=work, env=env,
+                           capture_output=True, text=True, timeout=900)
+        recs = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+        if p.returncode != 0 or not recs:
+            out["search"] = {"error": f"rc={p.returncode}", "stderr_tail": p.stderr[-600:]}
+        else:
+            r = json.loads(recs[-1])
+            out["search"] = r | {
+                "what": "LiveSongIdentification::search() over 128 six-second PCM16 WAV files (decode threads -> pinned ring "
+                        "-> H2D -> CQT -> projection -> match -> printed results), one process, "
+                        f"{'db::ShardedMemoryStorage over ' + str(world) + ' GPUs' if world > 1 else 'db::MemoryStorage'}",
+                "vs_python_e2e": r["queries_per_s"] / e2e_value if world == 1 else None,
+                "vs_python_e2e_note": "same 128 queries per batch, same DB size; N > 1: the C++ batch is 128 queries over N "
+                                      "GPUs (strong), the Python step 128*N (weak): not comparable"}
+        os.remove(os.path.join(work, "db.cereal"))
+        # ---- index leg: 3-minute PCM16 WAVs (32 distinct signals, the other names are links to them)
+        if args.cpp_index_tracks > 0:
+            idir = os.path.join(work, "tracks")
+            os.makedirs(idir)
+            n = int(EXTRACT_SECONDS * EXTRACT_SR)
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(4242)
+            tt = torch.arange(n, device=dev, dtype=torch.float32) / EXTRACT_SR
+            uniq = min(32, args.cpp_index_tracks)
+            for b in range(uniq):
+                x = 0.05 * torch.randn(n, device=dev, generator=gen)
+                for _ in range(6):
+                    semis = int(torch.randint(0, 49, (1,), device=dev, generator=gen).item())
+                    f0 = 130.81 * 2.0 ** (semis / 12.0)
+                    rate = float(torch.rand(1, device=dev, generator=gen).item()) * 2.0 + 0.5
+                    x += 0.15 * torch.sin(2 * np.pi * f0 * tt) * (0.5 + 0.5 * torch.sin(2 * np.pi * rate * tt))
+                pcm = (x * 16384.0).clamp_(-32768, 32767).to(torch.int16).cpu().numpy()
+                bench_data.write_wav_pcm16(os.path.join(idir, f"song{b:05d}.wav"), pcm, EXTRACT_SR)
+            for i in range(uniq, args.cpp_index_tracks):
+                os.symlink(os.path.join(idir, f"song{i % uniq:05d}.wav"), os.path.join(idir, f"song{i:05d}.wav"))
+            del tt
+            shutil.rmtree(os.path.join(work, "cache"))
+            p = subprocess.run([exe, "index-sharded" if world > 1 else "index", "tracks", "2"], cwd=work, env=env,
+                               capture_output=True, text=True, timeout=900)
+            recs = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+            if p.returncode != 0 or not recs:
+                out["index"] = {"error": f"rc={p.returncode}", "stderr_tail": p.stderr[-600:]}
+            else:
+                out["index"] = json.loads(recs[-1]) | {
+                    "what": f"LiveSongIdentification::index() over {args.cpp_index_tracks} three-minute PCM16 WAV files on tmpfs: "
+                            "decode threads -> pinned ring -> H2D -> CQT -> covariance (filters learned, as the reference does) "
+                            "-> batched projection -> DB built device-to-device; cache/spectros written in the background",
+                    "host_threads": host_cores()}
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
     return out
 
 
@@ -526,9 +661,11 @@ def run_cuda(args):
     ex = hpfw_b200.HashprintExtractor(ctx)
     ex.set_filters(np.ascontiguousarray(golden["filters"]))
     audio_tracks = [synth.synth_track(900 + i, 30.0, 44100) for i in range(AUDIO_TRACKS)]
+    audio_hps = []
     if lo == 0:
         for i, a in enumerate(audio_tracks):
             hp_i = ex.calc_hashprint(a)
+            audio_hps.append(hp_i)
             d_words[i * TRACK_WORDS: i * TRACK_WORDS + len(hp_i)] = torch.from_numpy(hp_i.view(np.int64)).to(dev)
     d_q_local, _, truth_local = synth.device_hashprint_queries(torch, d_words, offs, 99 + rank, qpg, QUERY_WORDS, FLIP)
     truth_local[:, 0] += lo
@@ -624,6 +761,72 @@ def run_cuda(args):
     got = hpfw_b200.api.decode_keys(keys.cpu().numpy().view(np.uint64))
     top1_ok = float(np.mean((got["track"][:, 0] == truth[:, 0]) & (got["offset"][:, 0] == truth[:, 1])))
 
+    # ---- N > 1: the merged result of the sharded match must be byte-identical to ONE GPU matching the whole database
+    # (untimed): rank 0 rebuilds every rank's shard from its seed, concatenates them into the un-sharded DB and matches the
+    # same queries; the [Q][10] key arrays are compared on the device
+    sharded_identical = None
+    if world > 1 and not args.no_identity_check:
+        if rank == 0:
+            full = torch.empty(tracks * TRACK_WORDS, dtype=torch.int64, device=dev)
+            for r in range(world):
+                rlo, rhi = r * tracks // n, (r + 1) * tracks // n
+                w_r, _ = synth.device_hashprint_db(torch, dev, 1234 + r, rhi - rlo, TRACK_WORDS)
+                full[rlo * TRACK_WORDS: rhi * TRACK_WORDS] = w_r
+                del w_r
+            for i, hp_i in enumerate(audio_hps):
+                full[i * TRACK_WORDS: i * TRACK_WORDS + len(hp_i)] = torch.from_numpy(hp_i.view(np.int64)).to(dev)
+            one = hpfw_b200.MemoryStorage(ctx).build_device(full.data_ptr(), np.arange(tracks + 1, dtype=np.int64) * TRACK_WORDS,
+                                                            stream=stream)
+            del full
+            keys_one = torch.empty((nq, TOPK), dtype=torch.int64, device=dev)
+            one.match_device(d_q.data_ptr(), qoffs, TOPK, keys_one.data_ptr(), stream)
+            torch.cuda.synchronize()
+            sharded_identical = bool(torch.equal(keys_one, keys))
+            del one, keys_one
+            torch.cuda.empty_cache()
+        barrier()
+
+    # ---- strong-scaling view and latency (the weak-scaling step above keeps per-GPU work constant and hides the fixed costs):
+    # a FIXED batch of 128 queries over the N shards, and single find() calls (one query: integer-pipe kernel + all-gather +
+    # merge + top-k), p50 / p99 over 30 calls, device time from CUDA events, max over ranks
+    strong = None
+    if not args.no_strong_leg:
+        q128 = 128 * QUERY_WORDS
+        qo128 = np.arange(129, dtype=np.int64) * QUERY_WORDS
+        for _ in range(2):
+            st.search_device(d_q[:q128], qo128, TOPK)
+        barrier()
+        ctx.timing_read(_lib.K_MATCH_TC, reset=True)
+        ctx.timing_read(_lib.K_TOPK, reset=True)
+        ctx.timing_enable(True)
+        e0.record()
+        for _ in range(5):
+            st.search_device(d_q[:q128], qo128, TOPK)
+        e1.record()
+        barrier()
+        s_ms = max_over_ranks(e0.elapsed_time(e1)) / 5
+        s_tc_ms, _ = ctx.timing_read(_lib.K_MATCH_TC, reset=True)
+        s_topk_ms, _ = ctx.timing_read(_lib.K_TOPK, reset=True)
+        ctx.timing_enable(False)
+        qo1 = np.array([0, QUERY_WORDS], dtype=np.int64)
+        lat = []
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(32)]
+        for i, (a, b) in enumerate(evs):
+            if world > 1:
+                dist.barrier()
+            a.record()
+            st.search_device(d_q[i * QUERY_WORDS:(i + 1) * QUERY_WORDS], qo1, TOPK)
+            b.record()
+        torch.cuda.synchronize()
+        lat = sorted(max_over_ranks(a.elapsed_time(b)) for a, b in evs[2:])
+        strong = {"queries_per_step": 128, "ms_per_step": s_ms, "queries_per_s": 128 / (s_ms * 1e-3),
+                  "match_kernel_ms_this_rank": s_tc_ms / 5, "topk_merge_ms_this_rank": s_topk_ms / 5,
+                  "fixed_cost_us_per_step": (s_ms - s_tc_ms / 5) * 1e3,
+                  "fixed_cost_note": "step time minus match_tc_kernel on rank 0: query expansion, top-k, all-gather of "
+                                     "[128][10] keys, merge, launch gaps",
+                  "single_find_ms": {"p50": lat[len(lat) // 2], "p99": lat[-1], "calls": len(lat),
+                                     "note": "one 385-word query per call through the sharded path (integer-pipe kernel)"}}
+
     # ---- end-to-end arm (a13 search(): calc_hashprint + find per query): AUDIO in pinned host memory -> H2D -> CQT ->
     # projection/pack -> (all-gather of the hashprints) -> match -> (all-gather of keys, merge) -> D2H records, every step
     q_samples = int(6.0 * 44100)
@@ -644,14 +847,17 @@ def run_cuda(args):
     else:
         src_all = src_track
 
+    d_hp_all_buf = torch.empty(world * qpg * q_words, dtype=torch.int64, device=dev) if world > 1 else None
+
     def e2e_step():
         d_audio = h_audio.to(dev, non_blocking=True)
         ex.calc_hashprint_batch_device(d_audio.data_ptr(), q_offs, d_hp_local.data_ptr(),
                                        torch.cuda.current_stream().cuda_stream)
         if world > 1:
-            d_hp_all = torch.empty((world, qpg * q_words), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(d_hp_all.view(-1), d_hp_local)
-            d_hp_all = d_hp_all.view(-1)
+            # every rank extracted its own queries: one all-gather (NCCL, inside the library) hands all ranks all hashprints
+            st.allgatherv(d_hp_local.data_ptr(), d_hp_all_buf.data_ptr(), [8 * qpg * q_words] * world,
+                          torch.cuda.current_stream().cuda_stream)
+            d_hp_all = d_hp_all_buf
         else:
             d_hp_all = d_hp_local
         k = st.search_device(d_hp_all, qoffs, TOPK)
@@ -683,7 +889,17 @@ def run_cuda(args):
 
     extraction = None
     if not args.no_extraction:
-        extraction = run_extraction(args, ctx, rank, world, dev, max_over_ranks, barrier)
+        extraction = run_extraction(args, ctx, rank, world, dev, max_over_ranks, barrier, st)
+
+    cpp = None
+    if not args.no_cpp:
+        if rank == 0:
+            try:
+                cpp = run_cpp_leg(args, ctx, ex, dev, world, tracks, audio_tracks, audio_hps, h_audio, src_track,
+                                  np.ascontiguousarray(golden["filters"]), e2e_value)
+            except Exception as e:      # the C++ leg must never take the bench line down with it
+                cpp = {"error": f"{type(e).__name__}: {e}"}
+        barrier()
 
     if world > 1:
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
@@ -780,7 +996,7 @@ def run_cuda(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
-            "data": "synthetic", "config": workload_config(n) | {"tracks": tracks, "queries_per_step": nq},
+            "data": "synthetic", "config": workload_config(n, tracks, qpg),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_audio.numel() * 4 * n),
                     "d2h_bytes_per_step": int(h_out.numel() * 8), "ms_per_step": ms_e2e, "top1_ok": e2e_ok,
@@ -797,6 +1013,12 @@ def run_cuda(args):
             "top1_ok": top1_ok,
             "topk_ms_per_step": topk_ms / args.steps,
         }
+        if sharded_identical is not None:
+            line["sharded_bit_identical"] = sharded_identical
+        if strong is not None:
+            line["strong"] = strong
+        if cpp is not None:
+            line["e2e_cpp"] = cpp
         if roof_popc is not None:
             line["roofline_popc"] = roof_popc
             line["impls_bit_identical"] = impls_equal
@@ -806,11 +1028,12 @@ def run_cuda(args):
             cores = host_cores()
             nqc = max(cores, 8)
             sample_tracks = 2000
-            kind, dt, qps = cpu_sample(cores, sample_tracks, nqc)
+            kind, dt, qps = cpu_sample(cores, sample_tracks, nqc, tracks=tracks)
             line["cpu_baseline"] = {
                 "value": qps, "unit": UNIT, "cores": cores, "kind": kind,
+                "wordops_per_s_per_core": cpu_wordops_per_core(qps, cores, tracks),
                 "sample": f"{nqc} queries x {sample_tracks}-track subset ({dt:.1f} s on {cores} host threads), scaled "
-                          f"x{sample_tracks}/{TRACKS} to the 10k-track DB; reference MemoryStorage::find, "
+                          f"x{sample_tracks}/{tracks} to the {tracks}-track DB; reference MemoryStorage::find, "
                           f"-Ofast -march=native"}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
@@ -834,6 +1057,10 @@ def main():
                          "2 = default routing (hpfw_set_match_impl)")
     ap.add_argument("--no-popc-leg", action="store_true", help="skip timing the integer-pipe kernel beside the default")
     ap.add_argument("--no-extraction", action="store_true", help="skip the secondary hashprint-extraction leg")
+    ap.add_argument("--no-identity-check", action="store_true", help="N > 1: skip the untimed sharded-vs-one-GPU key comparison")
+    ap.add_argument("--no-strong-leg", action="store_true", help="skip the fixed-batch / single-find latency leg")
+    ap.add_argument("--no-cpp", action="store_true", help="skip the C++ API leg (examples/cpp/bench-liveid.cpp, e2e_cpp)")
+    ap.add_argument("--cpp-index-tracks", type=int, default=256, help="WAV files index() reads in the C++ leg (3-min PCM16)")
     ap.add_argument("--extract-tracks", type=int, default=1000, help="3-min tracks of the extraction leg (all GPUs together)")
     args = ap.parse_args()
     if args.impl == "reference":

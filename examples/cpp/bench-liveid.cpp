@@ -2,6 +2,7 @@
 // /root/reference/include/hpfw/audioproblems/live-song-id/live_song_id.h:31-54) on the B200 path, from WAV files.
 // bench.py runs it (rank 0, N = 1) and reports the numbers as `e2e_cpp`.
 //
+//   (index-sharded / search-sharded: the same with db::ShardedMemoryStorage, the DB spread over all visible GPUs)
 //   bench-liveid index  <wav_dir> [reps]
 //       one LiveSongIdentification per rep in the current directory (cache/ is created there, as in the reference);
 //       times index(files): decode threads -> pinned ring -> H2D -> CQT -> covariance -> filters -> batched projection -> DB
@@ -24,6 +25,7 @@
 #include <vector>
 
 #include <hpfw/audioproblems/live-song-id/live_song_id.h>
+#include <hpfw/audioproblems/live-song-id/sharded_storage.h>
 
 namespace {
 
@@ -39,6 +41,7 @@ struct CoutCapture {
     ~CoutCapture() { std::cout.rdbuf(old); }
 };
 
+template <typename LiveId>
 int run_index(int argc, char **argv) {
     const std::string dir = argv[2];
     const int reps = argc > 3 ? std::max(1, std::atoi(argv[3])) : 1;
@@ -55,7 +58,7 @@ int run_index(int argc, char **argv) {
     {
         // ONE application object, index() called reps + 1 times: call 0 pays the one-off costs (pinned staging ring, CQT plans,
         // arena chunks, first-touch of the scratch buffers) and is reported separately as index_first_s
-        hpfw::LiveSongIdentification<> liveid;
+        LiveId liveid;
         for (int r = 0; r <= reps; ++r) {
             const double t0 = now();
             liveid.index(files);
@@ -78,6 +81,7 @@ int run_index(int argc, char **argv) {
     return last_db == double(files.size()) ? 0 : 1;
 }
 
+template <typename LiveId>
 int run_search(int argc, char **argv) {
     const std::string dump = argv[2], qdir = argv[3];
     const int reps = argc > 4 ? std::max(1, std::atoi(argv[4])) : 3;
@@ -88,7 +92,7 @@ int run_search(int argc, char **argv) {
         while (is >> q >> t) expect[q] = t;
     }
     auto files = hpfw::utils::get_dir_files(qdir);
-    hpfw::LiveSongIdentification<> liveid;                   // loads cache/filters.cereal (live_song_id.h:23-25)
+    LiveId liveid;                                           // loads cache/filters.cereal (live_song_id.h:23-25)
     const double tl0 = now();
     liveid.get_storage().load(dump);
     const double load_s = now() - tl0;
@@ -133,9 +137,16 @@ int run_search(int argc, char **argv) {
 int main(int argc, char **argv) {
     std::ios_base::sync_with_stdio(false);
     try {
-        if (argc >= 3 && std::string(argv[1]) == "index") return run_index(argc, argv);
-        if (argc >= 4 && std::string(argv[1]) == "search") return run_search(argc, argv);
-        std::cerr << "usage: " << argv[0] << " index <wav_dir> [reps] | search <db_dump> <query_wav_dir> [reps] [expect.txt]"
+        using Coll = hpfw::DefaultLiveIdCollector;
+        using OneGpu = hpfw::LiveSongIdentification<>;
+        // the Storage plug-in is the only difference: every visible GPU (or HPFW_NUM_GPUS / HPFW_DEVICES) holds a shard of the DB
+        using Sharded = hpfw::LiveSongIdentification<Coll, hpfw::db::ShardedMemoryStorage<Coll>>;
+        const std::string cmd = argc > 1 ? argv[1] : "";
+        if (argc >= 3 && cmd == "index") return run_index<OneGpu>(argc, argv);
+        if (argc >= 4 && cmd == "search") return run_search<OneGpu>(argc, argv);
+        if (argc >= 3 && cmd == "index-sharded") return run_index<Sharded>(argc, argv);
+        if (argc >= 4 && cmd == "search-sharded") return run_search<Sharded>(argc, argv);
+        std::cerr << "usage: " << argv[0] << " index[-sharded] <wav_dir> [reps] | search[-sharded] <db_dump> <query_wav_dir> [reps] [expect.txt]"
                   << std::endl;
         return 2;
     } catch (const std::exception &e) {

@@ -27,6 +27,7 @@ _SIGS = {
     # name: (restype, argtypes)
     "hpfw_last_error": (C.c_char_p, []),
     "hpfw_version": (C.c_char_p, []),
+    "hpfw_device_count": (C.c_int, []),
     "hpfw_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "hpfw_ctx_destroy": (None, [C.c_void_p]),
     "hpfw_ctx_device": (C.c_int, [C.c_void_p]),
@@ -106,6 +107,27 @@ _SIGS = {
     "hpfw_xs_hashprints_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "hpfw_xs_build_db": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
     "hpfw_xs_match": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Match)]),
+    "hpfw_shard_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "hpfw_shard_nccl_version": (C.c_int, []),
+    "hpfw_shard_unique_id": (C.c_int, [C.c_void_p]),
+    "hpfw_shard_create_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "hpfw_shard_create_local": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "hpfw_shard_destroy": (None, [C.c_void_p]),
+    "hpfw_shard_world": (C.c_int, [C.c_void_p]),
+    "hpfw_shard_rank": (C.c_int, [C.c_void_p]),
+    "hpfw_shard_ctx": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "hpfw_shard_db": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "hpfw_shard_build_rank": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64]),
+    "hpfw_shard_build_rank_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
+    "hpfw_shard_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "hpfw_shard_build_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "hpfw_shard_match_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "hpfw_shard_find_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Match)]),
+    "hpfw_shard_find_topk_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Match)]),
+    "hpfw_shard_allreduce_cov": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hpfw_shard_allgather_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "hpfw_shard_allgatherv_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hpfw_shard_broadcast_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "hpfw_microbench_pipes": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

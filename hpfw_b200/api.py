@@ -316,3 +316,101 @@ class HashprintExtractor:
         so = np.ascontiguousarray(sample_offsets, dtype=np.int64)
         check(self._lib.hpfw_calc_hashprint_audio_batch_device(self.ctx.handle, C.c_void_p(d_audio_ptr), _ptr(so),
                                                                len(so) - 1, C.c_void_p(d_hp_out_ptr), stream_arg(stream)))
+
+
+XS_PCM16, XS_COV = 1, 2
+
+
+class ExtractionStream:
+    """hpfw_xs_*: the device-resident pipeline behind ParallelCollector::prepare / LiveSongIdentification::search
+    (include/hpfw_b200.h "extraction stream"; hpfw_b200/csrc/xstream.cu). Decoded buffers go into pinned staging slots, every
+    submit enqueues H2D -> [int16 -> float] -> CQT (-> covariance accumulate) and keeps the dB spectrogram in HBM; hash_kept()
+    runs the batched projection; the hashprints stay on the device."""
+
+    def __init__(self, ctx: Context, slots: int = 8, slot_bytes: int = 1 << 20):
+        self.ctx, self._lib = ctx, ctx._lib
+        h = C.c_void_p()
+        check(self._lib.hpfw_xs_create(ctx.handle, slots, slot_bytes, C.byref(h)))
+        self._h = h
+
+    def submit(self, samples: np.ndarray, cov: bool = False) -> int:
+        """samples: mono float32 or int16. Returns the track index in the stream (submission order)."""
+        a = np.ascontiguousarray(samples)
+        if a.dtype == np.int16:
+            flags = XS_PCM16
+        else:
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            flags = 0
+        slot, host = C.c_int(), C.c_void_p()
+        check(self._lib.hpfw_xs_acquire(self._h, a.nbytes, C.byref(slot), C.byref(host)))
+        C.memmove(host, a.ctypes.data, a.nbytes)
+        track = C.c_int()
+        check(self._lib.hpfw_xs_submit(self._h, slot.value, len(a), flags | (XS_COV if cov else 0), C.byref(track)))
+        return track.value
+
+    def wait(self) -> None:
+        check(self._lib.hpfw_xs_wait(self._h))
+
+    def hash_kept(self) -> None:
+        check(self._lib.hpfw_xs_hash_kept(self._h))
+
+    def reset(self) -> None:
+        check(self._lib.hpfw_xs_reset(self._h))
+
+    def drop_kept(self) -> None:
+        check(self._lib.hpfw_xs_drop_kept(self._h))
+
+    @property
+    def n_tracks(self) -> int:
+        return int(self._lib.hpfw_xs_tracks(self._h))
+
+    def hashprints_device(self):
+        """(device pointer of the hashprint store, offsets[n], lengths[n]) in store order; offset -1 = not hashed."""
+        n = self.n_tracks
+        ptr = C.c_void_p()
+        offs, lens = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64)
+        check(self._lib.hpfw_xs_hashprints_device(self._h, C.byref(ptr), _ptr(offs), _ptr(lens)))
+        return int(ptr.value or 0), offs, lens
+
+    def hashprint_host(self, track: int) -> np.ndarray:
+        cols, words, res = C.c_int(), C.c_int(), C.c_int()
+        check(self._lib.hpfw_xs_track_info(self._h, track, C.byref(cols), C.byref(words), C.byref(res)))
+        out = np.zeros(words.value, dtype=np.uint64)
+        check(self._lib.hpfw_xs_hashprint_host(self._h, track, _ptr(out)))
+        return out
+
+    def fetch_spectrogram(self, track: int) -> np.ndarray:
+        cols, words, res = C.c_int(), C.c_int(), C.c_int()
+        check(self._lib.hpfw_xs_track_info(self._h, track, C.byref(cols), C.byref(words), C.byref(res)))
+        out = np.zeros((cols.value, 121), dtype=np.float32)
+        check(self._lib.hpfw_xs_fetch_spectrogram(self._h, track, _ptr(out)))
+        return out
+
+    def build_db(self, storage: "MemoryStorage", order: Sequence[int], filenames=None, track_base: int = 0) -> "MemoryStorage":
+        """MemoryStorage from hashed tracks, device-to-device; DB index i = stream track order[i]."""
+        storage._free()
+        o = np.ascontiguousarray(order, dtype=np.int32)
+        h = C.c_void_p()
+        check(self._lib.hpfw_xs_build_db(self._h, _ptr(o), len(o), track_base, C.byref(h)))
+        storage._db = h
+        storage.track_base = track_base
+        storage.filenames = list(filenames) if filenames is not None else [str(track_base + i) for i in range(len(o))]
+        return storage
+
+    def match(self, storage: "MemoryStorage", topk: int) -> np.ndarray:
+        """All tracks of the stream as queries (store order) -> structured array [n, topk] (track, cnt, offset)."""
+        n = self.n_tracks
+        out = np.zeros((n, topk), dtype=np.dtype([("track", "<i8"), ("cnt", "<u8"), ("offset", "<i8")]))
+        check(self._lib.hpfw_xs_match(self._h, storage._require(), topk, out.ctypes.data_as(C.POINTER(Match))))
+        return out
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.hpfw_xs_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

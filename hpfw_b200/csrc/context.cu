@@ -19,6 +19,15 @@ extern "C" {
 const char *hpfw_last_error(void) { return hpfw_b200::g_err; }
 const char *hpfw_version(void) { return "hpfw_b200 0.1 (sm_100a)"; }
 
+int hpfw_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
 int hpfw_ctx_create(int device, hpfw_ctx **out) {
     if (!out) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_ctx_create: out is NULL");
     *out = nullptr;

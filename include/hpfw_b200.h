@@ -81,6 +81,7 @@ typedef struct hpfw_match {
 const char *hpfw_last_error(void);
 const char *hpfw_version(void);
 
+int hpfw_device_count(void);   /* visible CUDA devices (0 without a driver / GPU) */
 int hpfw_ctx_create(int device, hpfw_ctx **out);
 void hpfw_ctx_destroy(hpfw_ctx *ctx);
 int hpfw_ctx_device(const hpfw_ctx *ctx);
@@ -293,6 +294,54 @@ int hpfw_xs_hashprints_host(hpfw_xs *xs, uint64_t *out, int64_t n_words);   /* t
 int hpfw_xs_build_db(hpfw_xs *xs, const int *order, int n, int64_t track_base, hpfw_db **out);
 /* all tracks of the stream as queries (store order) against db: out[tracks * topk] */
 int hpfw_xs_match(hpfw_xs *xs, hpfw_db *db, int topk, hpfw_match *out);
+
+/* ------------------------------------------------------------------------- the database sharded over several GPUs (shard.cu) */
+/* DB partitioned by track into contiguous ranges balanced by matcher work, queries replicated, per-GPU top-k keys exchanged by
+ * ONE in-place ncclAllGather and merged by a kernel: bit-identical to the single-GPU result for any number of shards (keys order
+ * like the reference's strict '<' scan, storage.h:50-60). NCCL is called from inside the library (libnccl.so.2 is dlopen'ed on
+ * first use; a process that already carries an NCCL, e.g. PyTorch's, shares it).
+ *   local mode: one process drives n devices (hpfw_shard_create_local) - db::ShardedMemoryStorage in the C++ API;
+ *   rank mode:  one process per GPU (hpfw_shard_create_rank); rank 0 calls hpfw_shard_unique_id and the launcher carries the
+ *               128 bytes to the other ranks. */
+typedef struct hpfw_shard hpfw_shard;
+/* host-only (no device needed): bounds_out[n_shards + 1], shard s = tracks [bounds[s], bounds[s+1]) */
+int hpfw_shard_plan(const int64_t *track_words, int n_tracks, int n_shards, int query_words, int *bounds_out);
+int hpfw_shard_nccl_version(void);                     /* e.g. 22809; 0 when NCCL cannot be loaded */
+int hpfw_shard_unique_id(void *id128_out);
+int hpfw_shard_create_rank(hpfw_ctx *ctx, int rank, int world, const void *id128, hpfw_shard **out);
+/* devices = NULL: devices 0 .. n_devices-1; the shard owns one hpfw_ctx per device (hpfw_shard_ctx) */
+int hpfw_shard_create_local(const int *devices, int n_devices, hpfw_shard **out);
+void hpfw_shard_destroy(hpfw_shard *s);
+int hpfw_shard_world(const hpfw_shard *s);
+int hpfw_shard_rank(const hpfw_shard *s);
+hpfw_ctx *hpfw_shard_ctx(hpfw_shard *s, int local_index);
+hpfw_db *hpfw_shard_db(hpfw_shard *s, int local_index);
+/* rank mode: THIS rank's shard; track_base = global index of its first track */
+int hpfw_shard_build_rank(hpfw_shard *s, const uint64_t *words, const int64_t *offsets, int n_tracks, int64_t track_base);
+int hpfw_shard_build_rank_device(hpfw_shard *s, const uint64_t *d_words, const int64_t *offsets, int n_tracks,
+                                 int64_t track_base, void *stream);
+/* local mode: the WHOLE database (host words, or hashprints resident on device 0 as scattered segments in DB order); planned,
+ * split and placed on the devices here. query_words_hint balances the shards (0 = 385, six seconds). */
+int hpfw_shard_build(hpfw_shard *s, const uint64_t *words, const int64_t *offsets, int n_tracks, int query_words_hint);
+int hpfw_shard_build_device(hpfw_shard *s, const uint64_t *d_words, const int64_t *src_offsets, const int64_t *lengths,
+                            int n_tracks, int query_words_hint);
+/* rank mode, everything on the device and on `stream`: local match into this rank's slot of the gather buffer, in-place
+ * all-gather, merge; d_keys_out[n_queries * topk] is identical on every rank. Collective: every rank must call it. */
+int hpfw_shard_match_device(hpfw_shard *s, const uint64_t *d_qwords, const int64_t *qoffsets, int n_queries, int topk,
+                            uint64_t *d_keys_out, void *stream);
+/* local mode: host queries in (or queries resident on device 0, broadcast over NVLink), host records out */
+int hpfw_shard_find_topk(hpfw_shard *s, const uint64_t *qwords, const int64_t *qoffsets, int n_queries, int topk,
+                         hpfw_match *out);
+int hpfw_shard_find_topk_device(hpfw_shard *s, const uint64_t *d_qwords_dev0, const int64_t *qoffsets, int n_queries, int topk,
+                                hpfw_match *out);
+/* rank mode, index side: sum the contexts' covariance accumulators in place (parallel_collector.h:94-97 across GPUs);
+ * byte-wise all-gather / broadcast for the hashprint and filter exchange */
+int hpfw_shard_allreduce_cov(hpfw_shard *s, void *stream);
+int hpfw_shard_allgather_device(hpfw_shard *s, const void *d_send, void *d_recv, size_t bytes_per_rank, void *stream);
+/* ranks contribute bytes_per_rank[r] bytes each; d_recv receives them back to back in rank order (d_send may be NULL when this
+ * rank's bytes already sit at their place in d_recv) */
+int hpfw_shard_allgatherv_device(hpfw_shard *s, const void *d_send, void *d_recv, const size_t *bytes_per_rank, void *stream);
+int hpfw_shard_broadcast_device(hpfw_shard *s, void *d_buf, size_t bytes, int root, void *stream);
 
 /* ------------------------------------------------------------------------------------------------ measurement aids */
 /* Pipe microbenchmark used to pin the matcher's roofline denominator: runs register-only loops and reports
