@@ -530,6 +530,45 @@ def build_cpp_bench():
     return exe
 
 
+def cpp_index_leg(exe, work, env, dev, world, n_tracks, reps=2):
+    """LiveSongIdentification::index() over n_tracks three-minute PCM16 WAV files in `work`/tracks (32 distinct synthetic
+    signals; the other names are links to them, so every name is a separate track of the DB)."""
+    import torch
+    from hpfw_b200 import bench_data
+    idir = os.path.join(work, "tracks")
+    os.makedirs(idir)
+    n = int(EXTRACT_SECONDS * EXTRACT_SR)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4242)
+    tt = torch.arange(n, device=dev, dtype=torch.float32) / EXTRACT_SR
+    uniq = min(32, n_tracks)
+    for b in range(uniq):
+        x = 0.05 * torch.randn(n, device=dev, generator=gen)
+        for _ in range(6):
+            semis = int(torch.randint(0, 49, (1,), device=dev, generator=gen).item())
+            f0 = 130.81 * 2.0 ** (semis / 12.0)
+            rate = float(torch.rand(1, device=dev, generator=gen).item()) * 2.0 + 0.5
+            x += 0.15 * torch.sin(2 * np.pi * f0 * tt) * (0.5 + 0.5 * torch.sin(2 * np.pi * rate * tt))
+        pcm = (x * 16384.0).clamp_(-32768, 32767).to(torch.int16).cpu().numpy()
+        bench_data.write_wav_pcm16(os.path.join(idir, f"song{b:05d}.wav"), pcm, EXTRACT_SR)
+    for i in range(uniq, n_tracks):
+        os.symlink(os.path.join(idir, f"song{i % uniq:05d}.wav"), os.path.join(idir, f"song{i:05d}.wav"))
+    del tt
+    p = subprocess.run([exe, "index-sharded" if world > 1 else "index", "tracks", str(reps)], cwd=work, env=env,
+                       capture_output=True, text=True, timeout=900)
+    recs = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+    if p.returncode != 0 or not recs:
+        return {"error": f"rc={p.returncode}", "stderr_tail": p.stderr[-600:]}
+    out = json.loads(recs[-1]) | {
+        "what": f"LiveSongIdentification::index() over {n_tracks} three-minute PCM16 WAV files on tmpfs: "
+                "decode threads -> pinned ring -> H2D -> CQT -> covariance (filters learned, as the reference does) "
+                "-> batched projection -> DB built device-to-device; cache/spectros written in the background",
+        "host_threads": host_cores()}
+    if env.get("HPFW_TRACE"):
+        out["trace"] = [ln for ln in p.stderr.splitlines() if "[hpfw trace]" in ln]
+    return out
+
+
 def run_cpp_leg(args, ctx, ex, dev, world, tracks, audio_tracks, audio_hps, h_audio, src_track, filters, e2e_value):
     """The reference's own C++ API from WAV files (rank 0): hpfw::LiveSongIdentification::search() over the 128 query WAVs
     against the same database the Python arm uses (loaded from a MemoryStorage dump), and ::index() over 3-minute PCM16 WAVs.
@@ -587,37 +626,8 @@ def run_cpp_leg(args, ctx, ex, dev, world, tracks, audio_tracks, audio_hps, h_au
         os.remove(os.path.join(work, "db.cereal"))
         # ---- index leg: 3-minute PCM16 WAVs (32 distinct signals, the other names are links to them)
         if args.cpp_index_tracks > 0:
-            idir = os.path.join(work, "tracks")
-            os.makedirs(idir)
-            n = int(EXTRACT_SECONDS * EXTRACT_SR)
-            gen = torch.Generator(device=dev)
-            gen.manual_seed(4242)
-            tt = torch.arange(n, device=dev, dtype=torch.float32) / EXTRACT_SR
-            uniq = min(32, args.cpp_index_tracks)
-            for b in range(uniq):
-                x = 0.05 * torch.randn(n, device=dev, generator=gen)
-                for _ in range(6):
-                    semis = int(torch.randint(0, 49, (1,), device=dev, generator=gen).item())
-                    f0 = 130.81 * 2.0 ** (semis / 12.0)
-                    rate = float(torch.rand(1, device=dev, generator=gen).item()) * 2.0 + 0.5
-                    x += 0.15 * torch.sin(2 * np.pi * f0 * tt) * (0.5 + 0.5 * torch.sin(2 * np.pi * rate * tt))
-                pcm = (x * 16384.0).clamp_(-32768, 32767).to(torch.int16).cpu().numpy()
-                bench_data.write_wav_pcm16(os.path.join(idir, f"song{b:05d}.wav"), pcm, EXTRACT_SR)
-            for i in range(uniq, args.cpp_index_tracks):
-                os.symlink(os.path.join(idir, f"song{i % uniq:05d}.wav"), os.path.join(idir, f"song{i:05d}.wav"))
-            del tt
             shutil.rmtree(os.path.join(work, "cache"))
-            p = subprocess.run([exe, "index-sharded" if world > 1 else "index", "tracks", "2"], cwd=work, env=env,
-                               capture_output=True, text=True, timeout=900)
-            recs = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
-            if p.returncode != 0 or not recs:
-                out["index"] = {"error": f"rc={p.returncode}", "stderr_tail": p.stderr[-600:]}
-            else:
-                out["index"] = json.loads(recs[-1]) | {
-                    "what": f"LiveSongIdentification::index() over {args.cpp_index_tracks} three-minute PCM16 WAV files on tmpfs: "
-                            "decode threads -> pinned ring -> H2D -> CQT -> covariance (filters learned, as the reference does) "
-                            "-> batched projection -> DB built device-to-device; cache/spectros written in the background",
-                    "host_threads": host_cores()}
+            out["index"] = cpp_index_leg(exe, work, env, dev, world, args.cpp_index_tracks)
     finally:
         shutil.rmtree(work, ignore_errors=True)
     return out
@@ -1060,11 +1070,24 @@ def main():
     ap.add_argument("--no-identity-check", action="store_true", help="N > 1: skip the untimed sharded-vs-one-GPU key comparison")
     ap.add_argument("--no-strong-leg", action="store_true", help="skip the fixed-batch / single-find latency leg")
     ap.add_argument("--no-cpp", action="store_true", help="skip the C++ API leg (examples/cpp/bench-liveid.cpp, e2e_cpp)")
-    ap.add_argument("--cpp-index-tracks", type=int, default=256, help="WAV files index() reads in the C++ leg (3-min PCM16)")
+    ap.add_argument("--only-cpp-index", action="store_true", help="run only the C++ index() leg with HPFW_TRACE=1 (tuning aid)")
+    ap.add_argument("--cpp-index-tracks", type=int, default=1024, help="WAV files index() reads in the C++ leg (3-min PCM16)")
     ap.add_argument("--extract-tracks", type=int, default=1000, help="3-min tracks of the extraction leg (all GPUs together)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.only_cpp_index:
+        import tempfile
+        import shutil
+        import torch
+        work = tempfile.mkdtemp(prefix="hpfw_cpp_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            r = cpp_index_leg(build_cpp_bench(), work, dict(os.environ, HPFW_TRACE="1"), torch.device("cuda", 0), 1,
+                              args.cpp_index_tracks, reps=max(1, args.steps))
+        finally:
+            shutil.rmtree(work, ignore_errors=True)
+        print(json.dumps(r, indent=1))
+        return 0
     return run_cuda(args)
 
 

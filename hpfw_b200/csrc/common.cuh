@@ -122,6 +122,7 @@ struct hpfw_ctx {
 
     // filter learning (learn.cu): device-resident covariance accumulator (2420 x 2420) and scratch
     hpfw_b200::DeviceBuffer cov_accum, cov_scratch;
+    hpfw_b200::DeviceBuffer eig_scratch[6];   // hpfw_calc_filters: iteration blocks, Gram / rotation matrices, residuals
     uint64_t cov_tracks = 0;
 
     // cqt state

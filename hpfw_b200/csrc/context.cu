@@ -93,6 +93,7 @@ void hpfw_ctx_destroy(hpfw_ctx *c) {
     c->audio_f.release();
     c->cov_accum.release();
     c->cov_scratch.release();
+    for (auto &b : c->eig_scratch) b.release();
     hpfw_b200::cqt_cache_destroy(c->cqt);
     for (auto &r : c->timing_pending) {
         cudaEventDestroy(r.a);

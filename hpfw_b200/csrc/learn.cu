@@ -18,7 +18,9 @@
 // arbitrary in any solver (MKL ssyev vs Eigen's QL differ too); they are normalised so that the largest-magnitude component is
 // positive. Hamming distances do not depend on the sign as long as DB and queries use the same filters.
 #include "common.cuh"
+#include "eigh_host.h"
 
+#include <chrono>
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -568,7 +570,11 @@ int hpfw_calc_filters(hpfw_ctx *ctx, const float *cov, float *filters_out, float
     ctx->order_on(ctx->stream);
     const int n = LN_FS, p = LN_P, want = HPFW_NFILTERS;
     cudaStream_t s = ctx->stream;
-    DeviceBuffer dA, dV, dZ, dT, dG, dW, dR;
+    // scratch lives in the context: cudaMalloc / cudaFree per call synchronise the whole device, which stalls behind the
+    // background device->host copies of the index pipeline's cache writers (100-200 ms per call measured)
+    DeviceBuffer dA;
+    DeviceBuffer &dV = ctx->eig_scratch[0], &dZ = ctx->eig_scratch[1], &dT = ctx->eig_scratch[2], &dG = ctx->eig_scratch[3],
+                 &dW = ctx->eig_scratch[4], &dR = ctx->eig_scratch[5];
     const float *A = nullptr;
     if (cov) {
         HPFW_TRY(dA.reserve(sizeof(float) * (size_t)n * n));
@@ -612,12 +618,23 @@ int hpfw_calc_filters(hpfw_ctx *ctx, const float *cov, float *filters_out, float
 
     std::vector<float> Vf((size_t)n * p);
     std::vector<double> H, w, Q, Wq((size_t)p * p), theta(p), prev(want, 0.0), res(p);
+    int n_checks = 0, n_iters = 0;
+    const auto t_begin = std::chrono::steady_clock::now();
+    // Start block: random, except that the first 64 columns are the filters this context already holds (when it holds any
+    // and HPFW_FILTERS_WARM_START is not 0): re-indexing a collection that grew by a few tracks moves the dominant subspace
+    // only slightly, and the iteration then converges at its first checkpoint. Any start in general position converges to
+    // the same subspace; the stopping rule below is unchanged.
+    bool warm = ctx->have_filters && ctx->filters_host.size() == (size_t)want * n;
+    if (const char *env = getenv("HPFW_FILTERS_WARM_START")) warm = warm && atoi(env) != 0;
     if (status == HPFW_OK) {
         uint64_t lcg = 0x9E3779B97F4A7C15ull;
         for (auto &v : Vf) {
             lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
             v = (float)((double)((lcg >> 11) & 0xFFFFFF) / 16777216.0 - 0.5);
         }
+        if (warm)
+            for (int f = 0; f < want; ++f)
+                for (int k = 0; k < n; ++k) Vf[(size_t)f * n + k] = ctx->filters_host[(size_t)f + (size_t)want * k];
         if (cudaMemcpyAsync(Z, Vf.data(), blk, cudaMemcpyHostToDevice, s) != cudaSuccess) fail(HPFW_ERR_CUDA);
         orth(Z, T, V);
     }
@@ -627,6 +644,7 @@ int hpfw_calc_filters(hpfw_ctx *ctx, const float *cov, float *filters_out, float
     int next_check = 4;
     bool done = false;
     for (int it = 1; status == HPFW_OK && !done; ++it) {
+        n_iters = it;
         { KernelScope ks(ctx, HPFW_K_OTHER, s); symm_block_mul_kernel<<<g_mul, 256, 0, s>>>(A, V, Z, n, p); }
         if (it < next_check && it < max_it) {
             orth(Z, T, V);
@@ -639,7 +657,12 @@ int hpfw_calc_filters(hpfw_ctx *ctx, const float *cov, float *filters_out, float
         if (e != cudaSuccess) { set_error("hpfw_calc_filters: %s", cudaGetErrorString(e)); fail(HPFW_ERR_CUDA); break; }
         for (int i = 0; i < p; ++i)
             for (int j = i + 1; j < p; ++j) H[(size_t)i * p + j] = H[(size_t)j * p + i] = 0.5 * (H[(size_t)i * p + j] + H[(size_t)j * p + i]);
-        jacobi_eigh(H, p, w, Q);
+        {
+            // Rayleigh-Ritz: tridiagonalisation + implicit QL (eigh_host.h, ~9 ms at p = 128); the cyclic Jacobi is the fallback
+            std::vector<double> Hc = H;
+            if (!sym_eigh_ql(Hc, p, w, Q)) jacobi_eigh(H, p, w, Q);
+        }
+        ++n_checks;
         std::vector<int> order(p);
         for (int i = 0; i < p; ++i) order[i] = i;
         std::sort(order.begin(), order.end(), [&](int a, int b) { return w[a] > w[b]; });
@@ -689,7 +712,11 @@ int hpfw_calc_filters(hpfw_ctx *ctx, const float *cov, float *filters_out, float
         }
     }
     cudaStreamSynchronize(s);
-    dA.release(); dV.release(); dZ.release(); dT.release(); dG.release(); dW.release(); dR.release();
+    dA.release();
+    if (getenv("HPFW_TRACE"))
+        fprintf(stderr, "[hpfw trace] calc_filters: %d iterations, %d Rayleigh-Ritz checkpoints, %s start, %.1f ms\n", n_iters,
+                n_checks, warm ? "warm" : "cold",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
     return status;
 }
 

@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <filesystem>
@@ -52,6 +53,19 @@ struct has_raw_cache : std::false_type {};
 template <typename C>
 struct has_raw_cache<C, std::void_t<decltype(std::declval<const C &>().set_spectro_raw(
                             std::declval<const std::string &>(), std::declval<const float *>(), 0, 0))>> : std::true_type {};
+
+/// HPFW_TRACE=1: phase timings of prepare() / search batches on stderr
+struct PhaseTrace {
+    bool on = std::getenv("HPFW_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char *what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::cerr << "[hpfw trace] " << what << ": " << std::chrono::duration<double, std::milli>(t1 - t0).count() << " ms"
+                  << std::endl;
+        t0 = t1;
+    }
+};
 
 inline unsigned worker_count(size_t jobs) {
     unsigned hw = std::thread::hardware_concurrency();
@@ -125,6 +139,7 @@ public:
     /// cache writers have finished (flush_cache_writes(), called by the next prepare / the destructor).
     template <bool B = batched, typename = std::enable_if_t<B>>
     DeviceHashprints prepare_device(const std::vector<std::string> &filenames) {
+        detail::PhaseTrace trace;
         flush_cache_writes();
         std::unique_lock<std::mutex> l(ctx->mutex());
         if (have_cov) device::check(hpfw_cov_set(ctx->get(), accum_cov.data()));
@@ -173,7 +188,9 @@ public:
                 std::cerr << "[hpfw] Error preprocessing '" << filenames[i] << "': " << what << std::endl;
             },
             l);
+        trace.mark("prepare: decode + upload + CQT + covariance enqueued");
         device::check(hpfw_xs_wait(xs));
+        trace.mark("prepare: pipeline drained");
         if (added == 0 && !have_cov) {
             if (!have_filters)
                 throw Error(HPFW_ERR_STATE, "prepare(): no readable audio file and no cached covariance to learn filters from");
@@ -186,9 +203,11 @@ public:
             have_cov = true;
             install_filters_locked(f);
         }
+        trace.mark("prepare: covariance fetched, filters learned");
         l.unlock();
         save();                                             // reference :50
         l.lock();
+        trace.mark("prepare: save()");
 
         // ---- phase 2 (reference :115-137): hashprints of EVERY spectrogram in the cache: the resident ones from HBM, the rest
         // (earlier runs, or spilled above) from their files
@@ -210,6 +229,7 @@ public:
         }
         device::check(hpfw_xs_hash_kept(xs));
 
+        trace.mark("prepare: hashed");
         DeviceHashprints out;
         out.xs = ixs;
         out.ctx = ctx;
@@ -514,7 +534,7 @@ private:
             wq.push_back({filename, track});
         }
         writers_used = true;
-        if (writers.size() < 2) writers.emplace_back([this] { writer_loop(); });
+        if (writers.size() < 4) writers.emplace_back([this] { writer_loop(); });
         wq_cv.notify_one();
     }
 

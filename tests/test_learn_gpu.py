@@ -138,7 +138,7 @@ def test_partial_accumulators_sum_to_the_whole(ctx, hashprint_golden):
     import ctypes as C
     import torch
     from hpfw_b200._lib import check
-    from hpfw_b200.sharded import allreduce_covariance
+    from hpfw_b200.sharded import ShardedMemoryStorage
     ex = HashprintExtractor(ctx)
     g = hashprint_golden
     specs = [g["spec0"][:400], g["q_spec"], g["spec0"][300:900], g["spec0"][150:500]]
@@ -159,9 +159,11 @@ def test_partial_accumulators_sum_to_the_whole(ctx, hashprint_golden):
     check(ctx._lib.hpfw_cov_set_device(ctx.handle, C.c_void_p(total.data_ptr()), None))
     got = ex.cov_get()
     assert np.max(np.abs(got - whole)) <= 1e-5 * np.abs(whole).max()
-    # world = 1: the all-reduce is the identity and leaves the accumulator as it is
-    allreduce_covariance(ctx)
+    # world = 1: the all-reduce (hpfw_shard_allreduce_cov, in place on the accumulator) is the identity
+    st = ShardedMemoryStorage(ctx, 0, 1)
+    st.allreduce_covariance()
     torch.cuda.synchronize()
+    st.close()
     assert np.array_equal(ex.cov_get(), got)
 
 
