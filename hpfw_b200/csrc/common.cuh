@@ -122,6 +122,8 @@ struct hpfw_ctx {
 
     // filter learning (learn.cu): device-resident covariance accumulator (2420 x 2420) and scratch
     hpfw_b200::DeviceBuffer cov_accum, cov_scratch;
+    hpfw_b200::DeviceBuffer cov_accum_side, cov_scratch_side;   // second covariance slot of the extraction stream
+    bool cov_side_dirty = false;
     hpfw_b200::DeviceBuffer eig_scratch[6];   // hpfw_calc_filters: iteration blocks, Gram / rotation matrices, residuals
     uint64_t cov_tracks = 0;
 
@@ -185,7 +187,8 @@ void cqt_cache_destroy(CqtPlanCache *);
 int ctx_lanes_init(hpfw_ctx *ctx);                 // creates ctx->lane_stream[] / lane_join[] / lane_fork on first use
 int cqt_run_lane(hpfw_ctx *ctx, const float *d_audio, int64_t n_samples, float *d_out, cudaStream_t stream, int lane);
 int pcm16_convert(hpfw_ctx *ctx, const int16_t *d_pcm, float *d_out, int64_t n, cudaStream_t s);
-int cov_add_device(hpfw_ctx *ctx, const float *d_spec, int cols, cudaStream_t s);
+int cov_add_device(hpfw_ctx *ctx, const float *d_spec, int cols, cudaStream_t s, int slot = 0);
+int cov_fold_side(hpfw_ctx *ctx, cudaStream_t s);      // main accumulator += side accumulator (slot 1), side = 0
 int project_tc_set_filters(hpfw_ctx *ctx, const float *filters_colmajor);
 int project_tc_run(hpfw_ctx *ctx, int impl, const float *d_spectro, const int64_t *col_offsets, int n, uint64_t *d_hp,
                    cudaStream_t stream);

@@ -93,6 +93,8 @@ void hpfw_ctx_destroy(hpfw_ctx *c) {
     c->audio_f.release();
     c->cov_accum.release();
     c->cov_scratch.release();
+    c->cov_accum_side.release();
+    c->cov_scratch_side.release();
     for (auto &b : c->eig_scratch) b.release();
     hpfw_b200::cqt_cache_destroy(c->cqt);
     for (auto &r : c->timing_pending) {

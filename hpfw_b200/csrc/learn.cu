@@ -430,19 +430,47 @@ static int cov_impl() {
     return (v && *v) ? atoi(v) : 1;
 }
 
-int hpfw_b200::cov_add_device(hpfw_ctx *ctx, const float *d_spec, int cols, cudaStream_t s) {
-    const int nf = cols - (LN_CTX - 1);
-    if (nf < 2) HPFW_FAIL(HPFW_ERR_SHORT, "covariance needs at least 21 spectrogram columns (got %d)", cols);
+// accum += other; other = 0 (the side accumulator of the extraction stream's second covariance slot)
+__global__ void __launch_bounds__(256) cov_fold_kernel(float *__restrict__ accum, float *__restrict__ other, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        accum[i] += other[i];
+        other[i] = 0.f;
+    }
+}
+
+int hpfw_b200::cov_fold_side(hpfw_ctx *ctx, cudaStream_t s) {
+    if (!ctx->cov_accum_side.ptr || !ctx->cov_side_dirty) return HPFW_OK;
     if (!ctx->cov_accum.ptr) {
         HPFW_TRY(ctx->cov_accum.reserve(sizeof(float) * (size_t)LN_FS * LN_FS));
         HPFW_CUDA_TRY(cudaMemsetAsync(ctx->cov_accum.ptr, 0, sizeof(float) * (size_t)LN_FS * LN_FS, s));
     }
+    KernelScope ks(ctx, HPFW_K_OTHER, s);
+    cov_fold_kernel<<<ctx->sm_count * 4, 256, 0, s>>>(ctx->cov_accum.as<float>(), ctx->cov_accum_side.as<float>(),
+                                                      (size_t)LN_FS * LN_FS);
+    HPFW_CUDA_TRY(cudaGetLastError());
+    ctx->cov_side_dirty = false;
+    return HPFW_OK;
+}
+
+// slot 0 = the context's accumulator and scratch (every public entry point); slot 1 = a second scratch set and a side
+// accumulator, so that the extraction stream can run the (latency-bound, 9-kernel) covariance of two tracks concurrently on two
+// streams; cov_fold_side adds the side accumulator into the main one when the stream joins.
+int hpfw_b200::cov_add_device(hpfw_ctx *ctx, const float *d_spec, int cols, cudaStream_t s, int slot) {
+    const int nf = cols - (LN_CTX - 1);
+    if (nf < 2) HPFW_FAIL(HPFW_ERR_SHORT, "covariance needs at least 21 spectrogram columns (got %d)", cols);
+    DeviceBuffer &accum = slot ? ctx->cov_accum_side : ctx->cov_accum;
+    DeviceBuffer &scratch = slot ? ctx->cov_scratch_side : ctx->cov_scratch;
+    if (!accum.ptr) {
+        HPFW_TRY(accum.reserve(sizeof(float) * (size_t)LN_FS * LN_FS));
+        HPFW_CUDA_TRY(cudaMemsetAsync(accum.ptr, 0, sizeof(float) * (size_t)LN_FS * LN_FS, s));
+    }
+    if (slot) ctx->cov_side_dirty = true;
     // scratch: [part | hi | lo | Sc | T0 | rs | sum0 | partial sums (double)]; hi / lo start on 1 KB boundaries for the TMA maps
     const size_t n_part = (size_t)LN_KS * LN_CTX * 128 * 128, n_pad = ((size_t)std::max(cols, 128) * 128 + 255) & ~size_t(255);
     const size_t n_sc = ((size_t)cols * LN_BINS + 255) & ~size_t(255), n_t0 = ((size_t)LN_CTX * LN_BINS * LN_BINS + 255) & ~size_t(255);
     const size_t n_rs = 128 * LN_CTX, n_floats = n_part + 2 * n_pad + n_sc + n_t0 + n_rs + 256;
-    HPFW_TRY(ctx->cov_scratch.reserve(sizeof(float) * n_floats + sizeof(double) * LN_SUM_CTAS * 2 * 128));
-    float *part = ctx->cov_scratch.as<float>();
+    HPFW_TRY(scratch.reserve(sizeof(float) * n_floats + sizeof(double) * LN_SUM_CTAS * 2 * 128));
+    float *part = scratch.as<float>();
     float *hi = part + n_part, *lo = hi + n_pad;
     float *Sc = lo + n_pad;
     float *T0 = Sc + n_sc, *rs = T0 + n_t0, *sum0 = rs + n_rs, *mean = sum0 + 128;
@@ -480,7 +508,7 @@ int hpfw_b200::cov_add_device(hpfw_ctx *ctx, const float *d_spec, int cols, cuda
     }
     {
         KernelScope ks(ctx, HPFW_K_OTHER, s);
-        cov_block_kernel<<<(LN_BINS * LN_BINS + 3) / 4, 128, 0, s>>>(Sc, nf, T0, rs, ctx->cov_accum.as<float>());
+        cov_block_kernel<<<(LN_BINS * LN_BINS + 3) / 4, 128, 0, s>>>(Sc, nf, T0, rs, accum.as<float>());
     }
     HPFW_CUDA_TRY(cudaGetLastError());
     ctx->cov_tracks++;
@@ -495,6 +523,9 @@ int hpfw_cov_reset(hpfw_ctx *ctx) {
     ctx->order_on(ctx->stream);
     HPFW_TRY(ctx->cov_accum.reserve(sizeof(float) * (size_t)LN_FS * LN_FS));
     HPFW_CUDA_TRY(cudaMemsetAsync(ctx->cov_accum.ptr, 0, sizeof(float) * (size_t)LN_FS * LN_FS, ctx->stream));
+    if (ctx->cov_accum_side.ptr)
+        HPFW_CUDA_TRY(cudaMemsetAsync(ctx->cov_accum_side.ptr, 0, sizeof(float) * (size_t)LN_FS * LN_FS, ctx->stream));
+    ctx->cov_side_dirty = false;
     ctx->cov_tracks = 0;
     return HPFW_OK;
 }
@@ -641,7 +672,9 @@ int hpfw_calc_filters(hpfw_ctx *ctx, const float *cov, float *filters_out, float
     // Block subspace iteration V <- orth(A V), entirely on the device; a Rayleigh-Ritz checkpoint (p x p eigenproblem on the
     // host, cyclic Jacobi in double) at iterations 4, 8, 16, ... rotates the block to Ritz vectors and tests the residuals.
     const int max_it = 4096;
-    int next_check = 4;
+    // a Rayleigh-Ritz checkpoint costs as much as ~7 iterations (host eigen-solve + two synchronisations): a warm start is
+    // tested at once, a cold start first after 16 iterations and then every 8
+    int next_check = warm ? 4 : 16;
     bool done = false;
     for (int it = 1; status == HPFW_OK && !done; ++it) {
         n_iters = it;
@@ -690,7 +723,7 @@ int hpfw_calc_filters(hpfw_ctx *ctx, const float *cov, float *filters_out, float
         } else {
             orth(V, Z, T);                                     // next block = orth(A * Ritz vectors) -> T
             std::swap(V, T);
-            next_check = std::min(next_check * 2, it + 512);
+            next_check = it < 64 ? it + 8 : std::min(it * 2, it + 512);
         }
     }
     if (status == HPFW_OK) {

@@ -365,6 +365,7 @@ static int db_alloc_common(hpfw_ctx *ctx, const int64_t *offsets, int n_tracks, 
     }
     hpfw_db *db = new hpfw_db();
     db->ctx = ctx;
+    db->device = ctx->device;
     db->n_tracks = n_tracks;
     db->track_base = track_base;
     db->total_words = n_tracks ? offsets[n_tracks] - offsets[0] : 0;
@@ -590,7 +591,7 @@ int hpfw_db_build_gather_device(hpfw_ctx *ctx, const uint64_t *d_words, const in
 
 void hpfw_db_destroy(hpfw_db *db) {
     if (!db) return;
-    DeviceGuard g(db->ctx->device);
+    DeviceGuard g(db->device);
     cudaDeviceSynchronize();
     if (db->d_words) cudaFree(db->d_words);
     if (db->d_track_start) cudaFree(db->d_track_start);

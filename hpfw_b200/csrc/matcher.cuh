@@ -33,6 +33,7 @@ inline int xt_word_bytes(int f4) { return f4 ? 32 : 64; }   // expanded bytes pe
 
 struct hpfw_db {
     hpfw_ctx *ctx = nullptr;
+    int device = 0;          // = ctx->device, kept here so that destroying a DB after its context is not a wild read
     int n_tracks = 0;
     int64_t total_words = 0;
     int64_t track_base = 0;

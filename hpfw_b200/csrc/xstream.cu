@@ -67,8 +67,9 @@ struct hpfw_xs {
     int nl = 4;                         // lanes in use
     int next_lane = 0;
     DeviceBuffer lane_in[HPFW_CTX_LANES], lane_audio[HPFW_CTX_LANES];
-    cudaStream_t cov_stream = nullptr, fetch_stream = nullptr;
-    cudaEvent_t cov_done = nullptr;
+    cudaStream_t cov_stream[2] = {nullptr, nullptr}, fetch_stream = nullptr;
+    cudaEvent_t cov_done[2] = {nullptr, nullptr};
+    int next_cov = 0;
     bool forked = false;                // the lanes have work that ctx->stream has not joined yet
     std::vector<XsChunk> chunks;
     size_t arena_budget = 0, arena_bytes = 0, chunk_floats = 0;
@@ -96,7 +97,7 @@ static int xs_fork(hpfw_xs *xs) {
     ctx->order_on(ctx->stream);
     HPFW_CUDA_TRY(cudaEventRecord(ctx->lane_fork, ctx->stream));
     for (int l = 0; l < xs->nl; ++l) HPFW_CUDA_TRY(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->lane_fork, 0));
-    HPFW_CUDA_TRY(cudaStreamWaitEvent(xs->cov_stream, ctx->lane_fork, 0));
+    for (int c = 0; c < 2; ++c) HPFW_CUDA_TRY(cudaStreamWaitEvent(xs->cov_stream[c], ctx->lane_fork, 0));
     xs->forked = true;
     return HPFW_OK;
 }
@@ -110,8 +111,11 @@ static int xs_join(hpfw_xs *xs) {
         HPFW_CUDA_TRY(cudaEventRecord(ctx->lane_join[l], ctx->lane_stream[l]));
         HPFW_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->lane_join[l], 0));
     }
-    HPFW_CUDA_TRY(cudaEventRecord(xs->cov_done, xs->cov_stream));
-    HPFW_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, xs->cov_done, 0));
+    for (int c = 0; c < 2; ++c) {
+        HPFW_CUDA_TRY(cudaEventRecord(xs->cov_done[c], xs->cov_stream[c]));
+        HPFW_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, xs->cov_done[c], 0));
+    }
+    HPFW_TRY(cov_fold_side(ctx, ctx->stream));      // the second covariance slot's accumulator joins the context's
     xs->forked = false;
     return HPFW_OK;
 }
@@ -187,9 +191,11 @@ int hpfw_xs_create(hpfw_ctx *ctx, int slots, size_t slot_bytes, hpfw_xs **out) {
             else s.cap = slot_bytes;
         }
     }
-    if (st == HPFW_OK && cudaStreamCreateWithFlags(&xs->cov_stream, cudaStreamNonBlocking) != cudaSuccess) st = HPFW_ERR_CUDA;
+    for (int c = 0; c < 2; ++c)
+        if (st == HPFW_OK && cudaStreamCreateWithFlags(&xs->cov_stream[c], cudaStreamNonBlocking) != cudaSuccess) st = HPFW_ERR_CUDA;
     if (st == HPFW_OK && cudaStreamCreateWithFlags(&xs->fetch_stream, cudaStreamNonBlocking) != cudaSuccess) st = HPFW_ERR_CUDA;
-    if (st == HPFW_OK && cudaEventCreateWithFlags(&xs->cov_done, cudaEventDisableTiming) != cudaSuccess) st = HPFW_ERR_CUDA;
+    for (int c = 0; c < 2; ++c)
+        if (st == HPFW_OK && cudaEventCreateWithFlags(&xs->cov_done[c], cudaEventDisableTiming) != cudaSuccess) st = HPFW_ERR_CUDA;
     size_t free_b = 0, total_b = 0;
     if (st == HPFW_OK && cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) st = HPFW_ERR_CUDA;
     if (st != HPFW_OK) {
@@ -226,9 +232,11 @@ void hpfw_xs_destroy(hpfw_xs *xs) {
         xs->lane_audio[l].release();
     }
     xs->hp.release();
-    if (xs->cov_stream) cudaStreamDestroy(xs->cov_stream);
+    for (int c = 0; c < 2; ++c) {
+        if (xs->cov_stream[c]) cudaStreamDestroy(xs->cov_stream[c]);
+        if (xs->cov_done[c]) cudaEventDestroy(xs->cov_done[c]);
+    }
     if (xs->fetch_stream) cudaStreamDestroy(xs->fetch_stream);
-    if (xs->cov_done) cudaEventDestroy(xs->cov_done);
     delete xs;
 }
 
@@ -364,9 +372,11 @@ static int xs_submit_common(hpfw_xs *xs, int slot, int64_t n_samples, int cols, 
     }
     if (st == HPFW_OK && cudaEventRecord(t.ready, s) != cudaSuccess) st = HPFW_ERR_CUDA;
     if (st == HPFW_OK && (flags & HPFW_XS_COV)) {
-        // one serial stream for the accumulator (learn.cu keeps one scratch set per context); it trails the lanes
-        if (cudaStreamWaitEvent(xs->cov_stream, t.ready, 0) != cudaSuccess) st = HPFW_ERR_CUDA;
-        if (st == HPFW_OK) st = cov_add_device(ctx, d_spec, cols, xs->cov_stream);
+        // two covariance slots (own scratch and accumulator each, learn.cu) on two streams that trail the lanes: the nine
+        // small kernels of one track overlap the next track's
+        const int c = xs->next_cov++ & 1;
+        if (cudaStreamWaitEvent(xs->cov_stream[c], t.ready, 0) != cudaSuccess) st = HPFW_ERR_CUDA;
+        if (st == HPFW_OK) st = cov_add_device(ctx, d_spec, cols, xs->cov_stream[c], c);
     }
     if (st != HPFW_OK) return bail(st);
     {

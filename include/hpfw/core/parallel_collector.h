@@ -111,6 +111,7 @@ public:
         filters.resize(Algo::NumOfFilters, Algo::FrameSize);
         static std::atomic<uint64_t> next_id{1};
         id_ = next_id.fetch_add(1) << 32;
+        if (const char *env = std::getenv("HPFW_CACHE_SPECTROGRAMS")) cache_spectrograms = std::atoi(env) != 0;
     }
     ~ParallelCollector() {
         try { flush_cache_writes(); } catch (...) {}

@@ -49,5 +49,6 @@ def test_failed_selftest_is_loud_and_keeps_results_exact(monkeypatch, capfd):
         ms, n = ctx.timing_read(hpfw_b200._lib.K_MATCH_TC)
         assert n == 0                                   # ... and none of them was match_tc_kernel
         assert ctx.timing_read(hpfw_b200._lib.K_MATCH)[1] > 0
+        del st                                          # a database goes before its context
     finally:
         ctx.close()
