@@ -655,8 +655,12 @@ def run_cuda(args):
     sys.stdout.flush()
     json_fd = os.dup(1)
     os.dup2(2, 1)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # a host-side group for the one long wait (rank 0 runs the C++ leg): an NCCL barrier would park a spinning kernel on
+        # every other GPU, and the C++ process uses those GPUs
+        cpu_group = dist.new_group(backend="gloo")
     ctx = hpfw_b200.Context(local_rank)
 
     # ---- synthetic DB shard in HBM + planted queries (setup, untimed)
@@ -903,12 +907,15 @@ def run_cuda(args):
 
     cpp = None
     if not args.no_cpp:
+        barrier()
         if rank == 0:
             try:
                 cpp = run_cpp_leg(args, ctx, ex, dev, world, tracks, audio_tracks, audio_hps, h_audio, src_track,
                                   np.ascontiguousarray(golden["filters"]), e2e_value)
             except Exception as e:      # the C++ leg must never take the bench line down with it
                 cpp = {"error": f"{type(e).__name__}: {e}"}
+        if world > 1:
+            dist.barrier(group=cpu_group)   # the other ranks wait on the host, their GPUs stay free for the C++ process
         barrier()
 
     if world > 1:
