@@ -46,7 +46,11 @@ __device__ __forceinline__ void lds_block8(const uint64_t *p, uint2 (&w)[8]) {
 
 template <int QB>
 __device__ __forceinline__ void load_q(const uint64_t *p, uint2 (&q)[QB]) {
-    static_assert(QB % 2 == 0, "QB must be even");
+    static_assert(QB == 1 || QB % 2 == 0, "QB must be 1 or even");
+    if (QB == 1) {      // a lone query (a single find(), or the odd one of a length class): no padding partner to pay for
+        q[0] = *reinterpret_cast<const uint2 *>(p);
+        return;
+    }
     const uint4 *v = reinterpret_cast<const uint4 *>(p);
 #pragma unroll
     for (int i = 0; i < QB / 2; ++i) {
@@ -682,7 +686,7 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
     // host metadata: [qstart int64 (n_queries+1)] then per chunk
     //   integer-pipe kernel: [qb_idx int32 (nb*QB)] [qb_k int32 (nb)]
     //   tensor-core kernel:  [XtGroup (ng)] [row_q int32 (ng*128)] [row_k int32 (ng*128)]
-    struct ChunkMeta { size_t idx_off, k_off, grp_off, rowq_off, rowk_off; int nb, q0, nq, ng, kpad_max; size_t exp_bytes; };
+    struct ChunkMeta { size_t idx_off, k_off, idx1_off, k1_off, grp_off, rowq_off, rowk_off; int nb, nb1, q0, nq, ng, kpad_max; size_t exp_bytes; };
     std::vector<ChunkMeta> cm(n_chunks);
     size_t meta_bytes = sizeof(int64_t) * (size_t(n_queries) + 1);
     std::vector<int32_t> tables;
@@ -722,22 +726,35 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
         cm[c].rowk_off = meta_bytes + tables.size() * sizeof(int32_t);
         tables.insert(tables.end(), rk.begin(), rk.end());
 
-        std::vector<int32_t> idx, ks;
+        // register blocks of MT_QB equal-length queries; a query without a partner of its length runs as a block of one
+        // (match_kernel<1>) instead of being paired with a copy of itself
+        std::vector<int32_t> idx, ks, idx1, ks1;
         const int np = int(popc_list.size());
         for (int i = 0; i < np;) {
             const int64_t k = klen(popc_list[i]);
             int32_t blk[MT_QB];
             int got = 0;
             while (got < MT_QB && i < np && klen(popc_list[i]) == k) blk[got++] = popc_list[i++];
-            for (int f = got; f < MT_QB; ++f) blk[f] = blk[got - 1];  // pad a short block by repeating a query
-            for (int f = 0; f < MT_QB; ++f) idx.push_back(blk[f]);
-            ks.push_back(int32_t(k));
+            if (got == MT_QB) {
+                for (int f = 0; f < MT_QB; ++f) idx.push_back(blk[f]);
+                ks.push_back(int32_t(k));
+            } else {
+                for (int f = 0; f < got; ++f) {
+                    idx1.push_back(blk[f]);
+                    ks1.push_back(int32_t(k));
+                }
+            }
         }
         cm[c].nb = int(ks.size());
         cm[c].idx_off = meta_bytes + tables.size() * sizeof(int32_t);
         tables.insert(tables.end(), idx.begin(), idx.end());
         cm[c].k_off = meta_bytes + tables.size() * sizeof(int32_t);
         tables.insert(tables.end(), ks.begin(), ks.end());
+        cm[c].nb1 = int(ks1.size());
+        cm[c].idx1_off = meta_bytes + tables.size() * sizeof(int32_t);
+        tables.insert(tables.end(), idx1.begin(), idx1.end());
+        cm[c].k1_off = meta_bytes + tables.size() * sizeof(int32_t);
+        tables.insert(tables.end(), ks1.begin(), ks1.end());
     }
     const size_t total_meta = meta_bytes + tables.size() * sizeof(int32_t);
 
@@ -760,12 +777,13 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
     const int nload = MT_TILE + kpad + 8;
     const size_t smem = sizeof(uint64_t) * (size_t(nload / 8) * MT_PITCH + size_t(kpad) * MT_QB);
     bool any_blocks = false;
-    for (int c = 0; c < n_chunks; ++c) any_blocks |= cm[c].nb > 0;
+    for (int c = 0; c < n_chunks; ++c) any_blocks |= cm[c].nb > 0 || cm[c].nb1 > 0;
     if (any_blocks) {
         if (smem > size_t(ctx->max_smem_optin))
             HPFW_FAIL(HPFW_ERR_LIMIT, "hpfw_db_match_device: query of %d words needs %zu B shared memory (> %d)", kmax,
                       smem, ctx->max_smem_optin);
         HPFW_CUDA_TRY(cudaFuncSetAttribute(match_kernel<MT_QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        HPFW_CUDA_TRY(cudaFuncSetAttribute(match_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     }
 
     const char *meta = ctx->qmeta.as<char>();
@@ -790,6 +808,17 @@ int hpfw_db_match_device(hpfw_db *db, const uint64_t *d_qwords, const int64_t *q
                 db->d_words, db->d_track_start, db->d_tiles, d_q, d_qstart + cm[c].q0,
                 reinterpret_cast<const int32_t *>(meta + cm[c].idx_off),
                 reinterpret_cast<const int32_t *>(meta + cm[c].k_off), cm[c].nb, per_group, R, kpad, best);
+            HPFW_CUDA_TRY(cudaGetLastError());
+        }
+        if (db->n_tiles > 0 && cm[c].nb1 > 0) {
+            const int per_group = std::min(cm[c].nb1, MT_BLOCKS_PER_CTA);
+            const int groups = (cm[c].nb1 + per_group - 1) / per_group;
+            dim3 grid(db->n_tiles, groups);
+            KernelScope ks(ctx, HPFW_K_MATCH, stream);
+            match_kernel<1><<<grid, MT_THREADS, smem, stream>>>(
+                db->d_words, db->d_track_start, db->d_tiles, d_q, d_qstart + cm[c].q0,
+                reinterpret_cast<const int32_t *>(meta + cm[c].idx1_off),
+                reinterpret_cast<const int32_t *>(meta + cm[c].k1_off), cm[c].nb1, per_group, R, kpad, best);
             HPFW_CUDA_TRY(cudaGetLastError());
         }
         KernelScope ks(ctx, HPFW_K_TOPK, stream);
