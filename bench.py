@@ -579,7 +579,20 @@ def run_cpp_leg(args, ctx, ex, dev, world, tracks, audio_tracks, audio_hps, h_au
     import torch
     from hpfw_b200 import bench_data
     exe = build_cpp_bench()
-    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    # tmpfs when it has room (WAVs 0.5 GB + DB dump 1.2 GB + 7 MB of cached spectrogram per indexed track), else the default
+    # temporary directory; the index leg shrinks to what fits
+    need = lambda n_idx: (2.0 + 0.0075 * n_idx) * 1e9
+    base = None
+    for cand in ("/dev/shm", tempfile.gettempdir()):
+        if os.path.isdir(cand) and os.access(cand, os.W_OK):
+            free = shutil.disk_usage(cand).free
+            if free > need(64):
+                base = cand
+                while args.cpp_index_tracks > 64 and free < need(args.cpp_index_tracks):
+                    args.cpp_index_tracks //= 2
+                break
+    if base is None:
+        return {"skipped": "no writable directory with 3 GB free for the WAV files"}
     work = tempfile.mkdtemp(prefix="hpfw_cpp_", dir=base)
     out = {"binary": "examples/cpp/bench-liveid (g++ -O2, include/hpfw/*.h over libhpfw_b200.so)", "work_dir": work}
     env = dict(os.environ, HPFW_NUM_GPUS=str(world))

@@ -467,6 +467,14 @@ __device__ float2 *smem_fft(float2 *a, float2 *b, const FftDesc &d, int G, const
 // shared-memory index padding of the register kernels: one extra element per 16 (thread strides of 2..16 elements stay
 // conflict-free or 2-way)
 __device__ __forceinline__ int cr_pad(int i) { return i + (i >> 4); }
+#ifndef HPFW_CQT_CHAIN_TW
+#define HPFW_CQT_CHAIN_TW 0
+#endif
+#ifndef HPFW_CQT_NOPAD0
+#define HPFW_CQT_NOPAD0 0
+#endif
+// pass kernels: MODE 0 (columns interleaved, every access linear in the thread index) can run without padding
+template <int MODE> __device__ __forceinline__ int ps_pad(int i) { return (MODE == 0 && HPFW_CQT_NOPAD0) ? i : cr_pad(i); }
 __host__ __device__ constexpr int hibit(int u) { int h = 1; while (h * 2 <= u) h *= 2; return h; }
 
 // v[u] *= w^u, u = 1 .. R-1
@@ -515,7 +523,7 @@ __device__ __forceinline__ void pass_first(const float2 *__restrict__ in, float2
         }
         dft_r<R>(v, sign);
 #pragma unroll
-        for (int u = 0; u < R; ++u) S[cr_pad(MODE == 0 ? (j * R + u) * G + g : g * n + j * R + u)] = v[u];
+        for (int u = 0; u < R; ++u) S[ps_pad<MODE>(MODE == 0 ? (j * R + u) * G + g : g * n + j * R + u)] = v[u];
     }
 }
 
@@ -534,12 +542,12 @@ __device__ __forceinline__ void pass_mid(const float2 *Sin, float2 *Sout, int n,
         const int blk = fastdiv(j, mg_ns), k = j - blk * Ns;
         float2 v[R];
 #pragma unroll
-        for (int u = 0; u < R; ++u) v[u] = Sin[cr_pad(MODE == 0 ? idx + u * tot : g * n + j + u * m)];
+        for (int u = 0; u < R; ++u) v[u] = Sin[ps_pad<MODE>(MODE == 0 ? idx + u * tot : g * n + j + u * m)];
         apply_powers<R>(v, tw_dir(T[step * k], sign));
         dft_r<R>(v, sign);
         const int base = blk * Ns * R + k;
 #pragma unroll
-        for (int u = 0; u < R; ++u) Sout[cr_pad(MODE == 0 ? (base + u * Ns) * G + g : g * n + base + u * Ns)] = v[u];
+        for (int u = 0; u < R; ++u) Sout[ps_pad<MODE>(MODE == 0 ? (base + u * Ns) * G + g : g * n + base + u * Ns)] = v[u];
     }
 }
 
@@ -562,16 +570,27 @@ __device__ __forceinline__ void pass_last(const float2 *Sin, float2 *Sout, int n
         else { g = fastdiv(idx, mg_m); j = idx - g * m; }
         float2 v[R];
 #pragma unroll
-        for (int u = 0; u < R; ++u) v[u] = Sin[cr_pad(MODE == 0 ? idx + u * tot : g * n + j + u * m)];
+        for (int u = 0; u < R; ++u) v[u] = Sin[ps_pad<MODE>(MODE == 0 ? idx + u * tot : g * n + j + u * m)];
         if (R > 1) apply_powers<R>(v, tw_dir(T[j], sign));
         dft_r<R>(v, sign);
         if (MODE == 0) {
             // inter-pass twiddle W_H^{b d} = W_H^{b j} (W_H^{b m})^u, then staged for the column-adjacent store
             const int bcol = po.first + g;
             const float2 wa = twiddle2(po.tw_hi, po.tw_lo, (long long)bcol * j, sign);
+#if HPFW_CQT_CHAIN_TW
+            // q_u = wa * wm^u by a running product: R - 1 complex multiplies instead of a power tree plus a second multiply
+            float2 q = wa;
+            const float2 wm = twiddle2(po.tw_hi, po.tw_lo, (long long)bcol * m, sign);
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                Sout[ps_pad<MODE>(idx + u * tot)] = cmul(v[u], q);
+                if (u + 1 < R) q = cmul(q, wm);
+            }
+#else
             if (R > 1) apply_powers<R>(v, twiddle2(po.tw_hi, po.tw_lo, (long long)bcol * m, sign));
 #pragma unroll
-            for (int u = 0; u < R; ++u) Sout[cr_pad(idx + u * tot)] = cmul(v[u], wa);
+            for (int u = 0; u < R; ++u) Sout[ps_pad<MODE>(idx + u * tot)] = cmul(v[u], wa);
+#endif
         } else if (g < g_here) {
             const int c = po.first + g, mlo = po.H - po.khi, mhi = po.H - po.klo;
 #pragma unroll
@@ -617,7 +636,7 @@ fft_pass_kernel(const float2 *__restrict__ in, float2 *__restrict__ out_lo, floa
     const int first = blockIdx.x * G;
     const int pitch = MODE == 0 ? other : n;                   // row pitch n2 of the n1 x n2 matrix
     const int g_here = min(G, (MODE == 0 ? other : other) - first);   // MODE 0: columns left (n2); MODE 1: rows left (n1)
-    float2 *S0 = fsm, *S1 = fsm + cr_pad(G * n) + 16;
+    float2 *S0 = fsm, *S1 = fsm + ps_pad<MODE>(G * n) + 16;
     const float2 *src = MODE == 0 ? in + first : in + (long long)first * pitch;
     PassOut po{MODE == 0 ? out_lo + first : out_lo, out_hi, twH_hi, twH_lo, other, first, klo, khi, H, keep_all};
 
@@ -640,7 +659,7 @@ fft_pass_kernel(const float2 *__restrict__ in, float2 *__restrict__ out_lo, floa
 #pragma unroll 4
         for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
             const int c = fastdiv(idx, mg_g), g = idx - c * G;
-            if (g < g_here) po.lo[c * pitch + g] = nxt[cr_pad(idx)];
+            if (g < g_here) po.lo[c * pitch + g] = nxt[ps_pad<MODE>(idx)];
         }
     }
 }
