@@ -52,7 +52,10 @@ constexpr int CQ_MAXRAD = 14;      // stages per shared-memory FFT (8192 = 16*16
 constexpr int CQ_TW_S = 1024;         // two-level twiddle: W^m = hi[m / S] * lo[m % S]
 constexpr int CQ_THREADS = 256;
 constexpr int CQ_LANES = HPFW_CTX_LANES;   // concurrent tracks of a batch (streams + scratch sets)
-constexpr int CQ_FFT_THREADS = 256;   // FFT kernels: 3 CTAs per SM (80 registers, <= 74 KB shared memory each)
+#ifndef CQ_FFT_THREADS_N
+#define CQ_FFT_THREADS_N 256
+#endif
+constexpr int CQ_FFT_THREADS = CQ_FFT_THREADS_N;   // FFT kernels: 3 CTAs per SM (80 registers, <= 74 KB shared memory each)
 #ifndef CQ_ROWS3_CTAS
 #define CQ_ROWS3_CTAS 3
 #endif

@@ -1,6 +1,5 @@
-for v in "" chain nopad both ctas4 ctas2; do
-  if [ -z "$v" ]; then lib=hpfw_b200/libhpfw_b200.so; else lib=hpfw_b200/libhpfw_b200_$v.so; fi
-  echo "== variant '$v'"; HPFW_B200_LIB=$lib python scripts/cqt_tune.py 48 2>&1 | tail -1
-done
-echo "== lanes"; for l in 2 3 6; do HPFW_CQT_LANES=$l python scripts/cqt_tune.py 48 2>&1 | tail -1; done
-echo "== G1/G2"; HPFW_CQT_G1=2 python scripts/cqt_tune.py 48 2>&1 | tail -1; HPFW_CQT_G1=8 python scripts/cqt_tune.py 48 2>&1 | tail -1; HPFW_CQT_G2=2 python scripts/cqt_tune.py 48 2>&1 | tail -1
+echo "== base"; python scripts/cqt_tune.py 48 2>&1 | tail -1
+for kb in 37 28 74; do echo "== t128 smem_kb $kb"; HPFW_CQT_SMEM_KB=$kb HPFW_B200_LIB=hpfw_b200/libhpfw_b200_t128.so python scripts/cqt_tune.py 48 2>&1 | tail -1; done
+for g in "HPFW_CQT_G1=2 HPFW_CQT_G2=2" "HPFW_CQT_G1=4 HPFW_CQT_G2=2" "HPFW_CQT_G1=2 HPFW_CQT_G2=1"; do echo "== t128 $g"; env $g HPFW_B200_LIB=hpfw_b200/libhpfw_b200_t128.so python scripts/cqt_tune.py 48 2>&1 | tail -1; done
+echo "== t128c5"; HPFW_CQT_SMEM_KB=44 HPFW_B200_LIB=hpfw_b200/libhpfw_b200_t128c5.so python scripts/cqt_tune.py 48 2>&1 | tail -1
+echo "== t512"; HPFW_CQT_SMEM_KB=200 HPFW_B200_LIB=hpfw_b200/libhpfw_b200_t512.so python scripts/cqt_tune.py 48 2>&1 | tail -1
