@@ -818,22 +818,31 @@ def run_cuda(args):
     # merge + top-k), p50 / p99 over 30 calls, device time from CUDA events, max over ranks
     strong = None
     if not args.no_strong_leg:
-        q128 = 128 * QUERY_WORDS
-        qo128 = np.arange(129, dtype=np.int64) * QUERY_WORDS
-        for _ in range(2):
-            st.search_device(d_q[:q128], qo128, TOPK)
+        sq = min(args.strong_queries, nq) if args.strong_queries <= nq else args.strong_queries
+        if sq > nq:      # a fixed batch larger than the weak step: the step's queries repeated (same work per query)
+            reps_q = (sq + nq - 1) // nq
+            d_qs = d_q.repeat(reps_q)[:sq * QUERY_WORDS].contiguous()
+        else:
+            d_qs = d_q
+        q128 = sq * QUERY_WORDS
+        qo128 = np.arange(sq + 1, dtype=np.int64) * QUERY_WORDS
+        s_reps = 5 if sq <= 1024 else 2
+        for _ in range(2 if sq <= 1024 else 1):
+            st.search_device(d_qs[:q128], qo128, TOPK)
         barrier()
         ctx.timing_read(_lib.K_MATCH_TC, reset=True)
         ctx.timing_read(_lib.K_TOPK, reset=True)
         ctx.timing_enable(True)
         e0.record()
-        for _ in range(5):
-            st.search_device(d_q[:q128], qo128, TOPK)
+        for _ in range(s_reps):
+            st.search_device(d_qs[:q128], qo128, TOPK)
         e1.record()
         barrier()
-        s_ms = max_over_ranks(e0.elapsed_time(e1)) / 5
+        s_ms = max_over_ranks(e0.elapsed_time(e1)) / s_reps
         s_tc_ms, _ = ctx.timing_read(_lib.K_MATCH_TC, reset=True)
         s_topk_ms, _ = ctx.timing_read(_lib.K_TOPK, reset=True)
+        s_tc_ms, s_topk_ms = s_tc_ms * 5 / s_reps, s_topk_ms * 5 / s_reps     # reported per step below (/ 5)
+        del d_qs
         ctx.timing_enable(False)
         qo1 = np.array([0, QUERY_WORDS], dtype=np.int64)
         lat = []
@@ -846,7 +855,7 @@ def run_cuda(args):
             b.record()
         torch.cuda.synchronize()
         lat = sorted(max_over_ranks(a.elapsed_time(b)) for a, b in evs[2:])
-        strong = {"queries_per_step": 128, "ms_per_step": s_ms, "queries_per_s": 128 / (s_ms * 1e-3),
+        strong = {"queries_per_step": sq, "ms_per_step": s_ms, "queries_per_s": sq / (s_ms * 1e-3),
                   "match_kernel_ms_this_rank": s_tc_ms / 5, "topk_merge_ms_this_rank": s_topk_ms / 5,
                   "fixed_cost_us_per_step": (s_ms - s_tc_ms / 5) * 1e3,
                   "fixed_cost_note": "step time minus match_tc_kernel on rank 0: query expansion, top-k, all-gather of "
@@ -1089,6 +1098,8 @@ def main():
     ap.add_argument("--no-extraction", action="store_true", help="skip the secondary hashprint-extraction leg")
     ap.add_argument("--no-identity-check", action="store_true", help="N > 1: skip the untimed sharded-vs-one-GPU key comparison")
     ap.add_argument("--no-strong-leg", action="store_true", help="skip the fixed-batch / single-find latency leg")
+    ap.add_argument("--strong-queries", type=int, default=128,
+                    help="size of the FIXED query batch of the strong-scaling leg (128; BASELINE configs[3] uses 10000)")
     ap.add_argument("--no-cpp", action="store_true", help="skip the C++ API leg (examples/cpp/bench-liveid.cpp, e2e_cpp)")
     ap.add_argument("--only-cpp-index", action="store_true", help="run only the C++ index() leg with HPFW_TRACE=1 (tuning aid)")
     ap.add_argument("--cpp-index-tracks", type=int, default=1024, help="WAV files index() reads in the C++ leg (3-min PCM16)")

@@ -470,6 +470,12 @@ __device__ float2 *smem_fft(float2 *a, float2 *b, const FftDesc &d, int G, const
 // shared-memory index padding of the register kernels: one extra element per 16 (thread strides of 2..16 elements stay
 // conflict-free or 2-way)
 __device__ __forceinline__ int cr_pad(int i) { return i + (i >> 4); }
+#ifndef HPFW_CQT_UNROLL
+#define HPFW_CQT_UNROLL 1
+#endif
+#define HPFW_CQT_PRAGMA_(x) _Pragma(#x)
+#define HPFW_CQT_PRAGMA(x) HPFW_CQT_PRAGMA_(x)
+#define HPFW_CQT_IDX_UNROLL HPFW_CQT_PRAGMA(unroll HPFW_CQT_UNROLL)
 #ifndef HPFW_CQT_CHAIN_TW
 #define HPFW_CQT_CHAIN_TW 0
 #endif
@@ -512,6 +518,7 @@ template <int R, int MODE>
 __device__ __forceinline__ void pass_first(const float2 *__restrict__ in, float2 *S, int n, int G, int g_here, int pitch,
                                            int sign, unsigned long long mg_g, unsigned long long mg_m) {
     const int m = n / R, tot = G * m;
+    HPFW_CQT_IDX_UNROLL
     for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
         int g, j;
         if (MODE == 0) { j = fastdiv(idx, mg_g); g = idx - j * G; }     // adjacent columns are adjacent in memory
@@ -538,6 +545,7 @@ __device__ __forceinline__ void pass_mid(const float2 *Sin, float2 *Sout, int n,
                                          int sign, unsigned long long mg_g, unsigned long long mg_m,
                                          unsigned long long mg_ns) {
     const int m = n / R, tot = G * m, step = m / Ns;      // W_{Ns R}^k = W_n^{step k}
+    HPFW_CQT_IDX_UNROLL
     for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
         int g, j;
         if (MODE == 0) { j = fastdiv(idx, mg_g); g = idx - j * G; }
@@ -567,6 +575,7 @@ __device__ __forceinline__ void pass_last(const float2 *Sin, float2 *Sout, int n
                                           const float2 *__restrict__ T, int sign, unsigned long long mg_g,
                                           unsigned long long mg_m, const PassOut &po) {
     const int m = n / R, tot = G * m;       // Ns = m: blk = 0, k = j; outputs d = j + u m
+    HPFW_CQT_IDX_UNROLL
     for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
         int g, j;
         if (MODE == 0) { j = fastdiv(idx, mg_g); g = idx - j * G; }
