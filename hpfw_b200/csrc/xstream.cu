@@ -53,7 +53,7 @@ struct XsTrack {
 struct XsChunk {
     float *ptr = nullptr;
     size_t cap = 0, used = 0;    // floats
-    int first_track = -1, n_tracks = 0;
+    int n_tracks = 0;            // spectrograms that live in this chunk
 };
 
 }  // namespace
@@ -121,7 +121,7 @@ static int xs_join(hpfw_xs *xs) {
 }
 
 // room for one spectrogram of `floats` floats; HPFW_ERR_LIMIT when the arena budget is exhausted
-static int xs_arena_alloc(hpfw_xs *xs, size_t floats, int track, int *chunk_out, size_t *off_out) {
+static int xs_arena_alloc(hpfw_xs *xs, size_t floats, int *chunk_out, size_t *off_out) {
     if (!xs->chunks.empty()) {
         XsChunk &c = xs->chunks.back();
         if (c.used + floats <= c.cap) {
@@ -147,7 +147,6 @@ static int xs_arena_alloc(hpfw_xs *xs, size_t floats, int track, int *chunk_out,
     HPFW_CUDA_TRY(cudaMalloc(&c.ptr, want * sizeof(float)));
     c.cap = want;
     c.used = floats;
-    c.first_track = track;
     c.n_tracks = 1;
     xs->arena_bytes += want * sizeof(float);
     xs->chunks.push_back(c);
@@ -319,7 +318,7 @@ static int xs_submit_common(hpfw_xs *xs, int slot, int64_t n_samples, int cols, 
     int st;
     {
         std::lock_guard<std::mutex> lk(xs->m);       // hpfw_xs_fetch_spectrogram reads the chunk table from other threads
-        st = xs_arena_alloc(xs, floats, track, &chunk, &off);
+        st = xs_arena_alloc(xs, floats, &chunk, &off);
     }
     if (st != HPFW_OK) {
         fail_slot();
@@ -522,7 +521,6 @@ int hpfw_xs_drop_kept(hpfw_xs *xs) {
     for (auto &c : xs->chunks) {
         c.used = 0;
         c.n_tracks = 0;
-        c.first_track = -1;
     }
     return HPFW_OK;
 }
