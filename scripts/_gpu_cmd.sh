@@ -1,5 +1,8 @@
-echo "== base"; python scripts/cqt_tune.py 48 2>&1 | tail -1
-echo "== u2"; HPFW_B200_LIB=hpfw_b200/libhpfw_b200_u2.so python scripts/cqt_tune.py 48 2>&1 | tail -1
-echo "== u2 maxradix8"; HPFW_CQT_MAXRADIX=8 HPFW_B200_LIB=hpfw_b200/libhpfw_b200_u2.so python scripts/cqt_tune.py 48 2>&1 | tail -1
-echo "== u2c2"; HPFW_B200_LIB=hpfw_b200/libhpfw_b200_u2c2.so python scripts/cqt_tune.py 48 2>&1 | tail -1
-echo "== u2c2 smem 110"; HPFW_CQT_SMEM_KB=110 HPFW_B200_LIB=hpfw_b200/libhpfw_b200_u2c2.so python scripts/cqt_tune.py 48 2>&1 | tail -1
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29551 bench.py --gpus 4 --steps 3 --warmup 3 > gpurun_out/r2h_bench_4gpu.json 2> gpurun_out/r2h_bench_4gpu.err; echo rc=$?
+tail -c 400 gpurun_out/r2h_bench_4gpu.err
+python - <<'PY'
+import json
+d=json.load(open("gpurun_out/r2h_bench_4gpu.json"))
+print(json.dumps({k:d.get(k) for k in ("value","ms_per_step","n_gpus","sharded_bit_identical","top1_ok","strong")})[:1500])
+print(d["e2e"]["value"], json.dumps(d["e2e_cpp"]["search"])[:300], d["e2e_cpp"]["index"].get("frames_per_s"), d["extraction"]["value"])
+PY
