@@ -1221,6 +1221,7 @@ struct CqtPlan {
     int klo = 0, khi = 0;
     FftDesc d1{}, d2{};
     int G1 = 1, G2 = 1;
+    int T1 = CQ_FFT_THREADS, T2 = CQ_FFT_THREADS;   // threads per CTA of pass A / pass B (<= CQ_FFT_THREADS)
     size_t smem1 = 0, smem2 = 0;
     PlanMem mem;
     DeviceBuffer bhat;          // Bluestein: FFT_P of the shifted chirp filter
@@ -1453,6 +1454,30 @@ static void fft_group_sizes(hpfw_ctx *ctx, int n1, int n2, int &G1, int &G2, siz
     smem2 = fft_pass_smem(n2, G2);
 }
 
+// Threads per CTA of a pass kernel. A stage of radix R has G * n / R butterflies, one per thread and loop trip: with 256
+// threads a stage of 300 butterflies keeps 59 % of the lanes busy over its two trips. `forced` (HPFW_CQT_T1 / T2) overrides;
+// 0 = CQ_FFT_THREADS (the automatic choice below is only taken when HPFW_CQT_TAUTO is set: see profiles/r01y follow-up).
+static int pass_threads(const FftDesc &d, int G, int forced) {
+    if (forced >= 32 && forced <= CQ_FFT_THREADS) return forced / 32 * 32;
+    if (!env_int("HPFW_CQT_TAUTO", 0)) return CQ_FFT_THREADS;
+    int best_t = CQ_FFT_THREADS;
+    double best_u = 0.0;
+    for (int t = CQ_FFT_THREADS; t >= 128; t -= 32) {
+        double busy = 0.0, slots = 0.0;
+        for (int s = 0; s < d.nrad; ++s) {
+            const int tot = G * (d.n / std::max(d.rad[s], 1));
+            busy += tot;
+            slots += (double)((tot + t - 1) / t) * t;
+        }
+        const double u = busy / slots * (0.75 + 0.25 * t / CQ_FFT_THREADS);   // fewer warps hide less latency
+        if (u > best_u + 1e-9) {
+            best_u = u;
+            best_t = t;
+        }
+    }
+    return best_t;
+}
+
 // every FFT kernel may use up to the device's opt-in shared memory (plans of different sizes share the kernels)
 static int set_smem_limits(hpfw_ctx *ctx) {
     const int lim = ctx->max_smem_optin - 2048;   // dynamic + static shared memory must stay within the opt-in limit
@@ -1470,13 +1495,13 @@ static int fft_two_pass(hpfw_ctx *ctx, const CqtPlan &pl, const float2 *in, floa
     const int n1 = pl.d1.n, n2 = pl.d2.n, len = pl.bluestein ? pl.P : pl.H;
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
-        fft_pass_kernel<0><<<(n2 + pl.G1 - 1) / pl.G1, CQ_FFT_THREADS, pl.smem1, stream>>>(
+        fft_pass_kernel<0><<<(n2 + pl.G1 - 1) / pl.G1, pl.T1, pl.smem1, stream>>>(
             in, tmp, nullptr, pl.d1, n2, pl.G1, magic40((unsigned long long)pl.G1), pl.tw1, pl.twH_hi, pl.twH_lo, 0, 0, len,
             1, sign);
     }
     {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
-        fft_pass_kernel<1><<<(n1 + pl.G2 - 1) / pl.G2, CQ_FFT_THREADS, pl.smem2, stream>>>(
+        fft_pass_kernel<1><<<(n1 + pl.G2 - 1) / pl.G2, pl.T2, pl.smem2, stream>>>(
             tmp, out_lo, out_hi, pl.d2, n1, pl.G2, magic40((unsigned long long)pl.G2), pl.tw2, nullptr, nullptr, klo, khi,
             len, keep_all, sign);
     }
@@ -1544,6 +1569,15 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
     fft_group_sizes(ctx, n1, n2, pl.G1, pl.G2, pl.smem1, pl.smem2);
     pad_single_stage(pl.d1);
     pad_single_stage(pl.d2);
+    pl.T1 = pass_threads(pl.d1, pl.G1, env_int("HPFW_CQT_T1", 0));
+    pl.T2 = pass_threads(pl.d2, pl.G2, env_int("HPFW_CQT_T2", 0));
+    if (env_int("HPFW_CQT_DEBUG", 0)) {
+        fprintf(stderr, "[hpfw cqt] N=%lld H=%d n1=%d (G=%d, T=%d, radices", (long long)N, pl.H, n1, pl.G1, pl.T1);
+        for (int s2 = 0; s2 < pl.d1.nrad; ++s2) fprintf(stderr, " %d", pl.d1.rad[s2]);
+        fprintf(stderr, ") n2=%d (G=%d, T=%d, radices", n2, pl.G2, pl.T2);
+        for (int s2 = 0; s2 < pl.d2.nrad; ++s2) fprintf(stderr, " %d", pl.d2.rad[s2]);
+        fprintf(stderr, ")\n");
+    }
 
     // CZT layout
     std::vector<BandMeta> bands(CQ_BINS);
