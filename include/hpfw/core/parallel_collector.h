@@ -10,7 +10,7 @@
 //   prepare(files)   N decode threads read each file straight into a pinned staging slot -> H2D -> CQT on 4 lane streams
 //                    -> the dB spectrogram STAYS in HBM; its frame covariance is added to accum_cov on a side stream (:92-97);
 //                    cache/spectros/<stem> is written by background threads from a device->host copy, off the critical path
-//                    (:99); filters = calc_filters(accum_cov) (:111); then ONE batched projection/threshold/pack over all
+//                    (:99; they start when the pipeline has drained and finish after prepare() has returned); filters = calc_filters(accum_cov) (:111); then ONE batched projection/threshold/pack over all
 //                    resident spectrograms plus every older file in cache/spectros/ (:115-137). prepare_device() leaves the
 //                    hashprints in HBM for Storage::build_device; prepare() copies them out as the reference's pair list.
 //   calc_hashprints_device(files)   the query side of the same pipeline (search(): all query files in one batch).
@@ -231,6 +231,7 @@ public:
         device::check(hpfw_xs_hash_kept(xs));
 
         trace.mark("prepare: hashed");
+        start_cache_writers();
         DeviceHashprints out;
         out.xs = ixs;
         out.ctx = ctx;
@@ -366,6 +367,7 @@ public:
 
     /// Wait for the background cache writers and release the resident spectrograms of the last prepare().
     void flush_cache_writes() {
+        start_cache_writers();
         {
             std::unique_lock<std::mutex> wl(wq_m);
             wq_stop = true;
@@ -535,8 +537,19 @@ private:
             wq.push_back({filename, track});
         }
         writers_used = true;
-        if (writers.size() < 4) writers.emplace_back([this] { writer_loop(); });
-        wq_cv.notify_one();
+    }
+
+    /// The writer threads start once the extraction pipeline has drained (end of prepare_device, or a flush): while the decode
+    /// threads stream files at the host's memory bandwidth, the writers' device->host copies and file writes would compete with
+    /// them (measured: index() 10 % slower). The spectrograms stay resident in HBM until the writers are done either way.
+    void start_cache_writers() {
+        size_t pending;
+        {
+            std::unique_lock<std::mutex> wl(wq_m);
+            pending = wq.size();
+        }
+        while (pending > 0 && writers.size() < std::min<size_t>(4, pending)) writers.emplace_back([this] { writer_loop(); });
+        wq_cv.notify_all();
     }
 
     void writer_loop() {

@@ -1,4 +1,2 @@
-echo "== base"; HPFW_CQT_DEBUG=1 python scripts/cqt_tune.py 48 2>&1 | grep -E "hpfw cqt|us/track" | sort -u | tail -3
-for t in 128 160 192 224; do echo "== T2=$t"; HPFW_CQT_T2=$t python scripts/cqt_tune.py 48 2>&1 | tail -1; done
-for t in 192 224; do echo "== T1=$t"; HPFW_CQT_T1=$t python scripts/cqt_tune.py 48 2>&1 | tail -1; done
-echo "== auto"; HPFW_CQT_TAUTO=1 HPFW_CQT_DEBUG=1 python scripts/cqt_tune.py 48 2>&1 | grep -E "hpfw cqt|us/track" | sort -u | tail -3
+timeout 600 python -m pytest tests/test_pipeline_gpu.py tests/test_cpp_api.py tests/test_stream_order_gpu.py -m gpu -x -q 2>&1 | tail -4
+python bench.py --only-cpp-index --cpp-index-tracks 1024 --steps 3 2>&1 | grep -E "\"frames_per_s|\"index_|enqueued|learned" | tail -14
