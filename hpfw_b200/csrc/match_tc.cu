@@ -19,10 +19,12 @@
 //     a tile reads (tile + k) words instead of tile * k. Rows beyond the end of the track are zeros and contribute
 //     nothing, which is exactly the reference's truncation of a query that is longer than the track (storage.h:34-38).
 //   * query operand: expanded once per call by xt_expand_queries_kernel to [word j][chunk c][query m][16 B] (the words
-//     beyond a shorter query's end are zeros), streamed by 1-D bulk TMA copies through a 4-stage mbarrier ring
-//     (32 KB per stage; the 1.6 / 3 MB of a group stay in L2 for all 148 CTAs).
-//   * warp roles: 0 = TMA producer, 1 = MMA issuer, 2-5 = reference expanders (double-buffered R), 6-13 = epilogue.
-//   * epilogue: tcgen05.ld 64 columns at a time (warps 6-9: columns below 256, warps 10-13: the rest); per query (lane)
+//     beyond a shorter query's end are zeros), streamed by 1-D bulk TMA copies through an mbarrier ring (fp4: ten 16 KB
+//     stages of 4 words, int8: four 32 KB stages; the 1.6 / 3 MB of a group stay in L2 for all 148 CTAs).
+//   * warp roles: 0 = TMA producer, 1 = MMA issuer of the first N half, 2-5 = reference expanders (double-buffered R),
+//     6-13 = epilogue, 14 = MMA issuer of the second N half (LAG stages behind the first).
+//   * epilogue: tcgen05.ld 32 / 64 columns at a time (warps 6-9: the first N half of the tile, warps 10-13: the second,
+//     which the issuer runs a few stages behind the first so that the TMEM drains overlap MMAs); per query (lane)
 //     the maximum of (dot, lowest column) over the valid offsets; one 64-bit atomicMin per (query, tile, column half) into
 //     best[query][track], the array match_kernel and topk_kernel share — its key carries the offset, so ties resolve to the
 //     lowest offset as the reference's strict '<' does.
@@ -30,6 +32,7 @@
 #include "tc_ptx.cuh"
 
 #include <algorithm>
+#include <type_traits>
 
 namespace hpfw_b200 {
 
@@ -51,13 +54,30 @@ struct Xt {
     static constexpr uint32_t R_BYTES = CPW * R_LBO;               // 45,056 / 29,696
     static constexpr uint32_t Q_LBO = XT_NQ * 16;                  // 2,048
     static constexpr uint32_t QWORD_BYTES = CPW * Q_LBO;           // one query word of a group: 8,192 / 4,096
-    static constexpr uint32_t STAGE_BYTES = JS * QWORD_BYTES;      // 32,768
+    static constexpr uint32_t STAGE_BYTES = JS * QWORD_BYTES;      // int8: 32,768; fp4: 16,384
     static constexpr int KSTEPS = F4 ? 1 : 2;                      // MMAs (per N half) per word
     static constexpr int ECH = F4 ? 32 : 64;                       // TMEM columns per epilogue load
+    // The two N halves of a tile have their own accumulator barriers AND their own issuing thread (warp 1 and warp 14): the
+    // second half's issuer stays LAG stages behind the first (it waits for the first half to have issued stage i + LAG, or the
+    // tile's last stage), so at a tile boundary the first half finishes LAG stages early and is drained by its epilogue warps
+    // while the second half's last MMAs run, and the second half is drained while the next tile's first half starts. The TMEM
+    // drain (128 lanes x 240 columns at 64 B/clk = 1,920 clk per half, ~2,500 with latencies) is hidden when
+    // LAG * JS * (clk per word and half) covers it. A stage stays in the ring until both halves have read it, so the ring holds
+    // LAG + 1 stages in use plus the prefetch. Two issuing threads also halve the instruction budget each must meet (one MMA
+    // per 240 clk instead of 120): a single thread walking both halves through a queue of stage descriptors could not keep the
+    // tensor pipe fed (measured: -12 % with the queue, -25 % with 4-word stages).
+#ifndef XT_F4_STAGES
+#define XT_F4_STAGES 5
+#endif
+#ifndef XT_F4_LAG
+#define XT_F4_LAG 1
+#endif
+    static constexpr int STAGES = F4 ? XT_F4_STAGES : 4;           // query ring depth
+    static constexpr int LAG = F4 ? XT_F4_LAG : 0;                 // stages the second half trails the first
     static_assert(JCMAX % JS == 0, "chunk boundaries must be stage boundaries");
+    static_assert(LAG + 2 <= STAGES, "the ring must hold the lag plus at least one stage in flight");
 };
-constexpr int XT_STAGES = 4;                                   // query ring depth
-constexpr int XT_THREADS = 448;                                // TMA, MMA, 4 expander and 8 epilogue warps
+constexpr int XT_THREADS = 480;                                // TMA, MMA (first half), 4 expander, 8 epilogue warps, MMA (second half)
 constexpr int XT_BIAS = (1 << 18) + 1;                         // dot + bias >= 1 for every valid offset
 constexpr uint32_t XT_SF_COL = 480;                            // F4: TMEM columns 480..511 = scale factors, all 1.0
 
@@ -205,8 +225,10 @@ match_tc_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ 
     extern __shared__ uint8_t xsm_raw[];
     uint8_t *xsm = xsm_raw + ((128u - (smem_u32(xsm_raw) & 127u)) & 127u);
     uint8_t *r_s = xsm;                              // 2 x R_BYTES
-    uint8_t *q_s = xsm + 2 * G::R_BYTES;             // XT_STAGES x STAGE_BYTES
-    __shared__ __align__(8) uint64_t q_full[XT_STAGES], q_empty[XT_STAGES], r_full[2], r_empty[2], acc_full, acc_empty;
+    uint8_t *q_s = xsm + 2 * G::R_BYTES;             // STAGES x STAGE_BYTES
+    constexpr int XT_STAGES = G::STAGES;
+    __shared__ __align__(8) uint64_t q_full[XT_STAGES], q_empty[XT_STAGES], h0_issued[XT_STAGES], r_full[2], r_empty[2],
+        acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -220,14 +242,17 @@ match_tc_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ 
     if (threadIdx.x == 32) {
         for (int s = 0; s < XT_STAGES; ++s) {
             mbar_init(&q_full[s], 1);
-            mbar_init(&q_empty[s], 1);
+            mbar_init(&q_empty[s], 2);          // both issuing threads have read the stage
+            mbar_init(&h0_issued[s], 1);        // the first half's MMAs of this stage have been issued
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&r_full[b], 128);
-            mbar_init(&r_empty[b], 1);
+            mbar_init(&r_empty[b], 2);          // both halves have finished with the reference buffer
         }
-        mbar_init(&acc_full, 1);
-        mbar_init(&acc_empty, 256);
+        for (int h = 0; h < 2; ++h) {
+            mbar_init(&acc_full[h], 1);
+            mbar_init(&acc_empty[h], 128);      // the four epilogue warps of that half
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
@@ -259,21 +284,26 @@ match_tc_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ 
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp == 14) {
         if (lane == 0) {
-            // ===== MMA issuer =====
-            uint32_t sidx = 0, ridx = 0, tcount = 0;
-            const uint64_t a_hi = xt_desc(0, G::Q_LBO, 128), b_hi = xt_desc(0, G::R_LBO, 128);
+            // ===== MMA issuers: warp 1 = first N half of every tile (TMEM columns [0, HALF)), warp 14 = second half =====
+            // Both walk the same sequence of stages (JS query words of one K chunk of one tile). Everything a stage needs sits in
+            // registers before its MMAs go out; per MMA the thread does two 64-bit adds and the instruction itself.
+            const int H = warp == 1 ? 0 : 1;
+            const uint64_t a_hi = xt_desc(0, G::Q_LBO, 128), b_hi = xt_desc(0, G::R_LBO, 128) + (uint64_t)(H ? G::HALF : 0);
             const uint32_t sfa = tmem_base + XT_SF_COL, sfb = tmem_base + XT_SF_COL + 16;
+            const uint32_t d = tmem_base + (H ? G::HALF : 0);
+            uint32_t sidx = 0, ridx = 0, cnt = 0;
             for (long long item = blockIdx.x; item < total; item += gridDim.x) {
                 const XtItem it = xt_item<F4>(item, n_tiles, tiles, track_start, groups);
                 if (it.need <= 0) continue;
-                const int n1 = min(G::HALF, (it.need + 15) & ~15);
-                const int n2 = it.need > G::HALF ? (it.need - G::HALF + 15) & ~15 : 0;
-                const uint32_t id1 = F4 ? xt_idesc_f4(n1) : xt_idesc(n1);
-                const uint32_t id2 = F4 ? xt_idesc_f4(n2 ? n2 : 16) : xt_idesc(n2 ? n2 : 16);
-                if (tcount > 0) mbar_wait(&acc_empty, (tcount - 1) & 1);     // epilogue has drained the accumulators
-                tc_fence_after();
+                const int n = H ? (it.need > G::HALF ? (it.need - G::HALF + 15) & ~15 : 0) : min(G::HALF, (it.need + 15) & ~15);
+                const uint32_t id = F4 ? xt_idesc_f4(n ? n : 16) : xt_idesc(n ? n : 16);
+                const uint32_t sidx_last = sidx + (uint32_t)((it.kmax + G::JS - 1) / G::JS) - 1;   // last stage of this tile
+                if (n) {
+                    if (cnt > 0) mbar_wait(&acc_empty[H], (cnt - 1) & 1);     // the epilogue has drained this half
+                    tc_fence_after();
+                }
                 uint32_t acc = 0;
                 for (int c = 0; c < it.nchunks; ++c, ++ridx) {
                     const uint32_t rb = ridx & 1;
@@ -283,34 +313,46 @@ match_tc_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ 
                     const uint64_t b_base = b_hi + (uint64_t)(smem_u32(r_s + rb * G::R_BYTES) >> 4);
                     for (int j = j0; j < j1; j += G::JS, ++sidx) {
                         const uint32_t s = sidx % XT_STAGES;
+                        if (H && G::LAG > 0) {
+                            // stay LAG stages behind the first half (or wait for its last stage of this tile)
+                            const uint32_t g = min(sidx + (uint32_t)G::LAG, sidx_last);
+                            mbar_wait(&h0_issued[g % XT_STAGES], (g / XT_STAGES) & 1);
+                        }
                         mbar_wait(&q_full[s], (sidx / XT_STAGES) & 1);
                         tc_fence_after();
-                        const uint64_t a_base = a_hi + (uint64_t)(smem_u32(q_s + s * G::STAGE_BYTES) >> 4);
-                        const int nj = min(G::JS, j1 - j);
-                        for (int jj = 0; jj < nj; ++jj) {
+                        if (n) {
+                            const uint64_t a_base = a_hi + (uint64_t)(smem_u32(q_s + s * G::STAGE_BYTES) >> 4);
+                            const uint64_t b_row = b_base + (uint64_t)(j - j0);
+                            const int nj = min(G::JS, j1 - j);
+                            auto one = [&](int jj) {
 #pragma unroll
-                            for (int kk = 0; kk < G::KSTEPS; ++kk) {
-                                const uint64_t a_desc = a_base + (uint64_t)((jj * G::QWORD_BYTES + kk * 2 * G::Q_LBO) >> 4);
-                                const uint64_t b_desc = b_base + (uint64_t)(j - j0 + jj) + (uint64_t)((kk * 2 * G::R_LBO) >> 4);
-                                if (F4) {
-                                    tc_mma_mxf4(tmem_base, a_desc, b_desc, id1, sfa, sfb, acc);
-                                    if (n2) tc_mma_mxf4(tmem_base + G::HALF, a_desc, b_desc + G::HALF, id2, sfa, sfb, acc);
-                                } else {
-                                    tc_mma_i8(tmem_base, a_desc, b_desc, id1, acc);
-                                    if (n2) tc_mma_i8(tmem_base + G::HALF, a_desc, b_desc + G::HALF, id2, acc);
+                                for (int kk = 0; kk < G::KSTEPS; ++kk) {
+                                    const uint64_t a_desc = a_base + (uint64_t)((jj * G::QWORD_BYTES + kk * 2 * G::Q_LBO) >> 4);
+                                    const uint64_t b_desc = b_row + (uint64_t)jj + (uint64_t)((kk * 2 * G::R_LBO) >> 4);
+                                    if (F4) tc_mma_mxf4(d, a_desc, b_desc, id, sfa, sfb, acc);
+                                    else tc_mma_i8(d, a_desc, b_desc, id, acc);
+                                    acc = 1;
                                 }
-                                acc = 1;
+                            };
+                            if (nj == G::JS) {
+#pragma unroll
+                                for (int jj = 0; jj < G::JS; ++jj) one(jj);
+                            } else {
+                                for (int jj = 0; jj < nj; ++jj) one(jj);
                             }
                         }
-                        tc_commit(&q_empty[s]);
+                        if (!H) mbar_arrive(&h0_issued[s]);
+                        tc_commit(&q_empty[s]);        // this half is done with the stage (a commit without MMAs arrives at once)
                     }
                     tc_commit(&r_empty[rb]);
                 }
-                tc_commit(&acc_full);
-                ++tcount;
+                if (n) {
+                    tc_commit(&acc_full[H]);
+                    ++cnt;
+                }
             }
         }
-    } else if (warp < 6) {
+    } else if (warp >= 2 && warp < 6) {
         // ===== reference expanders: rows [tile_start + j0, + NOFF + (j1 - j0)) of the track, chunk-column layout =====
         const int et = threadIdx.x - 64;
         uint32_t ridx = 0;
@@ -337,11 +379,12 @@ match_tc_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ 
                 mbar_arrive(&r_full[rb]);
             }
         }
-    } else {
-        // ===== epilogue: 8 warps. Warp w reads TMEM lanes 32 (w % 4) .. +31 = queries; warps 6-9 take the columns (offsets)
-        // [0, 256) of the tile, warps 10-13 the columns from 256 on, 64 columns per tcgen05.ld. Each thread keeps the best
-        // (dot, column) of its columns; the two partial minima of a query meet in the 64-bit atomicMin, whose key carries the
-        // offset, so the lowest offset wins among equal distances. =====
+    } else if (warp >= 6 && warp < 14) {
+        // ===== epilogue: 8 warps. Warp w reads TMEM lanes 32 (w % 4) .. +31 = queries; warps 6-9 own the first N half of every
+        // tile (columns = offsets [0, HALF)), warps 10-13 the second half, each with its own full / empty barrier pair, so a
+        // half is drained as soon as ITS last MMA has completed (the issuer runs the second half LAG stages behind the first).
+        // Each thread keeps the best (dot, column) of its columns; the two partial minima of a query meet in the 64-bit
+        // atomicMin, whose key carries the offset, so the lowest offset wins among equal distances. =====
         const int half = (warp - 6) >> 2;
         const int m = (warp & 3) * 32 + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
@@ -349,49 +392,46 @@ match_tc_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ 
         for (long long item = blockIdx.x; item < total; item += gridDim.x) {
             const XtItem it = xt_item<F4>(item, n_tiles, tiles, track_start, groups);
             if (it.need <= 0) continue;
+            const int c_base = half * G::HALF;
+            if (it.need <= c_base) continue;                             // the tile has no second half (its last, short tile)
             const int q = row_q[it.g * XT_NQ + m];
             const int k_eff = min(row_k[it.g * XT_NQ + m], it.n_r);      // storage.h:34-38
-            // valid columns: n <= lim. Clamped to the tile: the last 64-column load of the fp4 kernel also covers the scale
-            // factor columns 480..511, which must never be taken for distances.
+            // valid columns of the tile: n <= lim; this half covers [c_base, c_base + ncol)
             const int lim = q >= 0 ? min((it.n_r - k_eff) - it.tile_start, it.need - 1) : -1;
-            const int c_begin = half * 256, c_end = half ? it.need : min(it.need, 256);
-            mbar_wait(&acc_full, tcount & 1);
+            const int ncol = min(G::HALF, it.need - c_base);
+            mbar_wait(&acc_full[half], tcount & 1);
             tc_fence_after();
             int best_d = 0, best_n = 0;      // best_d = dot + XT_BIAS of the best column so far (0: none)
 #pragma unroll 1
-            for (int c0 = c_begin; c0 < c_end; c0 += 64) {
-                uint32_t v[64];
-                tmem_ld_x64(t_lane + (uint32_t)c0, v);
+            for (int c0 = 0; c0 < ncol; c0 += G::ECH) {
+                // a load never crosses into the other half (whose accumulator is live) nor into the scale-factor columns: the
+                // last chunk of a 240-column half is moved back to end at the boundary; re-evaluated columns cannot win again
+                // (a column only replaces the best one with a strictly larger dot)
+                const int cc = c_base + min(c0, G::HALF - G::ECH);
+                const int li = lim - cc;
                 if (F4) {
-                    // f32 accumulators holding exact integers: key = dot * 32 + (31 - i) stays below 2^24, exact in f32.
-                    // Both warp votes come before any lane-dependent branch.
-                    const int li = lim - c0;
-                    const bool all0 = __all_sync(0xFFFFFFFFu, li >= 31), all1 = __all_sync(0xFFFFFFFFu, li >= 63);
-                    float bk[2] = {-3.0e38f, -3.0e38f};
+                    // f32 accumulators holding exact integers: key = dot * 32 + (31 - i) stays below 2^24, exact in f32
+                    uint32_t v[32];
+                    tmem_ld_x32(t_lane + (uint32_t)cc, v);
+                    float bk = -3.0e38f;
+                    if (__all_sync(0xFFFFFFFFu, li >= 31)) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (h ? all1 : all0) {
+                        for (int i = 0; i < 32; ++i) bk = fmaxf(bk, fmaf(__uint_as_float(v[i]), 32.0f, float(31 - i)));
+                    } else {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                bk[h] = fmaxf(bk[h], fmaf(__uint_as_float(v[32 * h + i]), 32.0f, float(31 - i)));
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const float key = fmaf(__uint_as_float(v[32 * h + i]), 32.0f, float(31 - i));
-                                bk[h] = fmaxf(bk[h], 32 * h + i <= li ? key : -3.0e38f);
-                            }
+                        for (int i = 0; i < 32; ++i) {
+                            const float key = fmaf(__uint_as_float(v[i]), 32.0f, float(31 - i));
+                            bk = fmaxf(bk, i <= li ? key : -3.0e38f);
                         }
                     }
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int ki = __float2int_rn(fmaxf(bk[h], -1.0e9f));
-                        const int d = bk[h] > -1.0e38f ? (ki >> 5) + XT_BIAS : 0;
-                        const bool better = d > best_d;    // strict: an equal distance at a higher offset never replaces
-                        best_n = better ? c0 + 32 * h + 31 - (ki & 31) : best_n;
-                        best_d = better ? d : best_d;
-                    }
+                    const int ki = __float2int_rn(fmaxf(bk, -1.0e9f));
+                    const int d = bk > -1.0e38f ? (ki >> 5) + XT_BIAS : 0;
+                    const bool better = d > best_d;    // strict: an equal distance at a higher offset never replaces
+                    best_n = better ? cc + 31 - (ki & 31) : best_n;
+                    best_d = better ? d : best_d;
                 } else {
-                    const int li = lim - c0;
+                    uint32_t v[64];
+                    tmem_ld_x64(t_lane + (uint32_t)cc, v);
                     uint32_t bk = 0;
                     if (__all_sync(0xFFFFFFFFu, li >= 63)) {
 #pragma unroll
@@ -407,12 +447,12 @@ match_tc_kernel(const uint64_t *__restrict__ words, const int64_t *__restrict__ 
                     const int d = int(bk >> 6);
                     if (d > best_d) {
                         best_d = d;
-                        best_n = c0 + 63 - int(bk & 63u);
+                        best_n = cc + 63 - int(bk & 63u);
                     }
                 }
             }
             tc_fence_before();
-            mbar_arrive(&acc_empty);
+            mbar_arrive(&acc_empty[half]);
             if (best_d > 0) {
                 const long long dot = (long long)best_d - XT_BIAS;
                 const unsigned long long dist = (unsigned long long)((64ll * k_eff - dot) >> 1);
@@ -445,7 +485,7 @@ static int match_tc_launch(hpfw_ctx *ctx, const hpfw_db *db, const uint64_t *d_q
                                                                                      d_row_k, d_qexp);
         HPFW_CUDA_TRY(cudaGetLastError());
     }
-    const size_t smem = 2 * (size_t)G::R_BYTES + (size_t)XT_STAGES * G::STAGE_BYTES + 128;
+    const size_t smem = 2 * (size_t)G::R_BYTES + (size_t)G::STAGES * G::STAGE_BYTES + 128;
     if (smem > size_t(ctx->max_smem_optin))
         HPFW_FAIL(HPFW_ERR_LIMIT, "match_tc: needs %zu B shared memory (> %d)", smem, ctx->max_smem_optin);
     HPFW_CUDA_TRY(cudaFuncSetAttribute(match_tc_kernel<F4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));

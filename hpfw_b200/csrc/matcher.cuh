@@ -16,7 +16,10 @@ constexpr int XT_NQ = 128;      // queries per group = M of the MMA (TMEM lanes)
 constexpr int XT_NOFF = 512;    // int8 kernel: alignment offsets per tile = 2 x N(256) = all 512 TMEM columns
 constexpr int XT_NOFF_F4 = 480; // fp4 kernel: 2 x N(240); 32 TMEM columns are left for the block scale factors
 constexpr int XT_JS = 4;        // int8 kernel: query words per TMA stage (64 bytes per word and query)
-constexpr int XT_JS_F4 = 8;     // fp4 kernel (32 bytes per word and query)
+#ifndef XT_JS_F4_N
+#define XT_JS_F4_N 8
+#endif
+constexpr int XT_JS_F4 = XT_JS_F4_N;     // fp4 kernel (32 bytes per word and query): 32 KB stages
 
 // one group of up to XT_NQ queries of similar length: its expanded words start at exp_off bytes into the scratch
 struct XtGroup {
