@@ -393,7 +393,8 @@ def run_extraction(args, ctx, rank, world, dev, max_over_ranks, barrier, st):
         f16_peak = float(pk["bf16_tflops_sustained"])
         f16_src = ("the measured sustained bf16 cuBLAS rate (MEASURED_PEAKS.json; fp16 and bf16 share the tensor rate). The kernel "
                    "itself is bound by shared-memory operand reads: N = 64 filters means 6 KB of operands per 32-clk MMA, 192 "
-                   "B/clk against the 128 B/clk an SM delivers")
+                   "B/clk against the 128 B/clk an SM delivers (67 % of the tensor rate at best); the pre-pass that writes the fp16 "
+                   "difference matrix (HBM-bound, ~2 us per track) is inside this time")
     except (NameError, KeyError, ValueError):
         f16_peak, f16_src = 1590.0, "the fallback bf16 rate (B200_PROFILING.md)"
     cq_per_track = max(1e-6, (ms * reps - pj_ms) / max(1, per_rank * reps))
@@ -425,7 +426,7 @@ def run_extraction(args, ctx, rank, world, dev, max_over_ranks, barrier, st):
                          "peak_how": "pinned host -> device copy of 256 MiB measured in this run (cudaMemcpyAsync, best of 5)",
                          "float32": {"achieved": 4.0 * n * e2e_tracks / e2e_s / 1e9,
                                      "frac": 4.0 * n * e2e_tracks / e2e_s / 1e9 / pcie_gbs if pcie_gbs else None}},
-        "roofline_projection": {"bound": "tensor", "kernel": "project_tc_kernel<3> (tcgen05 kind::f16, fp16 operands, + tc_delta_kernel pre-pass)",
+        "roofline_projection": {"bound": "tensor", "kernel": "project_tc_multi_kernel<2> (tcgen05 kind::f16, fp16 operands, 2 tiles per CTA share the filter stream, one issuing thread per tile) + tc_delta_kernel pre-pass",
                                 "achieved": 2.0 * 64 * 2420 * frames * per_rank * reps / (pj_ms * 1e-3) / 1e12,
                                 "peak": f16_peak, "unit": "TFLOP/s",
                                 "ms_per_track": pj_ms / max(1, per_rank * reps), "launches": pj_n,

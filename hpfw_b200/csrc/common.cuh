@@ -117,7 +117,8 @@ struct hpfw_ctx {
     hpfw_b200::DeviceBuffer spectro, hp, yproj, colmeta;
     hpfw_b200::DeviceBuffer filters_tc16;           // project_tc.cu impl 3: fp16 filters [tap][filter][band]
     hpfw_b200::DeviceBuffer filters_tc, delta_tc;   // project_tc.cu: tf32 filters [tap][filter][band], differenced spectrogram
-    int project_impl = 3;                           // 3 = tcgen05, fp16 operands (default); 1 = tcgen05, tf32 operands;
+    int project_impl = 4;                           // 4 = tcgen05, fp16 operands, 2 tiles per CTA share the filter stream (default);
+                                                    // 5 = the same with 4 tiles; 3 = one tile per CTA; 1 = tcgen05, tf32 operands;
                                                     // 2 = tcgen05, tf32, A window reloaded per tap; 0 = CUDA-core kernel
 
     // filter learning (learn.cu): device-resident covariance accumulator (2420 x 2420) and scratch

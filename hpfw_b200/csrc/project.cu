@@ -250,7 +250,7 @@ int hpfw_hashprint_from_spectrogram_device(hpfw_ctx *ctx, const float *d_spectro
 }
 
 int hpfw_set_projection_impl(hpfw_ctx *ctx, int impl) {
-    if (!ctx || impl < 0 || impl > 3) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_set_projection_impl: impl must be 0, 1, 2 or 3");
+    if (!ctx || impl < 0 || impl > 5) HPFW_FAIL(HPFW_ERR_ARG, "hpfw_set_projection_impl: impl must be 0 .. 5");
     ctx->project_impl = impl;
     return HPFW_OK;
 }

@@ -225,6 +225,118 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 }
 
+// ---- impl 4 / 5: NT tiles per CTA share the filter stream -----------------------------------------------------------------
+// In project_tc_kernel every 128-frame tile streams all 20 taps of the fp16 filters (320 KB) from L2 for its 160 MMAs: at the
+// full tensor rate that is 64 B/clk per SM, 9.5 KB/clk over the chip, more than the L2 -> SM path delivers (~6.3 KB/clk), and
+// one thread issues every MMA of the CTA (a 32-clk MMA leaves it ~30 instructions). Here a CTA owns NT consecutive tiles: one
+// A block, one 64-column TMEM accumulator and ONE ISSUING THREAD per tile, all fed from the same ring of filter stages (a stage
+// is released when every tile's issuer has committed it), so the filter stream per frame drops by NT and the issue budget per
+// thread grows by NT. Per tile the MMAs, their order and their operands are those of impl 3: identical hashprints.
+// Warps: 0-3 epilogue (warp 0 lane 0 also the TMA producer), 4 .. 4+NT-1 the issuers.
+template <int NT>
+__global__ void __launch_bounds__(128 + 32 * NT, NT == 2 ? 2 : 1)
+project_tc_multi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const TcTile *__restrict__ tiles, int n_tiles, const TcTrack *__restrict__ tracks,
+                        uint64_t *__restrict__ hp_out) {
+    extern __shared__ uint8_t msm_raw[];
+    uint8_t *msm = msm_raw + ((1024u - (smem_u32(msm_raw) & 1023u)) & 1023u);
+    constexpr int KB = 2, XS = 64, STAGES = TC_STAGES_1;
+    constexpr uint32_t A_BLOCK = KB * TC_A_ATOM_BYTES;          // 38,912 bytes per tile
+    uint8_t *smA = msm;
+    uint8_t *smB = msm + NT * A_BLOCK;
+    __shared__ __align__(8) uint64_t bar_a[NT], bar_full[STAGES], bar_empty[STAGES], bar_acc[NT];
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int first = blockIdx.x * NT;
+    const int nt = min(NT, n_tiles - first);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "r"((uint32_t)(NT * TC_TMEM_COLS)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x == 32) {
+        for (int i = 0; i < NT; ++i) {
+            mbar_init(&bar_a[i], 1);
+            mbar_init(&bar_acc[i], 1);
+        }
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_empty[s], (uint32_t)nt);      // every tile's issuer has read the stage
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer: the A block of every tile, then the 40 filter stages =====
+        for (int i = 0; i < nt; ++i) {
+            const TcTile tile = tiles[first + i];
+            const int row0 = (int)(tracks[tile.track].row_base + tile.t0);
+            mbar_expect_tx(&bar_a[i], A_BLOCK);
+            for (int kb = 0; kb < KB; ++kb) tma_load_2d(&tmA, &bar_a[i], smA + i * A_BLOCK + kb * TC_A_ATOM_BYTES, kb * XS, row0);
+        }
+        for (int it = 0; it < TC_CTX * KB; ++it) {
+            const int s = it % STAGES, c = it / KB, kb = it % KB;
+            if (it >= STAGES) mbar_wait(&bar_empty[s], ((it / STAGES) - 1) & 1);
+            mbar_expect_tx(&bar_full[s], TC_B_ATOM_BYTES);
+            tma_load_2d(&tmB, &bar_full[s], smB + s * TC_B_ATOM_BYTES, kb * XS, c * TC_NF);
+        }
+    } else if (warp >= 4 && warp - 4 < nt && lane == 0) {
+        // ===== MMA issuer of tile (warp - 4): descriptors advance by constants, two 64-bit adds per MMA =====
+        const int i = warp - 4;
+        mbar_wait(&bar_a[i], 0);
+        tc_fence_after();
+        const uint64_t a_tile = smem_desc_sw128(smem_u32(smA + i * A_BLOCK));
+        const uint64_t b_ring = smem_desc_sw128(smem_u32(smB));
+        const uint32_t d = tmem_base + (uint32_t)(i * TC_TMEM_COLS);
+        uint32_t acc = 0;
+        for (int it = 0; it < TC_CTX * KB; ++it) {
+            const int s = it % STAGES, c = it / KB, kb = it % KB;
+            mbar_wait(&bar_full[s], (it / STAGES) & 1);
+            tc_fence_after();
+            const uint64_t a_desc = a_tile + (uint64_t)((kb * TC_A_ATOM_BYTES + c * 128) >> 4);
+            const uint64_t b_desc = b_ring + (uint64_t)((s * TC_B_ATOM_BYTES) >> 4);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {       // 16 fp16 = 32 bytes per MMA along K inside the 128-byte swizzle atom
+                tc_mma_f16(d, a_desc + (uint64_t)(k4 * 2), b_desc + (uint64_t)(k4 * 2), TC_IDESC_H, acc);
+                acc = 1;
+            }
+            tc_commit(&bar_empty[s]);
+        }
+        tc_commit(&bar_acc[i]);
+    }
+
+    // ===== epilogue: warps 0-3; warp w owns TMEM lanes (= frames) 32w .. 32w+31 of every tile's accumulator =====
+    if (warp < 4) {
+        for (int i = 0; i < nt; ++i) {
+            const TcTile tile = tiles[first + i];
+            const TcTrack trk = tracks[tile.track];
+            mbar_wait(&bar_acc[i], 0);
+            tc_fence_after();
+            uint32_t v[64];
+            tmem_ld_x64(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(i * TC_TMEM_COLS), v);
+            uint64_t word = 0;
+#pragma unroll
+            for (int f = 0; f < 64; ++f) word |= (uint64_t)(__uint_as_float(v[f]) >= 0.f ? 1u : 0u) << (63 - f);
+            const int t = tile.t0 + warp * 32 + lane;
+            if (t < trk.n_out) hp_out[trk.out_start + t] = word;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(NT * TC_TMEM_COLS))
+                     : "memory");
+    }
+}
+
 static int tc_make_map_2d_t(CUtensorMap *map, const void *base, uint64_t rows, uint32_t box_rows, bool atom32, bool half);
 int tc_make_map_2d(CUtensorMap *map, const void *base, uint64_t rows, uint32_t box_rows, bool atom32) {
     return tc_make_map_2d_t(map, base, rows, box_rows, atom32, false);
@@ -328,7 +440,7 @@ int project_tc_run(hpfw_ctx *ctx, int impl, const float *d_spectro, const int64_
     // at least one TMA box of rows (rows past the last track are never part of a stored frame)
     const uint64_t map_rows = std::max<uint64_t>((uint64_t)rb, 256);
     HPFW_TRY(ctx->delta_tc.reserve(sizeof(float) * (size_t)map_rows * TC_BPAD));
-    const bool half = impl == 3;
+    const bool half = impl >= 3;
     {
         KernelScope ks(ctx, HPFW_K_PROJECT, stream);
         const int gx = std::max(1, std::min(64, (max_rows * TC_BPAD + 256 * 8 - 1) / (256 * 8)));
@@ -352,7 +464,19 @@ int project_tc_run(hpfw_ctx *ctx, int impl, const float *d_spectro, const int64_
     const size_t smem3 = 2 * TC_A_ATOM_BYTES + TC_STAGES_1 * TC_B_ATOM_BYTES + 1024;
     {
         KernelScope ks(ctx, HPFW_K_PROJECT, stream);
-        if (impl == 3) {
+        if (impl == 4 || impl == 5) {
+            const int nt = impl == 4 ? 2 : 4, n_tiles = (int)tiles.size();
+            const size_t smem_m = (size_t)nt * 2 * TC_A_ATOM_BYTES + TC_STAGES_1 * TC_B_ATOM_BYTES + 1024;
+            if (nt == 2) {
+                HPFW_CUDA_TRY(cudaFuncSetAttribute(project_tc_multi_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
+                project_tc_multi_kernel<2><<<(unsigned)((n_tiles + 1) / 2), 192, smem_m, stream>>>(
+                    tmA, tmB, reinterpret_cast<const TcTile *>(dm + o_tiles), n_tiles, reinterpret_cast<const TcTrack *>(dm), d_hp);
+            } else {
+                HPFW_CUDA_TRY(cudaFuncSetAttribute(project_tc_multi_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
+                project_tc_multi_kernel<4><<<(unsigned)((n_tiles + 3) / 4), 256, smem_m, stream>>>(
+                    tmA, tmB, reinterpret_cast<const TcTile *>(dm + o_tiles), n_tiles, reinterpret_cast<const TcTrack *>(dm), d_hp);
+            }
+        } else if (impl == 3) {
             HPFW_CUDA_TRY(cudaFuncSetAttribute(project_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
             project_tc_kernel<3><<<(unsigned)tiles.size(), 128, smem3, stream>>>(
                 tmA, tmB, reinterpret_cast<const TcTile *>(dm + o_tiles), reinterpret_cast<const TcTrack *>(dm), d_hp);

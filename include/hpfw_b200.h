@@ -169,7 +169,8 @@ int hpfw_hashprint_from_spectrogram(hpfw_ctx *ctx, const float *spectrogram, int
  * d_hp_out receives track i's words at hp_offsets[i] = sum_{j<i} max(cols_j - 99, 0). */
 int hpfw_hashprint_from_spectrogram_device(hpfw_ctx *ctx, const float *d_spectrograms, const int64_t *col_offsets,
                                            int n, uint64_t *d_hp_out, void *stream);
-/* which kernel runs stages 2-3: 1 = tcgen05/TMEM/TMA implicit GEMM, tf32 inputs, fp32 accumulate, one context
+/* which kernel runs stages 2-3: 4 (default) = 3 with two 128-frame tiles per CTA sharing the filter stream and one MMA-issuing
+ * thread per tile (5: four tiles); 1 = tcgen05/TMEM/TMA implicit GEMM, tf32 inputs, fp32 accumulate, one context
  * block per tile addressed with row-offset descriptors (project_tc.cu); 3 = the same with fp16 inputs (the 10 mantissa bits of
  * tf32; half the MMAs and operand bytes); 2 = as 1 but reloading the window per tap; 0 = fp32 CUDA-core FFMA kernel
  * (project.cu), kept as the measurement baseline and for bit-level comparisons. */

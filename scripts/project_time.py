@@ -35,3 +35,5 @@ for impl in impls:
 for impl in [i for i in impls if i != 0 and 0 in res]:
     d = int(np.unpackbits((res[impl] ^ res[0]).view(np.uint8)).sum())
     print(f"impl {impl} vs 0: {d} of {64*len(res[0])} bits differ ({100.0*d/(64*len(res[0])):.5f} %)")
+for impl in [i for i in impls if i in (4, 5) and 3 in res]:
+    print(f"impl {impl} vs 3: identical = {bool(np.array_equal(res[impl], res[3]))}")

@@ -1,5 +1,5 @@
 """The tcgen05 / TMEM / TMA projection (hpfw_b200/csrc/project_tc.cu) against the CUDA-core kernel, the oracle and the
-reference-generated golden hashprints. Inputs are rounded to tf32 (impl 1, 2) or fp16 (impl 3) — a 10-bit mantissa either way — by this path, so bits may differ
+reference-generated golden hashprints. Inputs are rounded to tf32 (impl 1, 2) or fp16 (impl 3, and impl 4 / 5 = the same arithmetic with 2 / 4 tiles per CTA sharing the filter stream) — a 10-bit mantissa either way — by this path, so bits may differ
 where |delta| is within that rounding noise: the bar is north_star's >= 99.9 % of bits (SURVEY probe: 99.999 % expected for
 delta-first tf32) and identical top-1."""
 import ctypes as C
@@ -24,10 +24,10 @@ def ex(ctx, hashprint_golden):
     e = HashprintExtractor(ctx)
     e.set_filters(hashprint_golden["filters"])
     yield e
-    check(ctx._lib.hpfw_set_projection_impl(ctx.handle, 3))
+    check(ctx._lib.hpfw_set_projection_impl(ctx.handle, 4))
 
 
-@pytest.mark.parametrize("impl", [2, 1, 3])
+@pytest.mark.parametrize("impl", [2, 1, 3, 4, 5])
 def test_tc_vs_cuda_core_and_reference(ctx, ex, hashprint_golden, impl):
     g = hashprint_golden
     for spec_key, hp_key in (("q_spec", "hpq"), ("spec0", "hp0")):
@@ -47,7 +47,7 @@ def test_tc_vs_cuda_core_and_reference(ctx, ex, hashprint_golden, impl):
             assert abs(delta[t, 63 - int(bit)]) <= 2e-2 * typical
 
 
-@pytest.mark.parametrize("impl", [2, 1, 3])
+@pytest.mark.parametrize("impl", [2, 1, 3, 4, 5])
 def test_tc_bit_order_single_tap_filters(ctx, impl):
     """One non-zero tap per filter: y is a copy of one band, the expected word is known in closed form (filter f -> bit
     63-f). Spectrogram values are tf32-exact so the tensor-core path must reproduce the comparison exactly."""
@@ -65,7 +65,7 @@ def test_tc_bit_order_single_tap_filters(ctx, impl):
     try:
         hp = e.hashprint_from_spectrogram(spec)
     finally:
-        check(ctx._lib.hpfw_set_projection_impl(ctx.handle, 3))
+        check(ctx._lib.hpfw_set_projection_impl(ctx.handle, 4))
     n = cols - 99
     exp = np.zeros(n, dtype=np.uint64)
     for f, (b, c) in enumerate(taps):
@@ -74,7 +74,7 @@ def test_tc_bit_order_single_tap_filters(ctx, impl):
     assert np.array_equal(hp, exp)
 
 
-@pytest.mark.parametrize("impl", [2, 1, 3])
+@pytest.mark.parametrize("impl", [2, 1, 3, 4, 5])
 def test_tc_batched_ragged(ctx, ex, hashprint_golden, impl):
     import torch
     g = hashprint_golden
@@ -101,7 +101,7 @@ def test_tc_batched_ragged(ctx, ex, hashprint_golden, impl):
         pos += n
 
 
-@pytest.mark.parametrize("impl", [1, 3])
+@pytest.mark.parametrize("impl", [1, 3, 4])
 def test_tc_identical_top1(ctx, ex, hashprint_golden, collector_golden, impl):
     g, c = hashprint_golden, collector_golden
     check(ctx._lib.hpfw_set_projection_impl(ctx.handle, impl))
