@@ -42,7 +42,7 @@ __device__ __forceinline__ uint64_t cv_desc(uint32_t addr) {
 }
 
 // part[(split * 20 + d) * 128 * 128 + b * 128 + b'] = sum over this split's rows of Sc[u][b] * Sc[u + d][b']
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(256, 1)
 cov_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo, int ksteps_total,
               int ksteps_per_split, float *__restrict__ part) {
     extern __shared__ uint8_t csm_raw[];
@@ -65,9 +65,9 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ 
     if (threadIdx.x == 32) {
         for (int s = 0; s < CV_STAGES; ++s) {
             mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_empty[s], 1);
+            mbar_init(&bar_empty[s], CV_LAGS);      // every lag's issuing thread has read the stage
         }
-        mbar_init(&bar_acc, 1);
+        mbar_init(&bar_acc, CV_LAGS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
@@ -88,27 +88,33 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ 
                 tma_load_2d(&tmLo, &bar_full[s], dst + CV_PART_BYTES + kb * CV_ATOM_BYTES, kb * 32, row0);
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===== MMA issuer =====
-        uint32_t acc[CV_LAGS] = {0, 0, 0, 0};
+    } else if (warp >= 4 && lane == 0) {
+        // ===== MMA issuers: one thread per lag (warps 4-7), each with its own 128-column accumulator. A 64-clk MMA leaves a
+        // single issuing thread too few instructions for twelve MMAs per step (the matcher's lesson, match_tc.cu); with one
+        // thread per lag each issues three per step. The descriptors of a step differ from the previous step's by a constant. =====
+        const int dl = warp - 4, d = d0 + dl;
+        const bool active = d < CV_CTX;
+        const uint32_t dcol = tmem_base + (uint32_t)dl * 128u;
+        uint32_t acc = 0;
         for (int c = 0; c < nchunks; ++c) {
             const int s = c % CV_STAGES;
             mbar_wait(&bar_full[s], (c / CV_STAGES) & 1);
             tc_fence_after();
-            const uint32_t hi = smem_u32(csm + s * CV_STAGE_BYTES), lo = hi + CV_PART_BYTES;
-            const int steps = min(steps_per_chunk, nsteps - c * steps_per_chunk);
-            for (int k = 0; k < steps; ++k) {
-                const uint32_t a_off = (uint32_t)k * 1024u;                     // 8 rows further
-#pragma unroll
-                for (int dl = 0; dl < CV_LAGS; ++dl) {
-                    const int d = d0 + dl;
-                    if (d >= CV_CTX) break;
-                    const uint32_t b_off = a_off + (uint32_t)d * 128u;          // the same block, d rows down
-                    const uint32_t dcol = tmem_base + (uint32_t)dl * 128u;
-                    tc_mma_tf32(dcol, cv_desc(hi + a_off), cv_desc(hi + b_off), CV_IDESC, acc[dl]);
-                    tc_mma_tf32(dcol, cv_desc(hi + a_off), cv_desc(lo + b_off), CV_IDESC, 1);
-                    tc_mma_tf32(dcol, cv_desc(lo + a_off), cv_desc(hi + b_off), CV_IDESC, 1);
-                    acc[dl] = 1;
+            if (active) {
+                const uint32_t hi = smem_u32(csm + s * CV_STAGE_BYTES), lo = hi + CV_PART_BYTES;
+                const int steps = min(steps_per_chunk, nsteps - c * steps_per_chunk);
+                // operand A: the block at row 8k; operand B: the same block d rows further down
+                uint64_t a_hi = cv_desc(hi), a_lo = cv_desc(lo), b_hi = cv_desc(hi + (uint32_t)d * 128u),
+                         b_lo = cv_desc(lo + (uint32_t)d * 128u);
+                for (int k = 0; k < steps; ++k) {
+                    tc_mma_tf32(dcol, a_hi, b_hi, CV_IDESC, acc);
+                    tc_mma_tf32(dcol, a_hi, b_lo, CV_IDESC, 1);
+                    tc_mma_tf32(dcol, a_lo, b_hi, CV_IDESC, 1);
+                    acc = 1;
+                    a_hi += 64;     // 1,024 bytes = 8 rows further, in descriptor units of 16 bytes
+                    a_lo += 64;
+                    b_hi += 64;
+                    b_lo += 64;
                 }
             }
             tc_commit(&bar_empty[s]);
@@ -117,6 +123,7 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ 
     }
 
     // ===== epilogue: warp w owns TMEM lanes 32w .. 32w+31 = rows b of the four 128 x 128 accumulators =====
+    if (warp < 4) {
     mbar_wait(&bar_acc, 0);
     tc_fence_after();
     const int b = warp * 32 + lane;
@@ -136,6 +143,7 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ 
             for (int i = 0; i < 64; i += 4)
                 *reinterpret_cast<uint4 *>(dst + h * 64 + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
+    }
     }
     tc_fence_before();
     __syncthreads();
@@ -159,7 +167,7 @@ int cov_tc_run(hpfw_ctx *ctx, const float *d_hi, const float *d_lo, int cols, in
     const size_t smem = (size_t)CV_STAGES * CV_STAGE_BYTES + 1024;
     HPFW_CUDA_TRY(cudaFuncSetAttribute(cov_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KernelScope ks(ctx, HPFW_K_OTHER, stream);
-    cov_tc_kernel<<<dim3(splits, CV_CTX / CV_LAGS), 128, smem, stream>>>(tmHi, tmLo, ksteps, per, d_part);
+    cov_tc_kernel<<<dim3(splits, CV_CTX / CV_LAGS), 256, smem, stream>>>(tmHi, tmLo, ksteps, per, d_part);
     HPFW_CUDA_TRY(cudaGetLastError());
     return HPFW_OK;
 }

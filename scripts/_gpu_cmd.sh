@@ -1,2 +1,2 @@
-timeout 300 python scripts/project_time.py 32 0,3,4,5 2>&1 | tail -9
-timeout 300 python scripts/project_time.py 128 3,4,5 2>&1 | tail -5
+timeout 600 python -m pytest tests/test_learn_gpu.py tests/test_project_tc_gpu.py tests/test_project_gpu.py -m gpu -x -q 2>&1 | tail -4
+python scripts/cov_time.py 32
