@@ -531,7 +531,7 @@ def build_cpp_bench():
     return exe
 
 
-def cpp_index_leg(exe, work, env, dev, world, n_tracks, reps=2):
+def cpp_index_leg(exe, work, env, dev, world, n_tracks, reps=3):
     """LiveSongIdentification::index() over n_tracks three-minute PCM16 WAV files in `work`/tracks (32 distinct synthetic
     signals; the other names are links to them, so every name is a separate track of the DB)."""
     import torch
