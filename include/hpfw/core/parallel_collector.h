@@ -123,10 +123,19 @@ public:
             DeviceHashprints d = prepare_device(filenames);
             std::vector<FilenameFingerprintPair> out(d.names.size());
             std::scoped_lock l(ctx->mutex());
+            // one device->host copy of the whole hashprint store, then one slice per track
+            const int nt = hpfw_xs_tracks(d.xs->get());
+            std::vector<int64_t> off(static_cast<size_t>(nt)), len(static_cast<size_t>(nt));
+            device::check(hpfw_xs_hashprints_device(d.xs->get(), nullptr, off.data(), len.data()));
+            int64_t total = 0;
+            for (int t = 0; t < nt; ++t)
+                if (off[static_cast<size_t>(t)] >= 0) total = std::max(total, off[static_cast<size_t>(t)] + len[static_cast<size_t>(t)]);
+            std::vector<uint64_t> store(static_cast<size_t>(total));
+            device::check(hpfw_xs_hashprints_host(d.xs->get(), store.data(), total));
             for (size_t i = 0; i < d.names.size(); ++i) {
+                const size_t t = static_cast<size_t>(d.order[i]);
                 out[i].filename = d.names[i];
-                out[i].fingerprint.resize(static_cast<size_t>(d.words[i]));
-                device::check(hpfw_xs_hashprint_host(d.xs->get(), d.order[i], out[i].fingerprint.data()));
+                out[i].fingerprint.assign(store.begin() + off[t], store.begin() + off[t] + len[t]);
             }
             return out;
         } else {
