@@ -680,9 +680,46 @@ def run_cuda(args):
     # ---- synthetic DB shard in HBM + planted queries (setup, untimed)
     n = args.gpus
     tracks = args.tracks
-    lo, hi = rank * tracks // n, (rank + 1) * tracks // n
-    d_words, offs = synth.device_hashprint_db(torch, dev, 1234 + rank, hi - lo, TRACK_WORDS)
     qpg = args.queries_per_gpu
+    st = ShardedMemoryStorage(ctx, rank, world)
+    bounds = [r * tracks // n for r in range(n + 1)]
+    balance = None
+    if world > 1 and args.balance:
+        # The GPUs of one node do not run at the same clock under their power caps, and the all-gather of a step waits for the
+        # slowest rank. Calibration (setup, untimed): an equal split is matched three times, every rank reports the device
+        # time of its match kernel, and the track ranges are re-planned in proportion to the measured speeds
+        # (hpfw_shard_plan_weighted). The timed DB below is generated for the re-planned ranges.
+        from hpfw_b200.sharded import plan_shards
+        clo, chi = bounds[rank], bounds[rank + 1]
+        cw, coffs = synth.device_hashprint_db(torch, dev, 4321 + rank, chi - clo, TRACK_WORDS)
+        cq, _, _ = synth.device_hashprint_queries(torch, cw, coffs, 55 + rank, qpg * n, QUERY_WORDS, FLIP)
+        cqo = np.arange(qpg * n + 1, dtype=np.int64) * QUERY_WORDS
+        st.build_local_device(cw.data_ptr(), coffs, track_base=clo, stream=torch.cuda.current_stream().cuda_stream)
+        st.search_device(cq, cqo, TOPK)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ctx.timing_read(_lib.K_MATCH_TC, reset=True)
+        ctx.timing_enable(True)
+        for _ in range(3):
+            st.search_device(cq, cqo, TOPK)
+        torch.cuda.synchronize()
+        t_ms, t_n = ctx.timing_read(_lib.K_MATCH_TC, reset=True)
+        ctx.timing_enable(False)
+        t_all = torch.zeros(world, dtype=torch.float64, device=dev)
+        t_all[rank] = t_ms / max(1, t_n)
+        dist.all_reduce(t_all)
+        times = t_all.cpu().numpy()
+        speeds = 1.0 / np.maximum(times, 1e-6)
+        sh = plan_shards([TRACK_WORDS] * tracks, n, QUERY_WORDS, speeds=speeds)
+        bounds = [a for a, _ in sh] + [sh[-1][1]]
+        balance = {"how": "track ranges proportional to 1 / (match kernel time of an equal split), measured per rank before "
+                          "the timed DB is built (hpfw_shard_plan_weighted)",
+                   "calibration_ms_per_rank": [float(x) for x in times],
+                   "tracks_per_rank": [bounds[r + 1] - bounds[r] for r in range(n)]}
+        del cw, cq
+        torch.cuda.empty_cache()
+    lo, hi = bounds[rank], bounds[rank + 1]
+    d_words, offs = synth.device_hashprint_db(torch, dev, 1234 + rank, hi - lo, TRACK_WORDS)
     # audio-derived part of the DB for the end-to-end arm: the first AUDIO_TRACKS tracks of the DB start with the hashprints
     # of synthetic 30 s tracks (extracted on the GPU); the e2e queries are noisy, pitch-shifted 6 s slices of those tracks
     golden = np.load(os.path.join(ROOT, "tests", "golden", "hashprint.npz"))
@@ -708,7 +745,6 @@ def run_cuda(args):
         d_q, truth = d_q_local, truth_local
     nq = qpg * n
     qoffs = np.arange(nq + 1, dtype=np.int64) * QUERY_WORDS
-    st = ShardedMemoryStorage(ctx, rank, world)
     stream = torch.cuda.current_stream().cuda_stream
     st.build_local_device(d_words.data_ptr(), offs, track_base=lo, stream=stream)
     del d_words
@@ -797,7 +833,7 @@ def run_cuda(args):
         if rank == 0:
             full = torch.empty(tracks * TRACK_WORDS, dtype=torch.int64, device=dev)
             for r in range(world):
-                rlo, rhi = r * tracks // n, (r + 1) * tracks // n
+                rlo, rhi = bounds[r], bounds[r + 1]
                 w_r, _ = synth.device_hashprint_db(torch, dev, 1234 + r, rhi - rlo, TRACK_WORDS)
                 full[rlo * TRACK_WORDS: rhi * TRACK_WORDS] = w_r
                 del w_r
@@ -1076,6 +1112,8 @@ def run_cuda(args):
         }
         if sharded_identical is not None:
             line["sharded_bit_identical"] = sharded_identical
+        if balance is not None:
+            line["shard_balance"] = balance
         if strong is not None:
             line["strong"] = strong
         if cpp is not None:
@@ -1118,6 +1156,10 @@ def main():
                          "2 = default routing (hpfw_set_match_impl)")
     ap.add_argument("--no-popc-leg", action="store_true", help="skip timing the integer-pipe kernel beside the default")
     ap.add_argument("--no-extraction", action="store_true", help="skip the secondary hashprint-extraction leg")
+    ap.add_argument("--balance", action="store_true",
+                    help="N > 1: re-plan the track ranges by each GPU's measured match speed (hpfw_shard_plan_weighted). Off by "
+                         "default: measured on 2 GPUs the sustained, power-capped speeds differ less than the calibration's "
+                         "short runs suggest and the step time does not change (2,243 vs 2,240 queries/s)")
     ap.add_argument("--no-identity-check", action="store_true", help="N > 1: skip the untimed sharded-vs-one-GPU key comparison")
     ap.add_argument("--no-strong-leg", action="store_true", help="skip the fixed-batch / single-find latency leg")
     ap.add_argument("--strong-queries", type=int, default=128,

@@ -108,6 +108,7 @@ _SIGS = {
     "hpfw_xs_build_db": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
     "hpfw_xs_match": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Match)]),
     "hpfw_shard_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "hpfw_shard_plan_weighted": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "hpfw_shard_nccl_version": (C.c_int, []),
     "hpfw_shard_unique_id": (C.c_int, [C.c_void_p]),
     "hpfw_shard_create_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),

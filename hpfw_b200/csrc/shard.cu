@@ -119,7 +119,8 @@ struct hpfw_shard {
     std::vector<int> bounds;  // local mode: track range of device d = [bounds[d], bounds[d+1])
 };
 
-static void plan_bounds(const int64_t *track_words, int n_tracks, int n_shards, int query_words, std::vector<int> &bounds) {
+static void plan_bounds(const int64_t *track_words, int n_tracks, int n_shards, int query_words, std::vector<int> &bounds,
+                        const double *speed = nullptr) {
     // contiguous ranges (the global track index = DB order, which the tie rule relies on) balanced by sum (n_r - k + 1) * k
     std::vector<double> csum(size_t(n_tracks) + 1, 0.0);
     for (int r = 0; r < n_tracks; ++r) {
@@ -127,9 +128,14 @@ static void plan_bounds(const int64_t *track_words, int n_tracks, int n_shards, 
         csum[size_t(r) + 1] = csum[size_t(r)] + double((n - k + 1) * std::max<int64_t>(k, 1));
     }
     const double total = csum[size_t(n_tracks)];
+    // shard s gets the share speed[s] / sum(speed) of the work (equal shares without speeds): GPUs of one node do not run at
+    // the same clock under their power caps, and a collective waits for the slowest rank
+    double speed_sum = 0.0, speed_acc = 0.0;
+    for (int s = 0; s < n_shards; ++s) speed_sum += speed ? std::max(speed[s], 1e-9) : 1.0;
     bounds.assign(1, 0);
     for (int s = 1; s < n_shards; ++s) {
-        const double target = total * double(s) / double(n_shards);
+        speed_acc += speed ? std::max(speed[s - 1], 1e-9) : 1.0;
+        const double target = total * speed_acc / speed_sum;
         int b = int(std::lower_bound(csum.begin(), csum.end(), target) - csum.begin());
         if (b > 0 && std::fabs(csum[size_t(b) - 1] - target) <= std::fabs(csum[size_t(std::min(b, n_tracks))] - target)) --b;
         bounds.push_back(std::min(std::max(b, bounds.back()), n_tracks));
@@ -144,6 +150,16 @@ int hpfw_shard_plan(const int64_t *track_words, int n_tracks, int n_shards, int 
         HPFW_FAIL(HPFW_ERR_ARG, "hpfw_shard_plan: bad argument");
     std::vector<int> b;
     plan_bounds(track_words, n_tracks, n_shards, query_words > 0 ? query_words : 385, b);
+    memcpy(bounds_out, b.data(), sizeof(int) * b.size());
+    return HPFW_OK;
+}
+
+int hpfw_shard_plan_weighted(const int64_t *track_words, int n_tracks, int n_shards, int query_words, const double *speed,
+                             int *bounds_out) {
+    if (n_tracks < 0 || n_shards < 1 || !bounds_out || !speed || (n_tracks > 0 && !track_words))
+        HPFW_FAIL(HPFW_ERR_ARG, "hpfw_shard_plan_weighted: bad argument");
+    std::vector<int> b;
+    plan_bounds(track_words, n_tracks, n_shards, query_words > 0 ? query_words : 385, b, speed);
     memcpy(bounds_out, b.data(), sizeof(int) * b.size());
     return HPFW_OK;
 }

@@ -30,13 +30,22 @@ def pack_key(dist: int, track: int, offset: int) -> int:
     return (int(dist) << KEY_DIST_SHIFT) | (int(track) << KEY_OFFSET_BITS) | int(offset)
 
 
-def plan_shards(track_words: Sequence[int], n_shards: int, query_words: int = 385) -> List[Tuple[int, int]]:
+def plan_shards(track_words: Sequence[int], n_shards: int, query_words: int = 385,
+                speeds: Sequence[float] | None = None) -> List[Tuple[int, int]]:
     """Contiguous track ranges [begin, end) per shard, balanced by matcher work sum (n_r - k + 1) * k. Contiguous ranges keep
     the global track index = DB order, which the tie rule (earliest track) relies on. Computed by the library
     (hpfw_shard_plan, host-only: needs no GPU) so that Python and the C++ ShardedMemoryStorage split a DB identically."""
     lens = np.ascontiguousarray(track_words, dtype=np.int64)
     bounds = np.zeros(n_shards + 1, dtype=np.int32)
-    check(_lib.load().hpfw_shard_plan(_ptr(lens) if len(lens) else None, len(lens), n_shards, query_words, _ptr(bounds)))
+    if speeds is not None:
+        # share of shard s = speeds[s] / sum(speeds): balance by measured device speed (hpfw_shard_plan_weighted)
+        sp = np.ascontiguousarray(speeds, dtype=np.float64)
+        if len(sp) != n_shards:
+            raise ValueError("one speed per shard")
+        check(_lib.load().hpfw_shard_plan_weighted(_ptr(lens) if len(lens) else None, len(lens), n_shards, query_words,
+                                                   _ptr(sp), _ptr(bounds)))
+    else:
+        check(_lib.load().hpfw_shard_plan(_ptr(lens) if len(lens) else None, len(lens), n_shards, query_words, _ptr(bounds)))
     return [(int(bounds[i]), int(bounds[i + 1])) for i in range(n_shards)]
 
 

@@ -307,6 +307,10 @@ int hpfw_xs_match(hpfw_xs *xs, hpfw_db *db, int topk, hpfw_match *out);
 typedef struct hpfw_shard hpfw_shard;
 /* host-only (no device needed): bounds_out[n_shards + 1], shard s = tracks [bounds[s], bounds[s+1]) */
 int hpfw_shard_plan(const int64_t *track_words, int n_tracks, int n_shards, int query_words, int *bounds_out);
+/* the same with the work shared in proportion to speed[s] (e.g. 1 / measured match time of rank s on an equal split): the GPUs
+ * of a node do not run at the same clock under their power caps, and the all-gather waits for the slowest rank */
+int hpfw_shard_plan_weighted(const int64_t *track_words, int n_tracks, int n_shards, int query_words, const double *speed,
+                             int *bounds_out);
 int hpfw_shard_nccl_version(void);                     /* e.g. 22809; 0 when NCCL cannot be loaded */
 int hpfw_shard_unique_id(void *id128_out);
 int hpfw_shard_create_rank(hpfw_ctx *ctx, int rank, int world, const void *id128, hpfw_shard **out);

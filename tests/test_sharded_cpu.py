@@ -27,6 +27,26 @@ def test_plan_shards_contiguous_and_balanced():
     assert sum(b - a for a, b in plan_shards([5, 5], 4)) == 2
 
 
+def test_plan_shards_weighted_by_device_speed():
+    """hpfw_shard_plan_weighted: shard s gets speeds[s] / sum(speeds) of the matcher work (GPUs of one node run at different
+    clocks under their power caps; the all-gather waits for the slowest rank)."""
+    lens = np.full(10000, 14411)
+    sh = plan_shards(lens, 4, speeds=[1.0, 1.0, 1.0, 1.0])
+    assert [b - a for a, b in sh] == [2500] * 4
+    sh = plan_shards(lens, 4, speeds=[1.02, 1.0, 0.98, 1.0])
+    sizes = [b - a for a, b in sh]
+    assert sum(sizes) == 10000 and sh[0][0] == 0 and sh[-1][1] == 10000
+    assert sizes[0] == 2550 and sizes[2] == 2450 and sizes[1] == sizes[3] == 2500
+    rng = np.random.default_rng(2)
+    rl = rng.integers(0, 20000, size=3000)
+    sp = [1.0, 2.0, 1.0]
+    sh = plan_shards(rl, 3, speeds=sp)
+    k = np.minimum(rl, 385)
+    work = (rl - k + 1) * np.maximum(k, 1)
+    per = np.array([work[a:b].sum() for a, b in sh], dtype=np.float64)
+    assert abs(per[1] / per.sum() - 0.5) < 0.01 and abs(per[0] / per.sum() - 0.25) < 0.01
+
+
 def test_pack_key_orders_like_the_reference_scan():
     # smaller distance first, then earlier track, then lower offset (storage.h:50-60)
     keys = [pack_key(5, 3, 7), pack_key(5, 3, 6), pack_key(5, 2, 900), pack_key(4, 1000, 1 << 19), pack_key(6, 0, 0)]
