@@ -30,6 +30,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -1242,11 +1243,39 @@ struct CqtPlan {
     cudaEvent_t last_done[CQ_LANES] = {};   // per lane: recorded after the latest transform that used this plan
     cudaStream_t created_on = nullptr;
     uint64_t last_use = 0;
+    struct CqtGang *gangs = nullptr;     // CQ_GANGS captured launch graphs of this plan (batch entry), created on first use
 };
 
 // per-lane scratch, shared by all plans (grow-only): tracks of a batch run concurrently on CQ_LANES streams
 struct CqtLane {
     DeviceBuffer zbuf, zlo, zhi, work, power, pmax, bl_a;
+    uint64_t gen = 0;           // bumped whenever a buffer above moves: captured graphs that point into it are stale
+};
+
+// A gang = CQ_GANG_LANES tracks of one length transformed by ONE cudaGraphLaunch: the six launch stages of every lane are
+// captured once per (plan, gang) as parallel branches; a replay only re-points the first node of each branch at the lane's
+// audio and the last at its output. The host cost of a track drops from ~10 runtime calls (75-80 us on the bench host, close
+// to the 117 us the GPU needs) to a quarter of one graph launch plus two node updates.
+constexpr int CQ_GANG_LANES = 4;
+constexpr int CQ_GANGS = CQ_LANES / CQ_GANG_LANES;
+constexpr int CQ_PASS_ARGS = 15, CQ_DB_ARGS = 6;
+struct CqtGang {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaGraphNode_t in_node[CQ_GANG_LANES] = {}, out_node[CQ_GANG_LANES] = {};
+    cudaKernelNodeParams in_params[CQ_GANG_LANES] = {}, out_params[CQ_GANG_LANES] = {};
+    void *in_args[CQ_GANG_LANES][CQ_PASS_ARGS] = {}, *out_args[CQ_GANG_LANES][CQ_DB_ARGS] = {};
+    const float2 *in_ptr[CQ_GANG_LANES] = {};
+    float *out_ptr[CQ_GANG_LANES] = {};
+    uint64_t lane_gen[CQ_GANG_LANES] = {};
+    int window = -1;
+    int kernels = 0;            // kernel nodes per replay (for the context's launch counter)
+    void destroy() {
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+        exec = nullptr;
+        graph = nullptr;
+    }
 };
 
 struct CqtPlanCache {
@@ -1255,11 +1284,17 @@ struct CqtPlanCache {
     std::vector<DeviceBuffer> free_big;
     std::vector<cudaEvent_t> free_events;
     CqtLane lanes[CQ_LANES];
+    cudaEvent_t cap_fork = nullptr, cap_join[CQ_LANES] = {};   // fork / join events used only inside gang captures
     bool smem_set = false;
     uint64_t tick = 0;
 };
 
 static void plan_release(CqtPlanCache *c, CqtPlan &p, bool recycle) {
+    if (p.gangs) {
+        for (int g = 0; g < CQ_GANGS; ++g) p.gangs[g].destroy();
+        delete[] p.gangs;
+        p.gangs = nullptr;
+    }
     if (recycle) {
         if (p.mem.dev.ptr) c->free_mem.push_back(p.mem);
         if (p.bhat.ptr) c->free_big.push_back(p.bhat);
@@ -1286,6 +1321,9 @@ void cqt_cache_destroy(CqtPlanCache *c) {
     for (auto &m : c->free_mem) { m.dev.release(); m.pin.release(); }
     for (auto &b : c->free_big) b.release();
     for (auto e : c->free_events) cudaEventDestroy(e);
+    if (c->cap_fork) cudaEventDestroy(c->cap_fork);
+    for (auto e : c->cap_join)
+        if (e) cudaEventDestroy(e);
     for (auto &l : c->lanes) {
         l.zbuf.release(); l.zlo.release(); l.zhi.release(); l.work.release(); l.power.release(); l.pmax.release();
         l.bl_a.release();
@@ -1323,6 +1361,16 @@ static int reserve_roomy(DeviceBuffer &b, size_t bytes) { return bytes <= b.cap 
 static int lane_reserve(CqtPlanCache *c, const CqtPlan &pl, int lane) {
     CqtLane &sc = c->lanes[lane];
     const size_t nkeep = (size_t)(pl.khi - pl.klo + 1);
+    const void *before[7] = {sc.zbuf.ptr, sc.zlo.ptr, sc.zhi.ptr, sc.work.ptr, sc.power.ptr, sc.pmax.ptr, sc.bl_a.ptr};
+    struct Bump {
+        CqtLane &l;
+        const void **b;
+        ~Bump() {
+            const void *after[7] = {l.zbuf.ptr, l.zlo.ptr, l.zhi.ptr, l.work.ptr, l.power.ptr, l.pmax.ptr, l.bl_a.ptr};
+            for (int i = 0; i < 7; ++i)
+                if (after[i] != b[i]) { ++l.gen; break; }
+        }
+    } bump{sc, before};
     HPFW_TRY(reserve_roomy(sc.zbuf, sizeof(float2) * (size_t)(pl.bluestein ? pl.P : pl.H)));
     HPFW_TRY(reserve_roomy(sc.zlo, sizeof(float2) * nkeep));
     if (pl.bluestein) HPFW_TRY(reserve_roomy(sc.bl_a, sizeof(float2) * (size_t)pl.P));
@@ -1490,22 +1538,27 @@ static int set_smem_limits(hpfw_ctx *ctx) {
 }
 
 // the plan's two-pass FFT (H points for the packed path, P for Bluestein): in -> tmp -> out_lo / out_hi
+static int fft_pass_a(hpfw_ctx *ctx, const CqtPlan &pl, const float2 *in, float2 *tmp, int sign, cudaStream_t stream) {
+    const int n2 = pl.d2.n, len = pl.bluestein ? pl.P : pl.H;
+    KernelScope ks(ctx, HPFW_K_CQT, stream);
+    fft_pass_kernel<0><<<(n2 + pl.G1 - 1) / pl.G1, pl.T1, pl.smem1, stream>>>(
+        in, tmp, nullptr, pl.d1, n2, pl.G1, magic40((unsigned long long)pl.G1), pl.tw1, pl.twH_hi, pl.twH_lo, 0, 0, len, 1,
+        sign);
+    return HPFW_OK;
+}
+static int fft_pass_b(hpfw_ctx *ctx, const CqtPlan &pl, const float2 *tmp, float2 *out_lo, float2 *out_hi, int klo, int khi,
+                      int keep_all, int sign, cudaStream_t stream) {
+    const int n1 = pl.d1.n, len = pl.bluestein ? pl.P : pl.H;
+    KernelScope ks(ctx, HPFW_K_CQT, stream);
+    fft_pass_kernel<1><<<(n1 + pl.G2 - 1) / pl.G2, pl.T2, pl.smem2, stream>>>(
+        tmp, out_lo, out_hi, pl.d2, n1, pl.G2, magic40((unsigned long long)pl.G2), pl.tw2, nullptr, nullptr, klo, khi, len,
+        keep_all, sign);
+    return HPFW_OK;
+}
 static int fft_two_pass(hpfw_ctx *ctx, const CqtPlan &pl, const float2 *in, float2 *tmp, float2 *out_lo, float2 *out_hi,
                         int klo, int khi, int keep_all, int sign, cudaStream_t stream) {
-    const int n1 = pl.d1.n, n2 = pl.d2.n, len = pl.bluestein ? pl.P : pl.H;
-    {
-        KernelScope ks(ctx, HPFW_K_CQT, stream);
-        fft_pass_kernel<0><<<(n2 + pl.G1 - 1) / pl.G1, pl.T1, pl.smem1, stream>>>(
-            in, tmp, nullptr, pl.d1, n2, pl.G1, magic40((unsigned long long)pl.G1), pl.tw1, pl.twH_hi, pl.twH_lo, 0, 0, len,
-            1, sign);
-    }
-    {
-        KernelScope ks(ctx, HPFW_K_CQT, stream);
-        fft_pass_kernel<1><<<(n1 + pl.G2 - 1) / pl.G2, pl.T2, pl.smem2, stream>>>(
-            tmp, out_lo, out_hi, pl.d2, n1, pl.G2, magic40((unsigned long long)pl.G2), pl.tw2, nullptr, nullptr, klo, khi,
-            len, keep_all, sign);
-    }
-    return HPFW_OK;
+    HPFW_TRY(fft_pass_a(ctx, pl, in, tmp, sign, stream));
+    return fft_pass_b(ctx, pl, tmp, out_lo, out_hi, klo, khi, keep_all, sign, stream);
 }
 
 // {2,3,5,7}-smooth numbers in [lo, hi], ascending
@@ -1816,44 +1869,71 @@ static int plan_get(hpfw_ctx *ctx, int64_t N, CqtPlan **out, cudaStream_t stream
     return HPFW_OK;
 }
 
-// mode 0: dB spectrogram; mode 1: linear magnitudes. d_audio must be 8-byte aligned.
-static int cqt_run(hpfw_ctx *ctx, const float *d_audio, int64_t N, float *d_out, int mode, cudaStream_t stream,
-                   int lane = 0) {
+// One transform = six launch stages (main FFT pass A, pass B, chirp-z columns, rows, output, dB). cqt_run issues them back to
+// back on one stream; the batch entry can issue stage by stage across its lanes instead (HPFW_CQT_WAVE), so that the lanes
+// run the same kernel at the same time.
+struct CqtJob {
     CqtPlan *pl = nullptr;
-    HPFW_TRY(plan_get(ctx, N, &pl, stream, lane));
+    CqtLane *sc = nullptr;
+    const float *d_audio = nullptr;
+    int64_t N = 0;
+    float *d_out = nullptr;
+    int mode = 0;
+    cudaStream_t stream = nullptr;
+    int lane = 0;
+    bool captured = false;      // inside a stream capture: no event bookkeeping (the gang records it after the graph launch)
+};
+constexpr int CQ_STAGES = 6;
+
+static int cqt_prepare(hpfw_ctx *ctx, CqtJob &jb) {
+    HPFW_TRY(plan_get(ctx, jb.N, &jb.pl, jb.stream, jb.lane));
     CqtPlanCache *cache = ctx->cqt;
-    HPFW_TRY(lane_reserve(cache, *pl, lane));
-    CqtLane *sc = &cache->lanes[lane];
-    if (stream != pl->created_on) HPFW_CUDA_TRY(cudaStreamWaitEvent(stream, pl->ready, 0));
+    HPFW_TRY(lane_reserve(cache, *jb.pl, jb.lane));
+    jb.sc = &cache->lanes[jb.lane];
+    if (jb.stream != jb.pl->created_on) HPFW_CUDA_TRY(cudaStreamWaitEvent(jb.stream, jb.pl->ready, 0));
+    if (!jb.pl->bluestein && (reinterpret_cast<uintptr_t>(jb.d_audio) & 7) != 0)
+        HPFW_FAIL(HPFW_ERR_ARG, "CQT: the audio buffer must be 8-byte aligned");
+    return HPFW_OK;
+}
+
+static int cqt_stage(hpfw_ctx *ctx, const CqtJob &jb, int stage) {
+    CqtPlan *pl = jb.pl;
+    CqtLane *sc = jb.sc;
+    cudaStream_t stream = jb.stream;
     const CqtDesign &d = pl->des;
-    if (!pl->bluestein) {
-        if ((reinterpret_cast<uintptr_t>(d_audio) & 7) != 0)
-            HPFW_FAIL(HPFW_ERR_ARG, "CQT: the audio buffer must be 8-byte aligned");
-        HPFW_TRY(fft_two_pass(ctx, *pl, reinterpret_cast<const float2 *>(d_audio), sc->zbuf.as<float2>(),
-                              sc->zlo.as<float2>(), sc->zhi.as<float2>(), pl->klo, pl->khi, 0, -1, stream));
-    } else {
-        const int P = pl->P, K = pl->khi - pl->klo + 1, gb = (P + CQ_THREADS - 1) / CQ_THREADS;
-        {
-            KernelScope ks(ctx, HPFW_K_CQT, stream);
-            bl_prep_kernel<<<gb, CQ_THREADS, 0, stream>>>(d_audio, (long long)N, P, sc->bl_a.as<float2>());
-        }
-        HPFW_TRY(fft_two_pass(ctx, *pl, sc->bl_a.as<float2>(), sc->zbuf.as<float2>(), sc->bl_a.as<float2>(), nullptr, 0, 0,
-                              1, -1, stream));
-        {
-            KernelScope ks(ctx, HPFW_K_CQT, stream);
-            bl_mul_kernel<<<gb, CQ_THREADS, 0, stream>>>(sc->bl_a.as<float2>(), pl->bhat.as<float2>(), P);
-        }
-        HPFW_TRY(fft_two_pass(ctx, *pl, sc->bl_a.as<float2>(), sc->zbuf.as<float2>(), sc->zlo.as<float2>(), nullptr, 0,
-                              K - 1, 0, +1, stream));
-        {
-            KernelScope ks(ctx, HPFW_K_CQT, stream);
-            bl_post_kernel<<<(K + CQ_THREADS - 1) / CQ_THREADS, CQ_THREADS, 0, stream>>>(sc->zlo.as<float2>(), (long long)N,
-                                                                                         P, pl->klo, K);
-        }
-    }
-    HPFW_CUDA_TRY(cudaMemsetAsync(sc->pmax.ptr, 0, sizeof(unsigned int), stream));
     const dim3 gcol((pl->max_L2 + CQ_THREADS - 1) / CQ_THREADS, CQ_BINS);
-    {
+    switch (stage) {
+    case 0:
+        if (!pl->bluestein) {
+            HPFW_TRY(fft_pass_a(ctx, *pl, reinterpret_cast<const float2 *>(jb.d_audio), sc->zbuf.as<float2>(), -1, stream));
+        } else {
+            const int P = pl->P, K = pl->khi - pl->klo + 1, gb = (P + CQ_THREADS - 1) / CQ_THREADS;
+            {
+                KernelScope ks(ctx, HPFW_K_CQT, stream);
+                bl_prep_kernel<<<gb, CQ_THREADS, 0, stream>>>(jb.d_audio, (long long)jb.N, P, sc->bl_a.as<float2>());
+            }
+            HPFW_TRY(fft_two_pass(ctx, *pl, sc->bl_a.as<float2>(), sc->zbuf.as<float2>(), sc->bl_a.as<float2>(), nullptr, 0, 0,
+                                  1, -1, stream));
+            {
+                KernelScope ks(ctx, HPFW_K_CQT, stream);
+                bl_mul_kernel<<<gb, CQ_THREADS, 0, stream>>>(sc->bl_a.as<float2>(), pl->bhat.as<float2>(), P);
+            }
+            HPFW_TRY(fft_two_pass(ctx, *pl, sc->bl_a.as<float2>(), sc->zbuf.as<float2>(), sc->zlo.as<float2>(), nullptr, 0,
+                                  K - 1, 0, +1, stream));
+            {
+                KernelScope ks(ctx, HPFW_K_CQT, stream);
+                bl_post_kernel<<<(K + CQ_THREADS - 1) / CQ_THREADS, CQ_THREADS, 0, stream>>>(sc->zlo.as<float2>(),
+                                                                                             (long long)jb.N, P, pl->klo, K);
+            }
+        }
+        break;
+    case 1:
+        if (!pl->bluestein)
+            HPFW_TRY(fft_pass_b(ctx, *pl, sc->zbuf.as<float2>(), sc->zlo.as<float2>(), sc->zhi.as<float2>(), pl->klo, pl->khi,
+                                0, -1, stream));
+        break;
+    case 2: {
+        HPFW_CUDA_TRY(cudaMemsetAsync(sc->pmax.ptr, 0, sizeof(unsigned int), stream));
         KernelScope ks(ctx, HPFW_K_CQT, stream);
         float2 *zlo = sc->zlo.as<float2>(), *zhi = sc->zhi.as<float2>(), *wk = sc->work.as<float2>();
         if (pl->bluestein) {
@@ -1877,20 +1957,21 @@ static int cqt_run(hpfw_ctx *ctx, const float *d_audio, int64_t N, float *d_out,
                 czt_cols_kernel<0, 64><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, zlo, zhi, pl->klo, pl->khi, pl->twN_hi,
                                                                         pl->twN_lo, pl->chirp, d.M, d.F, wk, ctx->cqt_window);
         }
+        break;
     }
-    if (pl->n_tiles3 > 0) {
-        KernelScope ks(ctx, HPFW_K_CQT, stream);
-        czt_rows3_kernel<<<pl->n_tiles3, 256, rows3_smem(), stream>>>(
-            pl->d_bands, pl->d_tiles3, sc->work.as<float2>(),
-            pl->d_btab_ptrs, pl->d_tt_ptrs);
-    }
-    if (pl->n_tiles > 0) {
-        KernelScope ks(ctx, HPFW_K_CQT, stream);
-        czt_rows_kernel<0><<<pl->n_tiles, CQ_FFT_THREADS, pl->smem_rows, stream>>>(
-            pl->d_bands, pl->d_tiles, sc->work.as<float2>(),
-            pl->d_btab_ptrs, pl->d_descs, pl->d_tw_ptrs);
-    }
-    {
+    case 3:
+        if (pl->n_tiles3 > 0) {
+            KernelScope ks(ctx, HPFW_K_CQT, stream);
+            czt_rows3_kernel<<<pl->n_tiles3, 256, rows3_smem(), stream>>>(pl->d_bands, pl->d_tiles3, sc->work.as<float2>(),
+                                                                          pl->d_btab_ptrs, pl->d_tt_ptrs);
+        }
+        if (pl->n_tiles > 0) {
+            KernelScope ks(ctx, HPFW_K_CQT, stream);
+            czt_rows_kernel<0><<<pl->n_tiles, CQ_FFT_THREADS, pl->smem_rows, stream>>>(
+                pl->d_bands, pl->d_tiles, sc->work.as<float2>(), pl->d_btab_ptrs, pl->d_descs, pl->d_tw_ptrs);
+        }
+        break;
+    case 4: {
         KernelScope ks(ctx, HPFW_K_CQT, stream);
         if (pl->L1 == 16)
             czt_out_kernel<16><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, sc->work.as<float2>(), d.M, d.F, pl->fpitch,
@@ -1901,20 +1982,154 @@ static int cqt_run(hpfw_ctx *ctx, const float *d_audio, int64_t N, float *d_out,
         else
             czt_out_kernel<64><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, sc->work.as<float2>(), d.M, d.F, pl->fpitch,
                                                                 sc->power.as<float>(), sc->pmax.as<unsigned int>());
+        break;
     }
-    {
-        KernelScope ks(ctx, HPFW_K_CQT, stream);
-        const int gb = (d.cols + 31) / 32;
-        if (mode == 0)
-            db_kernel<0><<<gb, CQ_THREADS, 0, stream>>>(sc->power.as<float>(), sc->pmax.as<unsigned int>(), d.F, d.cols,
-                                                         pl->fpitch, d_out);
-        else
-            db_kernel<1><<<gb, CQ_THREADS, 0, stream>>>(sc->power.as<float>(), sc->pmax.as<unsigned int>(), d.F, d.cols,
-                                                         pl->fpitch, d_out);
+    default: {
+        {
+            KernelScope ks(ctx, HPFW_K_CQT, stream);
+            const int gb = (d.cols + 31) / 32;
+            if (jb.mode == 0)
+                db_kernel<0><<<gb, CQ_THREADS, 0, stream>>>(sc->power.as<float>(), sc->pmax.as<unsigned int>(), d.F, d.cols,
+                                                             pl->fpitch, jb.d_out);
+            else
+                db_kernel<1><<<gb, CQ_THREADS, 0, stream>>>(sc->power.as<float>(), sc->pmax.as<unsigned int>(), d.F, d.cols,
+                                                             pl->fpitch, jb.d_out);
+        }
+        if (jb.captured) break;
+        HPFW_CUDA_TRY(cudaGetLastError());
+        if (!pl->last_done[jb.lane]) HPFW_TRY(event_get(ctx->cqt, &pl->last_done[jb.lane]));
+        HPFW_CUDA_TRY(cudaEventRecord(pl->last_done[jb.lane], stream));
+        break;
     }
-    HPFW_CUDA_TRY(cudaGetLastError());
-    if (!pl->last_done[lane]) HPFW_TRY(event_get(cache, &pl->last_done[lane]));
-    HPFW_CUDA_TRY(cudaEventRecord(pl->last_done[lane], stream));
+    }
+    return HPFW_OK;
+}
+
+// The gang's launches as a graph: lane 0's stream is the origin, the other lanes are forked from it and joined back.
+static int gang_capture_body(hpfw_ctx *ctx, CqtJob *jobs, int gang) {
+    const int l0 = gang * CQ_GANG_LANES;
+    cudaStream_t gs = ctx->lane_stream[l0];
+    CqtPlanCache *c = ctx->cqt;
+    HPFW_CUDA_TRY(cudaEventRecord(c->cap_fork, gs));
+    for (int l = 1; l < CQ_GANG_LANES; ++l) HPFW_CUDA_TRY(cudaStreamWaitEvent(ctx->lane_stream[l0 + l], c->cap_fork, 0));
+    for (int st = 0; st < CQ_STAGES; ++st)
+        for (int l = 0; l < CQ_GANG_LANES; ++l) HPFW_TRY(cqt_stage(ctx, jobs[l], st));
+    for (int l = 1; l < CQ_GANG_LANES; ++l) {
+        HPFW_CUDA_TRY(cudaEventRecord(c->cap_join[l0 + l], ctx->lane_stream[l0 + l]));
+        HPFW_CUDA_TRY(cudaStreamWaitEvent(gs, c->cap_join[l0 + l], 0));
+    }
+    return HPFW_OK;
+}
+
+static int gang_build(hpfw_ctx *ctx, CqtJob *jobs, int gang, CqtGang &gg) {
+    const int l0 = gang * CQ_GANG_LANES;
+    cudaStream_t gs = ctx->lane_stream[l0];
+    gg.destroy();
+    CqtPlanCache *c = ctx->cqt;
+    if (!c->cap_fork) HPFW_CUDA_TRY(cudaEventCreateWithFlags(&c->cap_fork, cudaEventDisableTiming));
+    for (int l = 0; l < CQ_LANES; ++l)
+        if (!c->cap_join[l]) HPFW_CUDA_TRY(cudaEventCreateWithFlags(&c->cap_join[l], cudaEventDisableTiming));
+    const uint64_t launches_before = ctx->launches;
+    HPFW_CUDA_TRY(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+    for (int l = 0; l < CQ_GANG_LANES; ++l) jobs[l].captured = true;
+    const int st = gang_capture_body(ctx, jobs, gang);
+    for (int l = 0; l < CQ_GANG_LANES; ++l) jobs[l].captured = false;
+    const cudaError_t ce = cudaStreamEndCapture(gs, &gg.graph);
+    gg.kernels = (int)(ctx->launches - launches_before);
+    ctx->launches = launches_before;          // nothing ran yet: the replay counts them
+    if (st != HPFW_OK || ce != cudaSuccess) {
+        if (gg.graph) cudaGraphDestroy(gg.graph);
+        gg.graph = nullptr;
+        cudaGetLastError();
+        if (st != HPFW_OK) return st;
+        HPFW_FAIL(HPFW_ERR_CUDA, "CQT: stream capture failed: %s", cudaGetErrorString(ce));
+    }
+    size_t nn = 0;
+    HPFW_CUDA_TRY(cudaGraphGetNodes(gg.graph, nullptr, &nn));
+    std::vector<cudaGraphNode_t> nodes(nn);
+    HPFW_CUDA_TRY(cudaGraphGetNodes(gg.graph, nodes.data(), &nn));
+    int found_in = 0, found_out = 0;
+    for (cudaGraphNode_t nd : nodes) {
+        cudaGraphNodeType ty;
+        HPFW_CUDA_TRY(cudaGraphNodeGetType(nd, &ty));
+        if (ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp{};
+        HPFW_CUDA_TRY(cudaGraphKernelNodeGetParams(nd, &kp));
+        if (!kp.kernelParams) continue;
+        if (kp.func == (void *)fft_pass_kernel<0>) {
+            const float2 *in = *reinterpret_cast<const float2 *const *>(kp.kernelParams[0]);
+            for (int l = 0; l < CQ_GANG_LANES; ++l)
+                if (in == reinterpret_cast<const float2 *>(jobs[l].d_audio)) {
+                    gg.in_node[l] = nd;
+                    gg.in_params[l] = kp;
+                    for (int a = 0; a < CQ_PASS_ARGS; ++a) gg.in_args[l][a] = kp.kernelParams[a];
+                    gg.in_ptr[l] = in;
+                    gg.in_args[l][0] = &gg.in_ptr[l];
+                    gg.in_params[l].kernelParams = gg.in_args[l];
+                    ++found_in;
+                }
+        } else if (kp.func == (void *)db_kernel<0>) {
+            float *out = *reinterpret_cast<float *const *>(kp.kernelParams[CQ_DB_ARGS - 1]);
+            for (int l = 0; l < CQ_GANG_LANES; ++l)
+                if (out == jobs[l].d_out) {
+                    gg.out_node[l] = nd;
+                    gg.out_params[l] = kp;
+                    for (int a = 0; a < CQ_DB_ARGS; ++a) gg.out_args[l][a] = kp.kernelParams[a];
+                    gg.out_ptr[l] = out;
+                    gg.out_args[l][CQ_DB_ARGS - 1] = &gg.out_ptr[l];
+                    gg.out_params[l].kernelParams = gg.out_args[l];
+                    ++found_out;
+                }
+        }
+    }
+    if (found_in != CQ_GANG_LANES || found_out != CQ_GANG_LANES) {
+        gg.destroy();
+        HPFW_FAIL(HPFW_ERR_STATE, "CQT: captured graph has %d input and %d output nodes, expected %d each", found_in,
+                  found_out, CQ_GANG_LANES);
+    }
+    HPFW_CUDA_TRY(cudaGraphInstantiate(&gg.exec, gg.graph, 0));
+    for (int l = 0; l < CQ_GANG_LANES; ++l) gg.lane_gen[l] = jobs[l].sc->gen;
+    gg.window = ctx->cqt_window;
+    return HPFW_OK;
+}
+
+// CQ_GANG_LANES prepared jobs of ONE non-Bluestein plan (mode 0) on the lanes of `gang`: one graph launch.
+static int cqt_gang_run(hpfw_ctx *ctx, CqtJob *jobs, int gang) {
+    CqtPlan *pl = jobs[0].pl;
+    const int l0 = gang * CQ_GANG_LANES;
+    cudaStream_t gs = ctx->lane_stream[l0];
+    if (!pl->gangs) pl->gangs = new CqtGang[CQ_GANGS];
+    CqtGang &gg = pl->gangs[gang];
+    bool stale = !gg.exec || gg.window != ctx->cqt_window;
+    for (int l = 0; l < CQ_GANG_LANES; ++l) stale = stale || gg.lane_gen[l] != jobs[l].sc->gen;
+    if (stale) {
+        HPFW_TRY(gang_build(ctx, jobs, gang, gg));
+    } else {
+        for (int l = 0; l < CQ_GANG_LANES; ++l) {
+            if (gg.in_ptr[l] != reinterpret_cast<const float2 *>(jobs[l].d_audio)) {
+                gg.in_ptr[l] = reinterpret_cast<const float2 *>(jobs[l].d_audio);
+                HPFW_CUDA_TRY(cudaGraphExecKernelNodeSetParams(gg.exec, gg.in_node[l], &gg.in_params[l]));
+            }
+            if (gg.out_ptr[l] != jobs[l].d_out) {
+                gg.out_ptr[l] = jobs[l].d_out;
+                HPFW_CUDA_TRY(cudaGraphExecKernelNodeSetParams(gg.exec, gg.out_node[l], &gg.out_params[l]));
+            }
+        }
+    }
+    HPFW_CUDA_TRY(cudaGraphLaunch(gg.exec, gs));
+    ctx->launches += (uint64_t)gg.kernels;
+    if (!pl->last_done[l0]) HPFW_TRY(event_get(ctx->cqt, &pl->last_done[l0]));
+    HPFW_CUDA_TRY(cudaEventRecord(pl->last_done[l0], gs));
+    return HPFW_OK;
+}
+
+// mode 0: dB spectrogram; mode 1: linear magnitudes. d_audio must be 8-byte aligned.
+static int cqt_run(hpfw_ctx *ctx, const float *d_audio, int64_t N, float *d_out, int mode, cudaStream_t stream,
+                   int lane = 0) {
+    CqtJob jb;
+    jb.d_audio = d_audio; jb.N = N; jb.d_out = d_out; jb.mode = mode; jb.stream = stream; jb.lane = lane;
+    HPFW_TRY(cqt_prepare(ctx, jb));
+    for (int st = 0; st < CQ_STAGES; ++st) HPFW_TRY(cqt_stage(ctx, jb, st));
     return HPFW_OK;
 }
 
@@ -2102,14 +2317,83 @@ int hpfw_calc_hashprint_audio_batch_device(hpfw_ctx *ctx, const float *d_audio, 
         // fork: the tracks of the chunk run round-robin on CQ_LANES streams (own scratch each) so that the small tail waves
         // of one track's kernels overlap another track's; join before the chunk's single projection launch
         HPFW_TRY(ctx_lanes_init(ctx));
-        const int nl = std::max(1, std::min(std::min(CQ_LANES, env_int("HPFW_CQT_LANES", 4)), j - i));
+        const int nl = std::max(1, std::min(CQ_LANES, env_int("HPFW_CQT_LANES", CQ_LANES)));
         HPFW_CUDA_TRY(cudaEventRecord(ctx->lane_fork, s));
         for (int l = 0; l < nl; ++l) HPFW_CUDA_TRY(cudaStreamWaitEvent(ctx->lane_stream[l], ctx->lane_fork, 0));
-        for (int t = i; t < j; ++t) {
-            const int l = (t - i) % nl;
-            HPFW_TRY(cqt_run(ctx, d_audio + sample_offsets[t], sample_offsets[t + 1] - sample_offsets[t],
-                             ctx->spectro.as<float>() + size_t(co[t - i]) * CQ_BINS, 0, ctx->lane_stream[l], l));
+        // Tracks of one length whose transform takes the packed-FFT path go CQ_GANG_LANES at a time through a captured graph
+        // (cqt_gang_run), the gangs alternating so that two graphs overlap; the rest (odd lengths out, Bluestein lengths,
+        // timing mode) is launched kernel by kernel, one track per lane, stage by stage across the lanes.
+        std::vector<int> plain;
+        const bool trace = env_int("HPFW_TRACE", 0) != 0;
+        const auto t_enq = std::chrono::steady_clock::now();
+        const bool use_graph = env_int("HPFW_CQT_GRAPH", 1) != 0 && !ctx->timing && nl == CQ_LANES;
+        if (use_graph) {
+            std::map<int64_t, std::vector<int>> by_len;
+            for (int t = i; t < j; ++t) by_len[sample_offsets[t + 1] - sample_offsets[t]].push_back(t);
+            int gang = 0;
+            for (auto &kv : by_len) {
+                std::vector<int> &ts = kv.second;
+                size_t k = 0;
+                // capturing a graph costs a few plain tracks' worth of host time: only for lengths that repeat
+                auto it = ctx->cqt ? ctx->cqt->plans.find(kv.first) : std::map<int64_t, std::unique_ptr<CqtPlan>>::iterator();
+                const bool have = ctx->cqt && it != ctx->cqt->plans.end() && it->second->gangs != nullptr;
+                if (have || ts.size() >= 2 * (size_t)CQ_GANG_LANES) {
+                    for (; k + CQ_GANG_LANES <= ts.size(); k += CQ_GANG_LANES) {
+                        CqtJob jobs[CQ_GANG_LANES];
+                        for (int l = 0; l < CQ_GANG_LANES; ++l) {
+                            const int t = ts[k + (size_t)l];
+                            jobs[l].d_audio = d_audio + sample_offsets[t];
+                            jobs[l].N = kv.first;
+                            jobs[l].d_out = ctx->spectro.as<float>() + size_t(co[t - i]) * CQ_BINS;
+                            jobs[l].lane = gang * CQ_GANG_LANES + l;
+                            jobs[l].stream = ctx->lane_stream[jobs[l].lane];
+                            HPFW_TRY(cqt_prepare(ctx, jobs[l]));
+                        }
+                        if (jobs[0].pl->bluestein) break;
+                        HPFW_TRY(cqt_gang_run(ctx, jobs, gang));
+                        gang = (gang + 1) % CQ_GANGS;
+                    }
+                }
+                for (; k < ts.size(); ++k) plain.push_back(ts[k]);
+            }
+            std::sort(plain.begin(), plain.end());
+            // the lanes' scratch was last used by the graphs, which ran on each gang's first lane stream
+            if (!plain.empty())
+                for (int g = 0; g < CQ_GANGS; ++g) {
+                    const int l0 = g * CQ_GANG_LANES;
+                    HPFW_CUDA_TRY(cudaEventRecord(ctx->lane_join[l0], ctx->lane_stream[l0]));
+                    for (int l = 1; l < CQ_GANG_LANES; ++l)
+                        HPFW_CUDA_TRY(cudaStreamWaitEvent(ctx->lane_stream[l0 + l], ctx->lane_join[l0], 0));
+                }
+        } else {
+            for (int t = i; t < j; ++t) plain.push_back(t);
         }
+        for (size_t t0 = 0; t0 < plain.size(); t0 += (size_t)nl) {
+            CqtJob jobs[CQ_LANES];
+            const int nj = (int)std::min((size_t)nl, plain.size() - t0);
+            for (int l = 0; l < nj; ++l) {
+                const int t = plain[t0 + (size_t)l];
+                jobs[l].d_audio = d_audio + sample_offsets[t];
+                jobs[l].N = sample_offsets[t + 1] - sample_offsets[t];
+                jobs[l].d_out = ctx->spectro.as<float>() + size_t(co[t - i]) * CQ_BINS;
+                jobs[l].stream = ctx->lane_stream[l];
+                jobs[l].lane = l;
+                HPFW_TRY(cqt_prepare(ctx, jobs[l]));
+                // Bluestein plans are few (CQ_PLAN_CACHE_BLUESTEIN) and preparing the next one may evict this one: launch
+                // such a track at once; the packed-path plans of one wave are the most recently used of CQ_PLAN_CACHE
+                if (jobs[l].pl->bluestein) {
+                    for (int st = 0; st < CQ_STAGES; ++st) HPFW_TRY(cqt_stage(ctx, jobs[l], st));
+                    jobs[l].pl = nullptr;
+                }
+            }
+            for (int st = 0; st < CQ_STAGES; ++st)
+                for (int l = 0; l < nj; ++l)
+                    if (jobs[l].pl) HPFW_TRY(cqt_stage(ctx, jobs[l], st));
+        }
+        if (trace)
+            fprintf(stderr, "[hpfw] batch chunk: %d tracks, CQT launches enqueued in %.1f us/track (%zu kernel by kernel)\n",
+                    j - i, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_enq).count() / (j - i),
+                    plain.size());
         for (int l = 0; l < nl; ++l) {
             HPFW_CUDA_TRY(cudaEventRecord(ctx->lane_join[l], ctx->lane_stream[l]));
             HPFW_CUDA_TRY(cudaStreamWaitEvent(s, ctx->lane_join[l], 0));

@@ -189,6 +189,69 @@ def test_batch_of_distinct_lengths_equals_single_calls(ctx, hashprint_golden):
         ctx2.close()
 
 
+def test_batch_of_repeated_lengths_graph_replay(ctx, hashprint_golden):
+    """Tracks of equal length go four at a time through a captured launch graph (cqt.cu cqt_gang_run) whose input / output
+    nodes are re-pointed on every replay; lengths that occur fewer than 8 times, and odd (Bluestein) lengths, take the
+    kernel-by-kernel path in the same call. Two calls with the audio at different device addresses (the second replays the
+    first's graphs), then one with a longer track first (the lanes' scratch grows: the graphs are re-captured): every
+    hashprint must equal the single-track call of a fresh context."""
+    import torch
+    import hpfw_b200
+    ex = hpfw_b200.HashprintExtractor(ctx)
+    ex.set_filters(hashprint_golden["filters"])
+    base = synth.synth_track(78, 9.0, 44100)
+    ctx2 = hpfw_b200.Context(0)
+    try:
+        ex2 = hpfw_b200.HashprintExtractor(ctx2)
+        ex2.set_filters(hashprint_golden["filters"])
+        for rep, lens in enumerate([[132300] * 19 + [176400] * 9 + [154350] * 5 + [132301] * 2,
+                                    [132300] * 11 + [176400] * 8,
+                                    [352800] + [132300] * 9 + [176400] * 8]):
+            rng = np.random.default_rng(100 + rep)
+            parts = []
+            for i, n in enumerate(lens):
+                o = int(rng.integers(0, len(base) - n)) if n < len(base) else 0
+                seg = base[o:o + n] if n <= len(base) else np.concatenate([base, base])[:n]
+                parts.append((seg * np.float32(0.4 + 0.02 * i)).astype(np.float32))
+            so = np.zeros(len(lens) + 1, dtype=np.int64)
+            so[1:] = np.cumsum(lens)
+            # an odd length would misalign the tracks behind it: pad every track start to an even sample offset
+            starts, total = [], 0
+            for n in lens:
+                starts.append(total)
+                total += n + (n & 1)
+            pad = rep * 1024                      # a different base address on every call
+            host = np.zeros(total + pad, dtype=np.float32)
+            for st, part in zip(starts, parts):
+                host[pad + st:pad + st + len(part)] = part
+            words = [ex.words(n) for n in lens]
+            d_all = torch.from_numpy(host).cuda()
+            d_hp = torch.zeros(int(sum(words)), dtype=torch.int64, device="cuda")
+            if all(n % 2 == 0 for n in lens):
+                ex.calc_hashprint_batch_device(d_all.data_ptr() + 4 * pad, so, d_hp.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream)
+            else:
+                # contiguous offsets are the ABI: run the even-length prefix and the odd tail as two calls
+                k = next(i for i, n in enumerate(lens) if n % 2)
+                ex.calc_hashprint_batch_device(d_all.data_ptr() + 4 * pad, so[:k + 1], d_hp.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream)
+                w0 = int(sum(words[:k]))
+                for i in range(k, len(lens)):
+                    one = np.array([0, lens[i]], dtype=np.int64)
+                    ex.calc_hashprint_batch_device(d_all.data_ptr() + 4 * (pad + starts[i]), one, d_hp.data_ptr() + 8 * w0,
+                                                   torch.cuda.current_stream().cuda_stream)
+                    w0 += words[i]
+            torch.cuda.synchronize()
+            got = d_hp.cpu().numpy().view(np.uint64)
+            w0 = 0
+            for i, (n, part, w) in enumerate(zip(lens, parts, words)):
+                ref = ex2.calc_hashprint(part)
+                assert np.array_equal(got[w0:w0 + w], ref), f"call {rep}, track {i} ({n} samples) differs"
+                w0 += w
+    finally:
+        ctx2.close()
+
+
 def test_cqt_limits(ctx):
     from hpfw_b200 import HpfwError
     from hpfw_b200._lib import ERR_SHORT
