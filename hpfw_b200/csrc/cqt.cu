@@ -1902,6 +1902,10 @@ static int cqt_stage(hpfw_ctx *ctx, const CqtJob &jb, int stage) {
     cudaStream_t stream = jb.stream;
     const CqtDesign &d = pl->des;
     const dim3 gcol((pl->max_L2 + CQ_THREADS - 1) / CQ_THREADS, CQ_BINS);
+#ifdef HPFW_CQT_ABLATE
+    // timing ablation (never in the shipped build): HPFW_CQT_SKIP is a bit mask of stages whose launches are dropped
+    if (stage < CQ_STAGES - 1 && ((env_int("HPFW_CQT_SKIP", 0) >> stage) & 1)) return HPFW_OK;
+#endif
     switch (stage) {
     case 0:
         if (!pl->bluestein) {
