@@ -638,9 +638,16 @@ int hpfw_calc_filters(hpfw_ctx *ctx, const float *cov, float *filters_out, float
         gemm_nn_kernel<<<g_nn, 256, 0, s>>>(X, Wm, Y, n, p);
     };
     // dst = orthonormal basis of span(src) by CholQR2 (Gram matrices and triangular factors in double); src is overwritten
-    auto orth = [&](float *src, float *tmp, float *dst) {
+    // (twice = false: one pass, dst orthonormal to ~cond(src) * 1e-7 — enough between two multiplications by A, where the
+    // only job is to keep the block from collapsing onto the dominant vectors; the block a Rayleigh-Ritz checkpoint reads is
+    // always made by the two-pass form)
+    auto orth = [&](float *src, float *tmp, float *dst, bool twice = true) {
         gram(src, src);
         { KernelScope ks(ctx, HPFW_K_OTHER, s); chol_inv_kernel<<<1, 256, pp, s>>>(G, W, p); }
+        if (!twice) {
+            rotate(src, W, dst);
+            return;
+        }
         rotate(src, W, tmp);
         gram(tmp, tmp);
         { KernelScope ks(ctx, HPFW_K_OTHER, s); chol_inv_kernel<<<1, 256, pp, s>>>(G, W, p); }
@@ -680,7 +687,7 @@ int hpfw_calc_filters(hpfw_ctx *ctx, const float *cov, float *filters_out, float
         n_iters = it;
         { KernelScope ks(ctx, HPFW_K_OTHER, s); symm_block_mul_kernel<<<g_mul, 256, 0, s>>>(A, V, Z, n, p); }
         if (it < next_check && it < max_it) {
-            orth(Z, T, V);
+            orth(Z, T, V, it + 1 >= next_check || it + 1 >= max_it);
             continue;
         }
         gram(V, Z);                                            // H = V^T A V

@@ -82,8 +82,13 @@ private:
     // ---- index: device-to-device when both plug-ins support it
     template <class C, class St>
     static auto index_impl(C &c, St &st, const std::vector<std::string> &files, int)
-        -> decltype(st.build_device(c.prepare_device(files)), void()) {
-        st.build_device(c.prepare_device(files));
+        -> decltype(st.build_device(c.prepare_device(files, false)), c.begin_cache_writes(), void()) {
+        detail::PhaseTrace trace;
+        auto d = c.prepare_device(files, false);       // the collector's cache writers wait ...
+        trace.mark("index: prepare_device");
+        st.build_device(d);
+        trace.mark("index: storage build_device");
+        c.begin_cache_writes();                        // ... until the storage is built
     }
     template <class C, class St>
     static void index_impl(C &c, St &st, const std::vector<std::string> &files, long) {

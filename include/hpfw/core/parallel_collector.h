@@ -27,6 +27,7 @@
 #include <condition_variable>
 #include <deque>
 #include <filesystem>
+#include <functional>
 #include <iostream>
 #include <map>
 #include <memory>
@@ -147,8 +148,10 @@ public:
 
     /// prepare() with the result left on the GPU (see DeviceHashprints). The spectrograms stay resident until the background
     /// cache writers have finished (flush_cache_writes(), called by the next prepare / the destructor).
+    /// start_writers = false leaves the cache/spectros writers parked until begin_cache_writes() (or any flush): index() builds
+    /// its storage first, so that the writers' device->host copies do not sit between the storage's allocations and kernels.
     template <bool B = batched, typename = std::enable_if_t<B>>
-    DeviceHashprints prepare_device(const std::vector<std::string> &filenames) {
+    DeviceHashprints prepare_device(const std::vector<std::string> &filenames, bool start_writers = true) {
         detail::PhaseTrace trace;
         flush_cache_writes();
         std::unique_lock<std::mutex> l(ctx->mutex());
@@ -240,7 +243,7 @@ public:
         device::check(hpfw_xs_hash_kept(xs));
 
         trace.mark("prepare: hashed");
-        start_cache_writers();
+        if (start_writers) start_cache_writers();
         DeviceHashprints out;
         out.xs = ixs;
         out.ctx = ctx;
@@ -374,6 +377,9 @@ public:
     /// in HBM; a later run cannot re-hash them from the cache.
     void set_cache_spectrograms(bool on) { cache_spectrograms = on; }
 
+    /// Start the background cache writers of the last prepare_device(files, false); a no-op when nothing is pending.
+    void begin_cache_writes() { start_cache_writers(); }
+
     /// Wait for the background cache writers and release the resident spectrograms of the last prepare().
     void flush_cache_writes() {
         start_cache_writers();
@@ -460,6 +466,13 @@ private:
         std::condition_variable qcv;
         size_t outstanding = filenames.size();   // files not yet consumed by the submitting thread
         bool stop = false;
+        // HPFW_TRACE: where the wall time of this phase goes (summed over the decode threads / on the submitting thread)
+        const bool tracing = std::getenv("HPFW_TRACE") != nullptr;
+        std::atomic<int64_t> us_acquire{0}, us_decode{0};
+        int64_t us_starved = 0, us_submit = 0;
+        auto now_us = [] {
+            return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+        };
         auto worker = [&]() {
             for (;;) {
                 size_t i;
@@ -471,12 +484,20 @@ private:
                     todo.pop_front();
                 }
                 Ready r{i, -1, DecodeInfo(), ""};
+                const int64_t t_dec = tracing ? now_us() : 0;
+                int64_t t_acq = 0;
                 try {
                     r.info = SpectrogramHandler::decode(filenames[i], [&](size_t bytes) -> void * {
                         void *p = nullptr;
+                        const int64_t a0 = tracing ? now_us() : 0;
                         device::check(hpfw_xs_acquire(xs, bytes, &r.slot, &p));
+                        if (tracing) t_acq += now_us() - a0;
                         return p;
                     });
+                    if (tracing) {
+                        us_acquire += t_acq;
+                        us_decode += now_us() - t_dec - t_acq;
+                    }
                 } catch (const std::exception &e) {
                     r.error = e.what();
                     if (r.error.empty()) r.error = "decode failed";
@@ -496,12 +517,21 @@ private:
         std::exception_ptr fatal;
         while (outstanding > 0) {
             Ready r;
+            const int64_t t_wait = tracing ? now_us() : 0;
             {
                 std::unique_lock<std::mutex> ql(qm);
                 qcv.wait(ql, [&] { return !ready.empty(); });
                 r = std::move(ready.front());
                 ready.pop_front();
             }
+            const int64_t t_got = tracing ? now_us() : 0;
+            us_starved += t_got - t_wait;
+            struct SubmitTimer {
+                int64_t &acc, t0;
+                bool on;
+                std::function<int64_t()> clock;
+                ~SubmitTimer() { if (on) acc += clock() - t0; }
+            } submit_timer{us_submit, t_got, tracing, now_us};
             if (fatal) {                                   // draining after a fatal error: give the slots back
                 if (r.slot >= 0) hpfw_xs_release(xs, r.slot);
                 --outstanding;
@@ -536,6 +566,11 @@ private:
         }
         qcv.notify_all();
         for (auto &t : pool) t.join();
+        if (tracing)
+            std::cerr << "[hpfw trace] decoders: " << nthreads << " threads, per thread " << us_decode.load() / 1000 / std::max(1u, nthreads)
+                      << " ms reading files + " << us_acquire.load() / 1000 / std::max(1u, nthreads)
+                      << " ms waiting for a staging slot; submitting thread " << us_submit / 1000 << " ms in submit, "
+                      << us_starved / 1000 << " ms waiting for a decoded file" << std::endl;
         if (fatal) std::rethrow_exception(fatal);
     }
 
