@@ -638,6 +638,19 @@ __device__ __forceinline__ void pass_last(const float2 *Sin, float2 *Sout, int n
         default: { constexpr int R = 1; CALL; } break;                                                                  \
     }
 
+#ifdef HPFW_CQT_PHASECLK
+// tuning aid (never in the shipped build): clock cycles thread 0 of every CTA spends in each phase of a pass, summed
+__device__ unsigned long long g_phase_clk[2][6];
+#define HPFW_PHASE_MARK(i)                                                                   \
+    if (threadIdx.x == 0) {                                                                  \
+        const long long now_ = clock64();                                                    \
+        atomicAdd(&g_phase_clk[MODE][i], (unsigned long long)(now_ - phase_t_));             \
+        phase_t_ = now_;                                                                     \
+    }
+#else
+#define HPFW_PHASE_MARK(i)
+#endif
+
 template <int MODE>
 __global__ void __launch_bounds__(CQ_FFT_THREADS, CQ_PASS_CTAS)
 fft_pass_kernel(const float2 *__restrict__ in, float2 *__restrict__ out_lo, float2 *__restrict__ out_hi, FftDesc d,
@@ -653,8 +666,13 @@ fft_pass_kernel(const float2 *__restrict__ in, float2 *__restrict__ out_lo, floa
     const float2 *src = MODE == 0 ? in + first : in + (long long)first * pitch;
     PassOut po{MODE == 0 ? out_lo + first : out_lo, out_hi, twH_hi, twH_lo, other, first, klo, khi, H, keep_all};
 
+#ifdef HPFW_CQT_PHASECLK
+    long long phase_t_ = clock64();
+#endif
     HPFW_RADIX_SWITCH(d.rad[0], (pass_first<R, MODE>(src, S0, n, G, g_here, pitch, sign, mg_g, d.mg_m[0])));
+    HPFW_PHASE_MARK(0)        // thread 0's own first-stage work (global loads + butterflies)
     __syncthreads();
+    HPFW_PHASE_MARK(1)        // its wait at the barrier
     int Ns = d.rad[0];
     float2 *cur = S0, *nxt = S1;
     for (int s = 1; s + 1 < d.nrad; ++s) {
@@ -663,10 +681,13 @@ fft_pass_kernel(const float2 *__restrict__ in, float2 *__restrict__ out_lo, floa
         float2 *t = cur; cur = nxt; nxt = t;
         Ns *= d.rad[s];
     }
+    HPFW_PHASE_MARK(2)        // middle stages (with their barriers)
     const int sl = d.nrad - 1;
     HPFW_RADIX_SWITCH(d.rad[sl], (pass_last<R, MODE>(cur, nxt, n, G, g_here, T, sign, mg_g, d.mg_m[sl], po)));
+    HPFW_PHASE_MARK(3)        // last stage
     if (MODE == 0) {
         __syncthreads();
+        HPFW_PHASE_MARK(4)
         // nxt holds out-values at [g][c]; store with the G adjacent columns contiguous (32-byte runs for G = 4)
         const int tot = G * n;
 #pragma unroll 4
@@ -674,6 +695,7 @@ fft_pass_kernel(const float2 *__restrict__ in, float2 *__restrict__ out_lo, floa
             const int c = fastdiv(idx, mg_g), g = idx - c * G;
             if (g < g_here) po.lo[c * pitch + g] = nxt[ps_pad<MODE>(idx)];
         }
+        HPFW_PHASE_MARK(5)    // column-adjacent store
     }
 }
 
@@ -2200,6 +2222,17 @@ int hpfw_b200::ctx_lanes_init(hpfw_ctx *ctx) {
 }
 
 extern "C" {
+
+#ifdef HPFW_CQT_PHASECLK
+int hpfw_cqt_debug_phases(unsigned long long *out12, int reset) {
+    if (out12 && cudaMemcpyFromSymbol(out12, g_phase_clk, sizeof(unsigned long long) * 12) != cudaSuccess) return HPFW_ERR_CUDA;
+    if (reset) {
+        unsigned long long z[12] = {};
+        if (cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z)) != cudaSuccess) return HPFW_ERR_CUDA;
+    }
+    return HPFW_OK;
+}
+#endif
 
 int hpfw_cqt_design(int64_t n_samples, int *pos_out, int *lg_out, int *m_out) {
     CqtDesign d;
