@@ -8,7 +8,7 @@ ntr = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 ctx = hpfw_b200.Context(0)
 g = np.load("tests/golden/hashprint.npz")
 ex = hpfw_b200.HashprintExtractor(ctx); ex.set_filters(g["filters"])
-N = 7938000
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 7938000      # samples per track (default: 3 minutes)
 audio = (0.1 * torch.randn(ntr, N, device="cuda")).contiguous()
 t = torch.arange(N, device="cuda", dtype=torch.float32) / 44100
 audio += 0.2 * torch.sin(2 * np.pi * 440.0 * t) + 0.2 * torch.sin(2 * np.pi * 1318.5 * t)
@@ -27,4 +27,5 @@ host_us = (time.perf_counter() - h0) / 3 / ntr * 1e6     # host time to enqueue 
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3 / ntr
 env = {k: v for k, v in os.environ.items() if k.startswith("HPFW_CQT")}
-print(f"{env}: host enqueue {host_us:.1f} us/track; {ms*1e3:.1f} us/track ({14491/ms/1e3:.2f} M frames/s), checksum {int(hp[:words].sum().item()) & 0xFFFFFFFF:08x}")
+cols = ex.words(N) + 99
+print(f"N={N} {env}: host enqueue {host_us:.1f} us/track; {ms*1e3:.1f} us/track ({(words)/ms/1e3:.2f} M frames/s), checksum {int(hp[:words].sum().item()) & 0xFFFFFFFF:08x}")
