@@ -53,7 +53,7 @@ I8_OPS_PER_CLK_SM = 16384   # tcgen05.mma kind::i8, M=128 N=256 K=32 in 128 clk 
 F4_OPS_PER_CLK_SM = 32768   # tcgen05.mma kind::mxf4, M=128 N=256 K=64 in 128 clk: 16384 MAC/clk/SM (nominal 9 PFLOP/s fp4 dense)
 OPS_PER_WORDOP = 128        # tensor-core matcher: one 64-bit word-op = 64 s8 multiply-adds
 NCU_TC_TRAFFIC_RATIO = 243.07 / 233.8   # measured DRAM bytes / algorithmic bytes of match_tc_kernel<1> (profiles/r03d_*)
-NCU_CQT_TRAFFIC_PER_TRACK = 144.3e6     # measured DRAM bytes of the six CQT kernels on one 3-min track (profiles/r01y_*)
+NCU_CQT_TRAFFIC_PER_TRACK = 268.3e6     # measured DRAM bytes per 3-min track over a whole 48-track batch (profiles/r2q_*, r2n)
 
 
 def host_cores() -> int:
@@ -414,9 +414,11 @@ def run_extraction(args, ctx, rank, world, dev, max_over_ranks, barrier, st):
         "roofline": {"bound": "hbm", "kernel": "CQT (7 kernels per track, cqt.cu)", "achieved": cqt_bytes / (cq_per_track * 1e-3) / 1e9,
                      "peak": hbm, "unit": "GB/s", "frac": cqt_bytes / (cq_per_track * 1e-3) / 1e9 / hbm,
                      "traffic": NCU_CQT_TRAFFIC_PER_TRACK,
-                     "traffic_note": "per track: dram__bytes_read+write summed over the six CQT kernels of one 3-min track in the "
-                                     "ncu --set full capture profiles/r01y_cqt_kernels_ncu_full.md (two FFT passes + three "
-                                     "chirp-z passes re-read their predecessor's output)",
+                     "traffic_note": "per track: dram__bytes_read+write of a whole 48-track batch (8 lanes) from ncu --replay-mode "
+                                     "app-range, profiles/r2q_cqt_batch_range_lanes8.csv: 150 MB read + 118 MB written; two FFT "
+                                     "passes + three chirp-z passes, and 8 lanes of scratch (720 MB) cannot stay in the 126 MB L2; "
+                                     "one track in flight: 134 MB; the six kernels captured one by one with cold caches: 144 MB "
+                                     "(profiles/r01y_cqt_kernels_ncu_full.md)",
                      "ms_per_track": cq_per_track, "kernel_ms_sum_per_track_overlapped": cq_kernel_sum_per_track,
                      "peak_how": src,
                      "algorithmic_bytes_per_track": cqt_bytes},
