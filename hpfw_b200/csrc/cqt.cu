@@ -767,7 +767,10 @@ template <int MODE, int L1>
 __global__ void __launch_bounds__(CQ_THREADS)
 czt_cols_kernel(const BandMeta *__restrict__ bands, const float2 *__restrict__ z_lo, const float2 *__restrict__ z_hi,
                 int klo, int khi, const float2 *__restrict__ twN_hi, const float2 *__restrict__ twN_lo,
-                const float2 *__restrict__ chirp, int M, int F, float2 *__restrict__ work, int window) {
+                const float2 *__restrict__ chirp, int M, int F, float2 *__restrict__ work, int window,
+                unsigned int *__restrict__ pmax) {
+    // the track maximum czt_out_kernel accumulates (stream order: after this kernel) starts at 0: saves a memset launch
+    if (pmax != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *pmax = 0u;
     const BandMeta bm = bands[blockIdx.y];
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= bm.L2) return;
@@ -1264,6 +1267,7 @@ struct CqtPlan {
     cudaEvent_t ready = nullptr;     // recorded on the creating stream after the tables are filled
     cudaEvent_t last_done[CQ_LANES] = {};   // per lane: recorded after the latest transform that used this plan
     cudaStream_t created_on = nullptr;
+    bool settled = false;            // `ready` has been observed complete: no stream needs to wait for it any more
     uint64_t last_use = 0;
     struct CqtGang *gangs = nullptr;     // CQ_GANGS captured launch graphs of this plan (batch entry), created on first use
 };
@@ -1816,13 +1820,13 @@ static int plan_create(hpfw_ctx *ctx, int64_t N, CqtPlan &pl, cudaStream_t strea
             const dim3 gf((max_fL2 + CQ_THREADS - 1) / CQ_THREADS, nL);
             if (L1 == 16)
                 czt_cols_kernel<1, 16><<<gf, CQ_THREADS, 0, stream>>>(dfb, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr,
-                                                                      d.M, d.F, tab, 0);
+                                                                      d.M, d.F, tab, 0, nullptr);
             else if (L1 == 32)
                 czt_cols_kernel<1, 32><<<gf, CQ_THREADS, 0, stream>>>(dfb, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr,
-                                                                      d.M, d.F, tab, 0);
+                                                                      d.M, d.F, tab, 0, nullptr);
             else
                 czt_cols_kernel<1, 64><<<gf, CQ_THREADS, 0, stream>>>(dfb, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr,
-                                                                      d.M, d.F, tab, 0);
+                                                                      d.M, d.F, tab, 0, nullptr);
         }
         {
             KernelScope ks(ctx, HPFW_K_CQT, stream);
@@ -1912,7 +1916,14 @@ static int cqt_prepare(hpfw_ctx *ctx, CqtJob &jb) {
     CqtPlanCache *cache = ctx->cqt;
     HPFW_TRY(lane_reserve(cache, *jb.pl, jb.lane));
     jb.sc = &cache->lanes[jb.lane];
-    if (jb.stream != jb.pl->created_on) HPFW_CUDA_TRY(cudaStreamWaitEvent(jb.stream, jb.pl->ready, 0));
+    if (jb.stream != jb.pl->created_on && !jb.pl->settled) {
+        // the tables are filled once; as soon as that has been seen complete no later use needs to wait for it
+        if (cudaEventQuery(jb.pl->ready) == cudaSuccess) jb.pl->settled = true;
+        else {
+            cudaGetLastError();     // cudaErrorNotReady is not sticky, but clear it for the checks below
+            HPFW_CUDA_TRY(cudaStreamWaitEvent(jb.stream, jb.pl->ready, 0));
+        }
+    }
     if (!jb.pl->bluestein && (reinterpret_cast<uintptr_t>(jb.d_audio) & 7) != 0)
         HPFW_FAIL(HPFW_ERR_ARG, "CQT: the audio buffer must be 8-byte aligned");
     return HPFW_OK;
@@ -1959,29 +1970,28 @@ static int cqt_stage(hpfw_ctx *ctx, const CqtJob &jb, int stage) {
                                 0, -1, stream));
         break;
     case 2: {
-        HPFW_CUDA_TRY(cudaMemsetAsync(sc->pmax.ptr, 0, sizeof(unsigned int), stream));
         KernelScope ks(ctx, HPFW_K_CQT, stream);
         float2 *zlo = sc->zlo.as<float2>(), *zhi = sc->zhi.as<float2>(), *wk = sc->work.as<float2>();
         if (pl->bluestein) {
             if (pl->L1 == 16)
                 czt_cols_kernel<2, 16><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, zlo, nullptr, pl->klo, pl->khi, nullptr,
-                                                                        nullptr, pl->chirp, d.M, d.F, wk, ctx->cqt_window);
+                                                                        nullptr, pl->chirp, d.M, d.F, wk, ctx->cqt_window, sc->pmax.as<unsigned int>());
             else if (pl->L1 == 32)
                 czt_cols_kernel<2, 32><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, zlo, nullptr, pl->klo, pl->khi, nullptr,
-                                                                        nullptr, pl->chirp, d.M, d.F, wk, ctx->cqt_window);
+                                                                        nullptr, pl->chirp, d.M, d.F, wk, ctx->cqt_window, sc->pmax.as<unsigned int>());
             else
                 czt_cols_kernel<2, 64><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, zlo, nullptr, pl->klo, pl->khi, nullptr,
-                                                                        nullptr, pl->chirp, d.M, d.F, wk, ctx->cqt_window);
+                                                                        nullptr, pl->chirp, d.M, d.F, wk, ctx->cqt_window, sc->pmax.as<unsigned int>());
         } else {
             if (pl->L1 == 16)
                 czt_cols_kernel<0, 16><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, zlo, zhi, pl->klo, pl->khi, pl->twN_hi,
-                                                                        pl->twN_lo, pl->chirp, d.M, d.F, wk, ctx->cqt_window);
+                                                                        pl->twN_lo, pl->chirp, d.M, d.F, wk, ctx->cqt_window, sc->pmax.as<unsigned int>());
             else if (pl->L1 == 32)
                 czt_cols_kernel<0, 32><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, zlo, zhi, pl->klo, pl->khi, pl->twN_hi,
-                                                                        pl->twN_lo, pl->chirp, d.M, d.F, wk, ctx->cqt_window);
+                                                                        pl->twN_lo, pl->chirp, d.M, d.F, wk, ctx->cqt_window, sc->pmax.as<unsigned int>());
             else
                 czt_cols_kernel<0, 64><<<gcol, CQ_THREADS, 0, stream>>>(pl->d_bands, zlo, zhi, pl->klo, pl->khi, pl->twN_hi,
-                                                                        pl->twN_lo, pl->chirp, d.M, d.F, wk, ctx->cqt_window);
+                                                                        pl->twN_lo, pl->chirp, d.M, d.F, wk, ctx->cqt_window, sc->pmax.as<unsigned int>());
         }
         break;
     }
